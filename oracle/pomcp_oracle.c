@@ -1,0 +1,851 @@
+/*
+ * oracle/pomcp_oracle.c -- TEST INFRASTRUCTURE, NOT PRODUCT CODE.
+ *
+ * A plain-C, single-threaded CPU restatement of the POMCP hot path of
+ * pemami4911/POMDPy (the reference is pure Python; citations below are
+ * file:line in that tree).  Only tests/, __graft_entry__.smoke() and the
+ * cpu_baseline / --impl reference legs of bench.py may load this library;
+ * nothing under pomdpy_b200/ does.
+ *
+ * Two algorithms live here:
+ *
+ *  (1) "ref" -- the reference's *sequential* POMCP, quirks included
+ *      (per-level particle resampling, rollout from the pre-action node,
+ *      stale mean, input-state mutation on a rewarded SAMPLE; SURVEY.md
+ *      Appendix A.1-A.5, A.12).  Random draws come from one sequential
+ *      Philox stream so that the executed reference, with random.choice /
+ *      random.shuffle / np.random.binomial patched to the same stream
+ *      (oracle/refharness/), must agree with it bit for bit.  That
+ *      comparison is what pins this file to the reference.
+ *
+ *  (2) "gs"  -- the generation-synchronous tree-parallel POMCP that the CUDA
+ *      product implements: identical model function,
+ *      UCB1 rule, expansion rule, rollout policy and backup arithmetic, but
+ *      simulations advance in lock-step generations so that the result is a
+ *      deterministic function of (seed, inputs) for any degree of
+ *      parallelism.  With generation width 1 it is the textbook sequential
+ *      POMCP ("canonical" in SURVEY.md Appendix D).  The CUDA kernels must
+ *      reproduce its root statistics exactly.
+ *
+ * Build: make -C oracle   (gcc -O2 -ffp-contract=off: no FMA contraction, the
+ * floating-point sequences below are part of the specification).
+ */
+#include <math.h>
+#include <stdint.h>
+#include <stdio.h>
+#include <stdlib.h>
+#include <string.h>
+
+#define ORC_MAX_ACTIONS 32
+#define ORC_MAX_CELLS 256
+#define ORC_MAX_ROCKS 24
+#define ORC_CELL_EMPTY (-1)
+#define ORC_CELL_GOAL (-2)
+#define ORC_CELL_OBSTACLE (-3)
+#define ORC_QFIX_SCALE 16777216.0 /* 2^24 fixed-point scale of summed returns (gs mode) */
+
+/* ------------------------------------------------------------------------ */
+/* Philox4x32-10 (Salmon et al., SC'11) -- counter-based RNG shared by spec.  */
+/* ------------------------------------------------------------------------ */
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+{
+    uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
+    uint32_t k0 = key[0], k1 = key[1];
+    for (int r = 0; r < 10; ++r) {
+        uint64_t p0 = (uint64_t)0xD2511F53u * c0;
+        uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
+        uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
+        uint32_t n1 = (uint32_t)p1;
+        uint32_t n2 = (uint32_t)(p0 >> 32) ^ c3 ^ k1;
+        uint32_t n3 = (uint32_t)p0;
+        c0 = n0; c1 = n1; c2 = n2; c3 = n3;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
+}
+
+/* integer in [0, n): multiply-shift of one 32-bit word */
+static inline uint32_t randbelow32(uint32_t x, uint32_t n) { return (uint32_t)(((uint64_t)x * n) >> 32); }
+/* 53-bit uniform numerator, same bit recipe as MT19937 genrand_res53 (a>>5, b>>6) */
+static inline uint64_t u53_of(uint32_t a, uint32_t b) { return ((uint64_t)(a >> 5) << 26) | (uint64_t)(b >> 6); }
+
+/* stream domains (ctr[3]) */
+enum { DOM_SIM = 0, DOM_UPDATE = 1, DOM_FINAL = 2, DOM_AGENT = 3, DOM_SEQ = 7 };
+
+/* ------------------------------------------------------------------------ */
+/* RockSample model: examples/rock_sample/rock_model.py                      */
+/* ------------------------------------------------------------------------ */
+typedef struct {
+    int32_t rows, cols, n_rocks, n_actions, start_cell;
+    int8_t cell[ORC_MAX_CELLS];                  /* rock k>=0 | EMPTY -1 | GOAL -2 | OBSTACLE -3 (rock_model.py:24-32) */
+    uint32_t legal[ORC_MAX_CELLS];               /* per-cell legal-action bit mask (rock_model.py:218-247) */
+    uint64_t thr53[ORC_MAX_CELLS * ORC_MAX_ROCKS]; /* floor(thr * 2^53); CHECK is correct iff u53 <= thr53 */
+    double rew_illegal, rew_exit, rew_good, rew_bad; /* signed: -100, +10, +10, -10 (rock_sample_config.json) */
+} orc_model;
+
+typedef struct {
+    uint32_t actual_mask;  /* model.actual_rock_states (the REAL world; rock_model.py:263-265, A.5) */
+    uint32_t sampled_mask; /* model.unique_rocks_sampled (rock_model.py:267-272) */
+} orc_world;
+
+static int valid_cell(const orc_model *m, int i, int j)
+{ /* rock_model.py:213-216 is_valid_pos */
+    return i >= 0 && i < m->rows && j >= 0 && j < m->cols && m->cell[i * m->cols + j] != ORC_CELL_OBSTACLE;
+}
+
+/* rock_model.py:218-247 get_legal_actions == rock_position_history.py:139-168 */
+static uint32_t legal_mask_of_cell(const orc_model *m, int cell)
+{
+    static const int DI[4] = {-1, 0, 1, 0}, DJ[4] = {0, 1, 0, -1}; /* N E S W (rock_action.py:6-15) */
+    int i = cell / m->cols, j = cell % m->cols;
+    uint32_t mask = 0;
+    for (int a = 0; a < 4; ++a)
+        if (valid_cell(m, i + DI[a], j + DJ[a])) mask |= 1u << a;
+    if (m->cell[cell] >= 0 && m->cell[cell] < m->n_rocks) mask |= 1u << 4;
+    for (int k = 0; k < m->n_rocks; ++k) mask |= 1u << (5 + k);
+    return mask;
+}
+
+orc_model *orc_model_create(int rows, int cols, const int8_t *cell, int start_cell,
+                            const uint64_t *thr53 /* [rows*cols][n_rocks] */, const double rewards[4])
+{
+    if (rows * cols > ORC_MAX_CELLS) return NULL;
+    orc_model *m = (orc_model *)calloc(1, sizeof(orc_model));
+    m->rows = rows; m->cols = cols; m->start_cell = start_cell;
+    int nr = 0;
+    for (int c = 0; c < rows * cols; ++c) { m->cell[c] = cell[c]; if (cell[c] + 1 > nr) nr = cell[c] + 1; }
+    if (nr > ORC_MAX_ROCKS || 5 + nr > ORC_MAX_ACTIONS) { free(m); return NULL; }
+    m->n_rocks = nr; m->n_actions = 5 + nr;                    /* rock_model.py:290-297 */
+    for (int c = 0; c < rows * cols; ++c) {
+        m->legal[c] = legal_mask_of_cell(m, c);
+        for (int k = 0; k < nr; ++k) m->thr53[c * ORC_MAX_ROCKS + k] = thr53[c * nr + k];
+    }
+    m->rew_illegal = rewards[0]; m->rew_exit = rewards[1]; m->rew_good = rewards[2]; m->rew_bad = rewards[3];
+    return m;
+}
+void orc_model_destroy(orc_model *m) { free(m); }
+uint32_t orc_legal_mask(const orc_model *m, int cell) { return m->legal[cell]; }
+int orc_model_n_actions(const orc_model *m) { return m->n_actions; }
+
+typedef struct {
+    int32_t next_cell; uint32_t next_rocks;
+    int32_t obs_good, obs_empty, terminal, legal, used_uniform, rewarded_sample;
+    double reward;
+} orc_step_out;
+
+/* rock_model.py:451-465 generate_step, as a pure function of (state, action, world, u53).
+ * make_next_position :323-344, make_next_state :346-368, make_observation :370-412,
+ * make_reward :417-445.  `rewarded_sample` reports the A.4 side effect (the reference clears
+ * the *input* state's rock bit on a +10 SAMPLE, rock_model.py:433); callers decide whether to apply it. */
+void orc_step(const orc_model *m, const orc_world *w, int cell, uint32_t rocks, int a, uint64_t u53, orc_step_out *o)
+{
+    static const int DI[4] = {-1, 0, 1, 0}, DJ[4] = {0, 1, 0, -1};
+    int i = cell / m->cols, j = cell % m->cols, ni = i, nj = j, legal = 1;
+    if (a < 4) {
+        ni = i + DI[a]; nj = j + DJ[a];
+        if (!valid_cell(m, ni, nj)) { ni = i; nj = j; legal = 0; }
+    } else if (a == 4) {
+        int code = m->cell[cell];
+        legal = (code >= 0 && code < m->n_rocks);
+    }
+    int ncell = ni * m->cols + nj;
+    uint32_t nr = rocks;
+    if (legal && a == 4) nr &= ~(1u << m->cell[cell]);
+    int good = 0, empty = (a < 4), used = 0;
+    if (a >= 5) {
+        int k = a - 5;
+        if (!((w->sampled_mask >> k) & 1u)) {
+            int truth = (w->actual_mask >> k) & 1u;
+            int correct = (u53 <= m->thr53[ncell * ORC_MAX_ROCKS + k]);
+            used = 1;
+            good = correct ? truth : !truth;
+            if (good) nr |= (1u << k); else nr &= ~(1u << k);   /* particle overwritten by the observation */
+        }
+    }
+    int terminal = (m->cell[ncell] == ORC_CELL_GOAL);
+    double r = 0.0; int rs = 0;
+    if (!legal) r = m->rew_illegal;
+    else if (terminal) r = m->rew_exit;
+    else if (a == 4) {
+        int k = m->cell[cell];
+        if (((w->actual_mask >> k) & 1u) && ((rocks >> k) & 1u)) { r = m->rew_good; rs = 1; }
+        else r = m->rew_bad;
+    }
+    o->next_cell = ncell; o->next_rocks = nr; o->obs_good = good; o->obs_empty = empty;
+    o->terminal = terminal; o->legal = legal; o->used_uniform = used; o->rewarded_sample = rs; o->reward = r;
+}
+
+/* ======================================================================== */
+/* (1) "ref": the reference's sequential POMCP                                */
+/* ======================================================================== */
+typedef struct { int32_t cell; uint32_t rocks; } ref_particle;
+
+typedef struct {
+    int32_t cell; uint32_t legal;
+    int64_t N;                               /* DiscreteActionMapping.total_visit_count */
+    int64_t n[ORC_MAX_ACTIONS];              /* entry.visit_count   */
+    double total[ORC_MAX_ACTIONS];           /* entry.total_q_value */
+    double mean[ORC_MAX_ACTIONS];            /* entry.mean_q_value  */
+    int32_t child[ORC_MAX_ACTIONS][2];       /* belief child keyed (action, is_good); -1 = none */
+    int32_t first_obs[ORC_MAX_ACTIONS];      /* insertion order of the action node's child_map */
+    int32_t *bag; int32_t bag_n, bag_cap;    /* state_particles: indices into the particle pool (references!) */
+} ref_node;
+
+typedef struct {
+    const orc_model *m; orc_world w;
+    ref_node *nodes; int32_t n_nodes, cap_nodes;
+    ref_particle *pool; int64_t n_pool, cap_pool;
+    int32_t root;
+    int32_t disable_tree;
+    /* parameters (pomcp.py:13-43) */
+    int32_t max_depth, max_particle_count; double ucb_c, discount;
+    /* quirk switches (all 1 = reference behaviour) */
+    int32_t stale_mean, mutate_input, libm_log;
+    /* sequential draw stream */
+    uint32_t key[2]; uint64_t draw_idx; uint32_t stream_id;
+    /* counters */
+    int64_t n_steps, n_levels, n_rollout_steps, n_zero_backups, n_backups;
+} orc_ref;
+
+static void ref_draw(orc_ref *h, uint32_t x[4])
+{
+    uint32_t ctr[4] = {(uint32_t)h->draw_idx, (uint32_t)(h->draw_idx >> 32), h->stream_id, DOM_SEQ};
+    orc_philox4x32_10(ctr, h->key, x);
+    h->draw_idx++;
+}
+static uint32_t ref_randbelow(orc_ref *h, uint32_t n) { uint32_t x[4]; ref_draw(h, x); return randbelow32(x[0], n); }
+static uint64_t ref_u53(orc_ref *h) { uint32_t x[4]; ref_draw(h, x); return u53_of(x[1], x[2]); }
+
+static int32_t ref_new_particle(orc_ref *h, int32_t cell, uint32_t rocks)
+{
+    if (h->n_pool == h->cap_pool) {
+        h->cap_pool = h->cap_pool ? h->cap_pool * 2 : 4096;
+        h->pool = (ref_particle *)realloc(h->pool, sizeof(ref_particle) * h->cap_pool);
+    }
+    h->pool[h->n_pool].cell = cell; h->pool[h->n_pool].rocks = rocks;
+    return (int32_t)h->n_pool++;
+}
+static void ref_bag_push(ref_node *nd, int32_t p)
+{
+    if (nd->bag_n == nd->bag_cap) {
+        nd->bag_cap = nd->bag_cap ? nd->bag_cap * 2 : 8;
+        nd->bag = (int32_t *)realloc(nd->bag, sizeof(int32_t) * nd->bag_cap);
+    }
+    nd->bag[nd->bag_n++] = p;
+}
+/* discrete_action_mapping.py:16-34: zeroed entries, legal flags from the node's position */
+static int32_t ref_new_node(orc_ref *h, int32_t cell)
+{
+    if (h->n_nodes == h->cap_nodes) {
+        h->cap_nodes = h->cap_nodes ? h->cap_nodes * 2 : 1024;
+        h->nodes = (ref_node *)realloc(h->nodes, sizeof(ref_node) * h->cap_nodes);
+    }
+    ref_node *nd = &h->nodes[h->n_nodes];
+    memset(nd, 0, sizeof(*nd));
+    nd->cell = cell; nd->legal = h->m->legal[cell];
+    for (int a = 0; a < ORC_MAX_ACTIONS; ++a) { nd->child[a][0] = nd->child[a][1] = -1; nd->first_obs[a] = -1; }
+    return h->n_nodes++;
+}
+
+orc_ref *orc_ref_create(const orc_model *m, uint32_t actual_mask, uint32_t sampled_mask,
+                        const uint32_t *bag_rocks, int n_bag, /* belief_tree_solver.py:36-38 */
+                        int max_depth, int max_particle_count, double ucb_c, double discount,
+                        uint64_t seed, uint32_t stream_id)
+{
+    orc_ref *h = (orc_ref *)calloc(1, sizeof(orc_ref));
+    h->m = m; h->w.actual_mask = actual_mask; h->w.sampled_mask = sampled_mask;
+    h->max_depth = max_depth; h->max_particle_count = max_particle_count; h->ucb_c = ucb_c; h->discount = discount;
+    h->stale_mean = 1; h->mutate_input = 1; h->libm_log = 1;
+    h->key[0] = (uint32_t)seed; h->key[1] = (uint32_t)(seed >> 32); h->stream_id = stream_id;
+    h->root = ref_new_node(h, m->start_cell);
+    for (int i = 0; i < n_bag; ++i) ref_bag_push(&h->nodes[h->root], ref_new_particle(h, m->start_cell, bag_rocks[i]));
+    return h;
+}
+void orc_ref_destroy(orc_ref *h)
+{
+    if (!h) return;
+    for (int i = 0; i < h->n_nodes; ++i) free(h->nodes[i].bag);
+    free(h->nodes); free(h->pool); free(h);
+}
+void orc_ref_set_quirks(orc_ref *h, int stale_mean, int mutate_input, int libm_log)
+{ h->stale_mean = stale_mean; h->mutate_input = mutate_input; h->libm_log = libm_log; }
+void orc_ref_set_world(orc_ref *h, uint32_t actual, uint32_t sampled) { h->w.actual_mask = actual; h->w.sampled_mask = sampled; }
+uint64_t orc_ref_draws(const orc_ref *h) { return h->draw_idx; }
+int orc_ref_disabled(const orc_ref *h) { return h->disable_tree; }
+
+/* generate_step on a pooled particle (references: A.4 mutation applies to the pool entry) */
+static void ref_step(orc_ref *h, int32_t p, int a, orc_step_out *o)
+{
+    ref_particle *s = &h->pool[p];
+    uint64_t u = 0;
+    if (a >= 5 && !((h->w.sampled_mask >> (a - 5)) & 1u)) u = ref_u53(h);   /* np.random.binomial, rock_model.py:395 */
+    orc_step(h->m, &h->w, s->cell, s->rocks, a, u, o);
+    if (o->rewarded_sample && h->mutate_input) s->rocks &= ~(1u << h->m->cell[s->cell]);  /* rock_model.py:433 */
+    h->n_steps++;
+}
+
+/* action_selectors.py:6-37 ucb_action + solvers/pomcp.py:52-67 find_fast_ucb (closed form == table, A.11) */
+static int ref_ucb_action(orc_ref *h, ref_node *nd, int greedy)
+{
+    int A = h->m->n_actions;
+    int order[ORC_MAX_ACTIONS];
+    for (int a = 0; a < A; ++a) order[a] = a;
+    for (int i = A - 1; i >= 1; --i) {           /* random.shuffle: Fisher-Yates from the top */
+        int j = (int)ref_randbelow(h, (uint32_t)(i + 1));
+        int t = order[i]; order[i] = order[j]; order[j] = t;
+    }
+    double log_n = log((double)(nd->N + 1));     /* np.log(N + 1) */
+    double best_q = -INFINITY; int best[ORC_MAX_ACTIONS], nbest = 0;
+    for (int t = 0; t < A; ++t) {
+        int a = order[t];
+        if (!((nd->legal >> a) & 1u)) continue;
+        double q = nd->mean[a];
+        if (!greedy) {
+            if (nd->n[a] == 0) q += INFINITY;
+            else q += h->ucb_c * sqrt(log_n / (double)nd->n[a]);
+        }
+        if (q >= best_q) {
+            if (q > best_q) nbest = 0;
+            best_q = q; best[nbest++] = a;
+        }
+    }
+    return best[ref_randbelow(h, (uint32_t)nbest)];   /* random.choice(best_actions) */
+}
+
+/* belief_tree_solver.py:123-152 rollout: starts from a FRESH particle of `node` (A.2) */
+static double ref_rollout(orc_ref *h, int32_t node)
+{
+    ref_node *nd = &h->nodes[node];
+    uint32_t mask = nd->legal;                                   /* node.data.generate_legal_actions() */
+    int32_t p = nd->bag[ref_randbelow(h, (uint32_t)nd->bag_n)];  /* node.sample_particle() */
+    int terminal = 0, steps = 0; double sum = 0.0, disc = 1.0;
+    int32_t cur = p; int cur_is_temp = 0;
+    ref_particle tmp;
+    while (steps < h->max_depth && !terminal) {
+        int cnt = __builtin_popcount(mask);
+        int idx = (int)ref_randbelow(h, (uint32_t)cnt);          /* random.choice(legal_actions), ascending ids */
+        int a = -1;
+        for (int b = 0, seen = 0; b < ORC_MAX_ACTIONS; ++b)
+            if ((mask >> b) & 1u) { if (seen == idx) { a = b; break; } ++seen; }
+        orc_step_out o;
+        if (!cur_is_temp) ref_step(h, cur, a, &o);
+        else {                                                   /* later states are private objects */
+            uint64_t u = 0;
+            if (a >= 5 && !((h->w.sampled_mask >> (a - 5)) & 1u)) u = ref_u53(h);
+            orc_step(h->m, &h->w, tmp.cell, tmp.rocks, a, u, &o);
+            h->n_steps++;
+        }
+        terminal = o.terminal;
+        sum += o.reward * disc;
+        disc *= h->discount;
+        tmp.cell = o.next_cell; tmp.rocks = o.next_rocks; cur_is_temp = 1;
+        mask = h->m->legal[tmp.cell];                            /* model.get_legal_actions(state) */
+        ++steps; h->n_rollout_steps++;
+    }
+    return sum;
+}
+
+/* solvers/pomcp.py:87-137 traverse */
+static double ref_traverse(orc_ref *h, int32_t node, int depth)
+{
+    double delayed = 0.0;
+    ref_node *nd = &h->nodes[node];
+    int32_t p = nd->bag[ref_randbelow(h, (uint32_t)nd->bag_n)];  /* :90 sample_particle (A.1) */
+    int a = ref_ucb_action(h, nd, 0);                            /* :97 */
+    if (depth >= h->max_depth) return 0.0;                       /* :100 */
+    h->n_levels++;
+    orc_step_out o; ref_step(h, p, a, &o);                       /* :104 */
+    int og = o.obs_good ? 1 : 0;
+    int32_t child = nd->child[a][og];                            /* :106 */
+    if (child < 0 && !o.terminal && nd->N > 0) {                 /* :107-108 */
+        int32_t c = ref_new_node(h, o.next_cell);                /* child position: rock_position_history.py:96-99 */
+        nd = &h->nodes[node];                                    /* realloc may have moved the array */
+        nd->child[a][og] = c; if (nd->first_obs[a] < 0) nd->first_obs[a] = og;
+        child = c;
+    }
+    if (!o.terminal || !o.legal) {                               /* :110 */
+        if (child >= 0) {
+            ref_node *cn = &h->nodes[child];
+            if (cn->bag_n < h->max_particle_count)               /* :115-116 */
+                ref_bag_push(cn, ref_new_particle(h, o.next_cell, o.next_rocks));
+            delayed = ref_traverse(h, child, depth + 1);
+        } else delayed = ref_rollout(h, node);                   /* :119 */
+        nd = &h->nodes[node];
+    }
+    double q = nd->mean[a];                                      /* :128 */
+    q += (o.reward + (h->discount * delayed) - q);               /* :131 */
+    nd->n[a] += 1; nd->N += 1;                                   /* discrete_action_mapping.py:137-144 */
+    h->n_backups++;
+    if (q == 0) h->n_zero_backups++;
+    if (!(q == 0 && h->stale_mean)) {                            /* :146-172 (A.3: `if delta_total_q == 0: return`) */
+        nd->total[a] += q;
+        nd->mean[a] = nd->total[a] / (double)nd->n[a];
+    }
+    return q;
+}
+
+/* belief_tree_solver.py:90-121 rollout_search (degraded mode) */
+static void ref_rollout_search(orc_ref *h)
+{
+    int32_t node = h->root;
+    uint32_t mask = h->nodes[node].legal;
+    for (int a = 0; a < h->m->n_actions; ++a) {
+        if (!((mask >> a) & 1u)) continue;
+        ref_node *nd = &h->nodes[node];
+        int32_t p = nd->bag[ref_randbelow(h, (uint32_t)nd->bag_n)];
+        orc_step_out o; ref_step(h, p, a, &o);
+        double delayed = 0.0;
+        if (!o.terminal) {
+            int og = o.obs_good ? 1 : 0;
+            int32_t child = nd->child[a][og];
+            if (child < 0) {
+                child = ref_new_node(h, o.next_cell);
+                nd = &h->nodes[node];
+                nd->child[a][og] = child; if (nd->first_obs[a] < 0) nd->first_obs[a] = og;
+            }
+            ref_bag_push(&h->nodes[child], ref_new_particle(h, o.next_cell, o.next_rocks));
+            delayed = ref_rollout(h, child);
+            nd = &h->nodes[node];
+        }
+        double q = nd->mean[a];
+        q += (o.reward + h->discount * delayed - q);
+        nd->n[a] += 1; nd->N += 1;
+        if (!(q == 0 && h->stale_mean)) { nd->total[a] += q; nd->mean[a] = nd->total[a] / (double)nd->n[a]; }
+    }
+}
+
+/* solvers/pomcp.py:69-78 select_eps_greedy_action; belief_tree_solver.py:42-56 monte_carlo_approx */
+int orc_ref_search(orc_ref *h, int n_sims)
+{
+    if (h->disable_tree) ref_rollout_search(h);
+    else for (int i = 0; i < n_sims; ++i) ref_traverse(h, h->root, 0);
+    return ref_ucb_action(h, &h->nodes[h->root], 1);
+}
+void orc_ref_root_stats(const orc_ref *h, int64_t *n, double *total, double *mean, uint32_t *legal, int64_t *N)
+{
+    const ref_node *nd = &h->nodes[h->root];
+    for (int a = 0; a < h->m->n_actions; ++a) { n[a] = nd->n[a]; total[a] = nd->total[a]; mean[a] = nd->mean[a]; }
+    *legal = nd->legal; *N = nd->N;
+}
+void orc_ref_counters(const orc_ref *h, int64_t out[6])
+{ out[0] = h->n_steps; out[1] = h->n_levels; out[2] = h->n_rollout_steps; out[3] = h->n_backups; out[4] = h->n_zero_backups; out[5] = h->n_nodes; }
+
+/* agent.py:157 solver.belief_tree_index.sample_particle(): returns a pool reference */
+int32_t orc_ref_sample_root_particle(orc_ref *h)
+{
+    ref_node *nd = &h->nodes[h->root];
+    return nd->bag[ref_randbelow(h, (uint32_t)nd->bag_n)];
+}
+void orc_ref_particle(const orc_ref *h, int32_t p, int32_t *cell, uint32_t *rocks) { *cell = h->pool[p].cell; *rocks = h->pool[p].rocks; }
+
+/* agent.py:174 the real environment step; returns the pool index of next_state */
+int32_t orc_ref_env_step(orc_ref *h, int32_t p, int a, orc_step_out *o)
+{
+    ref_step(h, p, a, o);
+    if (!o->legal) return p;   /* make_next_state returns state.copy() sharing the rock list (:354-356) */
+    return ref_new_particle(h, o->next_cell, o->next_rocks);
+}
+
+/* belief_tree_solver.py:154-212 update + model.py:221-252 generate_particles.
+ * `sampled_mask_after` is the world after model.update(step_result) (rock_model.py:267-272). */
+int orc_ref_update(orc_ref *h, int action, int obs_good, uint32_t sampled_mask_after)
+{
+    h->w.sampled_mask = sampled_mask_after;                      /* :165 */
+    ref_node *root = &h->nodes[h->root];
+    int32_t child = root->child[action][obs_good ? 1 : 0];       /* :167 */
+    if (child < 0) {                                             /* :171-185 */
+        if (root->first_obs[action] < 0) { h->disable_tree = 1; return 1; }
+        child = root->child[action][root->first_obs[action]];
+        if (child < 0) child = root->child[action][1 - root->first_obs[action]];
+    }
+    /* generate_particles matches against obs_map.get_belief(obs): the observed child, or None when it was
+     * never created -- in which case no candidate can match an existing node ... the reference then loops
+     * forever (model.py:242-251, A.15); the oracle reports it instead. */
+    int32_t target = root->child[action][obs_good ? 1 : 0];
+    ref_node *cn = &h->nodes[child];
+    if (cn->bag_n < h->max_particle_count) {                     /* :188-195 */
+        if (target < 0) return -2;
+        int need = h->max_particle_count - cn->bag_n;
+        int32_t *fresh = (int32_t *)malloc(sizeof(int32_t) * (size_t)need); int got = 0;
+        int64_t tries = 0;
+        while (got < need) {
+            root = &h->nodes[h->root];
+            int32_t p = root->bag[ref_randbelow(h, (uint32_t)root->bag_n)];   /* random.choice(prev_particles) */
+            orc_step_out o; ref_step(h, p, action, &o);
+            if ((o.obs_good ? 1 : 0) == (obs_good ? 1 : 0)) fresh[got++] = ref_new_particle(h, o.next_cell, o.next_rocks);
+            if (++tries > 50000000) { free(fresh); return -3; }
+        }
+        for (int i = 0; i < got; ++i) ref_bag_push(&h->nodes[child], fresh[i]);
+        free(fresh);
+    }
+    if (h->nodes[child].bag_n == 0) { h->disable_tree = 1; return 1; }   /* :205-208 */
+    h->root = child;                                             /* :210; prune_siblings only frees memory */
+    return 0;
+}
+
+/* ======================================================================== */
+/* (2) "gs": generation-synchronous tree-parallel POMCP (the CUDA algorithm) */
+/* ======================================================================== */
+
+/* Deterministic natural log of a positive integer, IEEE +,-,*,/ only, fixed operation order.
+ * x = 2^e * m, m in [1/sqrt2*..., sqrt2); ln m = 2 atanh(f), f = (m-1)/(m+1); 13-term odd series. */
+double orc_det_log_u64(uint64_t x)
+{
+    int e = 63 - __builtin_clzll(x);
+    double m = (double)x / (double)(1ull << e);                  /* exact for x < 2^53 */
+    if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
+    double f = (m - 1.0) / (m + 1.0);
+    double f2 = f * f;
+    double s = 1.0 / 25.0;
+    s = s * f2 + 1.0 / 23.0; s = s * f2 + 1.0 / 21.0; s = s * f2 + 1.0 / 19.0; s = s * f2 + 1.0 / 17.0;
+    s = s * f2 + 1.0 / 15.0; s = s * f2 + 1.0 / 13.0; s = s * f2 + 1.0 / 11.0; s = s * f2 + 1.0 / 9.0;
+    s = s * f2 + 1.0 / 7.0;  s = s * f2 + 1.0 / 5.0;  s = s * f2 + 1.0 / 3.0;  s = s * f2 + 1.0;
+    double lnm = 2.0 * f * s;
+    return (double)e * 0.6931471803691238 + ((double)e * 1.9082149292705877e-10 + lnm);
+}
+
+typedef struct {
+    int32_t cell; uint32_t legal;
+    int64_t n[ORC_MAX_ACTIONS];
+    int64_t qfix[ORC_MAX_ACTIONS];             /* sum of llrint(q * 2^24) */
+    int32_t child[ORC_MAX_ACTIONS][2];
+} gs_node;
+
+typedef struct {
+    const orc_model *m; orc_world w;
+    gs_node *nodes; int32_t n_nodes, cap_nodes; int32_t root;
+    uint32_t *bag; int32_t n_bag;              /* packed states: cell | rocks << 8 */
+    int32_t max_depth, dcap; double ucb_c, discount;
+    uint32_t key[2];
+    int64_t n_levels, n_rollout_steps, n_created, n_alloc_nodes, n_generations;
+    int32_t max_tree_depth;
+} orc_gs;
+
+static int32_t gs_new_node(orc_gs *h, int32_t cell)
+{
+    if (h->n_nodes == h->cap_nodes) {
+        h->cap_nodes = h->cap_nodes ? h->cap_nodes * 2 : 1024;
+        h->nodes = (gs_node *)realloc(h->nodes, sizeof(gs_node) * (size_t)h->cap_nodes);
+    }
+    gs_node *nd = &h->nodes[h->n_nodes];
+    memset(nd, 0, sizeof(*nd));
+    nd->cell = cell; nd->legal = h->m->legal[cell];
+    for (int a = 0; a < ORC_MAX_ACTIONS; ++a) nd->child[a][0] = nd->child[a][1] = -1;
+    return h->n_nodes++;
+}
+
+orc_gs *orc_gs_create(const orc_model *m, uint32_t actual_mask, uint32_t sampled_mask,
+                      const uint32_t *bag_packed, int n_bag, int root_cell,
+                      int max_depth, int dcap, double ucb_c, double discount, uint64_t seed)
+{
+    orc_gs *h = (orc_gs *)calloc(1, sizeof(orc_gs));
+    h->m = m; h->w.actual_mask = actual_mask; h->w.sampled_mask = sampled_mask;
+    h->max_depth = max_depth; h->dcap = dcap; h->ucb_c = ucb_c; h->discount = discount;
+    h->key[0] = (uint32_t)seed; h->key[1] = (uint32_t)(seed >> 32);
+    h->bag = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(n_bag > 0 ? n_bag : 1));
+    memcpy(h->bag, bag_packed, sizeof(uint32_t) * (size_t)n_bag); h->n_bag = n_bag;
+    h->root = gs_new_node(h, root_cell);
+    return h;
+}
+void orc_gs_destroy(orc_gs *h) { if (!h) return; free(h->nodes); free(h->bag); free(h); }
+void orc_gs_set_world(orc_gs *h, uint32_t actual, uint32_t sampled) { h->w.actual_mask = actual; h->w.sampled_mask = sampled; }
+
+static void gs_block(const orc_gs *h, uint32_t k, uint32_t sim, uint32_t move, uint32_t dom, uint32_t x[4])
+{
+    uint32_t ctr[4] = {k, sim, move, dom};
+    orc_philox4x32_10(ctr, h->key, x);
+}
+
+/* Mean of an edge from its integer statistics (0 for an unvisited edge: entry.mean_q_value starts at 0). */
+static double gs_mean(const gs_node *nd, int a)
+{
+    if (nd->n[a] == 0) return 0.0;
+    return ((double)nd->qfix[a] * (1.0 / ORC_QFIX_SCALE)) / (double)nd->n[a];
+}
+
+/* sum of 32 lane values in butterfly order (xor 16, 8, 4, 2, 1) -- the order a warp shuffle reduction uses */
+static double butterfly_sum32(const double v[32])
+{
+    double x[32], y[32];
+    memcpy(x, v, sizeof(x));
+    for (int off = 16; off >= 1; off >>= 1) {
+        for (int i = 0; i < 32; ++i) y[i] = x[i] + x[i ^ off];
+        memcpy(x, y, sizeof(x));
+    }
+    return x[0];
+}
+
+/* Batch-UCB allocation for k >= 2 simultaneous arrivals at a node.
+ * Returns weights v[a] >= 0 (0 for illegal actions); arrivals sample an action with probability v[a]/sum. */
+static void gs_allocation(const orc_gs *h, const gs_node *nd, int64_t k, double v[32])
+{
+    int A = h->m->n_actions;
+    int64_t N = 0; int untried = 0, nlegal = 0;
+    for (int a = 0; a < 32; ++a) v[a] = 0.0;
+    for (int a = 0; a < A; ++a) if ((nd->legal >> a) & 1u) { N += nd->n[a]; nlegal++; if (nd->n[a] == 0) untried++; }
+    if (N == 0) { for (int a = 0; a < A; ++a) if ((nd->legal >> a) & 1u) v[a] = 1.0; return; }
+    if (untried >= k) { for (int a = 0; a < A; ++a) if (((nd->legal >> a) & 1u) && nd->n[a] == 0) v[a] = 1.0; return; }
+    double L = orc_det_log_u64((uint64_t)N + 1);
+    double c2L = (h->ucb_c * h->ucb_c) * L;
+    double qbar[32]; double qmax = -INFINITY; int64_t nbest = 0;
+    for (int a = 0; a < A; ++a) {
+        if (!((nd->legal >> a) & 1u)) continue;
+        qbar[a] = gs_mean(nd, a);
+        if (qbar[a] > qmax) { qmax = qbar[a]; nbest = nd->n[a]; }
+    }
+    if (!(c2L > 0.0)) { for (int a = 0; a < A; ++a) if (((nd->legal >> a) & 1u) && qbar[a] == qmax) v[a] = 1.0; return; }
+    double kd = (double)k;
+    double lo = qmax + 0.999 * sqrt(c2L / (kd + (double)nbest));
+    double hi = qmax + 1.001 * sqrt((c2L * (double)nlegal) / kd) + 1.0;
+    for (int it = 0; it < 32; ++it) {
+        double mid = 0.5 * (lo + hi);
+        double t[32];
+        for (int a = 0; a < 32; ++a) {
+            t[a] = 0.0;
+            if (a < A && ((nd->legal >> a) & 1u)) {
+                double d = mid - qbar[a];
+                double mm = c2L / (d * d);
+                if (nd->n[a] == 0) t[a] = mm > 1.0 ? mm : 1.0;
+                else { double e = mm - (double)nd->n[a]; t[a] = e > 0.0 ? e : 0.0; }
+            }
+        }
+        if (butterfly_sum32(t) >= kd) lo = mid; else hi = mid;
+    }
+    for (int a = 0; a < A; ++a) {
+        if (!((nd->legal >> a) & 1u)) continue;
+        double d = lo - qbar[a];
+        double mm = c2L / (d * d);
+        if (nd->n[a] == 0) v[a] = mm > 1.0 ? mm : 1.0;
+        else { double e = mm - (double)nd->n[a]; v[a] = e > 0.0 ? e : 0.0; }
+    }
+}
+
+/* UCB1 arg-max for a single arrival (action_selectors.py:6-37 with mean = sum/n), uniform tie-break by x0 */
+static int gs_ucb1(const orc_gs *h, const gs_node *nd, uint32_t x0)
+{
+    int A = h->m->n_actions;
+    int64_t N = 0;
+    for (int a = 0; a < A; ++a) if ((nd->legal >> a) & 1u) N += nd->n[a];
+    double L = orc_det_log_u64((uint64_t)N + 1);
+    double best = -INFINITY; int cand[32], nc = 0;
+    for (int a = 0; a < A; ++a) {
+        if (!((nd->legal >> a) & 1u)) continue;
+        double s;
+        if (nd->n[a] == 0) s = INFINITY;
+        else s = gs_mean(nd, a) + h->ucb_c * sqrt(L / (double)nd->n[a]);
+        if (s > best) { best = s; nc = 0; cand[nc++] = a; }
+        else if (s == best) cand[nc++] = a;
+    }
+    return cand[randbelow32(x0, (uint32_t)nc)];
+}
+
+typedef struct {
+    uint32_t sim;          /* global simulation index (stream id) */
+    int32_t cell; uint32_t rocks;
+    int32_t node, depth;   /* current node / number of path entries */
+    int32_t status;        /* 0 descending, 1 leaf: rollout pending, 2 done (terminal or horizon) */
+    int32_t *pnode; uint8_t *pact; double *prew;
+    double delayed;
+} gs_sim;
+
+/* belief_tree_solver.py:123-152, but from the post-action state (canonical) */
+static double gs_rollout(orc_gs *h, gs_sim *s, uint32_t move)
+{
+    double sum = 0.0, disc = 1.0; int t = 0, terminal = 0;
+    int cell = s->cell; uint32_t rocks = s->rocks;
+    while (t < h->max_depth && !terminal) {
+        uint32_t x[4]; gs_block(h, (uint32_t)(s->depth + 1 + t), s->sim, move, DOM_SIM, x);
+        uint32_t mask = h->m->legal[cell];
+        int idx = (int)randbelow32(x[0], (uint32_t)__builtin_popcount(mask)), a = -1;
+        for (int b = 0, seen = 0; b < 32; ++b) if ((mask >> b) & 1u) { if (seen == idx) { a = b; break; } ++seen; }
+        orc_step_out o; orc_step(h->m, &h->w, cell, rocks, a, u53_of(x[1], x[2]), &o);
+        terminal = o.terminal;
+        if (o.reward != 0.0) sum += o.reward * disc;
+        disc *= h->discount;
+        cell = o.next_cell; rocks = o.next_rocks;
+        ++t; h->n_rollout_steps++;
+    }
+    return sum;
+}
+
+/* One search: n_sims simulations with global ids [sim_offset, sim_offset + n_sims), in generations of width
+ * w0, w0*growth, ... capped at wmax. */
+int orc_gs_search(orc_gs *h, int64_t n_sims, uint32_t sim_offset, uint32_t move, int w0, int growth, int wmax)
+{
+    if (w0 < 1) w0 = 1; if (growth < 1) growth = 1; if (wmax < w0) wmax = w0;
+    int A = h->m->n_actions; (void)A;
+    int dcap = h->dcap;
+    int64_t done = 0; int64_t W = w0;
+    gs_sim *S = (gs_sim *)calloc((size_t)wmax, sizeof(gs_sim));
+    int32_t *pn = (int32_t *)malloc(sizeof(int32_t) * (size_t)wmax * (size_t)dcap);
+    uint8_t *pa = (uint8_t *)malloc((size_t)wmax * (size_t)dcap);
+    double *pr = (double *)malloc(sizeof(double) * (size_t)wmax * (size_t)dcap);
+    int64_t *arrivals = NULL; double *alloc_v = NULL; int32_t arr_cap = 0;
+    while (done < n_sims) {
+        int64_t w = W; if (w > n_sims - done) w = n_sims - done;
+        h->n_generations++;
+        for (int64_t i = 0; i < w; ++i) {
+            gs_sim *s = &S[i];
+            s->sim = sim_offset + (uint32_t)(done + i);
+            s->pnode = pn + i * dcap; s->pact = pa + i * dcap; s->prew = pr + i * dcap;
+            uint32_t x[4]; gs_block(h, 0, s->sim, move, DOM_SIM, x);
+            uint32_t st = h->bag[randbelow32(x[0], (uint32_t)h->n_bag)];
+            s->cell = (int32_t)(st & 0xFFu); s->rocks = st >> 8;
+            s->node = h->root; s->depth = 0; s->status = 0; s->delayed = 0.0;
+        }
+        for (;;) {                                  /* level steps */
+            int64_t active = 0;
+            for (int64_t i = 0; i < w; ++i) if (S[i].status == 0) active++;
+            if (!active) break;
+            int32_t nn0 = h->n_nodes;               /* snapshot: nodes created in this step are not visited until the next */
+            if (arr_cap < h->n_nodes) {
+                arr_cap = h->n_nodes * 2;
+                arrivals = (int64_t *)realloc(arrivals, sizeof(int64_t) * (size_t)arr_cap);
+                alloc_v = (double *)realloc(alloc_v, sizeof(double) * 32 * (size_t)arr_cap);
+            }
+            /* phase 1: count arrivals per node */
+            for (int64_t i = 0; i < w; ++i) if (S[i].status == 0) arrivals[S[i].node] = 0;
+            for (int64_t i = 0; i < w; ++i) if (S[i].status == 0) arrivals[S[i].node]++;
+            /* phase 2: allocation for nodes with >= 2 arrivals (sign bit marks "computed") */
+            for (int64_t i = 0; i < w; ++i) {
+                if (S[i].status != 0) continue;
+                int32_t X = S[i].node;
+                if (arrivals[X] >= 2) {
+                    gs_allocation(h, &h->nodes[X], arrivals[X], alloc_v + 32 * (size_t)X);
+                    arrivals[X] = -arrivals[X]; h->n_alloc_nodes++;
+                }
+            }
+            /* phase 3: choose, step, expand; statistics are read-only during the whole generation */
+            for (int64_t i = 0; i < w; ++i) {
+                gs_sim *s = &S[i];
+                if (s->status != 0) continue;
+                int32_t X = s->node; int d = s->depth;
+                if (d >= h->max_depth) { s->status = 2; s->delayed = 0.0; continue; }   /* solvers/pomcp.py:100 */
+                gs_node *nd = &h->nodes[X];
+                uint32_t x[4]; gs_block(h, (uint32_t)(d + 1), s->sim, move, DOM_SIM, x);
+                int a;
+                if (arrivals[X] == 1) a = gs_ucb1(h, nd, x[0]);
+                else {
+                    const double *v = alloc_v + 32 * (size_t)X;
+                    double V = butterfly_sum32(v);
+                    double t = ((double)x[0] + 0.5) * (V * (1.0 / 4294967296.0));
+                    double acc = 0.0; a = -1; int last = -1;
+                    for (int b = 0; b < 32; ++b) {
+                        if (!(v[b] > 0.0)) continue;
+                        last = b; acc += v[b];
+                        if (t < acc) { a = b; break; }
+                    }
+                    if (a < 0) a = last;
+                }
+                orc_step_out o; orc_step(h->m, &h->w, s->cell, s->rocks, a, u53_of(x[1], x[2]), &o);
+                h->n_levels++;
+                s->pnode[d] = X; s->pact[d] = (uint8_t)a; s->prew[d] = o.reward; s->depth = d + 1;
+                if (s->depth > h->max_tree_depth) h->max_tree_depth = s->depth;
+                int og = o.obs_good ? 1 : 0;
+                int32_t child = nd->child[a][og];
+                int64_t Nx = 0; for (int b = 0; b < 32; ++b) Nx += nd->n[b];
+                if (child < 0 && !o.terminal && Nx > 0 && d + 1 < dcap) {   /* solvers/pomcp.py:107 */
+                    child = gs_new_node(h, o.next_cell); nd = &h->nodes[X];
+                    nd->child[a][og] = child; h->n_created++;
+                }
+                s->cell = o.next_cell; s->rocks = o.next_rocks;
+                if (o.terminal) { s->status = 2; s->delayed = 0.0; }
+                else if (child >= 0) { s->node = child; }
+                else s->status = 1;
+                (void)nn0;
+            }
+        }
+        /* rollouts, then backup (commutative integer updates) */
+        for (int64_t i = 0; i < w; ++i) {
+            gs_sim *s = &S[i];
+            if (s->status == 1) s->delayed = gs_rollout(h, s, move);
+        }
+        for (int64_t i = 0; i < w; ++i) {
+            gs_sim *s = &S[i];
+            double delayed = s->delayed;
+            for (int d = s->depth - 1; d >= 0; --d) {
+                double q = s->prew[d] + h->discount * delayed;                 /* solvers/pomcp.py:131 */
+                gs_node *nd = &h->nodes[s->pnode[d]];
+                nd->n[s->pact[d]] += 1;                                        /* discrete_action_mapping.py:137-144 */
+                nd->qfix[s->pact[d]] += (int64_t)llrint(q * ORC_QFIX_SCALE);   /* :146-172, as an exact integer sum */
+                delayed = q;
+            }
+        }
+        done += w;
+        if (W < wmax) { W *= growth; if (W > wmax) W = wmax; }
+    }
+    free(S); free(pn); free(pa); free(pr); free(arrivals); free(alloc_v);
+    return 0;
+}
+
+void orc_gs_root_stats(const orc_gs *h, int64_t *n, int64_t *qfix, uint32_t *legal)
+{
+    const gs_node *nd = &h->nodes[h->root];
+    for (int a = 0; a < h->m->n_actions; ++a) { n[a] = nd->n[a]; qfix[a] = nd->qfix[a]; }
+    *legal = nd->legal;
+}
+void orc_gs_counters(const orc_gs *h, int64_t out[8])
+{
+    out[0] = h->n_levels; out[1] = h->n_rollout_steps; out[2] = h->n_created; out[3] = h->n_nodes;
+    out[4] = h->n_alloc_nodes; out[5] = h->n_generations; out[6] = h->max_tree_depth; out[7] = h->n_bag;
+}
+
+/* Statistics of the node reached from the root by a sequence of (action, obs) pairs; returns 0 if it exists. */
+int orc_gs_node_stats(const orc_gs *h, const int32_t *path_ao, int len, int64_t *n, int64_t *qfix, uint32_t *legal, int32_t *cell)
+{
+    int32_t X = h->root;
+    for (int i = 0; i < len; ++i) { X = h->nodes[X].child[path_ao[2 * i]][path_ao[2 * i + 1]]; if (X < 0) return 1; }
+    const gs_node *nd = &h->nodes[X];
+    for (int a = 0; a < h->m->n_actions; ++a) { n[a] = nd->n[a]; qfix[a] = nd->qfix[a]; }
+    *legal = nd->legal; *cell = nd->cell;
+    return 0;
+}
+
+/* Greedy root action (solvers/pomcp.py:78): arg-max of the mean over legal actions (0 for unvisited), uniform
+ * tie-break from the DOM_FINAL stream.  n/qfix may be the all-reduced sums of several ranks. */
+int orc_gs_greedy(const int64_t *n, const int64_t *qfix, uint32_t legal, int n_actions, uint64_t seed, uint32_t move)
+{
+    double best = -INFINITY; int cand[32], nc = 0;
+    for (int a = 0; a < n_actions; ++a) {
+        if (!((legal >> a) & 1u)) continue;
+        double q = n[a] == 0 ? 0.0 : ((double)qfix[a] * (1.0 / ORC_QFIX_SCALE)) / (double)n[a];
+        if (q > best) { best = q; nc = 0; cand[nc++] = a; } else if (q == best) cand[nc++] = a;
+    }
+    uint32_t key[2] = {(uint32_t)seed, (uint32_t)(seed >> 32)}, ctr[4] = {0, 0, move, DOM_FINAL}, x[4];
+    orc_philox4x32_10(ctr, key, x);
+    return cand[randbelow32(x[0], (uint32_t)nc)];
+}
+
+/* Belief update (belief_tree_solver.py:154-212 + model.py:221-252), deterministic form: try t draws particle
+ * bag[randbelow] and one uniform from block (t, 0, move, DOM_UPDATE); the new bag is the first `need`
+ * accepted next-states in try order.  Returns the number accepted (< need only if max_tries was hit);
+ * status: 0 re-rooted at an existing child, 1 fresh root created (child never expanded). */
+int64_t orc_gs_update(orc_gs *h, int action, int obs_good, uint32_t sampled_mask_after, uint32_t move,
+                      int need, int64_t max_tries, int32_t *status, int64_t *tries_used)
+{
+    h->w.sampled_mask = sampled_mask_after;
+    uint32_t *nb = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)need);
+    int64_t got = 0, t = 0;
+    for (; t < max_tries && got < need; ++t) {
+        uint32_t x[4]; gs_block(h, (uint32_t)t, (uint32_t)(t >> 32), move, DOM_UPDATE, x);
+        uint32_t st = h->bag[randbelow32(x[0], (uint32_t)h->n_bag)];
+        orc_step_out o; orc_step(h->m, &h->w, (int)(st & 0xFFu), st >> 8, action, u53_of(x[1], x[2]), &o);
+        if ((o.obs_good ? 1 : 0) == (obs_good ? 1 : 0)) nb[got++] = (uint32_t)o.next_cell | (o.next_rocks << 8);
+    }
+    *tries_used = t;
+    if (got == 0) { free(nb); *status = 2; return 0; }
+    /* child position: make_next_position on the node's cell (rock_position_history.py:96-99) */
+    gs_node *root = &h->nodes[h->root];
+    int32_t child = root->child[action][obs_good ? 1 : 0];
+    *status = 0;
+    if (child < 0) {
+        orc_step_out o; orc_step(h->m, &h->w, root->cell, 0, action, 0, &o);
+        child = gs_new_node(h, o.next_cell); *status = 1;
+    }
+    h->root = child;
+    free(h->bag); h->bag = nb; h->n_bag = (int32_t)got;
+    return got;
+}
+void orc_gs_bag(const orc_gs *h, uint32_t *out) { memcpy(out, h->bag, sizeof(uint32_t) * (size_t)h->n_bag); }
+int orc_gs_bag_size(const orc_gs *h) { return h->n_bag; }
+int orc_gs_root_cell(const orc_gs *h) { return h->nodes[h->root].cell; }
