@@ -1,0 +1,102 @@
+/*
+ * pomcp_b200.h -- C ABI of the B200-native POMCP planner (libpomcp_b200.so).
+ *
+ * The reference (pemami4911/POMDPy) is pure Python and has no FFI; its solver boundary is the
+ * duck-typed object that pomdpy/agent.py drives.  Each entry point below names the reference
+ * call it replaces (file:line in the reference tree).  Plain pointers and sizes only; all host
+ * arrays are borrowed for the duration of the call; one host thread per handle.
+ *
+ * Return value: 0 ok, >0 degraded (documented per call), <0 error (text via pomcp_last_error).
+ */
+#ifndef POMCP_B200_H
+#define POMCP_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+#define POMCP_MAX_ACTIONS 32   /* |A| = 5 + n_rocks <= 32: one warp lane per action */
+#define POMCP_MAX_CELLS 256
+#define POMCP_MAX_ROCKS 24
+#define POMCP_QFIX_SCALE 16777216.0 /* root statistics carry sum(q) as a 2^-24 fixed-point integer */
+
+typedef struct pomcp_handle pomcp_handle;
+
+/* Hyper-parameters the reference solver reads from agent.model.<flag>
+ * (pomdpy/pomdp/model.py:30-31; flags pomcp.py:13-43). */
+typedef struct {
+    int32_t max_depth;          /* --max_depth: search horizon and rollout length */
+    int32_t tree_depth_cap;     /* path-buffer depth of the device tree (<= 64) */
+    int32_t max_particle_count; /* --max_particle_count: size of a re-rooted belief */
+    int32_t reserved0;
+    double ucb_coefficient;     /* --ucb_coefficient */
+    double discount;            /* --discount */
+    uint64_t seed;              /* Philox key */
+    int64_t node_capacity;      /* device tree arena, in belief nodes */
+    int32_t gen_w0;             /* generation schedule: w0, w0*growth, ... <= wmax simulations in flight */
+    int32_t gen_growth;
+    int32_t gen_wmax;
+    int32_t reserved1;
+} pomcp_config;
+
+/* POMCP.__init__ / POMCP.reset(agent)  (pomdpy/solvers/pomcp.py:23-50, belief_tree_solver.py:20-40) */
+int pomcp_create(const pomcp_config *cfg, int device, pomcp_handle **out);
+void pomcp_destroy(pomcp_handle *h);
+const char *pomcp_last_error(const pomcp_handle *h);
+
+/* RockModel tables (examples/rock_sample/rock_model.py:40-138): cell codes (rock k >= 0, EMPTY -1, GOAL -2,
+ * OBSTACLE -3), 53-bit sensor thresholds [cell][n_rocks] (floor(thr * 2^53), :148-150 + :395), signed rewards
+ * {illegal, exit, good sample, bad sample}. */
+int pomcp_set_model_rocksample(pomcp_handle *h, int rows, int cols, const int8_t *cell, int start_cell,
+                               const uint64_t *thr53, const double rewards[4]);
+
+/* model.actual_rock_states / model.unique_rocks_sampled as bit masks
+ * (rock_model.py:263-265 reset_for_epoch, :267-272 update). */
+int pomcp_set_world(pomcp_handle *h, uint32_t actual_rock_mask, uint32_t sampled_rock_mask);
+
+/* Root belief of a fresh tree: n packed states (cell | rocks << 8)
+ * (belief_tree_solver.py:30-40: tree reset + n_start_states x sample_an_init_state). */
+int pomcp_set_root_particles(pomcp_handle *h, const uint32_t *packed_states, int n, int root_cell);
+
+/* BeliefTreeSolver.monte_carlo_approx (belief_tree_solver.py:42-56): n_sims simulations with stream ids
+ * [sim_offset, sim_offset + n_sims) from the current root; asynchronous on `stream` (a cudaStream_t, may be 0).
+ * timeout_s <= 0 disables the wall-clock guard (solvers/pomcp.py:93-95).  Needs node_capacity - used >= n_sims;
+ * returns 1 (degraded) after dropping the subtree to make room. */
+int pomcp_search(pomcp_handle *h, int64_t n_sims, uint32_t sim_offset, uint32_t move, double timeout_s,
+                 void *stream);
+
+/* Root DiscreteActionMapping entries (discrete_action_mapping.py:113-184): visit_count[a], sum of q as a
+ * 2^-24 fixed-point integer, legal mask.  Synchronises with the search. */
+int pomcp_root_stats(pomcp_handle *h, int64_t *n, int64_t *qfix, uint32_t *legal_mask, int64_t *sims_done);
+
+/* Same, for the node reached from the root through (action, obs_good) pairs; 1 if it does not exist. */
+int pomcp_node_stats(pomcp_handle *h, const int32_t *path_ao, int len, int64_t *n, int64_t *qfix,
+                     uint32_t *legal_mask, int32_t *cell);
+
+/* BeliefTreeSolver.update (belief_tree_solver.py:154-212) + Model.generate_particles (model.py:221-252):
+ * re-root at (action, obs_good), refill the belief with max_particle_count rejection samples drawn from the
+ * old root belief.  *status: 0 re-rooted at an existing child, 1 fresh node (child never expanded),
+ * 2 no particle accepted (the reference's disable_tree). */
+int pomcp_advance(pomcp_handle *h, int action, int obs_good, uint32_t sampled_mask_after, uint32_t move,
+                  int64_t max_tries, int32_t *status, int64_t *tries_used, int32_t *accepted);
+
+/* The current root belief (BeliefNode.state_particles) */
+int pomcp_root_particles(pomcp_handle *h, uint32_t *out, int capacity, int32_t *n, int32_t *root_cell);
+
+/* generate_step (rock_model.py:451-465) for a batch: state, action, 53-bit uniform and world masks per item ->
+ * next state, flags (bit0 obs_good, bit1 obs_empty, bit2 terminal, bit3 legal), reward.  Host arrays. */
+int pomcp_generate_steps(pomcp_handle *h, int64_t n, const uint32_t *state, const uint8_t *action,
+                         const uint64_t *u53, const uint32_t *actual_mask, const uint32_t *sampled_mask,
+                         uint32_t *next_state, uint8_t *flags, double *reward);
+
+/* counters: [0] tree levels, [1] rollout steps, [2] nodes created, [3] nodes in arena, [4] allocation nodes,
+ * [5] generations, [6] level steps, [7] last search ns (device globaltimer), [8] sims of last search,
+ * [9] kernel launches so far, [10] cooperative grid blocks, [11] threads per block */
+int pomcp_counters(pomcp_handle *h, int64_t out[16]);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

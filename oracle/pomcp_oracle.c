@@ -575,48 +575,62 @@ static double butterfly_sum32(const double v[32])
     return x[0];
 }
 
-/* Batch-UCB allocation for k >= 2 simultaneous arrivals at a node.
- * Returns weights v[a] >= 0 (0 for illegal actions); arrivals sample an action with probability v[a]/sum. */
-static void gs_allocation(const orc_gs *h, const gs_node *nd, int64_t k, double v[32])
+/* Batch-UCB allocation for k >= 2 simultaneous arrivals at a node: weights v[a] >= 0 from a
+ * water-filling of k pulls over the UCB1 indices, turned into 32-bit cumulative thresholds.  An arrival with
+ * 32-bit draw x takes the first action a with x < thr[a], or `*last` if there is none. */
+static void gs_allocation(const orc_gs *h, const gs_node *nd, int64_t k, uint32_t thr[32], int *last)
 {
     int A = h->m->n_actions;
     int64_t N = 0; int untried = 0, nlegal = 0;
+    double v[32];
     for (int a = 0; a < 32; ++a) v[a] = 0.0;
     for (int a = 0; a < A; ++a) if ((nd->legal >> a) & 1u) { N += nd->n[a]; nlegal++; if (nd->n[a] == 0) untried++; }
-    if (N == 0) { for (int a = 0; a < A; ++a) if ((nd->legal >> a) & 1u) v[a] = 1.0; return; }
-    if (untried >= k) { for (int a = 0; a < A; ++a) if (((nd->legal >> a) & 1u) && nd->n[a] == 0) v[a] = 1.0; return; }
-    double L = orc_det_log_u64((uint64_t)N + 1);
-    double c2L = (h->ucb_c * h->ucb_c) * L;
-    double qbar[32]; double qmax = -INFINITY; int64_t nbest = 0;
-    for (int a = 0; a < A; ++a) {
-        if (!((nd->legal >> a) & 1u)) continue;
-        qbar[a] = gs_mean(nd, a);
-        if (qbar[a] > qmax) { qmax = qbar[a]; nbest = nd->n[a]; }
-    }
-    if (!(c2L > 0.0)) { for (int a = 0; a < A; ++a) if (((nd->legal >> a) & 1u) && qbar[a] == qmax) v[a] = 1.0; return; }
-    double kd = (double)k;
-    double lo = qmax + 0.999 * sqrt(c2L / (kd + (double)nbest));
-    double hi = qmax + 1.001 * sqrt((c2L * (double)nlegal) / kd) + 1.0;
-    for (int it = 0; it < 32; ++it) {
-        double mid = 0.5 * (lo + hi);
-        double t[32];
-        for (int a = 0; a < 32; ++a) {
-            t[a] = 0.0;
-            if (a < A && ((nd->legal >> a) & 1u)) {
-                double d = mid - qbar[a];
-                double mm = c2L / (d * d);
-                if (nd->n[a] == 0) t[a] = mm > 1.0 ? mm : 1.0;
-                else { double e = mm - (double)nd->n[a]; t[a] = e > 0.0 ? e : 0.0; }
+    if (N == 0) { for (int a = 0; a < A; ++a) if ((nd->legal >> a) & 1u) v[a] = 1.0; }
+    else if (untried >= k) { for (int a = 0; a < A; ++a) if (((nd->legal >> a) & 1u) && nd->n[a] == 0) v[a] = 1.0; }
+    else {
+        double L = orc_det_log_u64((uint64_t)N + 1);
+        double c2L = (h->ucb_c * h->ucb_c) * L;
+        double qbar[32]; double qmax = -INFINITY; int64_t nbest = 0;
+        for (int a = 0; a < A; ++a) {
+            if (!((nd->legal >> a) & 1u)) continue;
+            qbar[a] = gs_mean(nd, a);
+            if (qbar[a] > qmax) { qmax = qbar[a]; nbest = nd->n[a]; }
+        }
+        if (!(c2L > 0.0)) { for (int a = 0; a < A; ++a) if (((nd->legal >> a) & 1u) && qbar[a] == qmax) v[a] = 1.0; }
+        else {
+            double kd = (double)k;
+            double lo = qmax + 0.999 * sqrt(c2L / (kd + (double)nbest));
+            double hi = qmax + 1.001 * sqrt((c2L * (double)nlegal) / kd) + 1.0;
+            for (int it = 0; it <= 32; ++it) {          /* 32 bisection steps, then the weights at `lo` */
+                double mid = it < 32 ? 0.5 * (lo + hi) : lo;
+                double t[32];
+                for (int a = 0; a < 32; ++a) {
+                    t[a] = 0.0;
+                    if (a < A && ((nd->legal >> a) & 1u)) {
+                        double d = mid - qbar[a];
+                        double mm = c2L / (d * d);
+                        if (nd->n[a] == 0) t[a] = mm > 1.0 ? mm : 1.0;
+                        else { double e = mm - (double)nd->n[a]; t[a] = e > 0.0 ? e : 0.0; }
+                    }
+                }
+                if (it == 32) { memcpy(v, t, sizeof(t)); break; }
+                if (butterfly_sum32(t) >= kd) lo = mid; else hi = mid;
             }
         }
-        if (butterfly_sum32(t) >= kd) lo = mid; else hi = mid;
     }
-    for (int a = 0; a < A; ++a) {
-        if (!((nd->legal >> a) & 1u)) continue;
-        double d = lo - qbar[a];
-        double mm = c2L / (d * d);
-        if (nd->n[a] == 0) v[a] = mm > 1.0 ? mm : 1.0;
-        else { double e = mm - (double)nd->n[a]; v[a] = e > 0.0 ? e : 0.0; }
+    /* inclusive scan in Hillis-Steele order (what __shfl_up_sync steps 1,2,4,8,16 compute) */
+    double x[32], y[32];
+    memcpy(x, v, sizeof(x));
+    for (int off = 1; off < 32; off <<= 1) {
+        for (int i = 0; i < 32; ++i) y[i] = i >= off ? x[i] + x[i - off] : x[i];
+        memcpy(x, y, sizeof(x));
+    }
+    double V = x[31];
+    *last = 0;
+    for (int a = 0; a < 32; ++a) {
+        double f = (x[a] / V) * 4294967296.0;
+        thr[a] = f >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)f;
+        if (v[a] > 0.0) *last = a;
     }
 }
 
@@ -680,7 +694,7 @@ int orc_gs_search(orc_gs *h, int64_t n_sims, uint32_t sim_offset, uint32_t move,
     int32_t *pn = (int32_t *)malloc(sizeof(int32_t) * (size_t)wmax * (size_t)dcap);
     uint8_t *pa = (uint8_t *)malloc((size_t)wmax * (size_t)dcap);
     double *pr = (double *)malloc(sizeof(double) * (size_t)wmax * (size_t)dcap);
-    int64_t *arrivals = NULL; double *alloc_v = NULL; int32_t arr_cap = 0;
+    int64_t *arrivals = NULL; uint32_t *alloc_thr = NULL; int32_t *alloc_last = NULL; int32_t arr_cap = 0;
     while (done < n_sims) {
         int64_t w = W; if (w > n_sims - done) w = n_sims - done;
         h->n_generations++;
@@ -701,7 +715,8 @@ int orc_gs_search(orc_gs *h, int64_t n_sims, uint32_t sim_offset, uint32_t move,
             if (arr_cap < h->n_nodes) {
                 arr_cap = h->n_nodes * 2;
                 arrivals = (int64_t *)realloc(arrivals, sizeof(int64_t) * (size_t)arr_cap);
-                alloc_v = (double *)realloc(alloc_v, sizeof(double) * 32 * (size_t)arr_cap);
+                alloc_thr = (uint32_t *)realloc(alloc_thr, sizeof(uint32_t) * 32 * (size_t)arr_cap);
+                alloc_last = (int32_t *)realloc(alloc_last, sizeof(int32_t) * (size_t)arr_cap);
             }
             /* phase 1: count arrivals per node */
             for (int64_t i = 0; i < w; ++i) if (S[i].status == 0) arrivals[S[i].node] = 0;
@@ -711,7 +726,7 @@ int orc_gs_search(orc_gs *h, int64_t n_sims, uint32_t sim_offset, uint32_t move,
                 if (S[i].status != 0) continue;
                 int32_t X = S[i].node;
                 if (arrivals[X] >= 2) {
-                    gs_allocation(h, &h->nodes[X], arrivals[X], alloc_v + 32 * (size_t)X);
+                    gs_allocation(h, &h->nodes[X], arrivals[X], alloc_thr + 32 * (size_t)X, &alloc_last[X]);
                     arrivals[X] = -arrivals[X]; h->n_alloc_nodes++;
                 }
             }
@@ -726,16 +741,9 @@ int orc_gs_search(orc_gs *h, int64_t n_sims, uint32_t sim_offset, uint32_t move,
                 int a;
                 if (arrivals[X] == 1) a = gs_ucb1(h, nd, x[0]);
                 else {
-                    const double *v = alloc_v + 32 * (size_t)X;
-                    double V = butterfly_sum32(v);
-                    double t = ((double)x[0] + 0.5) * (V * (1.0 / 4294967296.0));
-                    double acc = 0.0; a = -1; int last = -1;
-                    for (int b = 0; b < 32; ++b) {
-                        if (!(v[b] > 0.0)) continue;
-                        last = b; acc += v[b];
-                        if (t < acc) { a = b; break; }
-                    }
-                    if (a < 0) a = last;
+                    const uint32_t *thr = alloc_thr + 32 * (size_t)X;
+                    a = alloc_last[X];
+                    for (int b = 0; b < 32; ++b) if (x[0] < thr[b]) { a = b; break; }
                 }
                 orc_step_out o; orc_step(h->m, &h->w, s->cell, s->rocks, a, u53_of(x[1], x[2]), &o);
                 h->n_levels++;
@@ -774,7 +782,7 @@ int orc_gs_search(orc_gs *h, int64_t n_sims, uint32_t sim_offset, uint32_t move,
         done += w;
         if (W < wmax) { W *= growth; if (W > wmax) W = wmax; }
     }
-    free(S); free(pn); free(pa); free(pr); free(arrivals); free(alloc_v);
+    free(S); free(pn); free(pa); free(pr); free(arrivals); free(alloc_thr); free(alloc_last);
     return 0;
 }
 

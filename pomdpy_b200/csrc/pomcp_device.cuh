@@ -1,0 +1,121 @@
+// pomcp_device.cuh -- device-side building blocks of the B200 POMCP planner (sm_100a).
+//
+// Everything here is integer work or IEEE-exact fp64 (+,-,*,/,sqrt; no FMA contraction: the file is built with
+// -fmad=false) so that a search is a deterministic function of its inputs.
+#pragma once
+#include <stdint.h>
+
+#define POMCP_AS 32             // action stride of the SoA node arena: one warp lane per action
+#define POMCP_CELL_GOAL (-2)
+#define POMCP_CELL_OBSTACLE (-3)
+
+enum { DOM_SIM = 0, DOM_UPDATE = 1, DOM_FINAL = 2, DOM_AGENT = 3 };
+enum { REW_NONE = 0, REW_ILLEGAL = 1, REW_EXIT = 2, REW_GOOD = 3, REW_BAD = 4 };
+
+// ---------------------------------------------------------------------------------------------------------
+// Philox4x32-10 counter-based generator: key = seed, counter = (block k, simulation id, move, domain).
+// ---------------------------------------------------------------------------------------------------------
+struct Philox4 { uint32_t x, y, z, w; };
+
+__device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
+                                                 uint32_t k0, uint32_t k1)
+{
+#pragma unroll
+    for (int r = 0; r < 10; ++r) {
+        const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
+        const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
+        const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
+        c0 = n0; c1 = lo1; c2 = n2; c3 = lo0;
+        k0 += 0x9E3779B9u; k1 += 0xBB67AE85u;
+    }
+    return Philox4{c0, c1, c2, c3};
+}
+__device__ __forceinline__ uint32_t randbelow32(uint32_t x, uint32_t n) { return __umulhi(x, n); }
+__device__ __forceinline__ uint64_t u53_of(uint32_t a, uint32_t b)
+{ return ((uint64_t)(a >> 5) << 26) | (uint64_t)(b >> 6); }
+
+// ---------------------------------------------------------------------------------------------------------
+// Deterministic ln of a positive integer: exponent by clz, 2*atanh series in Horner form, fdlibm ln2 split.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ double det_log_u64(uint64_t x)
+{
+    int e = 63 - __clzll((long long)x);
+    double m = (double)x / (double)(1ull << e);
+    if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
+    const double f = (m - 1.0) / (m + 1.0);
+    const double f2 = f * f;
+    double s = 1.0 / 25.0;
+    s = s * f2 + 1.0 / 23.0; s = s * f2 + 1.0 / 21.0; s = s * f2 + 1.0 / 19.0; s = s * f2 + 1.0 / 17.0;
+    s = s * f2 + 1.0 / 15.0; s = s * f2 + 1.0 / 13.0; s = s * f2 + 1.0 / 11.0; s = s * f2 + 1.0 / 9.0;
+    s = s * f2 + 1.0 / 7.0;  s = s * f2 + 1.0 / 5.0;  s = s * f2 + 1.0 / 3.0;  s = s * f2 + 1.0;
+    const double lnm = 2.0 * f * s;
+    return (double)e * 0.6931471803691238 + ((double)e * 1.9082149292705877e-10 + lnm);
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// RockSample tables as staged in shared memory (reference examples/rock_sample/rock_model.py).
+// ---------------------------------------------------------------------------------------------------------
+struct ModelHeader {            // lives in global memory; copied verbatim into shared memory
+    int32_t rows, cols, n_rocks, n_actions, n_cells, start_cell, pad0, pad1;
+    double rew[8];              // indexed by REW_*: 0, illegal, exit, good, bad
+    int32_t delta[4];           // cell offset of N, E, S, W
+    int8_t cell[256];           // rock k >= 0 | EMPTY -1 | GOAL -2 | OBSTACLE -3
+    uint32_t legal[256];        // legal-action bit mask of each cell (rock_model.py:218-247)
+    uint8_t nth5[32 * 8];       // nth5[m*8 + j] = index of the j-th set bit of the 5-bit mask m
+};
+
+struct SmemModel {
+    const ModelHeader *hdr;
+    const uint64_t *thr53;      // [n_cells][n_rocks]
+};
+
+struct StepResult {
+    uint32_t cell, rocks;
+    int good, empty, terminal, legal, rew;
+};
+
+// generate_step (rock_model.py:451-465) as a pure function of (state, action, world, u53).
+__device__ __forceinline__ StepResult rs_step(const SmemModel &M, uint32_t cell, uint32_t rocks, int a,
+                                              uint64_t u53, uint32_t actual, uint32_t sampled)
+{
+    const ModelHeader *H = M.hdr;
+    StepResult r;
+    const int lg = (a >= 5) ? 1 : (int)((H->legal[cell] >> a) & 1u);          // :323-344
+    uint32_t ncell = cell;
+    if (a < 4 && lg) ncell = (uint32_t)((int)cell + H->delta[a]);
+    uint32_t nr = rocks;
+    const int code = H->cell[cell];
+    if (a == 4 && lg) nr &= ~(1u << code);                                      // :346-368
+    int good = 0;
+    if (a >= 5) {                                                               // :370-412
+        const int k = a - 5;
+        if (!((sampled >> k) & 1u)) {
+            const int truth = (actual >> k) & 1u;
+            const int correct = u53 <= M.thr53[ncell * H->n_rocks + k];
+            good = correct ? truth : !truth;
+            nr = good ? (nr | (1u << k)) : (nr & ~(1u << k));
+        }
+    }
+    const int terminal = H->cell[ncell] == POMCP_CELL_GOAL;
+    int rew = REW_NONE;                                                         // :417-445
+    if (!lg) rew = REW_ILLEGAL;
+    else if (terminal) rew = REW_EXIT;
+    else if (a == 4) rew = (((actual & rocks) >> code) & 1u) ? REW_GOOD : REW_BAD;
+    r.cell = ncell; r.rocks = nr; r.good = good; r.empty = (a < 4); r.terminal = terminal; r.legal = lg; r.rew = rew;
+    return r;
+}
+
+// index of the j-th (0-based) set bit of a legal mask whose bits >= 5 are all set up to n_actions
+__device__ __forceinline__ int nth_legal(const ModelHeader *H, uint32_t mask, uint32_t j)
+{
+    const uint32_t low = mask & 31u;
+    const uint32_t m = (uint32_t)__popc(low);
+    return (j < m) ? (int)H->nth5[low * 8 + j] : (int)(5 + (j - m));
+}
+
+// j-th set bit of an arbitrary 32-bit mask
+__device__ __forceinline__ int nth_bit(uint32_t mask, uint32_t j)
+{
+    for (uint32_t i = 0; i < j; ++i) mask &= mask - 1;
+    return __ffs((int)mask) - 1;
+}

@@ -1,0 +1,947 @@
+// pomcp_kernels.cu -- B200 (sm_100a) POMCP planner: device tree, search / belief-update kernels and the C ABI.
+//
+// Replaces what happens inside POMCP.select_eps_greedy_action() and BeliefTreeSolver.update() of the reference
+// (pomdpy/solvers/pomcp.py:69-137, pomdpy/solvers/belief_tree_solver.py:42-56,123-212,
+// pomdpy/action_selection/action_selectors.py:6-37, pomdpy/pomdp/model.py:221-252).  See DESIGN.md.
+//
+// Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
+#include <cooperative_groups.h>
+#include <cuda_runtime.h>
+
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <vector>
+
+#include "../../include/pomcp_b200.h"
+#include "pomcp_device.cuh"
+
+namespace cg = cooperative_groups;
+
+#define AS POMCP_AS
+#define CHILD_LOCKED 0xFFFFFFFFu
+#define SEARCH_THREADS 256
+#define ADV_THREADS 1024
+#define ADV_TRIES 4
+
+// ---------------------------------------------------------------------------------------------------------
+// Device-resident state (one per handle).  Kernels read and write it without host round trips.
+// ---------------------------------------------------------------------------------------------------------
+struct DevState {
+    int32_t root;
+    int32_t node_count;
+    uint32_t actual, sampled;
+    int32_t n_bag, bag_sel;
+    int32_t wl_count[4];
+    int32_t stop, pad;
+    unsigned long long gstep;          // global level-step stamp, never reused
+    long long sims_done;               // simulations completed by the last search
+    long long counters[16];
+    // results of the last advance
+    int32_t adv_status, adv_accepted, adv_root_cell, adv_pad;
+    long long adv_tries;
+};
+
+struct Tree {                          // structure-of-arrays belief-tree arena
+    int32_t *n;                        // [cap][AS]   visit_count of edge (node, action)
+    long long *qfix;                   // [cap][AS]   sum of q in 2^-24 fixed point
+    uint32_t *child;                   // [cap][AS][2] child id + 1 keyed (action, obs_good); 0 = none
+    uint32_t *legal;                   // [cap]       legal-action mask (fixed at creation)
+    int32_t *cell;                     // [cap]       robot cell of the node
+    unsigned long long *arrive;        // [cap]       (stamp << 32) | arrivals in the current level step
+    int32_t *slot;                     // [cap]       worklist slot of the node in the current level step
+};
+
+struct SimBuf {                        // per simulation-in-flight scratch, SoA over the generation
+    uint32_t *state;                   // packed state cell | rocks << 8
+    int32_t *node;                     // current node, or child-slot index when `pending`
+    uint8_t *flag;                     // bits 0-1 status (0 descending, 1 rollout pending, 2 done), bit 2 pending
+    uint8_t *depth;                    // path entries recorded
+    int32_t *path_node;                // [dcap][wmax]
+    uint16_t *path_ar;                 // [dcap][wmax] action | obs_good << 5 | reward id << 8
+    int32_t *wl_node;                  // [wmax] worklist of nodes with arrivals in this level step
+    uint32_t *wl_thr;                  // [wmax][32] cumulative action thresholds for nodes with >= 2 arrivals
+    int32_t *wl_meta;                  // [wmax] last action (bits 0-7) | (N > 0) << 8
+};
+
+struct SearchParams {
+    DevState *S;
+    const ModelHeader *model;
+    const uint64_t *thr53;
+    Tree t;
+    SimBuf b;
+    const uint32_t *bag[2];
+    long long n_sims;
+    uint32_t sim_offset, move, key0, key1;
+    int32_t w0, growth, wmax, max_depth, dcap, n_thr;
+    double ucb_c, discount;
+    unsigned long long timeout_ns;     // 0 = no wall-clock guard; measured from kernel start
+};
+
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+__device__ __forceinline__ double edge_mean(long long qfix, int n)
+{
+    return ((double)qfix * (1.0 / POMCP_QFIX_SCALE)) / (double)n;
+}
+
+// Stage the model tables into shared memory; returns the first free byte offset (16-byte aligned).
+__device__ __forceinline__ size_t stage_model(unsigned char *smem, const ModelHeader *gm, const uint64_t *gthr,
+                                              int n_thr, SmemModel &M)
+{
+    const int nw = (int)(sizeof(ModelHeader) / 4);
+    uint32_t *dst = reinterpret_cast<uint32_t *>(smem);
+    const uint32_t *src = reinterpret_cast<const uint32_t *>(gm);
+    for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
+    size_t off = (sizeof(ModelHeader) + 15) & ~size_t(15);
+    uint64_t *thr = reinterpret_cast<uint64_t *>(smem + off);
+    for (int i = threadIdx.x; i < n_thr; i += blockDim.x) thr[i] = gthr[i];
+    off += ((size_t)n_thr * 8 + 15) & ~size_t(15);
+    M.hdr = reinterpret_cast<const ModelHeader *>(smem);
+    M.thr53 = thr;
+    return off;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Batch-UCB allocation for a node with k >= 2 simultaneous arrivals (warp-cooperative, lane = action).
+// Water-filling of k pulls over the UCB1 indices mean + c*sqrt(ln(N+1)/n); output: 32-bit cumulative thresholds.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_allocation(const SearchParams &p, int X, uint32_t k, int lane, int A,
+                                                uint32_t *thr_out, int32_t *meta_out)
+{
+    const unsigned full = 0xFFFFFFFFu;
+    const uint32_t mask = p.t.legal[X];
+    const bool legal = lane < A && ((mask >> lane) & 1u);
+    const int n = legal ? p.t.n[(size_t)X * AS + lane] : 0;
+    const long long qf = legal ? p.t.qfix[(size_t)X * AS + lane] : 0;
+    int N = n;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) N += __shfl_xor_sync(full, N, off);
+    const int untried = __popc(__ballot_sync(full, legal && n == 0));
+    const int nlegal = __popc(__ballot_sync(full, legal));
+    double v = 0.0;
+    if (N == 0) v = legal ? 1.0 : 0.0;
+    else if ((uint32_t)untried >= k) v = (legal && n == 0) ? 1.0 : 0.0;
+    else {
+        const double L = det_log_u64((uint64_t)N + 1);
+        const double c2L = (p.ucb_c * p.ucb_c) * L;
+        const double qbar = legal ? (n == 0 ? 0.0 : edge_mean(qf, n)) : -INFINITY;
+        double qmax = qbar;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) qmax = fmax(qmax, __shfl_xor_sync(full, qmax, off));
+        const unsigned best_lanes = __ballot_sync(full, legal && qbar == qmax);
+        const int nbest = __shfl_sync(full, n, __ffs((int)best_lanes) - 1);
+        if (!(c2L > 0.0)) v = (legal && qbar == qmax) ? 1.0 : 0.0;
+        else {
+            const double kd = (double)k;
+            double lo = qmax + 0.999 * sqrt(c2L / (kd + (double)nbest));
+            double hi = qmax + 1.001 * sqrt((c2L * (double)nlegal) / kd) + 1.0;
+            for (int it = 0; it <= 32; ++it) {
+                const double mid = it < 32 ? 0.5 * (lo + hi) : lo;
+                double t = 0.0;
+                if (legal) {
+                    const double d = mid - qbar;
+                    const double mm = c2L / (d * d);
+                    if (n == 0) t = mm > 1.0 ? mm : 1.0;
+                    else { const double e = mm - (double)n; t = e > 0.0 ? e : 0.0; }
+                }
+                if (it == 32) { v = t; break; }
+                double s = t;
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) s = s + __shfl_xor_sync(full, s, off);
+                if (s >= kd) lo = mid; else hi = mid;
+            }
+        }
+    }
+    double x = v;                                   // inclusive scan, Hillis-Steele order
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const double y = __shfl_up_sync(full, x, off);
+        if (lane >= off) x = x + y;
+    }
+    const double V = __shfl_sync(full, x, 31);
+    const double f = (x / V) * 4294967296.0;
+    thr_out[lane] = f >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)f;
+    const unsigned pos = __ballot_sync(full, v > 0.0);
+    if (lane == 0) *meta_out = (31 - __clz((int)pos)) | ((N > 0) ? 256 : 0);
+}
+
+// UCB1 arg-max for a single arrival (action_selectors.py:6-37), uniform tie-break with one 32-bit draw.
+__device__ __forceinline__ int ucb1_select(const SearchParams &p, int X, uint32_t mask, int A, uint32_t x0, bool &Npos)
+{
+    const int32_t *nrow = p.t.n + (size_t)X * AS;
+    int N = 0; uint32_t untried = 0;
+#pragma unroll
+    for (int q = 0; q < AS / 4; ++q) {
+        const int4 v4 = reinterpret_cast<const int4 *>(nrow)[q];
+        const uint32_t m4 = (mask >> (4 * q)) & 15u;
+        if (m4 & 1u) { N += v4.x; if (v4.x == 0) untried |= 1u << (4 * q); }
+        if (m4 & 2u) { N += v4.y; if (v4.y == 0) untried |= 2u << (4 * q); }
+        if (m4 & 4u) { N += v4.z; if (v4.z == 0) untried |= 4u << (4 * q); }
+        if (m4 & 8u) { N += v4.w; if (v4.w == 0) untried |= 8u << (4 * q); }
+    }
+    Npos = N > 0;
+    uint32_t ties;
+    if (untried) ties = untried;                    // n == 0 scores +inf (solvers/pomcp.py:64-65)
+    else {
+        const double L = det_log_u64((uint64_t)N + 1);
+        const long long *qrow = p.t.qfix + (size_t)X * AS;
+        double best = -INFINITY; ties = 0;
+        for (int a = 0; a < A; ++a) {
+            if (!((mask >> a) & 1u)) continue;
+            const int na = nrow[a];
+            const double s = edge_mean(qrow[a], na) + p.ucb_c * sqrt(L / (double)na);
+            if (s > best) { best = s; ties = 1u << a; }
+            else if (s == best) ties |= 1u << a;
+        }
+    }
+    return nth_bit(ties, randbelow32(x0, (uint32_t)__popc(ties)));
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K1: the search.  One persistent cooperative kernel per move; simulations advance in generations:
+//   level steps  [count arrivals | allocate | choose + step + expand]  (grid barrier after each phase)
+//   then         [rollout + backup]                                      (commutative integer atomics)
+// ---------------------------------------------------------------------------------------------------------
+extern "C" __global__ void __launch_bounds__(SEARCH_THREADS)
+pomcp_search_kernel(const SearchParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    cg::grid_group grid = cg::this_grid();
+    SmemModel M;
+    size_t off = stage_model(smem, p.model, p.thr53, p.n_thr, M);
+    double *disc = reinterpret_cast<double *>(smem + off);          // discount^t, t < max_depth
+    off += ((size_t)p.max_depth * 8 + 15) & ~size_t(15);
+    const int A = p.model->n_actions;
+    const int n_acc = (1 + 2 * A) * A;                               // root + depth-1 edges staged per block
+    long long *acc_q = reinterpret_cast<long long *>(smem + off);
+    off += (size_t)n_acc * 8;
+    int *acc_n = reinterpret_cast<int *>(smem + off);
+    if (threadIdx.x == 0) { double d = 1.0; for (int t = 0; t < p.max_depth; ++t) { disc[t] = d; d *= p.discount; } }
+    for (int i = threadIdx.x; i < n_acc; i += blockDim.x) { acc_q[i] = 0; acc_n[i] = 0; }
+    __syncthreads();
+    const ModelHeader *H = M.hdr;
+
+    DevState *S = p.S;
+    const int T = gridDim.x * blockDim.x;
+    const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = threadIdx.x & 31;
+    const int gwarp = gtid >> 5, nwarps = T >> 5;
+    const int root = S->root;
+    const uint32_t actual = S->actual, sampled = S->sampled;
+    const uint32_t *bag = p.bag[S->bag_sel];
+    const int n_bag = S->n_bag;
+    unsigned long long gstep = S->gstep;
+    const unsigned long long t_start = globaltimer_ns();
+    long long c_levels = 0, c_rollout = 0, c_created = 0, c_alloc = 0;
+    long long done = 0, gens = 0, lsteps = 0;
+    int W = p.w0;
+    grid.sync();                                                    // everyone has read S before anyone writes it
+
+    while (done < p.n_sims) {
+        const int w = (int)((p.n_sims - done) < (long long)W ? (p.n_sims - done) : (long long)W);
+        ++gens;
+        for (int i = gtid; i < w; i += T) {                          // belief_node.py:47-48 at the root
+            const uint32_t sim = p.sim_offset + (uint32_t)(done + i);
+            const Philox4 r = philox4x32_10(0u, sim, p.move, DOM_SIM, p.key0, p.key1);
+            p.b.state[i] = bag[randbelow32(r.x, (uint32_t)n_bag)];
+            p.b.node[i] = root; p.b.flag[i] = 0; p.b.depth[i] = 0;
+        }
+        for (;;) {                                                   // ---- level steps ----
+            ++gstep; ++lsteps;
+            const int ring = (int)(gstep & 3ull);
+            const unsigned long long stamp = gstep << 32;
+            // phase 1: resolve pending child ids, count arrivals per node, build the node worklist
+            for (int i = gtid; i < w; i += T) {
+                uint8_t f = p.b.flag[i];
+                if ((f & 3) != 0) continue;
+                int X = p.b.node[i];
+                if (f & 4) { X = (int)p.t.child[X] - 1; p.b.node[i] = X; p.b.flag[i] = 0; }
+                const unsigned long long old = atomicMax(&p.t.arrive[X], stamp);
+                if (old < stamp) {
+                    const int s = atomicAdd(&S->wl_count[ring], 1);
+                    p.b.wl_node[s] = X; p.t.slot[X] = s;
+                }
+                atomicAdd(&p.t.arrive[X], 1ull);
+            }
+            grid.sync();
+            const int nwl = *((volatile int32_t *)&S->wl_count[ring]);
+            if (gtid == 0) S->wl_count[(ring + 1) & 3] = 0;
+            if (nwl == 0) break;
+            // phase 2: nodes with >= 2 arrivals get a batch-UCB allocation (warp per node, lane = action)
+            for (int wi = gwarp; wi < nwl; wi += nwarps) {
+                const int X = p.b.wl_node[wi];
+                const uint32_t k = (uint32_t)p.t.arrive[X];
+                if (k < 2) continue;
+                warp_allocation(p, X, k, lane, A, p.b.wl_thr + (size_t)wi * 32, p.b.wl_meta + wi);
+                if (lane == 0) ++c_alloc;
+            }
+            grid.sync();
+            // phase 3: choose an action, step the model, expand (solvers/pomcp.py:97-117)
+            for (int i = gtid; i < w; i += T) {
+                if ((p.b.flag[i] & 3) != 0) continue;
+                const int X = p.b.node[i];
+                const int d = p.b.depth[i];
+                if (d >= p.max_depth) { p.b.flag[i] = 2; continue; }                       // :100
+                const uint32_t sim = p.sim_offset + (uint32_t)(done + i);
+                const Philox4 r = philox4x32_10((uint32_t)(d + 1), sim, p.move, DOM_SIM, p.key0, p.key1);
+                const uint32_t mask = p.t.legal[X];
+                const uint32_t k = (uint32_t)p.t.arrive[X];
+                bool Npos; int a;
+                if (k == 1) a = ucb1_select(p, X, mask, A, r.x, Npos);
+                else {
+                    const int s = p.t.slot[X];
+                    const uint32_t *thr = p.b.wl_thr + (size_t)s * 32;
+                    const int meta = p.b.wl_meta[s];
+                    Npos = (meta & 256) != 0; a = meta & 255;
+                    for (int bq = 0; bq < A; ++bq) if (r.x < thr[bq]) { a = bq; break; }
+                }
+                const uint32_t st = p.b.state[i];
+                const StepResult sr = rs_step(M, st & 0xFFu, st >> 8, a, u53_of(r.y, r.z), actual, sampled);  // :104
+                ++c_levels;
+                p.b.path_node[(size_t)d * p.wmax + i] = X;
+                p.b.path_ar[(size_t)d * p.wmax + i] = (uint16_t)(a | (sr.good << 5) | (sr.rew << 8));
+                p.b.depth[i] = (uint8_t)(d + 1);
+                p.b.state[i] = sr.cell | (sr.rocks << 8);
+                if (sr.terminal) { p.b.flag[i] = 2; continue; }
+                const size_t cslot = ((size_t)X * AS + a) * 2 + sr.good;
+                uint32_t c = p.t.child[cslot];                                              // :106
+                if (c == 0 && Npos && d + 1 < p.dcap) {                                     // :107-108
+                    c = atomicCAS(&p.t.child[cslot], 0u, CHILD_LOCKED);
+                    if (c == 0) {                                                           // this thread creates it
+                        const int id = atomicAdd(&S->node_count, 1);
+                        p.t.cell[id] = (int32_t)sr.cell;
+                        p.t.legal[id] = H->legal[sr.cell];
+                        atomicExch(&p.t.child[cslot], (uint32_t)id + 1u);
+                        ++c_created;
+                        c = CHILD_LOCKED;
+                    }
+                }
+                if (c != 0) { p.b.node[i] = (int32_t)cslot; p.b.flag[i] = 4; }              // descend next level step
+                else p.b.flag[i] = 1;                                                       // leaf: rollout (:119)
+            }
+            grid.sync();
+        }
+        // ---- rollout (belief_tree_solver.py:123-152, from the post-action state) + backup (:126-137) ----
+        for (int i = gtid; i < w; i += T) {
+            const int depth = p.b.depth[i];
+            double delayed = 0.0;
+            if ((p.b.flag[i] & 3) == 1) {
+                const uint32_t sim = p.sim_offset + (uint32_t)(done + i);
+                uint32_t st = p.b.state[i];
+                uint32_t cell = st & 0xFFu, rocks = st >> 8;
+                double sum = 0.0;
+                int t = 0;
+                for (; t < p.max_depth; ++t) {
+                    const Philox4 r = philox4x32_10((uint32_t)(depth + 1 + t), sim, p.move, DOM_SIM, p.key0, p.key1);
+                    const uint32_t mask = H->legal[cell];
+                    const int a = nth_legal(H, mask, randbelow32(r.x, (uint32_t)__popc(mask)));
+                    int rew = REW_NONE;
+                    if (a < 4) {
+                        cell = (uint32_t)((int)cell + H->delta[a]);
+                        if (H->cell[cell] == POMCP_CELL_GOAL) { sum += H->rew[REW_EXIT] * disc[t]; ++t; break; }
+                    } else if (a == 4) {
+                        const int code = H->cell[cell];
+                        rew = (((actual & rocks) >> code) & 1u) ? REW_GOOD : REW_BAD;
+                        rocks &= ~(1u << code);
+                        sum += H->rew[rew] * disc[t];
+                    } else {
+                        const int k = a - 5;
+                        if (!((sampled >> k) & 1u)) {
+                            const uint32_t truth = (actual >> k) & 1u;
+                            const uint32_t correct = u53_of(r.y, r.z) <= M.thr53[cell * H->n_rocks + k];
+                            const uint32_t good = correct ? truth : (truth ^ 1u);
+                            rocks = (rocks & ~(1u << k)) | (good << k);
+                        }
+                    }
+                }
+                c_rollout += t;
+                delayed = sum;
+            }
+            for (int d = depth - 1; d >= 0; --d) {
+                const int X = p.b.path_node[(size_t)d * p.wmax + i];
+                const uint32_t ar = p.b.path_ar[(size_t)d * p.wmax + i];
+                const int a = ar & 31;
+                const double q = H->rew[ar >> 8] + p.discount * delayed;
+                const long long qi = __double2ll_rn(q * POMCP_QFIX_SCALE);
+                if (d == 0) {
+                    atomicAdd(&acc_n[a], 1);
+                    atomicAdd(reinterpret_cast<unsigned long long *>(&acc_q[a]), (unsigned long long)qi);
+                } else if (d == 1) {
+                    const uint32_t ar0 = p.b.path_ar[i];
+                    const int e = (1 + (int)(ar0 & 31) * 2 + (int)((ar0 >> 5) & 1)) * A + a;
+                    atomicAdd(&acc_n[e], 1);
+                    atomicAdd(reinterpret_cast<unsigned long long *>(&acc_q[e]), (unsigned long long)qi);
+                } else {
+                    atomicAdd(&p.t.n[(size_t)X * AS + a], 1);
+                    atomicAdd(reinterpret_cast<unsigned long long *>(&p.t.qfix[(size_t)X * AS + a]), (unsigned long long)qi);
+                }
+                delayed = q;
+            }
+        }
+        __syncthreads();
+        for (int e = threadIdx.x; e < n_acc; e += blockDim.x) {      // flush the staged root / depth-1 edges
+            const int dn = acc_n[e];
+            if (dn == 0) continue;
+            const int slot = e / A, a = e - slot * A;
+            int X = root;
+            if (slot > 0) X = (int)p.t.child[(size_t)root * AS * 2 + (slot - 1)] - 1;
+            atomicAdd(&p.t.n[(size_t)X * AS + a], dn);
+            atomicAdd(reinterpret_cast<unsigned long long *>(&p.t.qfix[(size_t)X * AS + a]), (unsigned long long)acc_q[e]);
+            acc_n[e] = 0; acc_q[e] = 0;
+        }
+        done += w;
+        if (W < p.wmax) { long long nw = (long long)W * p.growth; W = nw > p.wmax ? p.wmax : (int)nw; }
+        if (p.timeout_ns && gtid == 0 && globaltimer_ns() - t_start > p.timeout_ns) S->stop = 1;
+        grid.sync();
+        if (p.timeout_ns && *((volatile int32_t *)&S->stop)) break;   // action_selection_timeout
+    }
+
+    // counters (warp-reduced) and persistent state
+#pragma unroll
+    for (int o = 16; o >= 1; o >>= 1) {
+        c_levels += __shfl_xor_sync(0xFFFFFFFFu, c_levels, o);
+        c_rollout += __shfl_xor_sync(0xFFFFFFFFu, c_rollout, o);
+        c_created += __shfl_xor_sync(0xFFFFFFFFu, c_created, o);
+        c_alloc += __shfl_xor_sync(0xFFFFFFFFu, c_alloc, o);
+    }
+    if (lane == 0) {
+        atomicAdd(reinterpret_cast<unsigned long long *>(&S->counters[0]), (unsigned long long)c_levels);
+        atomicAdd(reinterpret_cast<unsigned long long *>(&S->counters[1]), (unsigned long long)c_rollout);
+        atomicAdd(reinterpret_cast<unsigned long long *>(&S->counters[2]), (unsigned long long)c_created);
+        atomicAdd(reinterpret_cast<unsigned long long *>(&S->counters[4]), (unsigned long long)c_alloc);
+    }
+    if (gtid == 0) {
+        S->gstep = gstep;
+        S->sims_done = done;
+        S->stop = 0;
+        S->counters[5] += gens;
+        S->counters[6] += lsteps;
+        S->counters[7] = (long long)(globaltimer_ns() - t_start);
+        S->counters[8] = done;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// K2: belief update -- batched rejection sampling with an order-preserving (stream-compacted) survivor set,
+// then the re-root.  One block: a belief is only max_particle_count (2000) states.
+// ---------------------------------------------------------------------------------------------------------
+struct AdvanceParams {
+    DevState *S;
+    const ModelHeader *model;
+    const uint64_t *thr53;
+    Tree t;
+    uint32_t *bag[2];
+    int32_t action, obs_good, need, n_thr;
+    uint32_t sampled_after, move, key0, key1;
+    long long max_tries;
+};
+
+extern "C" __global__ void __launch_bounds__(ADV_THREADS)
+pomcp_advance_kernel(const AdvanceParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    SmemModel M;
+    size_t off = stage_model(smem, p.model, p.thr53, p.n_thr, M);
+    int *warp_tot = reinterpret_cast<int *>(smem + off);             // [32] + [2] broadcast cells
+    __shared__ long long sh_tries;
+    DevState *S = p.S;
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const int root = S->root;
+    const uint32_t actual = S->actual;
+    const uint32_t sampled = p.sampled_after;                        // belief_tree_solver.py:165 model.update first
+    const uint32_t *old_bag = p.bag[S->bag_sel];
+    uint32_t *new_bag = p.bag[S->bag_sel ^ 1];
+    const int n_old = S->n_bag;
+    if (tid == 0) sh_tries = -1;
+    __syncthreads();
+    int got = 0;
+    long long base = 0;
+    while (got < p.need && base < p.max_tries) {
+        uint32_t ns[ADV_TRIES]; uint32_t acc = 0;
+#pragma unroll
+        for (int r = 0; r < ADV_TRIES; ++r) {
+            const long long t = base + (long long)tid * ADV_TRIES + r;
+            if (t < p.max_tries) {                                   // model.py:242-251
+                const Philox4 x = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), p.move, DOM_UPDATE, p.key0, p.key1);
+                const uint32_t st = old_bag[randbelow32(x.x, (uint32_t)n_old)];
+                const StepResult sr = rs_step(M, st & 0xFFu, st >> 8, p.action, u53_of(x.y, x.z), actual, sampled);
+                ns[r] = sr.cell | (sr.rocks << 8);
+                if (sr.good == p.obs_good) acc |= 1u << r;
+            }
+        }
+        int cnt = __popc(acc), incl = cnt;                            // block-wide exclusive scan of cnt
+#pragma unroll
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            int v = warp_tot[lane], iv = v;
+#pragma unroll
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xFFFFFFFFu, iv, o); if (lane >= o) iv += y; }
+            warp_tot[lane] = iv - v;
+            if (lane == 31) warp_tot[32] = iv;
+        }
+        __syncthreads();
+        int pos = got + warp_tot[wid] + incl - cnt;
+        const int total = warp_tot[32];
+#pragma unroll
+        for (int r = 0; r < ADV_TRIES; ++r)
+            if ((acc >> r) & 1u) {
+                if (pos < p.need) new_bag[pos] = ns[r];
+                if (pos == p.need - 1) sh_tries = base + (long long)tid * ADV_TRIES + r + 1;
+                ++pos;
+            }
+        got += total;
+        base += (long long)ADV_THREADS * ADV_TRIES;
+        __syncthreads();
+    }
+    if (tid == 0) {
+        const int accepted = got < p.need ? got : p.need;
+        long long tries = sh_tries >= 0 ? sh_tries : (base < p.max_tries ? base : p.max_tries);
+        S->adv_tries = tries; S->adv_accepted = accepted;
+        S->sampled = sampled;                                        // belief_tree_solver.py:165 happens first
+        if (accepted == 0) { S->adv_status = 2; S->adv_root_cell = p.t.cell[root]; }
+        else {
+            uint32_t c = p.t.child[((size_t)root * AS + p.action) * 2 + p.obs_good];   // belief_tree_solver.py:167
+            int status = 0, id;
+            if (c == 0) {                                            // never expanded: fresh node at the next position
+                id = S->node_count++;
+                const StepResult sr = rs_step(M, (uint32_t)p.t.cell[root], 0u, p.action, 0ull, actual, sampled);
+                p.t.cell[id] = (int32_t)sr.cell; p.t.legal[id] = M.hdr->legal[sr.cell];
+                status = 1;
+            } else id = (int)c - 1;
+            S->root = id; S->n_bag = accepted; S->bag_sel ^= 1;                        // :210
+            S->adv_status = status; S->adv_root_cell = p.t.cell[id];
+        }
+    }
+}
+
+// generate_step over a batch (parity harness for rock_model.py:451-465)
+extern "C" __global__ void pomcp_step_batch_kernel(const ModelHeader *model, const uint64_t *thr53, int n_thr,
+                                                   long long n, const uint32_t *state, const uint8_t *action,
+                                                   const uint64_t *u53, const uint32_t *actual,
+                                                   const uint32_t *sampled, uint32_t *next_state, uint8_t *flags,
+                                                   double *reward)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    SmemModel M;
+    stage_model(smem, model, thr53, n_thr, M);
+    __syncthreads();
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const uint32_t st = state[i];
+        const StepResult sr = rs_step(M, st & 0xFFu, st >> 8, action[i], u53[i], actual[i], sampled[i]);
+        next_state[i] = sr.cell | (sr.rocks << 8);
+        flags[i] = (uint8_t)(sr.good | (sr.empty << 1) | (sr.terminal << 2) | (sr.legal << 3));
+        reward[i] = M.hdr->rew[sr.rew];
+    }
+}
+
+// Reset the arena prefix and plant a root (fresh tree).
+__global__ void pomcp_plant_root_kernel(DevState *S, Tree t, int root_cell, uint32_t legal, int n_bag, int bag_sel)
+{
+    if (blockIdx.x == 0 && threadIdx.x == 0) {
+        S->root = 0; S->node_count = 1; S->n_bag = n_bag; S->bag_sel = bag_sel;
+        t.cell[0] = root_cell; t.legal[0] = legal;
+    }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Host side: the handle and the C ABI
+// ---------------------------------------------------------------------------------------------------------
+struct pomcp_handle {
+    pomcp_config cfg;
+    int device = 0;
+    std::string err;
+    DevState *dS = nullptr;
+    ModelHeader hmodel;
+    ModelHeader *dmodel = nullptr;
+    uint64_t *dthr = nullptr;
+    int n_thr = 0;
+    bool have_model = false, have_root = false;
+    Tree t{};
+    SimBuf b{};
+    uint32_t *bag[2] = {nullptr, nullptr};
+    int bag_cap = 0;
+    long long cap = 0;
+    long long nodes_used = 0;       // host mirror (upper bound) of DevState.node_count
+    long long zeroed_upto = 0;      // arena prefix that may hold stale data
+    int root_cell = 0;
+    int n_bag = 0;
+    int coop_blocks = 0;
+    size_t search_smem = 0;
+    long long launches = 0;
+    void *stage = nullptr;          // pinned host staging
+    cudaStream_t last_stream = nullptr;
+};
+
+#define CK(call)                                                                               \
+    do {                                                                                       \
+        cudaError_t e_ = (call);                                                               \
+        if (e_ != cudaSuccess) {                                                               \
+            h->err = std::string(#call) + ": " + cudaGetErrorString(e_);                       \
+            return -1;                                                                         \
+        }                                                                                      \
+    } while (0)
+
+static int fail(pomcp_handle *h, const char *msg) { h->err = msg; return -1; }
+
+extern "C" const char *pomcp_last_error(const pomcp_handle *h) { return h ? h->err.c_str() : "null handle"; }
+
+static void free_all(pomcp_handle *h)
+{
+    cudaFree(h->dS); cudaFree(h->dmodel); cudaFree(h->dthr);
+    cudaFree(h->t.n); cudaFree(h->t.qfix); cudaFree(h->t.child); cudaFree(h->t.legal); cudaFree(h->t.cell);
+    cudaFree(h->t.arrive); cudaFree(h->t.slot);
+    cudaFree(h->b.state); cudaFree(h->b.node); cudaFree(h->b.flag); cudaFree(h->b.depth); cudaFree(h->b.path_node);
+    cudaFree(h->b.path_ar); cudaFree(h->b.wl_node); cudaFree(h->b.wl_thr); cudaFree(h->b.wl_meta);
+    cudaFree(h->bag[0]); cudaFree(h->bag[1]);
+    if (h->stage) cudaFreeHost(h->stage);
+}
+
+extern "C" void pomcp_destroy(pomcp_handle *h)
+{
+    if (!h) return;
+    cudaSetDevice(h->device);
+    cudaDeviceSynchronize();
+    free_all(h);
+    delete h;
+}
+
+extern "C" int pomcp_create(const pomcp_config *cfg, int device, pomcp_handle **out)
+{
+    if (!cfg || !out) return -1;
+    pomcp_handle *h = new pomcp_handle();
+    *out = h;                          // returned even on failure so that pomcp_last_error() can be read
+    h->cfg = *cfg; h->device = device;
+    if (cfg->max_depth < 1 || cfg->max_depth > 4096) return fail(h, "max_depth out of range [1, 4096]");
+    if (cfg->tree_depth_cap < 2 || cfg->tree_depth_cap > 64) return fail(h, "tree_depth_cap out of range [2, 64]");
+    if (cfg->gen_w0 < 1 || cfg->gen_growth < 1 || cfg->gen_wmax < cfg->gen_w0) return fail(h, "bad generation schedule");
+    if (cfg->node_capacity < 2 || cfg->node_capacity > (1ll << 25)) return fail(h, "node_capacity out of range [2, 2^25]");
+    if (cfg->max_particle_count < 1) return fail(h, "max_particle_count < 1");
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) return fail(h, "no CUDA device: the B200 POMCP planner has no CPU fallback");
+    CK(cudaSetDevice(device));
+    int coop = 0;
+    CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
+    if (!coop) return fail(h, "device lacks cooperative launch");
+    h->cap = cfg->node_capacity;
+    const size_t cap = (size_t)h->cap, wmax = (size_t)cfg->gen_wmax, dcap = (size_t)cfg->tree_depth_cap;
+    CK(cudaMalloc(&h->dS, sizeof(DevState)));
+    CK(cudaMemset(h->dS, 0, sizeof(DevState)));
+    CK(cudaMalloc(&h->dmodel, sizeof(ModelHeader)));
+    CK(cudaMalloc(&h->t.n, cap * AS * sizeof(int32_t)));
+    CK(cudaMalloc(&h->t.qfix, cap * AS * sizeof(long long)));
+    CK(cudaMalloc(&h->t.child, cap * AS * 2 * sizeof(uint32_t)));
+    CK(cudaMalloc(&h->t.legal, cap * sizeof(uint32_t)));
+    CK(cudaMalloc(&h->t.cell, cap * sizeof(int32_t)));
+    CK(cudaMalloc(&h->t.arrive, cap * sizeof(unsigned long long)));
+    CK(cudaMalloc(&h->t.slot, cap * sizeof(int32_t)));
+    CK(cudaMemset(h->t.n, 0, cap * AS * sizeof(int32_t)));
+    CK(cudaMemset(h->t.qfix, 0, cap * AS * sizeof(long long)));
+    CK(cudaMemset(h->t.child, 0, cap * AS * 2 * sizeof(uint32_t)));
+    CK(cudaMemset(h->t.arrive, 0, cap * sizeof(unsigned long long)));
+    CK(cudaMalloc(&h->b.state, wmax * sizeof(uint32_t)));
+    CK(cudaMalloc(&h->b.node, wmax * sizeof(int32_t)));
+    CK(cudaMalloc(&h->b.flag, wmax));
+    CK(cudaMalloc(&h->b.depth, wmax));
+    CK(cudaMalloc(&h->b.path_node, wmax * dcap * sizeof(int32_t)));
+    CK(cudaMalloc(&h->b.path_ar, wmax * dcap * sizeof(uint16_t)));
+    CK(cudaMalloc(&h->b.wl_node, wmax * sizeof(int32_t)));
+    CK(cudaMalloc(&h->b.wl_thr, wmax * 32 * sizeof(uint32_t)));
+    CK(cudaMalloc(&h->b.wl_meta, wmax * sizeof(int32_t)));
+    CK(cudaMallocHost(&h->stage, 1 << 16));
+    return 0;
+}
+
+extern "C" int pomcp_set_model_rocksample(pomcp_handle *h, int rows, int cols, const int8_t *cell, int start_cell,
+                                          const uint64_t *thr53, const double rewards[4])
+{
+    if (!h) return -1;
+    CK(cudaSetDevice(h->device));
+    if (rows < 1 || cols < 1 || rows * cols > POMCP_MAX_CELLS) return fail(h, "grid larger than 256 cells");
+    ModelHeader &m = h->hmodel;
+    memset(&m, 0, sizeof(m));
+    m.rows = rows; m.cols = cols; m.n_cells = rows * cols; m.start_cell = start_cell;
+    int nr = 0;
+    for (int c = 0; c < m.n_cells; ++c) { m.cell[c] = cell[c]; if (cell[c] + 1 > nr) nr = cell[c] + 1; }
+    if (nr < 1 || nr > POMCP_MAX_ROCKS || 5 + nr > POMCP_MAX_ACTIONS) return fail(h, "unsupported rock count");
+    m.n_rocks = nr; m.n_actions = 5 + nr;
+    m.rew[REW_NONE] = 0.0; m.rew[REW_ILLEGAL] = rewards[0]; m.rew[REW_EXIT] = rewards[1];
+    m.rew[REW_GOOD] = rewards[2]; m.rew[REW_BAD] = rewards[3];
+    m.delta[0] = -cols; m.delta[1] = 1; m.delta[2] = cols; m.delta[3] = -1;
+    const uint32_t checks = ((nr + 5 >= 32) ? 0xFFFFFFFFu : ((1u << (nr + 5)) - 1u)) & ~31u;
+    for (int i = 0; i < rows; ++i)
+        for (int j = 0; j < cols; ++j) {
+            const int c = i * cols + j;
+            if (m.cell[c] == POMCP_CELL_OBSTACLE) { m.legal[c] = 0; continue; }
+            uint32_t mask = checks;
+            if (i > 0 && m.cell[c - cols] != POMCP_CELL_OBSTACLE) mask |= 1u;
+            if (j + 1 < cols && m.cell[c + 1] != POMCP_CELL_OBSTACLE) mask |= 2u;
+            if (i + 1 < rows && m.cell[c + cols] != POMCP_CELL_OBSTACLE) mask |= 4u;
+            if (j > 0 && m.cell[c - 1] != POMCP_CELL_OBSTACLE) mask |= 8u;
+            if (m.cell[c] >= 0) mask |= 16u;
+            m.legal[c] = mask;
+        }
+    for (int mk = 0; mk < 32; ++mk) {
+        int j = 0;
+        for (int bit = 0; bit < 5; ++bit) if ((mk >> bit) & 1) m.nth5[mk * 8 + j++] = (uint8_t)bit;
+    }
+    h->n_thr = m.n_cells * nr;
+    cudaFree(h->dthr); h->dthr = nullptr;
+    CK(cudaMalloc(&h->dthr, (size_t)h->n_thr * sizeof(uint64_t)));
+    CK(cudaMemcpy(h->dthr, thr53, (size_t)h->n_thr * sizeof(uint64_t), cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(h->dmodel, &m, sizeof(m), cudaMemcpyHostToDevice));
+    // launch geometry of the cooperative search kernel
+    const int A = m.n_actions;
+    size_t smem = ((sizeof(ModelHeader) + 15) & ~size_t(15)) + (((size_t)h->n_thr * 8 + 15) & ~size_t(15)) +
+                  (((size_t)h->cfg.max_depth * 8 + 15) & ~size_t(15)) + (size_t)(1 + 2 * A) * A * 12 + 16;
+    h->search_smem = smem;
+    CK(cudaFuncSetAttribute(pomcp_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(pomcp_advance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(pomcp_step_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0, sms = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pomcp_search_kernel, SEARCH_THREADS, smem));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    if (per_sm < 1) return fail(h, "search kernel does not fit on an SM");
+    h->coop_blocks = per_sm * sms;
+    h->have_model = true;
+    return 0;
+}
+
+extern "C" int pomcp_set_world(pomcp_handle *h, uint32_t actual, uint32_t sampled)
+{
+    if (!h) return -1;
+    CK(cudaSetDevice(h->device));
+    uint32_t v[2] = {actual, sampled};
+    CK(cudaMemcpy(&h->dS->actual, v, sizeof(v), cudaMemcpyHostToDevice));
+    return 0;
+}
+
+// Zero the part of the arena that earlier searches touched.
+static int clear_arena(pomcp_handle *h, cudaStream_t s)
+{
+    const size_t n = (size_t)h->zeroed_upto;
+    if (n) {
+        CK(cudaMemsetAsync(h->t.n, 0, n * AS * sizeof(int32_t), s));
+        CK(cudaMemsetAsync(h->t.qfix, 0, n * AS * sizeof(long long), s));
+        CK(cudaMemsetAsync(h->t.child, 0, n * AS * 2 * sizeof(uint32_t), s));
+        // `arrive` keeps its stamps: they are never reused (gstep only grows)
+    }
+    h->zeroed_upto = 0;
+    return 0;
+}
+
+static int plant_root(pomcp_handle *h, int root_cell, int n_bag, int bag_sel, cudaStream_t s)
+{
+    if (clear_arena(h, s)) return -1;
+    pomcp_plant_root_kernel<<<1, 32, 0, s>>>(h->dS, h->t, root_cell, h->hmodel.legal[root_cell], n_bag, bag_sel);
+    CK(cudaGetLastError());
+    ++h->launches;
+    h->nodes_used = 1; h->zeroed_upto = 1; h->root_cell = root_cell; h->n_bag = n_bag;
+    return 0;
+}
+
+extern "C" int pomcp_set_root_particles(pomcp_handle *h, const uint32_t *packed, int n, int root_cell)
+{
+    if (!h) return -1;
+    if (!h->have_model) return fail(h, "set the model first");
+    if (n < 1) return fail(h, "empty belief");
+    if (root_cell < 0 || root_cell >= h->hmodel.n_cells) return fail(h, "root cell outside the grid");
+    CK(cudaSetDevice(h->device));
+    const int need = n > h->cfg.max_particle_count ? n : h->cfg.max_particle_count;
+    if (need > h->bag_cap) {
+        cudaFree(h->bag[0]); cudaFree(h->bag[1]); h->bag[0] = h->bag[1] = nullptr;
+        CK(cudaMalloc(&h->bag[0], (size_t)need * sizeof(uint32_t)));
+        CK(cudaMalloc(&h->bag[1], (size_t)need * sizeof(uint32_t)));
+        h->bag_cap = need;
+    }
+    CK(cudaMemcpy(h->bag[0], packed, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice));
+    if (plant_root(h, root_cell, n, 0, 0)) return -1;
+    CK(cudaDeviceSynchronize());
+    h->have_root = true;
+    return 0;
+}
+
+extern "C" int pomcp_search(pomcp_handle *h, int64_t n_sims, uint32_t sim_offset, uint32_t move, double timeout_s,
+                            void *stream)
+{
+    if (!h) return -1;
+    if (!h->have_root) return fail(h, "no root belief: call pomcp_set_root_particles first");
+    if (n_sims < 0) return fail(h, "n_sims < 0");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    h->last_stream = s;
+    int rc = 0;
+    if (h->nodes_used + n_sims + 2 > h->cap) {          // every simulation creates at most one node
+        if (n_sims + 3 > h->cap) return fail(h, "node_capacity smaller than n_sims + 3");
+        // drop the subtree, keep the belief (documented degradation; status 1)
+        int32_t sel = 0;
+        CK(cudaStreamSynchronize(s));
+        CK(cudaMemcpy(&sel, &h->dS->bag_sel, sizeof(sel), cudaMemcpyDeviceToHost));
+        if (plant_root(h, h->root_cell, h->n_bag, sel, s)) return -1;
+        rc = 1;
+    }
+    SearchParams p;
+    memset(&p, 0, sizeof(p));
+    p.S = h->dS; p.model = h->dmodel; p.thr53 = h->dthr; p.t = h->t; p.b = h->b;
+    p.bag[0] = h->bag[0]; p.bag[1] = h->bag[1];
+    p.n_sims = n_sims; p.sim_offset = sim_offset; p.move = move;
+    p.key0 = (uint32_t)h->cfg.seed; p.key1 = (uint32_t)(h->cfg.seed >> 32);
+    p.w0 = h->cfg.gen_w0; p.growth = h->cfg.gen_growth; p.wmax = h->cfg.gen_wmax;
+    p.max_depth = h->cfg.max_depth; p.dcap = h->cfg.tree_depth_cap; p.n_thr = h->n_thr;
+    p.ucb_c = h->cfg.ucb_coefficient; p.discount = h->cfg.discount;
+    p.timeout_ns = timeout_s > 0 ? (unsigned long long)(timeout_s * 1e9) : 0ull;   // checked between generations
+    long long widest = n_sims < (long long)p.wmax ? n_sims : (long long)p.wmax;
+    int blocks = (int)((widest + SEARCH_THREADS - 1) / SEARCH_THREADS);
+    if (blocks < 1) blocks = 1;
+    if (blocks > h->coop_blocks) blocks = h->coop_blocks;
+    void *args[] = {&p};
+    CK(cudaLaunchCooperativeKernel((void *)pomcp_search_kernel, dim3(blocks), dim3(SEARCH_THREADS), args,
+                                   h->search_smem, s));
+    ++h->launches;
+    h->nodes_used += n_sims;
+    h->zeroed_upto = h->nodes_used;
+    return rc;
+}
+
+extern "C" int pomcp_root_stats(pomcp_handle *h, int64_t *n, int64_t *qfix, uint32_t *legal_mask, int64_t *sims_done)
+{
+    if (!h) return -1;
+    if (!h->have_root) return fail(h, "no root belief");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->last_stream));
+    DevState st;
+    CK(cudaMemcpy(&st, h->dS, sizeof(st), cudaMemcpyDeviceToHost));
+    h->nodes_used = st.node_count;
+    const int A = h->hmodel.n_actions;
+    int32_t nn[AS]; long long qq[AS]; uint32_t lg;
+    CK(cudaMemcpy(nn, h->t.n + (size_t)st.root * AS, sizeof(nn), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(qq, h->t.qfix + (size_t)st.root * AS, sizeof(qq), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&lg, h->t.legal + st.root, sizeof(lg), cudaMemcpyDeviceToHost));
+    for (int a = 0; a < A; ++a) { n[a] = nn[a]; qfix[a] = qq[a]; }
+    if (legal_mask) *legal_mask = lg;
+    if (sims_done) *sims_done = st.sims_done;
+    return 0;
+}
+
+extern "C" int pomcp_node_stats(pomcp_handle *h, const int32_t *path_ao, int len, int64_t *n, int64_t *qfix,
+                                uint32_t *legal_mask, int32_t *cell)
+{
+    if (!h) return -1;
+    if (!h->have_root) return fail(h, "no root belief");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->last_stream));
+    int32_t X;
+    CK(cudaMemcpy(&X, &h->dS->root, sizeof(X), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < len; ++i) {
+        const int a = path_ao[2 * i], o = path_ao[2 * i + 1];
+        if (a < 0 || a >= h->hmodel.n_actions || o < 0 || o > 1) return fail(h, "bad path entry");
+        uint32_t c;
+        CK(cudaMemcpy(&c, h->t.child + ((size_t)X * AS + a) * 2 + o, sizeof(c), cudaMemcpyDeviceToHost));
+        if (c == 0 || c == CHILD_LOCKED) return 1;
+        X = (int32_t)c - 1;
+    }
+    int32_t nn[AS]; long long qq[AS];
+    CK(cudaMemcpy(nn, h->t.n + (size_t)X * AS, sizeof(nn), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(qq, h->t.qfix + (size_t)X * AS, sizeof(qq), cudaMemcpyDeviceToHost));
+    for (int a = 0; a < h->hmodel.n_actions; ++a) { n[a] = nn[a]; qfix[a] = qq[a]; }
+    if (legal_mask) CK(cudaMemcpy(legal_mask, h->t.legal + X, sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (cell) CK(cudaMemcpy(cell, h->t.cell + X, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int pomcp_advance(pomcp_handle *h, int action, int obs_good, uint32_t sampled_after, uint32_t move,
+                             int64_t max_tries, int32_t *status, int64_t *tries_used, int32_t *accepted)
+{
+    if (!h) return -1;
+    if (!h->have_root) return fail(h, "no root belief");
+    if (action < 0 || action >= h->hmodel.n_actions) return fail(h, "action out of range");
+    CK(cudaSetDevice(h->device));
+    if (h->nodes_used + 2 > h->cap) return fail(h, "node arena full");
+    AdvanceParams p;
+    memset(&p, 0, sizeof(p));
+    p.S = h->dS; p.model = h->dmodel; p.thr53 = h->dthr; p.t = h->t;
+    p.bag[0] = h->bag[0]; p.bag[1] = h->bag[1];
+    p.action = action; p.obs_good = obs_good ? 1 : 0; p.need = h->cfg.max_particle_count; p.n_thr = h->n_thr;
+    p.sampled_after = sampled_after; p.move = move;
+    p.key0 = (uint32_t)h->cfg.seed; p.key1 = (uint32_t)(h->cfg.seed >> 32);
+    p.max_tries = max_tries > 0 ? max_tries : 256ll * p.need;
+    cudaStream_t s = h->last_stream;
+    pomcp_advance_kernel<<<1, ADV_THREADS, h->search_smem, s>>>(p);
+    CK(cudaGetLastError());
+    ++h->launches;
+    CK(cudaStreamSynchronize(s));
+    DevState st;
+    CK(cudaMemcpy(&st, h->dS, sizeof(st), cudaMemcpyDeviceToHost));
+    h->nodes_used = st.node_count;
+    if (h->zeroed_upto < h->nodes_used) h->zeroed_upto = h->nodes_used;
+    h->root_cell = st.adv_root_cell; h->n_bag = st.n_bag;
+    if (status) *status = st.adv_status;
+    if (tries_used) *tries_used = st.adv_tries;
+    if (accepted) *accepted = st.adv_accepted;
+    return st.adv_status == 2 ? 1 : 0;
+}
+
+extern "C" int pomcp_root_particles(pomcp_handle *h, uint32_t *out, int capacity, int32_t *n, int32_t *root_cell)
+{
+    if (!h) return -1;
+    if (!h->have_root) return fail(h, "no root belief");
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->last_stream));
+    DevState st;
+    CK(cudaMemcpy(&st, h->dS, sizeof(st), cudaMemcpyDeviceToHost));
+    const int m = st.n_bag < capacity ? st.n_bag : capacity;
+    if (out && m > 0) CK(cudaMemcpy(out, h->bag[st.bag_sel], (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
+    if (n) *n = st.n_bag;
+    if (root_cell) CK(cudaMemcpy(root_cell, h->t.cell + st.root, sizeof(int32_t), cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int pomcp_generate_steps(pomcp_handle *h, int64_t n, const uint32_t *state, const uint8_t *action,
+                                    const uint64_t *u53, const uint32_t *actual, const uint32_t *sampled,
+                                    uint32_t *next_state, uint8_t *flags, double *reward)
+{
+    if (!h) return -1;
+    if (!h->have_model) return fail(h, "set the model first");
+    if (n <= 0) return 0;
+    CK(cudaSetDevice(h->device));
+    uint32_t *ds, *dn, *dw0, *dw1; uint8_t *da, *df; uint64_t *du; double *dr;
+    CK(cudaMalloc(&ds, n * 4)); CK(cudaMalloc(&dn, n * 4)); CK(cudaMalloc(&da, n)); CK(cudaMalloc(&df, n));
+    CK(cudaMalloc(&du, n * 8)); CK(cudaMalloc(&dr, n * 8)); CK(cudaMalloc(&dw0, n * 4)); CK(cudaMalloc(&dw1, n * 4));
+    CK(cudaMemcpy(dw0, actual, n * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dw1, sampled, n * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(ds, state, n * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(da, action, n, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(du, u53, n * 8, cudaMemcpyHostToDevice));
+    int blocks = (int)((n + 255) / 256); if (blocks > 1184) blocks = 1184;
+    pomcp_step_batch_kernel<<<blocks, 256, h->search_smem>>>(h->dmodel, h->dthr, h->n_thr, n, ds, da, du, dw0, dw1, dn, df, dr);
+    CK(cudaGetLastError());
+    ++h->launches;
+    CK(cudaMemcpy(next_state, dn, n * 4, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(flags, df, n, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(reward, dr, n * 8, cudaMemcpyDeviceToHost));
+    cudaFree(ds); cudaFree(dn); cudaFree(da); cudaFree(df); cudaFree(du); cudaFree(dr); cudaFree(dw0); cudaFree(dw1);
+    return 0;
+}
+
+extern "C" int pomcp_counters(pomcp_handle *h, int64_t out[16])
+{
+    if (!h) return -1;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->last_stream));
+    DevState st;
+    CK(cudaMemcpy(&st, h->dS, sizeof(st), cudaMemcpyDeviceToHost));
+    for (int i = 0; i < 16; ++i) out[i] = st.counters[i];
+    out[3] = st.node_count;
+    out[9] = h->launches;
+    out[10] = h->coop_blocks;
+    out[11] = SEARCH_THREADS;
+    return 0;
+}

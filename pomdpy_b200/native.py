@@ -1,0 +1,189 @@
+"""ctypes binding of the C ABI in include/pomcp_b200.h (libpomcp_b200.so).
+
+There is no CPU fallback: if the library is missing or no CUDA device is present, the calls raise.
+"""
+import ctypes as C
+import os
+
+import numpy as np
+
+from . import build as _build
+
+QFIX_SCALE = float(1 << 24)
+MAX_ACTIONS = 32
+_LIB = None
+
+
+class PomcpError(RuntimeError):
+    pass
+
+
+class Config(C.Structure):
+    _fields_ = [("max_depth", C.c_int32), ("tree_depth_cap", C.c_int32), ("max_particle_count", C.c_int32),
+                ("reserved0", C.c_int32), ("ucb_coefficient", C.c_double), ("discount", C.c_double),
+                ("seed", C.c_uint64), ("node_capacity", C.c_int64), ("gen_w0", C.c_int32),
+                ("gen_growth", C.c_int32), ("gen_wmax", C.c_int32), ("reserved1", C.c_int32)]
+
+
+EXPORTS = ["pomcp_create", "pomcp_destroy", "pomcp_last_error", "pomcp_set_model_rocksample", "pomcp_set_world",
+           "pomcp_set_root_particles", "pomcp_search", "pomcp_root_stats", "pomcp_node_stats", "pomcp_advance",
+           "pomcp_root_particles", "pomcp_generate_steps", "pomcp_counters"]
+
+
+def library_path():
+    return _build.LIB
+
+
+def load(build_if_missing=True):
+    """Load libpomcp_b200.so (building it first if the sources are newer and nvcc is present)."""
+    global _LIB
+    if _LIB is not None:
+        return _LIB
+    path = library_path()
+    if build_if_missing and _build.stale():
+        try:
+            _build.build()
+        except Exception as e:            # no nvcc on this box: a prebuilt library must already be there
+            if not os.path.exists(path):
+                raise PomcpError("libpomcp_b200.so is missing and cannot be built: %s" % e)
+    if not os.path.exists(path):
+        raise PomcpError("libpomcp_b200.so not found; run `python -m pomdpy_b200.build`")
+    L = C.CDLL(path)
+    vp, i32, u32, i64, u64, dbl = C.c_void_p, C.c_int32, C.c_uint32, C.c_int64, C.c_uint64, C.c_double
+    P = C.POINTER
+    L.pomcp_create.argtypes = [P(Config), C.c_int, P(vp)]
+    L.pomcp_destroy.argtypes = [vp]
+    L.pomcp_destroy.restype = None
+    L.pomcp_last_error.argtypes = [vp]
+    L.pomcp_last_error.restype = C.c_char_p
+    L.pomcp_set_model_rocksample.argtypes = [vp, C.c_int, C.c_int, P(C.c_int8), C.c_int, P(u64), P(dbl)]
+    L.pomcp_set_world.argtypes = [vp, u32, u32]
+    L.pomcp_set_root_particles.argtypes = [vp, P(u32), C.c_int, C.c_int]
+    L.pomcp_search.argtypes = [vp, i64, u32, u32, dbl, vp]
+    L.pomcp_root_stats.argtypes = [vp, P(i64), P(i64), P(u32), P(i64)]
+    L.pomcp_node_stats.argtypes = [vp, P(i32), C.c_int, P(i64), P(i64), P(u32), P(i32)]
+    L.pomcp_advance.argtypes = [vp, C.c_int, C.c_int, u32, u32, i64, P(i32), P(i64), P(i32)]
+    L.pomcp_root_particles.argtypes = [vp, P(u32), C.c_int, P(i32), P(i32)]
+    L.pomcp_generate_steps.argtypes = [vp, i64, P(u32), P(C.c_uint8), P(u64), P(u32), P(u32), P(u32), P(C.c_uint8),
+                                       P(dbl)]
+    L.pomcp_counters.argtypes = [vp, P(i64)]
+    _LIB = L
+    return L
+
+
+def _p(a, t):
+    return a.ctypes.data_as(C.POINTER(t))
+
+
+class Planner:
+    """One device-resident POMCP planner (tree arena + belief) behind the C ABI."""
+
+    def __init__(self, max_depth=100, tree_depth_cap=64, max_particle_count=2000, ucb_coefficient=3.0,
+                 discount=0.95, seed=0, node_capacity=1 << 20, gen_w0=32, gen_growth=2, gen_wmax=1 << 17, device=0):
+        self.lib = load()
+        self.cfg = Config(int(max_depth), int(tree_depth_cap), int(max_particle_count), 0, float(ucb_coefficient),
+                          float(discount), int(seed) & 0xFFFFFFFFFFFFFFFF, int(node_capacity), int(gen_w0),
+                          int(gen_growth), int(gen_wmax), 0)
+        self.h = C.c_void_p()
+        self.n_actions = 0
+        rc = self.lib.pomcp_create(C.byref(self.cfg), int(device), C.byref(self.h))
+        if rc != 0:
+            msg = self.lib.pomcp_last_error(self.h).decode() if self.h else "pomcp_create failed"
+            if self.h:
+                self.lib.pomcp_destroy(self.h)
+                self.h = C.c_void_p()
+            raise PomcpError(msg)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pomcp_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise PomcpError(self.lib.pomcp_last_error(self.h).decode())
+        return rc
+
+    def set_model_rocksample(self, rows, cols, cell, start_cell, thr53, rewards):
+        cell = np.ascontiguousarray(cell, dtype=np.int8).reshape(-1)
+        n_rocks = int(cell.max()) + 1
+        thr53 = np.ascontiguousarray(thr53, dtype=np.uint64).reshape(-1)
+        if thr53.size != rows * cols * n_rocks:
+            raise ValueError("thr53 must be [rows*cols][n_rocks]")
+        rewards = np.ascontiguousarray(rewards, dtype=np.float64)
+        self._ck(self.lib.pomcp_set_model_rocksample(self.h, int(rows), int(cols), _p(cell, C.c_int8),
+                                                     int(start_cell), _p(thr53, C.c_uint64),
+                                                     _p(rewards, C.c_double)))
+        self.n_actions = 5 + n_rocks
+
+    def set_world(self, actual_mask, sampled_mask):
+        self._ck(self.lib.pomcp_set_world(self.h, int(actual_mask), int(sampled_mask)))
+
+    def set_root_particles(self, packed, root_cell):
+        packed = np.ascontiguousarray(packed, dtype=np.uint32)
+        self._ck(self.lib.pomcp_set_root_particles(self.h, _p(packed, C.c_uint32), int(packed.size), int(root_cell)))
+
+    def search(self, n_sims, move=0, sim_offset=0, timeout_s=0.0, stream=None):
+        return self._ck(self.lib.pomcp_search(self.h, int(n_sims), int(sim_offset), int(move), float(timeout_s),
+                                              C.c_void_p(stream or 0)))
+
+    def root_stats(self):
+        n = np.zeros(self.n_actions, dtype=np.int64)
+        q = np.zeros(self.n_actions, dtype=np.int64)
+        legal, done = C.c_uint32(), C.c_int64()
+        self._ck(self.lib.pomcp_root_stats(self.h, _p(n, C.c_int64), _p(q, C.c_int64), C.byref(legal),
+                                           C.byref(done)))
+        return dict(n=n, qfix=q, legal=legal.value, sims_done=done.value)
+
+    def node_stats(self, path):
+        p = np.asarray(path, dtype=np.int32).reshape(-1)
+        n = np.zeros(self.n_actions, dtype=np.int64)
+        q = np.zeros(self.n_actions, dtype=np.int64)
+        legal, cell = C.c_uint32(), C.c_int32()
+        rc = self._ck(self.lib.pomcp_node_stats(self.h, _p(p, C.c_int32), p.size // 2, _p(n, C.c_int64),
+                                                _p(q, C.c_int64), C.byref(legal), C.byref(cell)))
+        if rc:
+            return None
+        return dict(n=n, qfix=q, legal=legal.value, cell=cell.value)
+
+    def advance(self, action, obs_good, sampled_mask_after, move=0, max_tries=0):
+        status, tries, acc = C.c_int32(), C.c_int64(), C.c_int32()
+        self._ck(self.lib.pomcp_advance(self.h, int(action), int(bool(obs_good)), int(sampled_mask_after), int(move),
+                                        int(max_tries), C.byref(status), C.byref(tries), C.byref(acc)))
+        return dict(status=status.value, tries=tries.value, accepted=acc.value)
+
+    def root_particles(self):
+        cap = max(int(self.cfg.max_particle_count), 1 << 16)
+        out = np.zeros(cap, dtype=np.uint32)
+        n, cell = C.c_int32(), C.c_int32()
+        self._ck(self.lib.pomcp_root_particles(self.h, _p(out, C.c_uint32), cap, C.byref(n), C.byref(cell)))
+        return out[:min(n.value, cap)].copy(), cell.value
+
+    def generate_steps(self, state, action, u53, actual_mask, sampled_mask):
+        state = np.ascontiguousarray(state, dtype=np.uint32)
+        actual_mask = np.ascontiguousarray(np.broadcast_to(actual_mask, state.shape), dtype=np.uint32)
+        sampled_mask = np.ascontiguousarray(np.broadcast_to(sampled_mask, state.shape), dtype=np.uint32)
+        action = np.ascontiguousarray(action, dtype=np.uint8)
+        u53 = np.ascontiguousarray(u53, dtype=np.uint64)
+        n = state.size
+        ns = np.zeros(n, dtype=np.uint32)
+        fl = np.zeros(n, dtype=np.uint8)
+        rw = np.zeros(n, dtype=np.float64)
+        self._ck(self.lib.pomcp_generate_steps(self.h, n, _p(state, C.c_uint32), _p(action, C.c_uint8),
+                                               _p(u53, C.c_uint64), _p(actual_mask, C.c_uint32),
+                                               _p(sampled_mask, C.c_uint32), _p(ns, C.c_uint32), _p(fl, C.c_uint8),
+                                               _p(rw, C.c_double)))
+        return ns, fl, rw
+
+    def counters(self):
+        c = np.zeros(16, dtype=np.int64)
+        self._ck(self.lib.pomcp_counters(self.h, _p(c, C.c_int64)))
+        names = ("levels", "rollout_steps", "created", "nodes", "alloc_nodes", "generations", "level_steps",
+                 "last_search_ns", "last_search_sims", "launches", "coop_blocks", "threads_per_block")
+        return dict(zip(names, c.tolist()))
