@@ -27,9 +27,9 @@ def test_generate_step_golden(tag):
     pl.close()
 
 
-def _pair(tag, seed, n_bag=2000, **kw):
+def _pair(tag, wseed, n_bag=2000, **kw):
     t = golden_tables(tag)
-    actual, bag, rng = random_world_and_bag(t, seed, n_bag)
+    actual, bag, rng = random_world_and_bag(t, wseed, n_bag)
     okw = dict(max_depth=kw.get("max_depth", 100), dcap=kw.get("tree_depth_cap", 64),
                ucb_c=kw.get("ucb_coefficient", 3.0), discount=kw.get("discount", 0.95), seed=kw.get("seed", 0))
     om = oracle_model(t)
