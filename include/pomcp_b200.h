@@ -71,6 +71,13 @@ int pomcp_search(pomcp_handle *h, int64_t n_sims, uint32_t sim_offset, uint32_t 
  * 2^-24 fixed-point integer, legal mask.  Synchronises with the search. */
 int pomcp_root_stats(pomcp_handle *h, int64_t *n, int64_t *qfix, uint32_t *legal_mask, int64_t *sims_done);
 
+/* Root statistics into a caller-provided DEVICE buffer of 64 int64 (n[0..32), qfix[0..32)), asynchronous on
+ * `stream`: the operand of the root-parallel merge (all-reduce(sum) across ranks before solvers/pomcp.py:78). */
+int pomcp_root_stats_device(pomcp_handle *h, int64_t *dev_out, void *stream);
+
+/* Fresh tree over the current root belief (BeliefTree.reset + initialize, belief_tree.py:19-49), asynchronous. */
+int pomcp_reset_tree(pomcp_handle *h, void *stream);
+
 /* Same, for the node reached from the root through (action, obs_good) pairs; 1 if it does not exist. */
 int pomcp_node_stats(pomcp_handle *h, const int32_t *path_ao, int len, int64_t *n, int64_t *qfix,
                      uint32_t *legal_mask, int32_t *cell);
@@ -93,7 +100,8 @@ int pomcp_generate_steps(pomcp_handle *h, int64_t n, const uint32_t *state, cons
 
 /* counters: [0] tree levels, [1] rollout steps, [2] nodes created, [3] nodes in arena, [4] allocation nodes,
  * [5] generations, [6] level steps, [7] last search ns (device globaltimer), [8] sims of last search,
- * [9] kernel launches so far, [10] cooperative grid blocks, [11] threads per block */
+ * [9] kernel launches so far, [10] cooperative grid blocks, [11] threads per block,
+ * [12] device-to-host bytes of one pomcp_root_stats call */
 int pomcp_counters(pomcp_handle *h, int64_t out[16]);
 
 #ifdef __cplusplus

@@ -552,6 +552,18 @@ __global__ void pomcp_plant_root_kernel(DevState *S, Tree t, int root_cell, uint
     }
 }
 
+// Root edge statistics as 2*AS 64-bit integers (n[0..AS), qfix[0..AS)) in a caller-provided device buffer: the
+// operand of the root-parallel merge (one all-reduce(sum) over NVLink per move).
+__global__ void pomcp_root_stats_kernel(const DevState *S, Tree t, long long *out)
+{
+    const int a = threadIdx.x;
+    if (a < AS) {
+        const int root = S->root;
+        out[a] = t.n[(size_t)root * AS + a];
+        out[AS + a] = t.qfix[(size_t)root * AS + a];
+    }
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // Host side: the handle and the C ABI
 // ---------------------------------------------------------------------------------------------------------
@@ -574,6 +586,7 @@ struct pomcp_handle {
     long long zeroed_upto = 0;      // arena prefix that may hold stale data
     int root_cell = 0;
     int n_bag = 0;
+    int bag_sel = 0;               // host mirror of DevState.bag_sel
     int coop_blocks = 0;
     size_t search_smem = 0;
     long long launches = 0;
@@ -765,7 +778,28 @@ extern "C" int pomcp_set_root_particles(pomcp_handle *h, const uint32_t *packed,
     CK(cudaMemcpy(h->bag[0], packed, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice));
     if (plant_root(h, root_cell, n, 0, 0)) return -1;
     CK(cudaDeviceSynchronize());
-    h->have_root = true;
+    h->have_root = true; h->bag_sel = 0;
+    return 0;
+}
+
+extern "C" int pomcp_reset_tree(pomcp_handle *h, void *stream)
+{
+    if (!h) return -1;
+    if (!h->have_root) return fail(h, "no root belief");
+    CK(cudaSetDevice(h->device));
+    cudaStream_t s = (cudaStream_t)stream;
+    h->last_stream = s;
+    return plant_root(h, h->root_cell, h->n_bag, h->bag_sel, s);
+}
+
+extern "C" int pomcp_root_stats_device(pomcp_handle *h, int64_t *dev_out, void *stream)
+{
+    if (!h) return -1;
+    if (!h->have_root) return fail(h, "no root belief");
+    CK(cudaSetDevice(h->device));
+    pomcp_root_stats_kernel<<<1, 64, 0, (cudaStream_t)stream>>>(h->dS, h->t, reinterpret_cast<long long *>(dev_out));
+    CK(cudaGetLastError());
+    ++h->launches;
     return 0;
 }
 
@@ -782,10 +816,7 @@ extern "C" int pomcp_search(pomcp_handle *h, int64_t n_sims, uint32_t sim_offset
     if (h->nodes_used + n_sims + 2 > h->cap) {          // every simulation creates at most one node
         if (n_sims + 3 > h->cap) return fail(h, "node_capacity smaller than n_sims + 3");
         // drop the subtree, keep the belief (documented degradation; status 1)
-        int32_t sel = 0;
-        CK(cudaStreamSynchronize(s));
-        CK(cudaMemcpy(&sel, &h->dS->bag_sel, sizeof(sel), cudaMemcpyDeviceToHost));
-        if (plant_root(h, h->root_cell, h->n_bag, sel, s)) return -1;
+        if (plant_root(h, h->root_cell, h->n_bag, h->bag_sel, s)) return -1;
         rc = 1;
     }
     SearchParams p;
@@ -882,7 +913,7 @@ extern "C" int pomcp_advance(pomcp_handle *h, int action, int obs_good, uint32_t
     CK(cudaMemcpy(&st, h->dS, sizeof(st), cudaMemcpyDeviceToHost));
     h->nodes_used = st.node_count;
     if (h->zeroed_upto < h->nodes_used) h->zeroed_upto = h->nodes_used;
-    h->root_cell = st.adv_root_cell; h->n_bag = st.n_bag;
+    h->root_cell = st.adv_root_cell; h->n_bag = st.n_bag; h->bag_sel = st.bag_sel;
     if (status) *status = st.adv_status;
     if (tries_used) *tries_used = st.adv_tries;
     if (accepted) *accepted = st.adv_accepted;
@@ -943,5 +974,6 @@ extern "C" int pomcp_counters(pomcp_handle *h, int64_t out[16])
     out[9] = h->launches;
     out[10] = h->coop_blocks;
     out[11] = SEARCH_THREADS;
+    out[12] = (int64_t)(sizeof(DevState) + AS * sizeof(int32_t) + AS * sizeof(long long) + sizeof(uint32_t));  // D2H bytes of pomcp_root_stats
     return 0;
 }

@@ -27,7 +27,8 @@ class Config(C.Structure):
 
 EXPORTS = ["pomcp_create", "pomcp_destroy", "pomcp_last_error", "pomcp_set_model_rocksample", "pomcp_set_world",
            "pomcp_set_root_particles", "pomcp_search", "pomcp_root_stats", "pomcp_node_stats", "pomcp_advance",
-           "pomcp_root_particles", "pomcp_generate_steps", "pomcp_counters"]
+           "pomcp_root_particles", "pomcp_generate_steps", "pomcp_counters", "pomcp_root_stats_device",
+           "pomcp_reset_tree"]
 
 
 def library_path():
@@ -67,6 +68,8 @@ def load(build_if_missing=True):
     L.pomcp_generate_steps.argtypes = [vp, i64, P(u32), P(C.c_uint8), P(u64), P(u32), P(u32), P(u32), P(C.c_uint8),
                                        P(dbl)]
     L.pomcp_counters.argtypes = [vp, P(i64)]
+    L.pomcp_root_stats_device.argtypes = [vp, vp, vp]
+    L.pomcp_reset_tree.argtypes = [vp, vp]
     _LIB = L
     return L
 
@@ -133,6 +136,13 @@ class Planner:
         return self._ck(self.lib.pomcp_search(self.h, int(n_sims), int(sim_offset), int(move), float(timeout_s),
                                               C.c_void_p(stream or 0)))
 
+    def reset_tree(self, stream=None):
+        self._ck(self.lib.pomcp_reset_tree(self.h, C.c_void_p(stream or 0)))
+
+    def root_stats_device(self, dev_ptr, stream=None):
+        """Write n[0..32), qfix[0..32) (int64) to the device buffer at `dev_ptr` (e.g. a torch tensor's data_ptr)."""
+        self._ck(self.lib.pomcp_root_stats_device(self.h, C.c_void_p(int(dev_ptr)), C.c_void_p(stream or 0)))
+
     def root_stats(self):
         n = np.zeros(self.n_actions, dtype=np.int64)
         q = np.zeros(self.n_actions, dtype=np.int64)
@@ -185,5 +195,6 @@ class Planner:
         c = np.zeros(16, dtype=np.int64)
         self._ck(self.lib.pomcp_counters(self.h, _p(c, C.c_int64)))
         names = ("levels", "rollout_steps", "created", "nodes", "alloc_nodes", "generations", "level_steps",
-                 "last_search_ns", "last_search_sims", "launches", "coop_blocks", "threads_per_block")
+                 "last_search_ns", "last_search_sims", "launches", "coop_blocks", "threads_per_block",
+                 "root_stats_d2h_bytes")
         return dict(zip(names, c.tolist()))

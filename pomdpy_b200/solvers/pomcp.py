@@ -1,0 +1,205 @@
+"""POMCP on the B200: the drop-in for the reference's solver path.
+
+Same surface as the reference's POMCP / BeliefTreeSolver (pomdpy/solvers/pomcp.py:14-137,
+pomdpy/solvers/belief_tree_solver.py:14-212) as far as Agent.run_pomcp touches it (agent.py:150-213):
+
+    POMCP.reset(agent)                        per-epoch factory; hyper-parameters come from agent.model.<flag>
+    solver.belief_tree_index.sample_particle()
+    solver.select_eps_greedy_action(eps, start_time) -> DiscreteAction
+    solver.update(step_result)                belief update + re-root; sets solver.disable_tree on failure
+    solver.history                            HistorySequence
+
+What happens inside is different: select_eps_greedy_action runs ``n_sims`` simulations as ONE cooperative CUDA
+kernel over a device-resident structure-of-arrays belief tree (pomcp_search), update() runs the batched
+rejection-sampling belief update (pomcp_advance).  With torch.distributed initialised the search is
+root-parallel: every rank grows its own tree with its share of the budget and the root statistics are summed
+with one all-reduce before the greedy choice (solvers/pomcp.py:78).  There is no CPU fallback."""
+import time
+
+import numpy as np
+
+from .. import dist as dist_mod
+from .. import native, philox
+from ..rock_sample.history_data import PositionAndRockData, RockData
+from ..rock_sample.types import GridPosition
+from ..util import console
+from .belief_view import BeliefNodeView
+from .solver import Solver
+
+module = "pomcp"
+
+
+def _dist():
+    try:
+        import torch.distributed as dist
+        if dist.is_available() and dist.is_initialized():
+            return dist
+    except Exception:
+        pass
+    return None
+
+
+def greedy_action(n, qfix, legal_mask, seed, move):
+    """solvers/pomcp.py:78 ucb_action(greedy=True): arg-max of the mean over legal actions (an unvisited edge
+    has mean 0, discrete_action_mapping.py:126), uniform tie-break."""
+    best, cand = None, []
+    for a in range(len(n)):
+        if not (legal_mask >> a) & 1:
+            continue
+        q = 0.0 if n[a] == 0 else (float(qfix[a]) * (1.0 / native.QFIX_SCALE)) / float(n[a])
+        if best is None or q > best:
+            best, cand = q, [a]
+        elif q == best:
+            cand.append(a)
+    return cand[philox.randbelow(seed, len(cand), 0, 0, move, philox.DOM_FINAL)]
+
+
+class POMCP(Solver):
+    # planners are expensive to create (the tree arena); one is kept per (agent, configuration)
+    _EPOCH_STRIDE = 1 << 12
+
+    def __init__(self, agent):
+        super(POMCP, self).__init__(agent)
+        model = self.model
+        if not hasattr(model, "device_spec"):
+            raise TypeError("the CUDA POMCP solver needs a model with device_spec()/world_masks()")
+        self.agent = agent
+        self.action_pool = agent.action_pool
+        self.observation_pool = agent.observation_pool
+        self.history = agent.histories.create_sequence()
+        self.disable_tree = False
+
+        self.n_sims = int(getattr(model, "n_sims", 500))
+        self.seed = int(getattr(model, "seed", 1993))
+        self.timeout = float(getattr(model, "action_selection_timeout", 60))
+        self.max_particle_count = int(getattr(model, "max_particle_count", 2000))
+        if getattr(model, "preferred_actions", False):
+            console(2, module, "--preferred_actions: in-tree action sets are the plain legal sets on the device")
+        d = _dist()
+        self.world = d.get_world_size() if d else 1
+        self.rank = d.get_rank() if d else 0
+        self.sims_per_rank, self.sim_offset = dist_mod.shard_budget(self.n_sims, self.rank, self.world)
+
+        self.planner = self._acquire_planner(agent)
+        self.epoch_index = agent._pomcp_epochs = getattr(agent, "_pomcp_epochs", -1) + 1
+        self.move_in_epoch = 0
+
+        spec = model.device_spec()
+        self.spec = spec
+        # belief_tree_solver.py:36-38: n_start_states draws of sample_an_init_state (numpy generator)
+        n_start = int(getattr(model, "n_start_states", 2000))
+        bag = np.fromiter((model.pack_state(model.sample_an_init_state()) for _ in range(n_start)),
+                          dtype=np.uint32, count=n_start)
+        self.planner.set_world(*model.world_masks())
+        self.planner.set_root_particles(bag, spec["start_cell"])
+        self._root_cell = spec["start_cell"]
+        self._stats = None
+        self.belief_tree_index = BeliefNodeView(self)
+        self.sims_done = 0
+        self.search_seconds = 0.0
+
+    # ---- plumbing -------------------------------------------------------------------------------------
+    def _acquire_planner(self, agent):
+        model = self.model
+        wmax = int(getattr(model, "gen_wmax", 0)) or max(32, min(1 << 18, self.sims_per_rank // 4 or 1))
+        w0 = int(getattr(model, "gen_w0", 0)) or max(1, min(1024, wmax // 16))
+        growth = int(getattr(model, "gen_growth", 0)) or 2
+        max_steps = int(getattr(model, "max_steps", 200))
+        cap = int(getattr(model, "node_capacity", 0)) or \
+            int(min(1 << 24, max(1 << 14, self.sims_per_rank * min(max_steps, 8) + 64)))
+        key = (int(model.max_depth), self.max_particle_count, float(model.ucb_coefficient), float(model.discount),
+               self.seed, cap, w0, growth, wmax, id(model))
+        cached = getattr(agent, "_pomcp_planner", None)
+        if cached is not None and cached[0] == key:
+            return cached[1]
+        if cached is not None:
+            cached[1].close()
+        device = 0
+        try:
+            import torch
+            if torch.cuda.is_available():
+                device = torch.cuda.current_device()
+        except Exception:
+            pass
+        pl = native.Planner(max_depth=int(model.max_depth), tree_depth_cap=min(64, max(2, int(model.max_depth))),
+                            max_particle_count=self.max_particle_count, ucb_coefficient=float(model.ucb_coefficient),
+                            discount=float(model.discount), seed=self.seed, node_capacity=cap, gen_w0=w0,
+                            gen_growth=growth, gen_wmax=wmax, device=device)
+        spec = model.device_spec()
+        pl.set_model_rocksample(spec["rows"], spec["cols"], spec["cell"], spec["start_cell"], spec["thr53"],
+                                spec["rewards"])
+        agent._pomcp_planner = (key, pl)
+        return pl
+
+    @property
+    def move(self):
+        """32-bit move id of the random streams: unique per (epoch, real step)."""
+        return (self.epoch_index * self._EPOCH_STRIDE + self.move_in_epoch) & 0xFFFFFFFF
+
+    @staticmethod
+    def reset(agent):
+        return POMCP(agent)
+
+    def root_statistics(self):
+        if self._stats is None:
+            self._stats = self.planner.root_stats()
+        return self._stats
+
+    def root_data(self):
+        cell = self._root_cell
+        pos = GridPosition(cell // self.model.n_cols, cell % self.model.n_cols)
+        return PositionAndRockData(self.model, pos, [RockData() for _ in range(self.model.n_rocks)], self)
+
+    def _merged_root_stats(self):
+        """Root statistics summed over the ranks: one all-reduce of 2*32 int64 per move."""
+        local = self.planner.root_stats()
+        if self.world == 1:
+            return local
+        d = _dist()
+        import torch
+        if torch.cuda.is_available() and d.get_backend() == "nccl":
+            n, q = dist_mod.merge_device(self.planner, len(local["n"]))
+        else:
+            n, q = dist_mod.merge_host(local["n"], local["qfix"])
+        return dict(n=n, qfix=q, legal=local["legal"], sims_done=local["sims_done"])
+
+    # ---- the solver API -------------------------------------------------------------------------------
+    def select_eps_greedy_action(self, eps, start_time):
+        """Run the Monte-Carlo tree search from the current belief and return the greedy action
+        (solvers/pomcp.py:69-78; `eps` is ignored there as well)."""
+        remaining = self.timeout - (time.time() - start_time)
+        stream = None
+        try:
+            import torch
+            stream = torch.cuda.current_stream().cuda_stream
+        except Exception:
+            pass
+        t0 = time.perf_counter()
+        self.planner.search(self.sims_per_rank, move=self.move, sim_offset=self.sim_offset,
+                            timeout_s=max(remaining, 1e-3), stream=stream)
+        st = self._merged_root_stats()
+        self.search_seconds += time.perf_counter() - t0
+        self.sims_done += int(st["sims_done"])
+        self._stats = st
+        a = greedy_action(st["n"], st["qfix"], st["legal"], self.seed, self.move)
+        return self.action_pool.sample_an_action(a)
+
+    def update(self, step_result, prune=True):
+        """belief_tree_solver.py:154-212: fold the real step into the model, re-root at (action, observation),
+        refill the belief by rejection sampling (on the device).  On failure: disable_tree, no exception."""
+        self.model.update(step_result)                                           # :165
+        _, sampled = self.model.world_masks()
+        res = self.planner.advance(step_result.action.bin_number, bool(step_result.observation.is_good), sampled,
+                                   move=self.move)
+        self._stats = None
+        self.move_in_epoch += 1
+        if res["status"] == 2:
+            console(1, module, "Couldn't refill particles, must use random rollout to finish episode")
+            self.disable_tree = True
+            return
+        if res["status"] == 1:
+            console(4, module, "observed child was never expanded: fresh root")
+        _, self._root_cell = self.planner.root_particles()
+
+    def prune(self, belief_node=None):
+        """Sibling subtrees are simply left behind in the arena (belief_tree.py:87-109 frees them)."""
