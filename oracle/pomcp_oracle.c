@@ -43,6 +43,8 @@
 #define ORC_CELL_GOAL (-2)
 #define ORC_CELL_OBSTACLE (-3)
 #define ORC_QFIX_SCALE 16777216.0 /* 2^24 fixed-point scale of summed returns (gs mode) */
+#define ORC_SEQ_ALLOC_MAX 16      /* arrivals <= this: exact virtual-pull allocation; more: water-filling */
+#define ORC_BISECT_ITERS 24
 
 /* ------------------------------------------------------------------------ */
 /* Philox4x32-10 (Salmon et al., SC'11) -- counter-based RNG shared by spec.  */
@@ -504,6 +506,21 @@ double orc_det_log_u64(uint64_t x)
     return (double)e * 0.6931471803691238 + ((double)e * 1.9082149292705877e-10 + lnm);
 }
 
+/* Single-precision twin used by the gs-mode UCB arithmetic (the CUDA kernels compute UCB in fp32). */
+float orc_det_logf_u32(uint32_t x)
+{
+    int e = 31 - __builtin_clz(x);
+    float m = (float)x / (float)(1u << e);
+    if (m > 1.41421356f) { m = m * 0.5f; e += 1; }
+    float f = (m - 1.0f) / (m + 1.0f);
+    float f2 = f * f;
+    float s = 1.0f / 11.0f;
+    s = s * f2 + 1.0f / 9.0f; s = s * f2 + 1.0f / 7.0f; s = s * f2 + 1.0f / 5.0f; s = s * f2 + 1.0f / 3.0f;
+    s = s * f2 + 1.0f;
+    float lnm = 2.0f * f * s;
+    return (float)e * 0.693145751953125f + ((float)e * 1.42860682030941723212e-6f + lnm);
+}
+
 typedef struct {
     int32_t cell; uint32_t legal;
     int64_t n[ORC_MAX_ACTIONS];
@@ -557,16 +574,16 @@ static void gs_block(const orc_gs *h, uint32_t k, uint32_t sim, uint32_t move, u
 }
 
 /* Mean of an edge from its integer statistics (0 for an unvisited edge: entry.mean_q_value starts at 0). */
-static double gs_mean(const gs_node *nd, int a)
+static float gs_mean(const gs_node *nd, int a)
 {
-    if (nd->n[a] == 0) return 0.0;
-    return ((double)nd->qfix[a] * (1.0 / ORC_QFIX_SCALE)) / (double)nd->n[a];
+    if (nd->n[a] == 0) return 0.0f;
+    return ((float)nd->qfix[a] * (1.0f / 16777216.0f)) / (float)nd->n[a];
 }
 
 /* sum of 32 lane values in butterfly order (xor 16, 8, 4, 2, 1) -- the order a warp shuffle reduction uses */
-static double butterfly_sum32(const double v[32])
+static float butterfly_sum32(const float v[32])
 {
-    double x[32], y[32];
+    float x[32], y[32];
     memcpy(x, v, sizeof(x));
     for (int off = 16; off >= 1; off >>= 1) {
         for (int i = 0; i < 32; ++i) y[i] = x[i] + x[i ^ off];
@@ -582,75 +599,104 @@ static void gs_allocation(const orc_gs *h, const gs_node *nd, int64_t k, uint32_
 {
     int A = h->m->n_actions;
     int64_t N = 0; int untried = 0, nlegal = 0;
-    double v[32];
-    for (int a = 0; a < 32; ++a) v[a] = 0.0;
+    float v[32]; const float cf = (float)h->ucb_c;
+    for (int a = 0; a < 32; ++a) v[a] = 0.0f;
     for (int a = 0; a < A; ++a) if ((nd->legal >> a) & 1u) { N += nd->n[a]; nlegal++; if (nd->n[a] == 0) untried++; }
-    if (N == 0) { for (int a = 0; a < A; ++a) if ((nd->legal >> a) & 1u) v[a] = 1.0; }
-    else if (untried >= k) { for (int a = 0; a < A; ++a) if (((nd->legal >> a) & 1u) && nd->n[a] == 0) v[a] = 1.0; }
+    if (N == 0) { for (int a = 0; a < A; ++a) if ((nd->legal >> a) & 1u) v[a] = 1.0f; }
+    else if (untried >= k) { for (int a = 0; a < A; ++a) if (((nd->legal >> a) & 1u) && nd->n[a] == 0) v[a] = 1.0f; }
     else {
-        double L = orc_det_log_u64((uint64_t)N + 1);
-        double c2L = (h->ucb_c * h->ucb_c) * L;
-        double qbar[32]; double qmax = -INFINITY; int64_t nbest = 0;
+        float L = orc_det_logf_u32((uint32_t)N + 1u);
+        float c2L = (cf * cf) * L;
+        float qbar[32]; float qmax = -INFINITY; int64_t nbest = 0;
         for (int a = 0; a < A; ++a) {
             if (!((nd->legal >> a) & 1u)) continue;
             qbar[a] = gs_mean(nd, a);
             if (qbar[a] > qmax) { qmax = qbar[a]; nbest = nd->n[a]; }
         }
-        if (!(c2L > 0.0)) { for (int a = 0; a < A; ++a) if (((nd->legal >> a) & 1u) && qbar[a] == qmax) v[a] = 1.0; }
+        if (!(c2L > 0.0f)) { for (int a = 0; a < A; ++a) if (((nd->legal >> a) & 1u) && qbar[a] == qmax) v[a] = 1.0f; }
         else {
-            double kd = (double)k;
-            double lo = qmax + 0.999 * sqrt(c2L / (kd + (double)nbest));
-            double hi = qmax + 1.001 * sqrt((c2L * (double)nlegal) / kd) + 1.0;
-            for (int it = 0; it <= 32; ++it) {          /* 32 bisection steps, then the weights at `lo` */
-                double mid = it < 32 ? 0.5 * (lo + hi) : lo;
-                double t[32];
+            float kd = (float)k;
+            float lo = qmax + 0.999f * sqrtf(c2L / (kd + (float)nbest));
+            float hi = qmax + 1.001f * sqrtf((c2L * (float)nlegal) / kd) + 1.0f;
+            for (int it = 0; it <= ORC_BISECT_ITERS; ++it) {          /* bisection steps, then the weights at `lo` */
+                float mid = it < ORC_BISECT_ITERS ? 0.5f * (lo + hi) : lo;
+                float t[32];
                 for (int a = 0; a < 32; ++a) {
-                    t[a] = 0.0;
+                    t[a] = 0.0f;
                     if (a < A && ((nd->legal >> a) & 1u)) {
-                        double d = mid - qbar[a];
-                        double mm = c2L / (d * d);
-                        if (nd->n[a] == 0) t[a] = mm > 1.0 ? mm : 1.0;
-                        else { double e = mm - (double)nd->n[a]; t[a] = e > 0.0 ? e : 0.0; }
+                        float d = mid - qbar[a];
+                        float mm = c2L / (d * d);
+                        if (nd->n[a] == 0) t[a] = mm > 1.0f ? mm : 1.0f;
+                        else { float e = mm - (float)nd->n[a]; t[a] = e > 0.0f ? e : 0.0f; }
                     }
                 }
-                if (it == 32) { memcpy(v, t, sizeof(t)); break; }
+                if (it == ORC_BISECT_ITERS) { memcpy(v, t, sizeof(t)); break; }
                 if (butterfly_sum32(t) >= kd) lo = mid; else hi = mid;
             }
         }
     }
     /* inclusive scan in Hillis-Steele order (what __shfl_up_sync steps 1,2,4,8,16 compute) */
-    double x[32], y[32];
+    float x[32], y[32];
     memcpy(x, v, sizeof(x));
     for (int off = 1; off < 32; off <<= 1) {
         for (int i = 0; i < 32; ++i) y[i] = i >= off ? x[i] + x[i - off] : x[i];
         memcpy(x, y, sizeof(x));
     }
-    double V = x[31];
+    float V = x[31];
     *last = 0;
     for (int a = 0; a < 32; ++a) {
-        double f = (x[a] / V) * 4294967296.0;
-        thr[a] = f >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)f;
-        if (v[a] > 0.0) *last = a;
+        float f = (x[a] / V) * 4294967296.0f;
+        thr[a] = f >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)f;
+        if (v[a] > 0.0f) *last = a;
     }
 }
 
-/* UCB1 arg-max for a single arrival (action_selectors.py:6-37 with mean = sum/n), uniform tie-break by x0 */
-static int gs_ucb1(const orc_gs *h, const gs_node *nd, uint32_t x0)
+static int nth_set_bit(uint32_t mask, uint32_t j)
 {
-    int A = h->m->n_actions;
-    int64_t N = 0;
-    for (int a = 0; a < A; ++a) if ((nd->legal >> a) & 1u) N += nd->n[a];
-    double L = orc_det_log_u64((uint64_t)N + 1);
-    double best = -INFINITY; int cand[32], nc = 0;
-    for (int a = 0; a < A; ++a) {
-        if (!((nd->legal >> a) & 1u)) continue;
-        double s;
-        if (nd->n[a] == 0) s = INFINITY;
-        else s = gs_mean(nd, a) + h->ucb_c * sqrt(L / (double)nd->n[a]);
-        if (s > best) { best = s; nc = 0; cand[nc++] = a; }
-        else if (s == best) cand[nc++] = a;
+    for (int b = 0, seen = 0; b < 32; ++b) if ((mask >> b) & 1u) { if ((uint32_t)seen == j) return b; ++seen; }
+    return -1;
+}
+
+/* Action of one simulation at a node with k <= ORC_SEQ_ALLOC_MAX arrivals.
+ *   k == 1: UCB1 arg-max (action_selectors.py:6-37 with mean = sum/n), uniform tie-break by the 32-bit draw x0.
+ *   k >= 2: the arrivals share the virtual-pull sequence "pull j takes the UCB1 arg-max (lowest id on ties) given
+ *           the statistics plus the virtual visits of pulls 0..j-1"; this simulation takes pull j = floor(x0*k/2^32).
+ * Untried actions score +inf (solvers/pomcp.py:64-65): with at least k of them the draw is uniform over them. */
+static int gs_select(const orc_gs *h, const gs_node *nd, uint32_t x0, int64_t k)
+{
+    int A = h->m->n_actions; const float cf = (float)h->ucb_c;
+    int64_t N = 0; uint32_t untried = 0;
+    for (int a = 0; a < A; ++a) if ((nd->legal >> a) & 1u) { N += nd->n[a]; if (nd->n[a] == 0) untried |= 1u << a; }
+    uint32_t nu = (uint32_t)__builtin_popcount(untried);
+    if ((int64_t)nu >= k) return nth_set_bit(untried, randbelow32(x0, nu));
+    float L = orc_det_logf_u32((uint32_t)N + 1u);
+    if (k == 1) {
+        float best = -INFINITY; uint32_t ties = 0;
+        for (int a = 0; a < A; ++a) {
+            if (!((nd->legal >> a) & 1u)) continue;
+            float s = gs_mean(nd, a) + cf * sqrtf(L / (float)nd->n[a]);
+            if (s > best) { best = s; ties = 1u << a; } else if (s == best) ties |= 1u << a;
+        }
+        return nth_set_bit(ties, randbelow32(x0, (uint32_t)__builtin_popcount(ties)));
     }
-    return cand[randbelow32(x0, (uint32_t)nc)];
+    float c2L = (cf * cf) * L;
+    float sc[32]; int64_t va[32]; float qmax = -INFINITY; uint32_t qties = 0;
+    for (int a = 0; a < A; ++a) {
+        va[a] = 0; sc[a] = -INFINITY;
+        if (!((nd->legal >> a) & 1u)) continue;
+        float qb = gs_mean(nd, a);
+        if (qb > qmax) { qmax = qb; qties = 1u << a; } else if (qb == qmax) qties |= 1u << a;
+        sc[a] = nd->n[a] == 0 ? INFINITY : qb + cf * sqrtf(L / (float)nd->n[a]);
+    }
+    if (!(c2L > 0.0f)) return nth_set_bit(qties, randbelow32(x0, (uint32_t)__builtin_popcount(qties)));
+    uint32_t j = randbelow32(x0, (uint32_t)k);
+    for (uint32_t pull = 0;; ++pull) {
+        int w = 0;
+        for (int a = 1; a < A; ++a) if (sc[a] > sc[w]) w = a;
+        if (pull == j) return w;
+        va[w] += 1;
+        sc[w] = gs_mean(nd, w) + cf * sqrtf(L / (float)(nd->n[w] + va[w]));
+    }
 }
 
 typedef struct {
@@ -725,7 +771,8 @@ int orc_gs_search(orc_gs *h, int64_t n_sims, uint32_t sim_offset, uint32_t move,
             for (int64_t i = 0; i < w; ++i) {
                 if (S[i].status != 0) continue;
                 int32_t X = S[i].node;
-                if (arrivals[X] >= 2) {
+                int64_t Nx = 0; for (int b = 0; b < 32; ++b) Nx += h->nodes[X].n[b];
+                if (arrivals[X] > ORC_SEQ_ALLOC_MAX && Nx > 0) {   /* few arrivals / no statistics: gs_select */
                     gs_allocation(h, &h->nodes[X], arrivals[X], alloc_thr + 32 * (size_t)X, &alloc_last[X]);
                     arrivals[X] = -arrivals[X]; h->n_alloc_nodes++;
                 }
@@ -739,7 +786,7 @@ int orc_gs_search(orc_gs *h, int64_t n_sims, uint32_t sim_offset, uint32_t move,
                 gs_node *nd = &h->nodes[X];
                 uint32_t x[4]; gs_block(h, (uint32_t)(d + 1), s->sim, move, DOM_SIM, x);
                 int a;
-                if (arrivals[X] == 1) a = gs_ucb1(h, nd, x[0]);
+                if (arrivals[X] > 0) a = gs_select(h, nd, x[0], arrivals[X]);
                 else {
                     const uint32_t *thr = alloc_thr + 32 * (size_t)X;
                     a = alloc_last[X];

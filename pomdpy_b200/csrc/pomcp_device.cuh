@@ -1,7 +1,7 @@
 // pomcp_device.cuh -- device-side building blocks of the B200 POMCP planner (sm_100a).
 //
-// Everything here is integer work or IEEE-exact fp64 (+,-,*,/,sqrt; no FMA contraction: the file is built with
-// -fmad=false) so that a search is a deterministic function of its inputs.
+// Everything here is integer work or IEEE-exact floating point (+,-,*,/,sqrt; no FMA contraction: the file is built
+// with -fmad=false) so that a search is a deterministic function of its inputs.
 #pragma once
 #include <stdint.h>
 
@@ -35,21 +35,22 @@ __device__ __forceinline__ uint64_t u53_of(uint32_t a, uint32_t b)
 { return ((uint64_t)(a >> 5) << 26) | (uint64_t)(b >> 6); }
 
 // ---------------------------------------------------------------------------------------------------------
-// Deterministic ln of a positive integer: exponent by clz, 2*atanh series in Horner form, fdlibm ln2 split.
+// Deterministic single-precision ln of a positive integer: exponent by clz, 2*atanh series in Horner form, ln2 split
+// in two floats.  IEEE +,-,*,/ only (no FMA contraction), so the CPU oracle reproduces it bit for bit.  The UCB
+// arithmetic is fp32 because fp64 issue is a scarce resource on this chip (profiles/README.md).
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ double det_log_u64(uint64_t x)
+__device__ __forceinline__ float det_logf_u32(uint32_t x)
 {
-    int e = 63 - __clzll((long long)x);
-    double m = (double)x / (double)(1ull << e);
-    if (m > 1.4142135623730951) { m = m * 0.5; e += 1; }
-    const double f = (m - 1.0) / (m + 1.0);
-    const double f2 = f * f;
-    double s = 1.0 / 25.0;
-    s = s * f2 + 1.0 / 23.0; s = s * f2 + 1.0 / 21.0; s = s * f2 + 1.0 / 19.0; s = s * f2 + 1.0 / 17.0;
-    s = s * f2 + 1.0 / 15.0; s = s * f2 + 1.0 / 13.0; s = s * f2 + 1.0 / 11.0; s = s * f2 + 1.0 / 9.0;
-    s = s * f2 + 1.0 / 7.0;  s = s * f2 + 1.0 / 5.0;  s = s * f2 + 1.0 / 3.0;  s = s * f2 + 1.0;
-    const double lnm = 2.0 * f * s;
-    return (double)e * 0.6931471803691238 + ((double)e * 1.9082149292705877e-10 + lnm);
+    int e = 31 - __clz((int)x);
+    float m = (float)x / (float)(1u << e);
+    if (m > 1.41421356f) { m = m * 0.5f; e += 1; }
+    const float f = (m - 1.0f) / (m + 1.0f);
+    const float f2 = f * f;
+    float s = 1.0f / 11.0f;
+    s = s * f2 + 1.0f / 9.0f; s = s * f2 + 1.0f / 7.0f; s = s * f2 + 1.0f / 5.0f; s = s * f2 + 1.0f / 3.0f;
+    s = s * f2 + 1.0f;
+    const float lnm = 2.0f * f * s;
+    return (float)e * 0.693145751953125f + ((float)e * 1.42860682030941723212e-6f + lnm);
 }
 
 // ---------------------------------------------------------------------------------------------------------

@@ -22,8 +22,13 @@ namespace cg = cooperative_groups;
 #define AS POMCP_AS
 #define CHILD_LOCKED 0xFFFFFFFFu
 #define SEARCH_THREADS 256
+#define SEARCH_MIN_BLOCKS 4
 #define ADV_THREADS 1024
 #define ADV_TRIES 4
+#define SEQ_ALLOC_MAX 16u      // arrivals <= this: exact virtual-pull allocation; more: water-filling
+#ifndef BISECT_ITERS
+#define BISECT_ITERS 24
+#endif
 
 // ---------------------------------------------------------------------------------------------------------
 // Device-resident state (one per handle).  Kernels read and write it without host round trips.
@@ -38,6 +43,8 @@ struct DevState {
     unsigned long long gstep;          // global level-step stamp, never reused
     long long sims_done;               // simulations completed by the last search
     long long counters[16];
+    long long phase_ns[8];            // device time per phase of the last search (thread 0's globaltimer)
+    long long steplog[128][8];        // last search, per level step: ns of [wait, allocate, wait, expand], worklist, heavy
     // results of the last advance
     int32_t adv_status, adv_accepted, adv_root_cell, adv_pad;
     long long adv_tries;
@@ -86,9 +93,10 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
     return t;
 }
 
-__device__ __forceinline__ double edge_mean(long long qfix, int n)
+// mean return of an edge in single precision (the UCB arithmetic is fp32; sums stay exact integers)
+__device__ __forceinline__ float edge_mean(long long qfix, int n)
 {
-    return ((double)qfix * (1.0 / POMCP_QFIX_SCALE)) / (double)n;
+    return ((float)qfix * (1.0f / 16777216.0f)) / (float)n;
 }
 
 // Stage the model tables into shared memory; returns the first free byte offset (16-byte aligned).
@@ -112,8 +120,8 @@ __device__ __forceinline__ size_t stage_model(unsigned char *smem, const ModelHe
 // Batch-UCB allocation for a node with k >= 2 simultaneous arrivals (warp-cooperative, lane = action).
 // Water-filling of k pulls over the UCB1 indices mean + c*sqrt(ln(N+1)/n); output: 32-bit cumulative thresholds.
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_allocation(const SearchParams &p, int X, uint32_t k, int lane, int A,
-                                                uint32_t *thr_out, int32_t *meta_out)
+__device__ __noinline__ void warp_allocation(const SearchParams &p, int X, uint32_t k, int lane, int A,
+                                             uint32_t *thr_out, int32_t *meta_out)
 {
     const unsigned full = 0xFFFFFFFFu;
     const uint32_t mask = p.t.legal[X];
@@ -125,57 +133,62 @@ __device__ __forceinline__ void warp_allocation(const SearchParams &p, int X, ui
     for (int off = 16; off >= 1; off >>= 1) N += __shfl_xor_sync(full, N, off);
     const int untried = __popc(__ballot_sync(full, legal && n == 0));
     const int nlegal = __popc(__ballot_sync(full, legal));
-    double v = 0.0;
-    if (N == 0) v = legal ? 1.0 : 0.0;
-    else if ((uint32_t)untried >= k) v = (legal && n == 0) ? 1.0 : 0.0;
+    const float cf = (float)p.ucb_c;
+    float v = 0.0f;
+    if (N == 0) v = legal ? 1.0f : 0.0f;
+    else if ((uint32_t)untried >= k) v = (legal && n == 0) ? 1.0f : 0.0f;
     else {
-        const double L = det_log_u64((uint64_t)N + 1);
-        const double c2L = (p.ucb_c * p.ucb_c) * L;
-        const double qbar = legal ? (n == 0 ? 0.0 : edge_mean(qf, n)) : -INFINITY;
-        double qmax = qbar;
+        const float L = det_logf_u32((uint32_t)N + 1u);
+        const float c2L = (cf * cf) * L;
+        const float qbar = legal ? (n == 0 ? 0.0f : edge_mean(qf, n)) : -INFINITY;
+        float qmax = qbar;
 #pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) qmax = fmax(qmax, __shfl_xor_sync(full, qmax, off));
+        for (int off = 16; off >= 1; off >>= 1) qmax = fmaxf(qmax, __shfl_xor_sync(full, qmax, off));
         const unsigned best_lanes = __ballot_sync(full, legal && qbar == qmax);
         const int nbest = __shfl_sync(full, n, __ffs((int)best_lanes) - 1);
-        if (!(c2L > 0.0)) v = (legal && qbar == qmax) ? 1.0 : 0.0;
+        if (!(c2L > 0.0f)) v = (legal && qbar == qmax) ? 1.0f : 0.0f;
         else {
-            const double kd = (double)k;
-            double lo = qmax + 0.999 * sqrt(c2L / (kd + (double)nbest));
-            double hi = qmax + 1.001 * sqrt((c2L * (double)nlegal) / kd) + 1.0;
-            for (int it = 0; it <= 32; ++it) {
-                const double mid = it < 32 ? 0.5 * (lo + hi) : lo;
-                double t = 0.0;
+            const float kd = (float)k;
+            float lo = qmax + 0.999f * sqrtf(c2L / (kd + (float)nbest));
+            float hi = qmax + 1.001f * sqrtf((c2L * (float)nlegal) / kd) + 1.0f;
+            for (int it = 0; it <= BISECT_ITERS; ++it) {
+                const float mid = it < BISECT_ITERS ? 0.5f * (lo + hi) : lo;
+                float t = 0.0f;
                 if (legal) {
-                    const double d = mid - qbar;
-                    const double mm = c2L / (d * d);
-                    if (n == 0) t = mm > 1.0 ? mm : 1.0;
-                    else { const double e = mm - (double)n; t = e > 0.0 ? e : 0.0; }
+                    const float d = mid - qbar;
+                    const float mm = c2L / (d * d);
+                    if (n == 0) t = mm > 1.0f ? mm : 1.0f;
+                    else { const float e = mm - (float)n; t = e > 0.0f ? e : 0.0f; }
                 }
-                if (it == 32) { v = t; break; }
-                double s = t;
+                if (it == BISECT_ITERS) { v = t; break; }
+                float s = t;
 #pragma unroll
                 for (int off = 16; off >= 1; off >>= 1) s = s + __shfl_xor_sync(full, s, off);
                 if (s >= kd) lo = mid; else hi = mid;
             }
         }
     }
-    double x = v;                                   // inclusive scan, Hillis-Steele order
+    float x = v;                                    // inclusive scan, Hillis-Steele order
 #pragma unroll
     for (int off = 1; off < 32; off <<= 1) {
-        const double y = __shfl_up_sync(full, x, off);
+        const float y = __shfl_up_sync(full, x, off);
         if (lane >= off) x = x + y;
     }
-    const double V = __shfl_sync(full, x, 31);
-    const double f = (x / V) * 4294967296.0;
-    thr_out[lane] = f >= 4294967295.0 ? 0xFFFFFFFFu : (uint32_t)f;
-    const unsigned pos = __ballot_sync(full, v > 0.0);
+    const float V = __shfl_sync(full, x, 31);
+    const float f = (x / V) * 4294967296.0f;
+    thr_out[lane] = f >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)f;
+    const unsigned pos = __ballot_sync(full, v > 0.0f);
     if (lane == 0) *meta_out = (31 - __clz((int)pos)) | ((N > 0) ? 256 : 0);
 }
 
-// UCB1 arg-max for a single arrival (action_selectors.py:6-37), uniform tie-break with one 32-bit draw.
-__device__ __forceinline__ int ucb1_select(const SearchParams &p, int X, uint32_t mask, int A, uint32_t x0, bool &Npos)
+// Action of one simulation at a node with k <= SEQ_ALLOC_MAX arrivals (thread-level; statistics are read-only).
+//   k == 1: UCB1 arg-max (action_selectors.py:6-37), uniform tie-break with the 32-bit draw x0.
+//   k >= 2: the k arrivals share the virtual-pull sequence "pull j takes the UCB1 arg-max (lowest id on ties) given
+//           the statistics plus the virtual visits of pulls 0..j-1"; this simulation takes pull j = floor(x0*k/2^32).
+__device__ __noinline__ int select_thread(const SearchParams &p, int X, uint32_t mask, int A, uint32_t x0, uint32_t k)
 {
     const int32_t *nrow = p.t.n + (size_t)X * AS;
+    const long long *qrow = p.t.qfix + (size_t)X * AS;
     int N = 0; uint32_t untried = 0;
 #pragma unroll
     for (int q = 0; q < AS / 4; ++q) {
@@ -186,30 +199,89 @@ __device__ __forceinline__ int ucb1_select(const SearchParams &p, int X, uint32_
         if (m4 & 4u) { N += v4.z; if (v4.z == 0) untried |= 4u << (4 * q); }
         if (m4 & 8u) { N += v4.w; if (v4.w == 0) untried |= 8u << (4 * q); }
     }
-    Npos = N > 0;
-    uint32_t ties;
-    if (untried) ties = untried;                    // n == 0 scores +inf (solvers/pomcp.py:64-65)
-    else {
-        const double L = det_log_u64((uint64_t)N + 1);
-        const long long *qrow = p.t.qfix + (size_t)X * AS;
-        double best = -INFINITY; ties = 0;
+    const uint32_t n_untried = (uint32_t)__popc(untried);
+    if (n_untried >= k) return nth_bit(untried, randbelow32(x0, n_untried));   // n == 0 scores +inf (pomcp.py:64-65)
+    const float L = det_logf_u32((uint32_t)N + 1u);
+    const float cf = (float)p.ucb_c;
+    if (k == 1) {
+        float best = -INFINITY; uint32_t ties = 0;
         for (int a = 0; a < A; ++a) {
             if (!((mask >> a) & 1u)) continue;
             const int na = nrow[a];
-            const double s = edge_mean(qrow[a], na) + p.ucb_c * sqrt(L / (double)na);
+            const float s = edge_mean(qrow[a], na) + cf * sqrtf(L / (float)na);
             if (s > best) { best = s; ties = 1u << a; }
             else if (s == best) ties |= 1u << a;
         }
+        return nth_bit(ties, randbelow32(x0, (uint32_t)__popc(ties)));
     }
-    return nth_bit(ties, randbelow32(x0, (uint32_t)__popc(ties)));
+    const float c2L = (cf * cf) * L;
+    float sc[AS]; uint8_t va[AS];
+    float qmax = -INFINITY; uint32_t qties = 0;
+    for (int a = 0; a < A; ++a) {
+        va[a] = 0; sc[a] = -INFINITY;
+        if (!((mask >> a) & 1u)) continue;
+        const int na = nrow[a];
+        const float qb = na == 0 ? 0.0f : edge_mean(qrow[a], na);
+        if (qb > qmax) { qmax = qb; qties = 1u << a; } else if (qb == qmax) qties |= 1u << a;
+        sc[a] = na == 0 ? INFINITY : qb + cf * sqrtf(L / (float)na);
+    }
+    if (!(c2L > 0.0f)) return nth_bit(qties, randbelow32(x0, (uint32_t)__popc(qties)));
+    const uint32_t j = randbelow32(x0, k);
+    for (uint32_t pull = 0;; ++pull) {
+        int w = 0; float bs = sc[0];
+        for (int a = 1; a < A; ++a) if (sc[a] > bs) { bs = sc[a]; w = a; }
+        if (pull == j) return w;
+        const int na = nrow[w];
+        const float qb = na == 0 ? 0.0f : edge_mean(qrow[w], na);
+        va[w] += 1;
+        sc[w] = qb + cf * sqrtf(L / (float)(na + (int)va[w]));
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// K1: the search.  One persistent cooperative kernel per move; simulations advance in generations:
-//   level steps  [count arrivals | allocate | choose + step + expand]  (grid barrier after each phase)
-//   then         [rollout + backup]                                      (commutative integer atomics)
+// K1: the search.  One persistent cooperative kernel per move; simulations advance in generations.  Within a
+// generation the tree statistics are read-only; per tree level:
+//     [allocate]  nodes with many (> 16) arrivals get a batch-UCB allocation (warp per node, lane = action)
+//     [expand]    every simulation chooses, steps the model, looks up / creates the child and -- if the child has
+//                 statistics -- registers its arrival there for the next level; a child without statistics
+//                 ("virgin": N = 0, e.g. just created) is finished on the spot: uniform action, step, leaf
+// (one grid barrier after each), then [rollout + backup] with commutative integer atomics.
 // ---------------------------------------------------------------------------------------------------------
-extern "C" __global__ void __launch_bounds__(SEARCH_THREADS)
+struct SimCtx {
+    const SearchParams &p;
+    const SmemModel &M;
+    uint32_t actual, sampled;
+};
+
+// A simulation standing at a node without statistics (N = 0): every legal action is untried, so UCB1 is a uniform
+// draw (action_selectors.py:6-37 with +inf bonuses), the node cannot be expanded (solvers/pomcp.py:107) and the
+// simulation ends in a rollout.  `node_ref` is the node id, or -1 - child_slot while the id is being published.
+__device__ __noinline__ void virgin_step(const SimCtx &c, int i, uint32_t sim, int node_ref, uint32_t cell,
+                                            uint32_t rocks, int d, long long &c_levels)
+{
+    const SearchParams &p = c.p;
+    if (d >= p.max_depth) { p.b.flag[i] = 2; p.b.depth[i] = (uint8_t)d; return; }          // solvers/pomcp.py:100
+    const Philox4 r = philox4x32_10((uint32_t)(d + 1), sim, p.move, DOM_SIM, p.key0, p.key1);
+    const uint32_t mask = c.M.hdr->legal[cell];
+    const int a = nth_legal(c.M.hdr, mask, randbelow32(r.x, (uint32_t)__popc(mask)));
+    const StepResult sr = rs_step(c.M, cell, rocks, a, u53_of(r.y, r.z), c.actual, c.sampled);
+    ++c_levels;
+    p.b.path_node[(size_t)d * p.wmax + i] = node_ref;
+    p.b.path_ar[(size_t)d * p.wmax + i] = (uint16_t)(a | (sr.good << 5) | (sr.rew << 8));
+    p.b.depth[i] = (uint8_t)(d + 1);
+    p.b.state[i] = sr.cell | (sr.rocks << 8);
+    p.b.flag[i] = sr.terminal ? 2 : 1;
+}
+
+__device__ __forceinline__ int row_sum(const int32_t *nrow)
+{
+    int N = 0;
+#pragma unroll
+    for (int q = 0; q < AS / 4; ++q) { const int4 v = reinterpret_cast<const int4 *>(nrow)[q]; N += v.x + v.y + v.z + v.w; }
+    return N;
+}
+
+extern "C" __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_BLOCKS)
 pomcp_search_kernel(const SearchParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
@@ -223,6 +295,9 @@ pomcp_search_kernel(const SearchParams p)
     long long *acc_q = reinterpret_cast<long long *>(smem + off);
     off += (size_t)n_acc * 8;
     int *acc_n = reinterpret_cast<int *>(smem + off);
+    off += (size_t)n_acc * 4;
+    int *arr1 = reinterpret_cast<int *>(smem + off);               // arrivals at the root's children, per block
+    for (int i = threadIdx.x; i < 2 * A; i += blockDim.x) arr1[i] = 0;
     if (threadIdx.x == 0) { double d = 1.0; for (int t = 0; t < p.max_depth; ++t) { disc[t] = d; d *= p.discount; } }
     for (int i = threadIdx.x; i < n_acc; i += blockDim.x) { acc_q[i] = 0; acc_n[i] = 0; }
     __syncthreads();
@@ -233,6 +308,7 @@ pomcp_search_kernel(const SearchParams p)
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
     const int gwarp = gtid >> 5, nwarps = T >> 5;
+    const int vwarp = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;   // warp index that walks the blocks first
     const int root = S->root;
     const uint32_t actual = S->actual, sampled = S->sampled;
     const uint32_t *bag = p.bag[S->bag_sel];
@@ -241,92 +317,161 @@ pomcp_search_kernel(const SearchParams p)
     const unsigned long long t_start = globaltimer_ns();
     long long c_levels = 0, c_rollout = 0, c_created = 0, c_alloc = 0;
     long long done = 0, gens = 0, lsteps = 0;
+    unsigned long long tp[6] = {0, 0, 0, 0, 0, 0}, tmark = t_start;   // phase clocks (gtid 0 only)
+#define PHASE_MARK(k) do { if (gtid == 0) { const unsigned long long now_ = globaltimer_ns(); tp[k] += now_ - tmark; tmark = now_; } } while (0)
+    const SimCtx ctx{p, M, actual, sampled};
     int W = p.w0;
     grid.sync();                                                    // everyone has read S before anyone writes it
 
     while (done < p.n_sims) {
         const int w = (int)((p.n_sims - done) < (long long)W ? (p.n_sims - done) : (long long)W);
         ++gens;
-        for (int i = gtid; i < w; i += T) {                          // belief_node.py:47-48 at the root
-            const uint32_t sim = p.sim_offset + (uint32_t)(done + i);
-            const Philox4 r = philox4x32_10(0u, sim, p.move, DOM_SIM, p.key0, p.key1);
-            p.b.state[i] = bag[randbelow32(r.x, (uint32_t)n_bag)];
-            p.b.node[i] = root; p.b.flag[i] = 0; p.b.depth[i] = 0;
-        }
-        for (;;) {                                                   // ---- level steps ----
-            ++gstep; ++lsteps;
-            const int ring = (int)(gstep & 3ull);
-            const unsigned long long stamp = gstep << 32;
-            // phase 1: resolve pending child ids, count arrivals per node, build the node worklist
-            for (int i = gtid; i < w; i += T) {
-                uint8_t f = p.b.flag[i];
-                if ((f & 3) != 0) continue;
-                int X = p.b.node[i];
-                if (f & 4) { X = (int)p.t.child[X] - 1; p.b.node[i] = X; p.b.flag[i] = 0; }
-                const unsigned long long old = atomicMax(&p.t.arrive[X], stamp);
-                if (old < stamp) {
-                    const int s = atomicAdd(&S->wl_count[ring], 1);
-                    p.b.wl_node[s] = X; p.t.slot[X] = s;
-                }
-                atomicAdd(&p.t.arrive[X], 1ull);
+        // ---- start of a generation: every simulation draws a root particle (belief_node.py:47-48) ----
+        const bool root_virgin = row_sum(p.t.n + (size_t)root * AS) == 0;
+        if (!root_virgin && gwarp == 0) {                            // all w simulations arrive at the root
+            if (lane == 0) {
+                const unsigned long long s1 = gstep + 1;
+                p.t.arrive[root] = (s1 << 32) | (unsigned long long)(unsigned)w;
+                p.t.slot[root] = 0; p.b.wl_node[0] = root; S->wl_count[(int)(s1 & 3ull)] = 1;
             }
-            grid.sync();
-            const int nwl = *((volatile int32_t *)&S->wl_count[ring]);
-            if (gtid == 0) S->wl_count[(ring + 1) & 3] = 0;
-            if (nwl == 0) break;
-            // phase 2: nodes with >= 2 arrivals get a batch-UCB allocation (warp per node, lane = action)
-            for (int wi = gwarp; wi < nwl; wi += nwarps) {
-                const int X = p.b.wl_node[wi];
-                const uint32_t k = (uint32_t)p.t.arrive[X];
-                if (k < 2) continue;
-                warp_allocation(p, X, k, lane, A, p.b.wl_thr + (size_t)wi * 32, p.b.wl_meta + wi);
+            if ((uint32_t)w > SEQ_ALLOC_MAX) {                       // its allocation is known now: no extra phase
+                warp_allocation(p, root, (uint32_t)w, lane, A, p.b.wl_thr, p.b.wl_meta);
                 if (lane == 0) ++c_alloc;
             }
-            grid.sync();
-            // phase 3: choose an action, step the model, expand (solvers/pomcp.py:97-117)
-            for (int i = gtid; i < w; i += T) {
-                if ((p.b.flag[i] & 3) != 0) continue;
-                const int X = p.b.node[i];
-                const int d = p.b.depth[i];
-                if (d >= p.max_depth) { p.b.flag[i] = 2; continue; }                       // :100
-                const uint32_t sim = p.sim_offset + (uint32_t)(done + i);
-                const Philox4 r = philox4x32_10((uint32_t)(d + 1), sim, p.move, DOM_SIM, p.key0, p.key1);
-                const uint32_t mask = p.t.legal[X];
-                const uint32_t k = (uint32_t)p.t.arrive[X];
-                bool Npos; int a;
-                if (k == 1) a = ucb1_select(p, X, mask, A, r.x, Npos);
-                else {
-                    const int s = p.t.slot[X];
-                    const uint32_t *thr = p.b.wl_thr + (size_t)s * 32;
-                    const int meta = p.b.wl_meta[s];
-                    Npos = (meta & 256) != 0; a = meta & 255;
-                    for (int bq = 0; bq < A; ++bq) if (r.x < thr[bq]) { a = bq; break; }
+        }
+        for (int i = gtid; i < w; i += T) {
+            const uint32_t sim = p.sim_offset + (uint32_t)(done + i);
+            const Philox4 r = philox4x32_10(0u, sim, p.move, DOM_SIM, p.key0, p.key1);
+            const uint32_t st = bag[randbelow32(r.x, (uint32_t)n_bag)];
+            if (root_virgin) virgin_step(ctx, i, sim, root, st & 0xFFu, st >> 8, 0, c_levels);
+            else { p.b.state[i] = st; p.b.node[i] = root; p.b.flag[i] = 0; p.b.depth[i] = 0; }
+        }
+        PHASE_MARK(0);
+        if (!root_virgin) for (int level = 0;; ++level) {            // ---- level steps ----
+            ++gstep; ++lsteps;
+            const int ring = (int)(gstep & 3ull), ring_next = (int)((gstep + 1) & 3ull);
+            const unsigned long long stamp_next = (gstep + 1) << 32;
+            grid.sync();                                             // arrivals of this level are complete
+            if (gtid == 0 && lsteps <= 128) S->steplog[lsteps - 1][0] = (long long)(globaltimer_ns() - tmark);
+            PHASE_MARK(1);
+            const int nwl = *((volatile int32_t *)&S->wl_count[ring]);
+            if (gtid == 0) S->wl_count[ring_next] = 0;
+            if (nwl == 0) break;
+            // [allocate] every warp inspects 32 worklist entries at once (strided by the warp count, so that the
+            // early, busy entries spread over all warps) and serves those with > SEQ_ALLOC_MAX arrivals
+            if (level > 0) {
+            for (int base = 0; base < nwl; base += nwarps * 32) {
+                const int e = base + lane * nwarps + vwarp;
+                int X = 0; uint32_t k = 0;
+                if (e < nwl) { X = p.b.wl_node[e]; k = (uint32_t)p.t.arrive[X]; }
+                unsigned todo = __ballot_sync(0xFFFFFFFFu, k > SEQ_ALLOC_MAX);
+                while (todo) {
+                    const int src = __ffs((int)todo) - 1;
+                    todo &= todo - 1;
+                    const int es = base + src * nwarps + vwarp;
+                    warp_allocation(p, __shfl_sync(0xFFFFFFFFu, X, src), __shfl_sync(0xFFFFFFFFu, k, src), lane, A,
+                                    p.b.wl_thr + (size_t)es * 32, p.b.wl_meta + es);
+                    if (lane == 0) ++c_alloc;
                 }
-                const uint32_t st = p.b.state[i];
-                const StepResult sr = rs_step(M, st & 0xFFu, st >> 8, a, u53_of(r.y, r.z), actual, sampled);  // :104
-                ++c_levels;
-                p.b.path_node[(size_t)d * p.wmax + i] = X;
-                p.b.path_ar[(size_t)d * p.wmax + i] = (uint16_t)(a | (sr.good << 5) | (sr.rew << 8));
-                p.b.depth[i] = (uint8_t)(d + 1);
-                p.b.state[i] = sr.cell | (sr.rocks << 8);
-                if (sr.terminal) { p.b.flag[i] = 2; continue; }
-                const size_t cslot = ((size_t)X * AS + a) * 2 + sr.good;
-                uint32_t c = p.t.child[cslot];                                              // :106
-                if (c == 0 && Npos && d + 1 < p.dcap) {                                     // :107-108
-                    c = atomicCAS(&p.t.child[cslot], 0u, CHILD_LOCKED);
-                    if (c == 0) {                                                           // this thread creates it
-                        const int id = atomicAdd(&S->node_count, 1);
-                        p.t.cell[id] = (int32_t)sr.cell;
-                        p.t.legal[id] = H->legal[sr.cell];
-                        atomicExch(&p.t.child[cslot], (uint32_t)id + 1u);
-                        ++c_created;
-                        c = CHILD_LOCKED;
+            }
+            if (gtid == 0 && lsteps <= 128) S->steplog[lsteps - 1][1] = (long long)(globaltimer_ns() - tmark);
+            grid.sync();
+            }
+            if (gtid == 0 && lsteps <= 128) { S->steplog[lsteps - 1][2] = (long long)(globaltimer_ns() - tmark) - S->steplog[lsteps - 1][1]; S->steplog[lsteps - 1][4] = nwl; }
+            PHASE_MARK(2);
+            // [expand] choose an action, step the model, look up / create the child (solvers/pomcp.py:97-117)
+            for (int base = gtid - lane; base < w; base += T) {
+                const int i = base + lane;
+                int arrive_at = -1, arrive_slot = 0;                 // non-virgin child this simulation descends to
+                if (i < w && (p.b.flag[i] & 3) == 0) {
+                    const int X = p.b.node[i];
+                    const int d = p.b.depth[i];
+                    const uint32_t sim = p.sim_offset + (uint32_t)(done + i);
+                    if (d >= p.max_depth) p.b.flag[i] = 2;                                  // :100
+                    else {
+                        const Philox4 r = philox4x32_10((uint32_t)(d + 1), sim, p.move, DOM_SIM, p.key0, p.key1);
+                        const uint32_t mask = p.t.legal[X];
+                        const uint32_t k = (uint32_t)p.t.arrive[X];
+                        int a;
+                        if (k <= SEQ_ALLOC_MAX) a = select_thread(p, X, mask, A, r.x, k);
+                        else {
+                            const int s = p.t.slot[X];
+                            const uint32_t *thr = p.b.wl_thr + (size_t)s * 32;
+                            a = p.b.wl_meta[s] & 255;
+                            for (int bq = 0; bq < A; ++bq) if (r.x < thr[bq]) { a = bq; break; }
+                        }
+                        const uint32_t st = p.b.state[i];
+                        const StepResult sr = rs_step(M, st & 0xFFu, st >> 8, a, u53_of(r.y, r.z), actual, sampled);  // :104
+                        ++c_levels;
+                        p.b.path_node[(size_t)d * p.wmax + i] = X;
+                        p.b.path_ar[(size_t)d * p.wmax + i] = (uint16_t)(a | (sr.good << 5) | (sr.rew << 8));
+                        p.b.depth[i] = (uint8_t)(d + 1);
+                        p.b.state[i] = sr.cell | (sr.rocks << 8);
+                        if (sr.terminal) p.b.flag[i] = 2;
+                        else {
+                            const size_t cslot = ((size_t)X * AS + a) * 2 + sr.good;
+                            uint32_t c = p.t.child[cslot];                                  // :106
+                            if (c == 0 && d + 1 < p.dcap) {                                 // :107-108 (N(X) > 0 here)
+                                c = atomicCAS(&p.t.child[cslot], 0u, CHILD_LOCKED);
+                                if (c == 0) {                                               // this thread creates it
+                                    const unsigned am = __activemask();                     // one arena bump per warp
+                                    const int rk = __popc(am & ((1u << lane) - 1u));
+                                    int id0 = 0;
+                                    if (rk == 0) id0 = atomicAdd(&S->node_count, __popc(am));
+                                    const int id = __shfl_sync(am, id0, __ffs((int)am) - 1) + rk;
+                                    p.t.cell[id] = (int32_t)sr.cell;
+                                    p.t.legal[id] = H->legal[sr.cell];
+                                    atomicExch(&p.t.child[cslot], (uint32_t)id + 1u);
+                                    ++c_created;
+                                    c = CHILD_LOCKED;
+                                }
+                            }
+                            if (c == 0) p.b.flag[i] = 1;                                    // depth cap: leaf (:119)
+                            else if (c == CHILD_LOCKED)                                     // created in this step
+                                virgin_step(ctx, i, sim, -1 - (int)cslot, sr.cell, sr.rocks, d + 1, c_levels);
+                            else {
+                                const int id = (int)c - 1;
+                                if (row_sum(p.t.n + (size_t)id * AS) == 0)
+                                    virgin_step(ctx, i, sim, id, sr.cell, sr.rocks, d + 1, c_levels);
+                                else { p.b.node[i] = id; arrive_at = id; arrive_slot = a * 2 + sr.good; }   // descend
+                            }
+                        }
                     }
                 }
-                if (c != 0) { p.b.node[i] = (int32_t)cslot; p.b.flag[i] = 4; }              // descend next level step
-                else p.b.flag[i] = 1;                                                       // leaf: rollout (:119)
+                __syncwarp();
+                // arrivals for the next level.  From the root: counted per block in shared memory (<= 2|A| children);
+                // deeper: aggregated per warp and node (match.any), one atomic per group
+                if (level == 0) { if (arrive_at >= 0) atomicAdd(&arr1[arrive_slot], 1); continue; }
+                const unsigned amask = __ballot_sync(0xFFFFFFFFu, arrive_at >= 0);
+                if (arrive_at >= 0) {
+                    const unsigned peers = __match_any_sync(amask, arrive_at);
+                    if (lane == __ffs((int)peers) - 1) {
+                        const unsigned long long old = atomicMax(&p.t.arrive[arrive_at], stamp_next);
+                        if (old < stamp_next) {
+                            const int s = atomicAdd(&S->wl_count[ring_next], 1);
+                            p.b.wl_node[s] = arrive_at; p.t.slot[arrive_at] = s;
+                        }
+                        atomicAdd(&p.t.arrive[arrive_at], (unsigned long long)__popc(peers));
+                    }
+                }
             }
-            grid.sync();
+            if (level == 0) {                                        // publish this block's arrivals at the root's children
+                __syncthreads();
+                for (int t = threadIdx.x; t < 2 * A; t += blockDim.x) {
+                    const int cnt = arr1[t];
+                    if (cnt == 0) continue;
+                    arr1[t] = 0;
+                    const int Xc = (int)p.t.child[(size_t)root * AS * 2 + t] - 1;
+                    const unsigned long long old = atomicMax(&p.t.arrive[Xc], stamp_next);
+                    if (old < stamp_next) {
+                        const int sl = atomicAdd(&S->wl_count[ring_next], 1);
+                        p.b.wl_node[sl] = Xc; p.t.slot[Xc] = sl;
+                    }
+                    atomicAdd(&p.t.arrive[Xc], (unsigned long long)(unsigned)cnt);
+                }
+            }
+            if (gtid == 0 && lsteps <= 128) S->steplog[lsteps - 1][3] = (long long)(globaltimer_ns() - tmark);
+            PHASE_MARK(3);
         }
         // ---- rollout (belief_tree_solver.py:123-152, from the post-action state) + backup (:126-137) ----
         for (int i = gtid; i < w; i += T) {
@@ -365,7 +510,6 @@ pomcp_search_kernel(const SearchParams p)
                 delayed = sum;
             }
             for (int d = depth - 1; d >= 0; --d) {
-                const int X = p.b.path_node[(size_t)d * p.wmax + i];
                 const uint32_t ar = p.b.path_ar[(size_t)d * p.wmax + i];
                 const int a = ar & 31;
                 const double q = H->rew[ar >> 8] + p.discount * delayed;
@@ -379,6 +523,8 @@ pomcp_search_kernel(const SearchParams p)
                     atomicAdd(&acc_n[e], 1);
                     atomicAdd(reinterpret_cast<unsigned long long *>(&acc_q[e]), (unsigned long long)qi);
                 } else {
+                    int X = p.b.path_node[(size_t)d * p.wmax + i];
+                    if (X < 0) X = (int)p.t.child[(size_t)(-1 - X)] - 1;     // id published after this sim passed
                     atomicAdd(&p.t.n[(size_t)X * AS + a], 1);
                     atomicAdd(reinterpret_cast<unsigned long long *>(&p.t.qfix[(size_t)X * AS + a]), (unsigned long long)qi);
                 }
@@ -400,6 +546,7 @@ pomcp_search_kernel(const SearchParams p)
         if (W < p.wmax) { long long nw = (long long)W * p.growth; W = nw > p.wmax ? p.wmax : (int)nw; }
         if (p.timeout_ns && gtid == 0 && globaltimer_ns() - t_start > p.timeout_ns) S->stop = 1;
         grid.sync();
+        PHASE_MARK(4);
         if (p.timeout_ns && *((volatile int32_t *)&S->stop)) break;   // action_selection_timeout
     }
 
@@ -425,6 +572,7 @@ pomcp_search_kernel(const SearchParams p)
         S->counters[6] += lsteps;
         S->counters[7] = (long long)(globaltimer_ns() - t_start);
         S->counters[8] = done;
+        for (int k = 0; k < 6; ++k) S->phase_ns[k] = (long long)tp[k];
     }
 }
 
@@ -714,9 +862,10 @@ extern "C" int pomcp_set_model_rocksample(pomcp_handle *h, int rows, int cols, c
     // launch geometry of the cooperative search kernel
     const int A = m.n_actions;
     size_t smem = ((sizeof(ModelHeader) + 15) & ~size_t(15)) + (((size_t)h->n_thr * 8 + 15) & ~size_t(15)) +
-                  (((size_t)h->cfg.max_depth * 8 + 15) & ~size_t(15)) + (size_t)(1 + 2 * A) * A * 12 + 16;
+                  (((size_t)h->cfg.max_depth * 8 + 15) & ~size_t(15)) + (size_t)(1 + 2 * A) * A * 12 + (size_t)2 * A * 4 + 16;
     h->search_smem = smem;
     CK(cudaFuncSetAttribute(pomcp_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(pomcp_search_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
     CK(cudaFuncSetAttribute(pomcp_advance_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(pomcp_step_batch_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     int per_sm = 0, sms = 0;
@@ -962,6 +1111,16 @@ extern "C" int pomcp_generate_steps(pomcp_handle *h, int64_t n, const uint32_t *
     return 0;
 }
 
+extern "C" int pomcp_debug_steplog(pomcp_handle *h, int64_t *out /* [128][4] */)
+{
+    if (!h) return -1;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->last_stream));
+    CK(cudaMemcpy(out, h->dS->steplog, sizeof(long long) * 128 * 8, cudaMemcpyDeviceToHost));
+
+    return 0;
+}
+
 extern "C" int pomcp_counters(pomcp_handle *h, int64_t out[16])
 {
     if (!h) return -1;
@@ -974,6 +1133,7 @@ extern "C" int pomcp_counters(pomcp_handle *h, int64_t out[16])
     out[9] = h->launches;
     out[10] = h->coop_blocks;
     out[11] = SEARCH_THREADS;
+    for (int i = 0; i < 3; ++i) out[13 + i] = st.phase_ns[1 + i];   // count / allocate / choose+step+expand
     out[12] = (int64_t)(sizeof(DevState) + AS * sizeof(int32_t) + AS * sizeof(long long) + sizeof(uint32_t));  // D2H bytes of pomcp_root_stats
     return 0;
 }

@@ -28,7 +28,7 @@ class Config(C.Structure):
 EXPORTS = ["pomcp_create", "pomcp_destroy", "pomcp_last_error", "pomcp_set_model_rocksample", "pomcp_set_world",
            "pomcp_set_root_particles", "pomcp_search", "pomcp_root_stats", "pomcp_node_stats", "pomcp_advance",
            "pomcp_root_particles", "pomcp_generate_steps", "pomcp_counters", "pomcp_root_stats_device",
-           "pomcp_reset_tree"]
+           "pomcp_reset_tree", "pomcp_debug_steplog"]
 
 
 def library_path():
@@ -40,8 +40,8 @@ def load(build_if_missing=True):
     global _LIB
     if _LIB is not None:
         return _LIB
-    path = library_path()
-    if build_if_missing and _build.stale():
+    path = os.environ.get("POMCP_B200_LIB") or library_path()      # override: experiment builds
+    if build_if_missing and not os.environ.get("POMCP_B200_LIB") and _build.stale():
         try:
             _build.build()
         except Exception as e:            # no nvcc on this box: a prebuilt library must already be there
@@ -70,6 +70,7 @@ def load(build_if_missing=True):
     L.pomcp_counters.argtypes = [vp, P(i64)]
     L.pomcp_root_stats_device.argtypes = [vp, vp, vp]
     L.pomcp_reset_tree.argtypes = [vp, vp]
+    L.pomcp_debug_steplog.argtypes = [vp, P(i64)]
     _LIB = L
     return L
 
@@ -191,10 +192,15 @@ class Planner:
                                                _p(rw, C.c_double)))
         return ns, fl, rw
 
+    def steplog(self):
+        out = np.zeros((128, 8), dtype=np.int64)
+        self._ck(self.lib.pomcp_debug_steplog(self.h, _p(out, C.c_int64)))
+        return out
+
     def counters(self):
         c = np.zeros(16, dtype=np.int64)
         self._ck(self.lib.pomcp_counters(self.h, _p(c, C.c_int64)))
         names = ("levels", "rollout_steps", "created", "nodes", "alloc_nodes", "generations", "level_steps",
                  "last_search_ns", "last_search_sims", "launches", "coop_blocks", "threads_per_block",
-                 "root_stats_d2h_bytes")
+                 "root_stats_d2h_bytes", "phase_count_ns", "phase_alloc_ns", "phase_expand_ns")
         return dict(zip(names, c.tolist()))
