@@ -30,7 +30,7 @@ import numpy as np  # noqa: E402
 
 MAP = "map-15-15"
 N_SIMS = 1_000_000
-SCHEDULE = (1024, 2, 1 << 18)           # generation widths: 1024, 2048, ... capped at 262144 simulations in flight
+SCHEDULE = (4096, 4, 1 << 19)           # generation widths: 4096, 16384, 65536, 262144, 524288 simulations in flight
 REF_SAMPLE_SIMS = 100_000               # per core and step, reference arm
 METRIC = "pomcp_sims_per_sec_rocksample_15_15"
 

@@ -8,6 +8,7 @@
 #include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
+#include <cstddef>
 #include <cstdio>
 #include <cstdlib>
 #include <cstring>
@@ -44,11 +45,13 @@ struct DevState {
     long long sims_done;               // simulations completed by the last search
     long long counters[16];
     long long phase_ns[8];            // device time per phase of the last search (thread 0's globaltimer)
-    long long steplog[128][8];        // last search, per level step: ns of [wait, allocate, wait, expand], worklist, heavy
     // results of the last advance
     int32_t adv_status, adv_accepted, adv_root_cell, adv_pad;
     long long adv_tries;
+    // ---- profiling aid, not copied by the hot calls ----
+    long long steplog[128][8];        // last search, per level step: ns of [wait, allocate, wait, expand], worklist
 };
+#define DEVSTATE_HEAD (offsetof(DevState, steplog))
 
 struct Tree {                          // structure-of-arrays belief-tree arena
     int32_t *n;                        // [cap][AS]   visit_count of edge (node, action)
@@ -998,7 +1001,7 @@ extern "C" int pomcp_root_stats(pomcp_handle *h, int64_t *n, int64_t *qfix, uint
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->last_stream));
     DevState st;
-    CK(cudaMemcpy(&st, h->dS, sizeof(st), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&st, h->dS, DEVSTATE_HEAD, cudaMemcpyDeviceToHost));
     h->nodes_used = st.node_count;
     const int A = h->hmodel.n_actions;
     int32_t nn[AS]; long long qq[AS]; uint32_t lg;
@@ -1059,7 +1062,7 @@ extern "C" int pomcp_advance(pomcp_handle *h, int action, int obs_good, uint32_t
     ++h->launches;
     CK(cudaStreamSynchronize(s));
     DevState st;
-    CK(cudaMemcpy(&st, h->dS, sizeof(st), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&st, h->dS, DEVSTATE_HEAD, cudaMemcpyDeviceToHost));
     h->nodes_used = st.node_count;
     if (h->zeroed_upto < h->nodes_used) h->zeroed_upto = h->nodes_used;
     h->root_cell = st.adv_root_cell; h->n_bag = st.n_bag; h->bag_sel = st.bag_sel;
@@ -1076,7 +1079,7 @@ extern "C" int pomcp_root_particles(pomcp_handle *h, uint32_t *out, int capacity
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->last_stream));
     DevState st;
-    CK(cudaMemcpy(&st, h->dS, sizeof(st), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&st, h->dS, DEVSTATE_HEAD, cudaMemcpyDeviceToHost));
     const int m = st.n_bag < capacity ? st.n_bag : capacity;
     if (out && m > 0) CK(cudaMemcpy(out, h->bag[st.bag_sel], (size_t)m * sizeof(uint32_t), cudaMemcpyDeviceToHost));
     if (n) *n = st.n_bag;
@@ -1127,13 +1130,13 @@ extern "C" int pomcp_counters(pomcp_handle *h, int64_t out[16])
     CK(cudaSetDevice(h->device));
     CK(cudaStreamSynchronize(h->last_stream));
     DevState st;
-    CK(cudaMemcpy(&st, h->dS, sizeof(st), cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(&st, h->dS, DEVSTATE_HEAD, cudaMemcpyDeviceToHost));
     for (int i = 0; i < 16; ++i) out[i] = st.counters[i];
     out[3] = st.node_count;
     out[9] = h->launches;
     out[10] = h->coop_blocks;
     out[11] = SEARCH_THREADS;
     for (int i = 0; i < 3; ++i) out[13 + i] = st.phase_ns[1 + i];   // count / allocate / choose+step+expand
-    out[12] = (int64_t)(sizeof(DevState) + AS * sizeof(int32_t) + AS * sizeof(long long) + sizeof(uint32_t));  // D2H bytes of pomcp_root_stats
+    out[12] = (int64_t)(DEVSTATE_HEAD + AS * sizeof(int32_t) + AS * sizeof(long long) + sizeof(uint32_t));  // D2H bytes of pomcp_root_stats
     return 0;
 }
