@@ -5,6 +5,7 @@ generation schedule of the CUDA planner.  Example:
     python pomcp.py --env RockSample --solver POMCP --max_steps 200 --n_epochs 10 --n_sims 500 --seed 123
 """
 import argparse
+import os
 
 import numpy as np
 
@@ -54,6 +55,18 @@ def main(argv=None):
     from pomdpy_b200.rock_sample import RockModel
     from pomdpy_b200.solvers import POMCP
     util.VERBOSITY = args.pop("verbosity")
+    world = int(os.environ.get("WORLD_SIZE", "1"))
+    if world > 1:                        # launched by torchrun: root-parallel search, one process per GPU
+        import torch
+        import torch.distributed as dist
+        local = int(os.environ.get("LOCAL_RANK", "0"))
+        if torch.cuda.is_available():
+            torch.cuda.set_device(local)
+            dist.init_process_group("nccl", device_id=torch.device("cuda", local))
+        else:
+            dist.init_process_group("gloo")
+        if dist.get_rank() != 0:
+            util.VERBOSITY = min(util.VERBOSITY, 0)
     np.random.seed(args["seed"])
     if args["solver"] != "POMCP":
         raise ValueError("solver not supported")
