@@ -1,0 +1,37 @@
+/*
+ * vi_b200.h -- C ABI of the value-iteration kernels (secondary path; same libpomcp_b200.so).
+ *
+ * Replaces ValueIteration.value_iteration / prune of the reference (pomdpy/solvers/value_iteration.py:24-142).
+ * Plain pointers and sizes; host arrays unless a parameter is named *_dev.
+ */
+#ifndef VI_B200_H
+#define VI_B200_H
+
+#include <stdint.h>
+
+#ifdef __cplusplus
+extern "C" {
+#endif
+
+/* value_iteration(t, o, r, horizon) (value_iteration.py:24-73) with the reference's projection formula
+ *   candidate(g,u,z)[i] = discount * (R[u][i] + sum_j (v_g[i] * O[u][i][z]) * T[u][j][i])        (:51-67)
+ * and the pointwise-dominance prune its pairwise LP computes (:88-142; delta = 1e-10): vector i is dropped iff some j has
+ * max_s(v_i - v_j) < delta and (i does not beat j the same way, or j comes first).  All fp64, no FMA contraction.
+ * T [A][S][S], O [A][S][Z], R [A][S]; outputs alpha [capacity][S], action [capacity], *n_out vectors.
+ * Returns 0, or < 0 on error (capacity exceeded, CUDA failure; text in err). */
+int vi_solve_reference(int device, int S, int A, int Z, const double *T, const double *O, const double *R, double discount,
+                       int horizon, int capacity, double *alpha_out, int32_t *action_out, int32_t *n_out,
+                       char *err, int errlen);
+
+/* Textbook projection for large |S| (BASELINE config 5):
+ *   proj[a][s][o*G + g] = sum_s' T[a][s][s'] * O[a][s'][o] * gamma[g][s']
+ * as |A| GEMMs [S x S] . [S x Z*G] on the fp64 tensor cores (DMMA), all pointers on the device, row-major.
+ * scratch_dev holds S*Z*G doubles.  Asynchronous on `stream`. */
+int vi_project_textbook_dev(int device, int S, int A, int Z, int G, const double *T_dev, const double *O_dev,
+                            const double *gamma_dev, double *scratch_dev, double *proj_dev, void *stream,
+                            char *err, int errlen);
+
+#ifdef __cplusplus
+}
+#endif
+#endif

@@ -24,7 +24,7 @@ class StepOut(C.Structure):
 
 def build(force=False):
     so = os.path.join(_HERE, "liboracle.so")
-    srcs = [os.path.join(_HERE, f) for f in ("pomcp_oracle.c", "vi_oracle.c")]
+    srcs = [os.path.join(_HERE, f) for f in ("pomcp_oracle.c",)]
     if force or not os.path.exists(so) or any(os.path.getmtime(s) > os.path.getmtime(so) for s in srcs):
         subprocess.check_call(["make", "-C", _HERE, "-s"] + (["-B"] if force else []))
     return so

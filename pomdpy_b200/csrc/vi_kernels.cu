@@ -1,0 +1,241 @@
+// vi_kernels.cu -- value-iteration alpha-vector backup and pointwise-dominance prune (sm_100a), fp64.
+//
+// Secondary path: pomdpy/solvers/value_iteration.py:24-142 of the reference.
+// Built with -fmad=false: products and sums are evaluated in the reference's order, so the alpha vectors equal the
+// numpy oracle's bit for bit.
+#include <cuda_runtime.h>
+
+#include <cstdint>
+#include <cstdio>
+#include <cstring>
+#include <string>
+
+#include "../../include/vi_b200.h"
+
+#define VCK(call)                                                                    \
+    do {                                                                             \
+        cudaError_t e_ = (call);                                                     \
+        if (e_ != cudaSuccess) {                                                     \
+            snprintf(err, errlen, "%s: %s", #call, cudaGetErrorString(e_));          \
+            return -1;                                                               \
+        }                                                                            \
+    } while (0)
+
+// candidate c = (u * Z + z) * G + g ; element i.   value_iteration.py:51-67
+__global__ void vi_backup_kernel(int S, int A, int Z, int G, const double *__restrict__ T, const double *__restrict__ O,
+                                 const double *__restrict__ R, const double *__restrict__ gamma, double discount,
+                                 double *__restrict__ cand, int32_t *__restrict__ cand_action)
+{
+    const long long total = (long long)A * Z * G * S;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int i = (int)(idx % S);
+        const long long c = idx / S;
+        const int g = (int)(c % G);
+        const int z = (int)((c / G) % Z);
+        const int u = (int)(c / ((long long)G * Z));
+        const double vo = gamma[(size_t)g * S + i] * O[((size_t)u * S + i) * Z + z];    // v.v[i] * o[u][i][z]
+        double acc = 0.0;
+        for (int j = 0; j < S; ++j) acc = acc + vo * T[((size_t)u * S + j) * S + i];     // ... * t[u][j][i], summed over j
+        cand[idx] = discount * (R[(size_t)u * S + i] + acc);
+        if (i == 0) cand_action[c] = u;
+    }
+}
+
+// value_iteration.py:88-142 as the pointwise test its LP computes.  One thread per vector i.
+__global__ void vi_prune_kernel(int S, int n, const double *__restrict__ v, double delta, int32_t *__restrict__ keep)
+{
+    for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < n; i += gridDim.x * blockDim.x) {
+        int beaten = 0;
+        for (int j = 0; j < n && !beaten; ++j) {
+            if (j == i) continue;
+            bool dom = true;                               // max_s (v_i - v_j) < delta
+            for (int s = 0; s < S; ++s)
+                if (!(v[(size_t)i * S + s] - v[(size_t)j * S + s] < delta)) { dom = false; break; }
+            if (!dom) continue;
+            bool mutual = true;                            // max_s (v_j - v_i) < delta
+            for (int s = 0; s < S; ++s)
+                if (!(v[(size_t)j * S + s] - v[(size_t)i * S + s] < delta)) { mutual = false; break; }
+            if (!mutual || j < i) beaten = 1;
+        }
+        keep[i] = !beaten;
+    }
+}
+
+// Order-preserving compaction of the kept vectors (one block; n is a few thousand at most on this path).
+__global__ void vi_compact_kernel(int S, int n, const double *__restrict__ v, const int32_t *__restrict__ act,
+                                  const int32_t *__restrict__ keep, double *__restrict__ out, int32_t *__restrict__ out_act,
+                                  int32_t *__restrict__ n_out)
+{
+    __shared__ int base, warp_tot[32];
+    const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    if (tid == 0) base = 0;
+    __syncthreads();
+    for (int start = 0; start < n; start += blockDim.x) {
+        const int i = start + tid;
+        const int k = (i < n) ? keep[i] : 0;
+        int incl = k;
+        for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xFFFFFFFFu, incl, o); if (lane >= o) incl += y; }
+        if (lane == 31) warp_tot[wid] = incl;
+        __syncthreads();
+        if (wid == 0) {
+            const int t = warp_tot[lane]; int it = t;
+            for (int o = 1; o < 32; o <<= 1) { const int y = __shfl_up_sync(0xFFFFFFFFu, it, o); if (lane >= o) it += y; }
+            warp_tot[lane] = it - t;
+        }
+        __syncthreads();
+        const int pos = base + warp_tot[wid] + incl - k;
+        if (k) {
+            for (int s = 0; s < S; ++s) out[(size_t)pos * S + s] = v[(size_t)i * S + s];
+            out_act[pos] = act[i];
+        }
+        __syncthreads();
+        if (tid == blockDim.x - 1) base = pos + k;
+        __syncthreads();
+    }
+    if (tid == 0) *n_out = base;
+}
+
+extern "C" int vi_solve_reference(int device, int S, int A, int Z, const double *T, const double *O, const double *R,
+                                  double discount, int horizon, int capacity, double *alpha_out, int32_t *action_out,
+                                  int32_t *n_out, char *err, int errlen)
+{
+    if (S < 1 || A < 1 || Z < 1 || horizon < 0 || capacity < 1) { snprintf(err, errlen, "bad sizes"); return -1; }
+    int ndev = 0;
+    if (cudaGetDeviceCount(&ndev) != cudaSuccess || ndev == 0) { snprintf(err, errlen, "no CUDA device: no CPU fallback"); return -1; }
+    VCK(cudaSetDevice(device));
+    double *dT, *dO, *dR, *dG, *dAll, *dNext; int32_t *dAct, *dAllAct, *dNextAct, *dKeep, *dN;
+    const size_t cap = (size_t)capacity, work = cap * (1 + (size_t)A * Z);       // gamma + candidates
+    VCK(cudaMalloc(&dT, sizeof(double) * A * S * S)); VCK(cudaMalloc(&dO, sizeof(double) * A * S * Z));
+    VCK(cudaMalloc(&dR, sizeof(double) * A * S));
+    VCK(cudaMalloc(&dG, sizeof(double) * cap * S)); VCK(cudaMalloc(&dAct, sizeof(int32_t) * cap));
+    VCK(cudaMalloc(&dAll, sizeof(double) * work * S)); VCK(cudaMalloc(&dAllAct, sizeof(int32_t) * work));
+    VCK(cudaMalloc(&dNext, sizeof(double) * work * S)); VCK(cudaMalloc(&dNextAct, sizeof(int32_t) * work));
+    VCK(cudaMalloc(&dKeep, sizeof(int32_t) * work)); VCK(cudaMalloc(&dN, sizeof(int32_t)));
+    VCK(cudaMemcpy(dT, T, sizeof(double) * A * S * S, cudaMemcpyHostToDevice));
+    VCK(cudaMemcpy(dO, O, sizeof(double) * A * S * Z, cudaMemcpyHostToDevice));
+    VCK(cudaMemcpy(dR, R, sizeof(double) * A * S, cudaMemcpyHostToDevice));
+    VCK(cudaMemset(dG, 0, sizeof(double) * S));                                  // the dummy zero vector (:38-40)
+    int minus1 = -1;
+    VCK(cudaMemcpy(dAct, &minus1, sizeof(int32_t), cudaMemcpyHostToDevice));
+    int G = 1, rc = 0;
+    for (int k = 0; k < horizon; ++k) {
+        const int ncand = A * Z * G;
+        const int keep_old = (k == 0) ? 0 : G;                                   // the dummy is dropped after pass 0 (:69-72)
+        const int n = keep_old + ncand;
+        if ((size_t)n > work) { snprintf(err, errlen, "capacity %d too small at horizon %d", capacity, k + 1); rc = -2; break; }
+        if (keep_old) {
+            VCK(cudaMemcpy(dAll, dG, sizeof(double) * (size_t)G * S, cudaMemcpyDeviceToDevice));
+            VCK(cudaMemcpy(dAllAct, dAct, sizeof(int32_t) * G, cudaMemcpyDeviceToDevice));
+        }
+        const long long total = (long long)ncand * S;
+        int blocks = (int)((total + 255) / 256); if (blocks > 148 * 8) blocks = 148 * 8;
+        vi_backup_kernel<<<blocks, 256>>>(S, A, Z, G, dT, dO, dR, dG, discount, dAll + (size_t)keep_old * S, dAllAct + keep_old);
+        int pb = (n + 127) / 128; if (pb > 148 * 8) pb = 148 * 8;
+        vi_prune_kernel<<<pb, 128>>>(S, n, dAll, 1e-10, dKeep);
+        vi_compact_kernel<<<1, 1024>>>(S, n, dAll, dAllAct, dKeep, dNext, dNextAct, dN);
+        VCK(cudaGetLastError());
+        int newG = 0;
+        VCK(cudaMemcpy(&newG, dN, sizeof(int32_t), cudaMemcpyDeviceToHost));
+        if (newG > capacity) { snprintf(err, errlen, "capacity %d too small: %d vectors at horizon %d", capacity, newG, k + 1); rc = -2; break; }
+        VCK(cudaMemcpy(dG, dNext, sizeof(double) * (size_t)newG * S, cudaMemcpyDeviceToDevice));
+        VCK(cudaMemcpy(dAct, dNextAct, sizeof(int32_t) * newG, cudaMemcpyDeviceToDevice));
+        G = newG;
+    }
+    if (rc == 0) {
+        VCK(cudaMemcpy(alpha_out, dG, sizeof(double) * (size_t)G * S, cudaMemcpyDeviceToHost));
+        VCK(cudaMemcpy(action_out, dAct, sizeof(int32_t) * G, cudaMemcpyDeviceToHost));
+        *n_out = G;
+    }
+    cudaFree(dT); cudaFree(dO); cudaFree(dR); cudaFree(dG); cudaFree(dAct); cudaFree(dAll); cudaFree(dAllAct);
+    cudaFree(dNext); cudaFree(dNextAct); cudaFree(dKeep); cudaFree(dN);
+    return rc;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Textbook projection for large |S|: B[s'][o*G+g] = O[a][s'][o] * gamma[g][s'], then C = T_a . B with the fp64
+// tensor cores (mma.sync m8n8k4 f64 -- tcgen05 has no fp64 kind; DMMA is the fp64 tensor path on Blackwell).
+// ---------------------------------------------------------------------------------------------------------
+__global__ void vi_scale_kernel(int S, int Z, int G, const double *__restrict__ Oa, const double *__restrict__ gamma,
+                                double *__restrict__ B)
+{
+    const long long total = (long long)S * Z * G;
+    for (long long idx = blockIdx.x * (long long)blockDim.x + threadIdx.x; idx < total;
+         idx += (long long)gridDim.x * blockDim.x) {
+        const int col = (int)(idx % ((long long)Z * G));
+        const int sp = (int)(idx / ((long long)Z * G));
+        const int o = col / G, g = col - o * G;
+        B[idx] = Oa[(size_t)sp * Z + o] * gamma[(size_t)g * S + sp];
+    }
+}
+
+// C[M x N] = A[M x K] . B[K x N], row-major fp64.  Block tile 64 x 64, k-step 16 through shared memory; 8 warps, each
+// owning a 16 x 32 sub-tile = 2 x 4 DMMA tiles of 8 x 8.  M, N multiples of 64 and K of 16.
+#define GT 64
+#define GK 16
+__global__ void __launch_bounds__(256) vi_dgemm_dmma_kernel(int M, int N, int K, const double *__restrict__ A,
+                                                            const double *__restrict__ B, double *__restrict__ C)
+{
+    __shared__ double sA[GT][GK + 1];        // +1: conflict-free column reads
+    __shared__ double sB[GK][GT + 2];
+    const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
+    const int bm = blockIdx.y * GT, bn = blockIdx.x * GT;
+    const int wm = (warp >> 1) * 16, wn = (warp & 1) * 32;
+    const int gid = lane >> 2, tig = lane & 3;                  // mma.m8n8k4 fragment coordinates
+    double acc[2][4][2];
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
+    for (int k0 = 0; k0 < K; k0 += GK) {
+        for (int e = tid; e < GT * GK; e += 256) {              // A tile: 64 rows x 16 k
+            const int r = e / GK, c = e - r * GK;
+            sA[r][c] = A[(size_t)(bm + r) * K + k0 + c];
+        }
+        for (int e = tid; e < GK * GT; e += 256) {              // B tile: 16 k x 64 cols
+            const int r = e / GT, c = e - r * GT;
+            sB[r][c] = B[(size_t)(k0 + r) * N + bn + c];
+        }
+        __syncthreads();
+#pragma unroll
+        for (int kk = 0; kk < GK; kk += 4) {
+            double a[2], b[4];
+#pragma unroll
+            for (int i = 0; i < 2; ++i) a[i] = sA[wm + i * 8 + gid][kk + tig];     // A fragment: row gid, col tig
+#pragma unroll
+            for (int j = 0; j < 4; ++j) b[j] = sB[kk + tig][wn + j * 8 + gid];     // B fragment: row tig, col gid
+#pragma unroll
+            for (int i = 0; i < 2; ++i)
+#pragma unroll
+                for (int j = 0; j < 4; ++j)
+                    asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
+                                 : "+d"(acc[i][j][0]), "+d"(acc[i][j][1]) : "d"(a[i]), "d"(b[j]));
+        }
+        __syncthreads();
+    }
+#pragma unroll
+    for (int i = 0; i < 2; ++i)
+#pragma unroll
+        for (int j = 0; j < 4; ++j) {                           // C fragment: row gid, cols 2*tig, 2*tig+1
+            const int r = bm + wm + i * 8 + gid, c = bn + wn + j * 8 + 2 * tig;
+            *reinterpret_cast<double2 *>(&C[(size_t)r * N + c]) = make_double2(acc[i][j][0], acc[i][j][1]);
+        }
+}
+
+extern "C" int vi_project_textbook_dev(int device, int S, int A, int Z, int G, const double *T_dev, const double *O_dev,
+                                       const double *gamma_dev, double *scratch_dev, double *proj_dev, void *stream,
+                                       char *err, int errlen)
+{
+    const int N = Z * G;
+    if (S % GT || N % GT || S % GK) { snprintf(err, errlen, "S and Z*G must be multiples of 64"); return -1; }
+    VCK(cudaSetDevice(device));
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int a = 0; a < A; ++a) {
+        vi_scale_kernel<<<148 * 8, 256, 0, st>>>(S, Z, G, O_dev + (size_t)a * S * Z, gamma_dev, scratch_dev);
+        dim3 grid(N / GT, S / GT);
+        vi_dgemm_dmma_kernel<<<grid, 256, 0, st>>>(S, N, S, T_dev + (size_t)a * S * S, scratch_dev,
+                                                   proj_dev + (size_t)a * S * N);
+    }
+    VCK(cudaGetLastError());
+    return 0;
+}

@@ -1,0 +1,155 @@
+"""Exact value iteration on the GPU: the drop-in for the reference's ValueIteration solver
+(pomdpy/solvers/value_iteration.py:9-181, pomdpy/solvers/alpha_vector.py:1-11).
+
+Same surface: ValueIteration.reset(agent), .value_iteration(t, o, r, horizon), .gamma (a set of AlphaVector),
+.select_action(belief, vector_set), .prune(n_states).  The alpha-vector backup (the reference's own projection
+formula) and the dominance prune run as CUDA kernels behind vi_solve_reference(); the prune is the
+pointwise test that the reference's pairwise linear program computes (delta = 1e-10), applied in a fixed order so
+that, unlike the reference (A.9), the result is deterministic."""
+import ctypes as C
+import time
+
+import numpy as np
+
+from . import native
+from .solvers.solver import Solver
+from .util import console, print_divider
+
+module = "ValueIteration"
+
+
+class AlphaVector(object):
+    """An alpha vector and the action it belongs to (alpha_vector.py:1-11)."""
+
+    def __init__(self, a, v):
+        self.action = a
+        self.v = v
+
+    def copy(self):
+        return AlphaVector(self.action, self.v)
+
+
+def _lib():
+    L = native.load()
+    if not getattr(L, "_vi_ready", False):
+        P, dbl, i32 = C.POINTER, C.c_double, C.c_int32
+        L.vi_solve_reference.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, P(dbl), P(dbl), P(dbl), dbl, C.c_int,
+                                         C.c_int, P(dbl), P(i32), P(i32), C.c_char_p, C.c_int]
+        L.vi_project_textbook_dev.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
+                                              C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+        L._vi_ready = True
+    return L
+
+
+def solve_reference(T, O, R, discount, horizon, capacity=4096, device=0):
+    """(alpha [n][S], action [n]) after `horizon` backups with the reference's formula; fp64 on the device."""
+    T = np.ascontiguousarray(T, dtype=np.float64)
+    O = np.ascontiguousarray(O, dtype=np.float64)
+    R = np.ascontiguousarray(R, dtype=np.float64)
+    A, S, _ = T.shape
+    Z = O.shape[2]
+    alpha = np.zeros((capacity, S), dtype=np.float64)
+    act = np.zeros(capacity, dtype=np.int32)
+    n = C.c_int32()
+    err = C.create_string_buffer(256)
+    p = lambda a, t: a.ctypes.data_as(C.POINTER(t))
+    rc = _lib().vi_solve_reference(int(device), S, A, Z, p(T, C.c_double), p(O, C.c_double), p(R, C.c_double),
+                                   float(discount), int(horizon), int(capacity), p(alpha, C.c_double),
+                                   p(act, C.c_int32), C.byref(n), err, 256)
+    if rc != 0:
+        raise native.PomcpError(err.value.decode() or "vi_solve_reference failed")
+    return alpha[:n.value].copy(), act[:n.value].copy()
+
+
+def project_textbook(T, O, gamma, device=0):
+    """proj[a][s][o*G+g] = sum_s' T[a,s,s'] O[a,s',o] gamma[g,s'] on the fp64 tensor cores (torch CUDA tensors in,
+    torch CUDA tensor out; |S| and |O|*|G| multiples of 64)."""
+    import torch
+    A, S, _ = T.shape
+    Z, G = O.shape[2], gamma.shape[0]
+    for t in (T, O, gamma):
+        assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+    scratch = torch.empty(S * Z * G, dtype=torch.float64, device=T.device)
+    proj = torch.empty((A, S, Z * G), dtype=torch.float64, device=T.device)
+    err = C.create_string_buffer(256)
+    rc = _lib().vi_project_textbook_dev(int(device), S, A, Z, G, T.data_ptr(), O.data_ptr(), gamma.data_ptr(),
+                                        scratch.data_ptr(), proj.data_ptr(),
+                                        C.c_void_p(torch.cuda.current_stream().cuda_stream), err, 256)
+    if rc != 0:
+        raise native.PomcpError(err.value.decode() or "vi_project_textbook_dev failed")
+    return proj
+
+
+class ValueIteration(Solver):
+    def __init__(self, agent):
+        super(ValueIteration, self).__init__(agent)
+        self.gamma = set()
+        self.history = agent.histories.create_sequence()
+        self.alpha = None
+        self.actions = None
+
+    @staticmethod
+    def reset(agent):
+        return ValueIteration(agent)
+
+    def value_iteration(self, t, o, r, horizon):
+        """Solve for `horizon` planning steps (value_iteration.py:24-73); fills self.gamma."""
+        self.alpha, self.actions = solve_reference(t, o, r, self.model.discount, horizon)
+        self.gamma = {AlphaVector(int(a), v.copy()) for a, v in zip(self.actions, self.alpha)}
+        for k in range(horizon):
+            console(3, module, "planning horizon {}...".format(k))
+        return self.gamma
+
+    def prune(self, n_states):
+        """Already applied after every backup on the device; kept for API compatibility."""
+        return self.gamma
+
+    @staticmethod
+    def select_action(belief, vector_set):
+        """Arg-max of alpha . b (value_iteration.py:161-181)."""
+        best, max_v = None, -np.inf
+        for av in vector_set:
+            v = float(np.dot(av.v, belief))
+            if v > max_v:
+                max_v, best = v, av
+        if best is None:
+            raise ValueError("Vector set should not be empty")
+        return best.action, best
+
+
+def run_value_iteration_experiment(agent):
+    """Agent.discounted_return, ValueIteration branch (agent.py:37-45, 215-264)."""
+    model = agent.model
+    solver = agent.solver_factory(agent)
+    t0 = time.time()
+    solver.value_iteration(model.get_transition_matrix(), model.get_observation_matrix(), model.get_reward_matrix(),
+                           model.planning_horizon)
+    vectors = sorted(solver.gamma, key=lambda av: (av.action, tuple(av.v)))     # deterministic scan order
+    b = model.get_initial_belief_state()
+    reward, discounted_reward, discount = 0, 0, 1.0
+    model.reset_for_epoch()
+    for i in range(model.max_steps):
+        action, _ = solver.select_action(b, vectors)
+        step_result = model.generate_step(action)
+        if not step_result.is_terminal:
+            b = model.belief_update(b, action, step_result.observation)
+        reward += step_result.reward
+        discounted_reward += discount * step_result.reward
+        discount *= model.discount
+        agent.display_step_result(i, step_result)
+        if step_result.is_terminal:
+            console(3, module, "Terminated after episode step " + str(i + 1))
+            break
+    agent.results.time.add(time.time() - t0)
+    agent.results.update_reward_results(reward, discounted_reward)
+    er, r = agent.experiment_results, agent.results
+    er.time.add(r.time.running_total)
+    er.undiscounted_return.add(r.undiscounted_return.running_total)
+    er.discounted_return.add(r.discounted_return.running_total)
+    if getattr(model, "save", False):
+        import pickle
+        with open("VI_planning_horizon_{}.pkl".format(model.planning_horizon), "wb") as f:
+            pickle.dump(solver.gamma, f, protocol=2)
+    console(2, module, "alpha vectors: " + str(len(solver.gamma)))
+    print_divider("medium")
+    return solver

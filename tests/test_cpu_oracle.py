@@ -142,6 +142,8 @@ def test_c_abi_exports_every_declared_symbol():
     hdr = open(os.path.join(ROOT, "include", "pomcp_b200.h")).read()
     declared = set(re.findall(r"\b(pomcp_[a-z_0-9]+)\s*\(", hdr))
     assert declared == set(native.EXPORTS), declared ^ set(native.EXPORTS)
+    declared |= set(re.findall(r"\b(vi_[a-z_0-9]+)\s*\(", open(os.path.join(ROOT, "include", "vi_b200.h")).read()))
+    assert {"vi_solve_reference", "vi_project_textbook_dev"} <= declared
     for name in declared:
         assert isinstance(getattr(L, name), ctypes._CFuncPtr)
 
