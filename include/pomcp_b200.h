@@ -52,6 +52,15 @@ const char *pomcp_last_error(const pomcp_handle *h);
 int pomcp_set_model_rocksample(pomcp_handle *h, int rows, int cols, const int8_t *cell, int start_cell,
                                const uint64_t *thr53, const double rewards[4]);
 
+/* --preferred_actions (pomcp.py:30-31; examples/rock_sample/rock_position_history.py:52-55, 96-137, 170-234): nodes
+ * carry per-rock statistics and their in-tree action set is generate_smart_actions(); prob is the sensor
+ * correctness probability [cell][n_rocks] (rock_model.py:148-150).  Call after the model, before the root belief. */
+int pomcp_set_preferred_actions(pomcp_handle *h, int enabled, const double *prob);
+
+/* RockData of the current root (rock_position_history.py:14-26): chance_good[n_rocks], goodness_number[n_rocks];
+ * returns 1 when preferred actions are off. */
+int pomcp_root_rock_data(pomcp_handle *h, double *chance, int32_t *good);
+
 /* model.actual_rock_states / model.unique_rocks_sampled as bit masks
  * (rock_model.py:263-265 reset_for_epoch, :267-272 update). */
 int pomcp_set_world(pomcp_handle *h, uint32_t actual_rock_mask, uint32_t sampled_rock_mask);

@@ -75,6 +75,12 @@ def lib():
         L.orc_gs_bag.argtypes = [vp, P(u32)]
         L.orc_gs_bag_size.argtypes = [vp]
         L.orc_gs_root_cell.argtypes = [vp]
+        L.orc_gs_set_preferred.argtypes = [vp, i32]
+        L.orc_model_set_prob.argtypes = [vp, P(dbl)]
+        L.orc_rockstats_init.argtypes = [vp, vp]
+        L.orc_rockstats_child.argtypes = [vp, vp, i32, i32, i32, vp]
+        L.orc_smart_mask.restype = u32
+        L.orc_smart_mask.argtypes = [vp, vp, i32]
         _LIB = L
     return _LIB
 
@@ -120,11 +126,37 @@ class Model:
     def legal_mask(self, cell):
         return int(lib().orc_legal_mask(self.h, int(cell)))
 
+    def set_prob(self, prob):
+        """Sensor correctness probabilities [cell][rock] (needed by the preferred-action heuristic)."""
+        p = np.ascontiguousarray(prob, dtype=np.float64).reshape(-1)
+        lib().orc_model_set_prob(self.h, _p(p, C.c_double))
+
     def step(self, cell, rocks, action, u53, actual_mask, sampled_mask):
         w = np.array([actual_mask, sampled_mask], dtype=np.uint32)
         o = StepOut()
         lib().orc_step(self.h, _p(w, C.c_uint32), int(cell), int(rocks), int(action), int(u53), C.byref(o))
         return o
+
+
+class RockStats(C.Structure):
+    """Per-node rock statistics of the preferred-action heuristic (rock_position_history.py:14-26)."""
+    _fields_ = [("chance", C.c_double * 24), ("good", C.c_int32 * 24)]
+
+
+def rockstats_init(model):
+    s = RockStats()
+    lib().orc_rockstats_init(model.h, C.byref(s))
+    return s
+
+
+def rockstats_child(model, parent, cell, action, obs_good):
+    c = RockStats()
+    lib().orc_rockstats_child(model.h, C.byref(parent), int(cell), int(action), int(bool(obs_good)), C.byref(c))
+    return c
+
+
+def smart_mask(model, stats, cell):
+    return int(lib().orc_smart_mask(model.h, C.byref(stats), int(cell)))
 
 
 class RefPOMCP:
@@ -207,6 +239,9 @@ class GsPOMCP:
 
     def set_world(self, actual, sampled):
         lib().orc_gs_set_world(self.h, int(actual), int(sampled))
+
+    def set_preferred(self, enabled=True):
+        lib().orc_gs_set_preferred(self.h, int(bool(enabled)))
 
     def search(self, n_sims, move=0, sim_offset=0, w0=1, growth=1, wmax=1):
         lib().orc_gs_search(self.h, int(n_sims), int(sim_offset), int(move), int(w0), int(growth), int(wmax))

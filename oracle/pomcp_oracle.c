@@ -83,6 +83,9 @@ typedef struct {
     uint32_t legal[ORC_MAX_CELLS];               /* per-cell legal-action bit mask (rock_model.py:218-247) */
     uint64_t thr53[ORC_MAX_CELLS * ORC_MAX_ROCKS]; /* floor(thr * 2^53); CHECK is correct iff u53 <= thr53 */
     double rew_illegal, rew_exit, rew_good, rew_bad; /* signed: -100, +10, +10, -10 (rock_sample_config.json) */
+    int32_t rock_cell[ORC_MAX_ROCKS];            /* cell of rock k */
+    double prob[ORC_MAX_CELLS * ORC_MAX_ROCKS];  /* sensor correctness probability [cell][rock] (rock_model.py:148-150) */
+    int32_t have_prob;
 } orc_model;
 
 typedef struct {
@@ -119,6 +122,7 @@ orc_model *orc_model_create(int rows, int cols, const int8_t *cell, int start_ce
     if (nr > ORC_MAX_ROCKS || 5 + nr > ORC_MAX_ACTIONS) { free(m); return NULL; }
     m->n_rocks = nr; m->n_actions = 5 + nr;                    /* rock_model.py:290-297 */
     for (int c = 0; c < rows * cols; ++c) {
+        if (m->cell[c] >= 0) m->rock_cell[m->cell[c]] = c;
         m->legal[c] = legal_mask_of_cell(m, c);
         for (int k = 0; k < nr; ++k) m->thr53[c * ORC_MAX_ROCKS + k] = thr53[c * nr + k];
     }
@@ -126,6 +130,12 @@ orc_model *orc_model_create(int rows, int cols, const int8_t *cell, int start_ce
     return m;
 }
 void orc_model_destroy(orc_model *m) { free(m); }
+void orc_model_set_prob(orc_model *m, const double *prob /* [cells][n_rocks] */)
+{
+    for (int c = 0; c < m->rows * m->cols; ++c)
+        for (int k = 0; k < m->n_rocks; ++k) m->prob[c * ORC_MAX_ROCKS + k] = prob[c * m->n_rocks + k];
+    m->have_prob = 1;
+}
 uint32_t orc_legal_mask(const orc_model *m, int cell) { return m->legal[cell]; }
 int orc_model_n_actions(const orc_model *m) { return m->n_actions; }
 
@@ -175,6 +185,50 @@ void orc_step(const orc_model *m, const orc_world *w, int cell, uint32_t rocks, 
     }
     o->next_cell = ncell; o->next_rocks = nr; o->obs_good = good; o->obs_empty = empty;
     o->terminal = terminal; o->legal = legal; o->used_uniform = used; o->rewarded_sample = rs; o->reward = r;
+}
+
+/* ------------------------------------------------------------------------ */
+/* Preferred-action heuristic: per-node rock statistics (clean per-node copies; */
+/* the reference shares one list across the tree)                  */
+/* examples/rock_sample/rock_position_history.py:96-137 and :170-234            */
+/* ------------------------------------------------------------------------ */
+typedef struct { double chance[ORC_MAX_ROCKS]; int32_t good[ORC_MAX_ROCKS]; } orc_rockstats;
+
+void orc_rockstats_init(const orc_model *m, orc_rockstats *s)
+{ for (int k = 0; k < m->n_rocks; ++k) { s->chance[k] = 0.5; s->good[k] = 0; } }
+
+/* create_child (:96-137): statistics of the node reached from a node at `cell` by (action, obs_good) */
+void orc_rockstats_child(const orc_model *m, const orc_rockstats *parent, int cell, int a, int obs_good, orc_rockstats *child)
+{
+    *child = *parent;
+    if (a == 4) {
+        int k = m->cell[cell];
+        if (k >= 0 && k < m->n_rocks) { child->chance[k] = 0.0; child->good[k] = -10; }
+    } else if (a >= 5) {
+        int k = a - 5;
+        double p_ok = m->prob[cell * ORC_MAX_ROCKS + k], p_no = 1 - p_ok;
+        double lg = child->chance[k], lb = 1 - lg;
+        if (obs_good) { child->good[k] += 1; lg *= p_ok; lb *= p_no; }
+        else { child->good[k] -= 1; lg *= p_no; lb *= p_ok; }
+        if (!(fabs(lg) < 0.01 && fabs(lb) < 0.01)) child->chance[k] = lg / (lg + lb);   /* :131-135 (the reset is a no-op) */
+    }
+}
+
+/* generate_smart_actions (:170-234) as a bit mask */
+uint32_t orc_smart_mask(const orc_model *m, const orc_rockstats *s, int cell)
+{
+    int code = m->cell[cell];
+    if (code >= 0 && code < m->n_rocks && (s->chance[code] == 1.0 || s->good[code] > 0)) return 1u << 4;
+    int target = -1;
+    for (int k = 0; k < m->n_rocks; ++k) if (s->chance[k] != 0.0 && s->good[k] >= 0) { target = k; break; }
+    if (target < 0) return 1u << 1;                                /* "just head east" */
+    int i = cell / m->cols, j = cell % m->cols, ri = m->rock_cell[target] / m->cols, rj = m->rock_cell[target] % m->cols;
+    uint32_t mask = 0;
+    if (ri > i) mask |= 1u << 2; else if (ri < i) mask |= 1u << 0;
+    if (rj > j) mask |= 1u << 1; else if (rj < j) mask |= 1u << 3;
+    for (int k = 0; k < m->n_rocks; ++k)
+        if (s->chance[k] != 0.0 && s->chance[k] != 1.0 && abs(s->good[k]) < 2) mask |= 1u << (5 + k);
+    return mask;
 }
 
 /* ======================================================================== */
@@ -526,6 +580,7 @@ typedef struct {
     int64_t n[ORC_MAX_ACTIONS];
     int64_t qfix[ORC_MAX_ACTIONS];             /* sum of llrint(q * 2^24) */
     int32_t child[ORC_MAX_ACTIONS][2];
+    orc_rockstats st;                          /* only meaningful with preferred actions */
 } gs_node;
 
 typedef struct {
@@ -536,6 +591,7 @@ typedef struct {
     uint32_t key[2];
     int64_t n_levels, n_rollout_steps, n_created, n_alloc_nodes, n_generations;
     int32_t max_tree_depth;
+    int32_t preferred;                         /* --preferred_actions: in-tree action sets from the rock statistics */
 } orc_gs;
 
 static int32_t gs_new_node(orc_gs *h, int32_t cell)
@@ -566,6 +622,25 @@ orc_gs *orc_gs_create(const orc_model *m, uint32_t actual_mask, uint32_t sampled
 }
 void orc_gs_destroy(orc_gs *h) { if (!h) return; free(h->nodes); free(h->bag); free(h); }
 void orc_gs_set_world(orc_gs *h, uint32_t actual, uint32_t sampled) { h->w.actual_mask = actual; h->w.sampled_mask = sampled; }
+
+/* --preferred_actions (rock_position_history.py:52-55): call right after orc_gs_create; the root gets fresh
+ * statistics (rock_model.py:302-304) and its action set becomes generate_smart_actions(). */
+void orc_gs_set_preferred(orc_gs *h, int enabled)
+{
+    h->preferred = enabled;
+    gs_node *r = &h->nodes[h->root];
+    orc_rockstats_init(h->m, &r->st);
+    r->legal = enabled ? orc_smart_mask(h->m, &r->st, r->cell) : h->m->legal[r->cell];
+}
+
+/* data.create_child + create_action_mapping for a new node (belief_node.py:96-124) */
+static void gs_init_child(orc_gs *h, int32_t child, int32_t parent, int a, int og)
+{
+    if (!h->preferred) return;
+    gs_node *c = &h->nodes[child]; const gs_node *p = &h->nodes[parent];
+    orc_rockstats_child(h->m, &p->st, p->cell, a, og, &c->st);
+    c->legal = orc_smart_mask(h->m, &c->st, c->cell);
+}
 
 static void gs_block(const orc_gs *h, uint32_t k, uint32_t sim, uint32_t move, uint32_t dom, uint32_t x[4])
 {
@@ -801,6 +876,7 @@ int orc_gs_search(orc_gs *h, int64_t n_sims, uint32_t sim_offset, uint32_t move,
                 int64_t Nx = 0; for (int b = 0; b < 32; ++b) Nx += nd->n[b];
                 if (child < 0 && !o.terminal && Nx > 0 && d + 1 < dcap) {   /* solvers/pomcp.py:107 */
                     child = gs_new_node(h, o.next_cell); nd = &h->nodes[X];
+                    gs_init_child(h, child, X, a, og);
                     nd->child[a][og] = child; h->n_created++;
                 }
                 s->cell = o.next_cell; s->rocks = o.next_rocks;
@@ -896,6 +972,7 @@ int64_t orc_gs_update(orc_gs *h, int action, int obs_good, uint32_t sampled_mask
     if (child < 0) {
         orc_step_out o; orc_step(h->m, &h->w, root->cell, 0, action, 0, &o);
         child = gs_new_node(h, o.next_cell); *status = 1;
+        gs_init_child(h, child, h->root, action, obs_good ? 1 : 0);
     }
     h->root = child;
     free(h->bag); h->bag = nb; h->n_bag = (int32_t)got;

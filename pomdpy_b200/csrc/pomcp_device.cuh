@@ -63,6 +63,7 @@ struct ModelHeader {            // lives in global memory; copied verbatim into 
     int8_t cell[256];           // rock k >= 0 | EMPTY -1 | GOAL -2 | OBSTACLE -3
     uint32_t legal[256];        // legal-action bit mask of each cell (rock_model.py:218-247)
     uint8_t nth5[32 * 8];       // nth5[m*8 + j] = index of the j-th set bit of the 5-bit mask m
+    int32_t rock_cell[24];      // cell of rock k (preferred-action heuristic)
 };
 
 struct SmemModel {
@@ -119,4 +120,51 @@ __device__ __forceinline__ int nth_bit(uint32_t mask, uint32_t j)
 {
     for (uint32_t i = 0; i < j; ++i) mask &= mask - 1;
     return __ffs((int)mask) - 1;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// --preferred_actions: per-node rock statistics (examples/rock_sample/rock_position_history.py).  A node keeps, per
+// rock, the Bayes estimate chance_good (fp64) and the goodness number; a child copies its parent's and updates the
+// one rock the (action, observation) pair concerns (create_child, :96-137); the node's in-tree action set is
+// generate_smart_actions (:170-234).  Clean per-node copies (the reference shares one list tree-wide).
+// ---------------------------------------------------------------------------------------------------------
+#define POMCP_RS 24            // rock stride of the statistics arrays
+
+// Statistics of the child of node X under (a, og) -> its smart-action mask; stored for node `store_id` if >= 0.
+__device__ __noinline__ uint32_t child_smart_mask(const ModelHeader *H, const double *prob, const double *chance,
+                                                  const int16_t *good, double *chance_out, int16_t *good_out,
+                                                  int pcell, int a, int og, int ccell)
+{
+    const int K = H->n_rocks;
+    int kmod = -1, gdk = 0; double chk = 0.0;
+    if (a == 4) {
+        const int k = H->cell[pcell];
+        if (k >= 0 && k < K) { kmod = k; chk = 0.0; gdk = -10; }
+    } else if (a >= 5) {
+        kmod = a - 5;
+        const double p_ok = prob[pcell * K + kmod], p_no = 1 - p_ok;
+        double lg = chance[kmod], lb = 1 - lg;
+        gdk = good[kmod];
+        if (og) { gdk += 1; lg *= p_ok; lb *= p_no; }
+        else { gdk -= 1; lg *= p_no; lb *= p_ok; }
+        chk = (fabs(lg) < 0.01 && fabs(lb) < 0.01) ? chance[kmod] : lg / (lg + lb);
+    }
+    const int code = H->cell[ccell];
+    int target = -1; uint32_t checks = 0; bool sample_only = false;
+    for (int k = 0; k < K; ++k) {
+        const double ch = (k == kmod) ? chk : chance[k];
+        const int gd = (k == kmod) ? gdk : (int)good[k];
+        if (chance_out) { chance_out[k] = ch; good_out[k] = (int16_t)gd; }
+        if (k == code && (ch == 1.0 || gd > 0)) sample_only = true;
+        if (target < 0 && ch != 0.0 && gd >= 0) target = k;
+        if (ch != 0.0 && ch != 1.0 && gd > -2 && gd < 2) checks |= 1u << (5 + k);
+    }
+    if (sample_only) return 1u << 4;
+    if (target < 0) return 1u << 1;
+    const int i = ccell / H->cols, j = ccell - i * H->cols;
+    const int ri = H->rock_cell[target] / H->cols, rj = H->rock_cell[target] - ri * H->cols;
+    uint32_t mask = checks;
+    if (ri > i) mask |= 1u << 2; else if (ri < i) mask |= 1u << 0;
+    if (rj > j) mask |= 1u << 1; else if (rj < j) mask |= 1u << 3;
+    return mask;
 }

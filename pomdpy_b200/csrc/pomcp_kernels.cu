@@ -61,6 +61,9 @@ struct Tree {                          // structure-of-arrays belief-tree arena
     int32_t *cell;                     // [cap]       robot cell of the node
     unsigned long long *arrive;        // [cap]       (stamp << 32) | arrivals in the current level step
     int32_t *slot;                     // [cap]       worklist slot of the node in the current level step
+    double *chance;                    // [cap][24]   --preferred_actions: chance_good per rock (null otherwise)
+    int16_t *good;                     // [cap][24]   --preferred_actions: goodness number per rock
+    const double *prob;                // [cells][n_rocks] sensor correctness probability
 };
 
 struct SimBuf {                        // per simulation-in-flight scratch, SoA over the generation
@@ -259,14 +262,13 @@ struct SimCtx {
 // A simulation standing at a node without statistics (N = 0): every legal action is untried, so UCB1 is a uniform
 // draw (action_selectors.py:6-37 with +inf bonuses), the node cannot be expanded (solvers/pomcp.py:107) and the
 // simulation ends in a rollout.  `node_ref` is the node id, or -1 - child_slot while the id is being published.
-__device__ __noinline__ void virgin_step(const SimCtx &c, int i, uint32_t sim, int node_ref, uint32_t cell,
-                                            uint32_t rocks, int d, long long &c_levels)
+__device__ __noinline__ void virgin_step(const SimCtx &c, int i, uint32_t sim, int node_ref, uint32_t mask,
+                                         uint32_t cell, uint32_t rocks, int d, long long &c_levels)
 {
     const SearchParams &p = c.p;
     if (d >= p.max_depth) { p.b.flag[i] = 2; p.b.depth[i] = (uint8_t)d; return; }          // solvers/pomcp.py:100
     const Philox4 r = philox4x32_10((uint32_t)(d + 1), sim, p.move, DOM_SIM, p.key0, p.key1);
-    const uint32_t mask = c.M.hdr->legal[cell];
-    const int a = nth_legal(c.M.hdr, mask, randbelow32(r.x, (uint32_t)__popc(mask)));
+    const int a = nth_bit(mask, randbelow32(r.x, (uint32_t)__popc(mask)));
     const StepResult sr = rs_step(c.M, cell, rocks, a, u53_of(r.y, r.z), c.actual, c.sampled);
     ++c_levels;
     p.b.path_node[(size_t)d * p.wmax + i] = node_ref;
@@ -331,6 +333,7 @@ pomcp_search_kernel(const SearchParams p)
         ++gens;
         // ---- start of a generation: every simulation draws a root particle (belief_node.py:47-48) ----
         const bool root_virgin = row_sum(p.t.n + (size_t)root * AS) == 0;
+        const uint32_t root_mask = p.t.legal[root];
         if (!root_virgin && gwarp == 0) {                            // all w simulations arrive at the root
             if (lane == 0) {
                 const unsigned long long s1 = gstep + 1;
@@ -346,7 +349,7 @@ pomcp_search_kernel(const SearchParams p)
             const uint32_t sim = p.sim_offset + (uint32_t)(done + i);
             const Philox4 r = philox4x32_10(0u, sim, p.move, DOM_SIM, p.key0, p.key1);
             const uint32_t st = bag[randbelow32(r.x, (uint32_t)n_bag)];
-            if (root_virgin) virgin_step(ctx, i, sim, root, st & 0xFFu, st >> 8, 0, c_levels);
+            if (root_virgin) virgin_step(ctx, i, sim, root, root_mask, st & 0xFFu, st >> 8, 0, c_levels);
             else { p.b.state[i] = st; p.b.node[i] = root; p.b.flag[i] = 0; p.b.depth[i] = 0; }
         }
         PHASE_MARK(0);
@@ -413,6 +416,7 @@ pomcp_search_kernel(const SearchParams p)
                         if (sr.terminal) p.b.flag[i] = 2;
                         else {
                             const size_t cslot = ((size_t)X * AS + a) * 2 + sr.good;
+                            uint32_t cmask = H->legal[sr.cell]; bool have_mask = false;     // the child's action set
                             uint32_t c = p.t.child[cslot];                                  // :106
                             if (c == 0 && d + 1 < p.dcap) {                                 // :107-108 (N(X) > 0 here)
                                 c = atomicCAS(&p.t.child[cslot], 0u, CHILD_LOCKED);
@@ -423,19 +427,30 @@ pomcp_search_kernel(const SearchParams p)
                                     if (rk == 0) id0 = atomicAdd(&S->node_count, __popc(am));
                                     const int id = __shfl_sync(am, id0, __ffs((int)am) - 1) + rk;
                                     p.t.cell[id] = (int32_t)sr.cell;
-                                    p.t.legal[id] = H->legal[sr.cell];
+                                    if (p.t.chance)                                         // create_child + smart action set
+                                        cmask = child_smart_mask(H, p.t.prob, p.t.chance + (size_t)X * POMCP_RS,
+                                                                 p.t.good + (size_t)X * POMCP_RS,
+                                                                 p.t.chance + (size_t)id * POMCP_RS,
+                                                                 p.t.good + (size_t)id * POMCP_RS, (int)(st & 0xFFu), a,
+                                                                 sr.good, (int)sr.cell);
+                                    p.t.legal[id] = cmask;
+                                    __threadfence();                                        // node fields before its id
                                     atomicExch(&p.t.child[cslot], (uint32_t)id + 1u);
                                     ++c_created;
-                                    c = CHILD_LOCKED;
+                                    c = CHILD_LOCKED; have_mask = true;
                                 }
                             }
                             if (c == 0) p.b.flag[i] = 1;                                    // depth cap: leaf (:119)
-                            else if (c == CHILD_LOCKED)                                     // created in this step
-                                virgin_step(ctx, i, sim, -1 - (int)cslot, sr.cell, sr.rocks, d + 1, c_levels);
-                            else {
+                            else if (c == CHILD_LOCKED) {                                   // created in this step
+                                if (p.t.chance && !have_mask)                               // id not published yet: derive the set
+                                    cmask = child_smart_mask(H, p.t.prob, p.t.chance + (size_t)X * POMCP_RS,
+                                                             p.t.good + (size_t)X * POMCP_RS, nullptr, nullptr,
+                                                             (int)(st & 0xFFu), a, sr.good, (int)sr.cell);
+                                virgin_step(ctx, i, sim, -1 - (int)cslot, cmask, sr.cell, sr.rocks, d + 1, c_levels);
+                            } else {
                                 const int id = (int)c - 1;
                                 if (row_sum(p.t.n + (size_t)id * AS) == 0)
-                                    virgin_step(ctx, i, sim, id, sr.cell, sr.rocks, d + 1, c_levels);
+                                    virgin_step(ctx, i, sim, id, p.t.legal[id], sr.cell, sr.rocks, d + 1, c_levels);
                                 else { p.b.node[i] = id; arrive_at = id; arrive_slot = a * 2 + sr.good; }   // descend
                             }
                         }
@@ -665,7 +680,13 @@ pomcp_advance_kernel(const AdvanceParams p)
             if (c == 0) {                                            // never expanded: fresh node at the next position
                 id = S->node_count++;
                 const StepResult sr = rs_step(M, (uint32_t)p.t.cell[root], 0u, p.action, 0ull, actual, sampled);
-                p.t.cell[id] = (int32_t)sr.cell; p.t.legal[id] = M.hdr->legal[sr.cell];
+                p.t.cell[id] = (int32_t)sr.cell;
+                uint32_t lm = M.hdr->legal[sr.cell];
+                if (p.t.chance)
+                    lm = child_smart_mask(M.hdr, p.t.prob, p.t.chance + (size_t)root * POMCP_RS, p.t.good + (size_t)root * POMCP_RS,
+                                          p.t.chance + (size_t)id * POMCP_RS, p.t.good + (size_t)id * POMCP_RS, p.t.cell[root],
+                                          p.action, p.obs_good, (int)sr.cell);
+                p.t.legal[id] = lm;
                 status = 1;
             } else id = (int)c - 1;
             S->root = id; S->n_bag = accepted; S->bag_sel ^= 1;                        // :210
@@ -694,12 +715,24 @@ extern "C" __global__ void pomcp_step_batch_kernel(const ModelHeader *model, con
     }
 }
 
-// Reset the arena prefix and plant a root (fresh tree).
-__global__ void pomcp_plant_root_kernel(DevState *S, Tree t, int root_cell, uint32_t legal, int n_bag, int bag_sel)
+// Plant a root (fresh tree).  With --preferred_actions the root gets fresh rock statistics (rock_model.py:302-304)
+// and the smart action set; `keep_stats` re-plants the current root's statistics (tree reset within an episode).
+__global__ void pomcp_plant_root_kernel(DevState *S, Tree t, const ModelHeader *H, int root_cell, uint32_t legal,
+                                        int n_bag, int bag_sel, int keep_stats)
 {
     if (blockIdx.x == 0 && threadIdx.x == 0) {
+        const int old_root = S->root;
         S->root = 0; S->node_count = 1; S->n_bag = n_bag; S->bag_sel = bag_sel;
-        t.cell[0] = root_cell; t.legal[0] = legal;
+        t.cell[0] = root_cell;
+        if (t.chance) {
+            double ch[POMCP_RS]; int16_t gd[POMCP_RS];
+            for (int k = 0; k < H->n_rocks; ++k) {
+                ch[k] = keep_stats ? t.chance[(size_t)old_root * POMCP_RS + k] : 0.5;
+                gd[k] = keep_stats ? t.good[(size_t)old_root * POMCP_RS + k] : (int16_t)0;
+            }
+            legal = child_smart_mask(H, t.prob, ch, gd, t.chance, t.good, root_cell, 0, 0, root_cell);   // a = 0: no update
+        }
+        t.legal[0] = legal;
     }
 }
 
@@ -762,7 +795,7 @@ static void free_all(pomcp_handle *h)
 {
     cudaFree(h->dS); cudaFree(h->dmodel); cudaFree(h->dthr);
     cudaFree(h->t.n); cudaFree(h->t.qfix); cudaFree(h->t.child); cudaFree(h->t.legal); cudaFree(h->t.cell);
-    cudaFree(h->t.arrive); cudaFree(h->t.slot);
+    cudaFree(h->t.arrive); cudaFree(h->t.slot); cudaFree(h->t.chance); cudaFree(h->t.good); cudaFree((void *)h->t.prob);
     cudaFree(h->b.state); cudaFree(h->b.node); cudaFree(h->b.flag); cudaFree(h->b.depth); cudaFree(h->b.path_node);
     cudaFree(h->b.path_ar); cudaFree(h->b.wl_node); cudaFree(h->b.wl_thr); cudaFree(h->b.wl_meta);
     cudaFree(h->bag[0]); cudaFree(h->bag[1]);
@@ -853,6 +886,7 @@ extern "C" int pomcp_set_model_rocksample(pomcp_handle *h, int rows, int cols, c
             if (m.cell[c] >= 0) mask |= 16u;
             m.legal[c] = mask;
         }
+    for (int c = 0; c < m.n_cells; ++c) if (m.cell[c] >= 0) m.rock_cell[m.cell[c]] = c;
     for (int mk = 0; mk < 32; ++mk) {
         int j = 0;
         for (int bit = 0; bit < 5; ++bit) if ((mk >> bit) & 1) m.nth5[mk * 8 + j++] = (uint8_t)bit;
@@ -880,6 +914,42 @@ extern "C" int pomcp_set_model_rocksample(pomcp_handle *h, int rows, int cols, c
     return 0;
 }
 
+extern "C" int pomcp_set_preferred_actions(pomcp_handle *h, int enabled, const double *prob)
+{
+    if (!h) return -1;
+    if (!h->have_model) return fail(h, "set the model first");
+    CK(cudaSetDevice(h->device));
+    CK(cudaDeviceSynchronize());
+    cudaFree(h->t.chance); cudaFree(h->t.good); cudaFree((void *)h->t.prob);
+    h->t.chance = nullptr; h->t.good = nullptr; h->t.prob = nullptr;
+    h->have_root = false;                                    // the tree must be re-planted
+    if (!enabled) return 0;
+    if (!prob) return fail(h, "preferred actions need the sensor probability table");
+    double *dp;
+    CK(cudaMalloc(&dp, sizeof(double) * (size_t)h->n_thr));
+    CK(cudaMemcpy(dp, prob, sizeof(double) * (size_t)h->n_thr, cudaMemcpyHostToDevice));
+    h->t.prob = dp;
+    CK(cudaMalloc(&h->t.chance, sizeof(double) * (size_t)h->cap * POMCP_RS));
+    CK(cudaMalloc(&h->t.good, sizeof(int16_t) * (size_t)h->cap * POMCP_RS));
+    return 0;
+}
+
+extern "C" int pomcp_root_rock_data(pomcp_handle *h, double *chance, int32_t *good)
+{
+    if (!h) return -1;
+    if (!h->have_root) return fail(h, "no root belief");
+    if (!h->t.chance) return 1;
+    CK(cudaSetDevice(h->device));
+    CK(cudaStreamSynchronize(h->last_stream));
+    int32_t root;
+    CK(cudaMemcpy(&root, &h->dS->root, sizeof(root), cudaMemcpyDeviceToHost));
+    int16_t gd[POMCP_RS];
+    CK(cudaMemcpy(chance, h->t.chance + (size_t)root * POMCP_RS, sizeof(double) * h->hmodel.n_rocks, cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(gd, h->t.good + (size_t)root * POMCP_RS, sizeof(gd), cudaMemcpyDeviceToHost));
+    for (int k = 0; k < h->hmodel.n_rocks; ++k) good[k] = gd[k];
+    return 0;
+}
+
 extern "C" int pomcp_set_world(pomcp_handle *h, uint32_t actual, uint32_t sampled)
 {
     if (!h) return -1;
@@ -903,10 +973,11 @@ static int clear_arena(pomcp_handle *h, cudaStream_t s)
     return 0;
 }
 
-static int plant_root(pomcp_handle *h, int root_cell, int n_bag, int bag_sel, cudaStream_t s)
+static int plant_root(pomcp_handle *h, int root_cell, int n_bag, int bag_sel, cudaStream_t s, int keep_stats)
 {
     if (clear_arena(h, s)) return -1;
-    pomcp_plant_root_kernel<<<1, 32, 0, s>>>(h->dS, h->t, root_cell, h->hmodel.legal[root_cell], n_bag, bag_sel);
+    pomcp_plant_root_kernel<<<1, 32, 0, s>>>(h->dS, h->t, h->dmodel, root_cell, h->hmodel.legal[root_cell], n_bag, bag_sel,
+                                             keep_stats);
     CK(cudaGetLastError());
     ++h->launches;
     h->nodes_used = 1; h->zeroed_upto = 1; h->root_cell = root_cell; h->n_bag = n_bag;
@@ -928,7 +999,7 @@ extern "C" int pomcp_set_root_particles(pomcp_handle *h, const uint32_t *packed,
         h->bag_cap = need;
     }
     CK(cudaMemcpy(h->bag[0], packed, (size_t)n * sizeof(uint32_t), cudaMemcpyHostToDevice));
-    if (plant_root(h, root_cell, n, 0, 0)) return -1;
+    if (plant_root(h, root_cell, n, 0, 0, 0)) return -1;
     CK(cudaDeviceSynchronize());
     h->have_root = true; h->bag_sel = 0;
     return 0;
@@ -941,7 +1012,7 @@ extern "C" int pomcp_reset_tree(pomcp_handle *h, void *stream)
     CK(cudaSetDevice(h->device));
     cudaStream_t s = (cudaStream_t)stream;
     h->last_stream = s;
-    return plant_root(h, h->root_cell, h->n_bag, h->bag_sel, s);
+    return plant_root(h, h->root_cell, h->n_bag, h->bag_sel, s, 1);
 }
 
 extern "C" int pomcp_root_stats_device(pomcp_handle *h, int64_t *dev_out, void *stream)
@@ -968,7 +1039,7 @@ extern "C" int pomcp_search(pomcp_handle *h, int64_t n_sims, uint32_t sim_offset
     if (h->nodes_used + n_sims + 2 > h->cap) {          // every simulation creates at most one node
         if (n_sims + 3 > h->cap) return fail(h, "node_capacity smaller than n_sims + 3");
         // drop the subtree, keep the belief (documented degradation; status 1)
-        if (plant_root(h, h->root_cell, h->n_bag, h->bag_sel, s)) return -1;
+        if (plant_root(h, h->root_cell, h->n_bag, h->bag_sel, s, 1)) return -1;
         rc = 1;
     }
     SearchParams p;

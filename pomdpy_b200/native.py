@@ -28,7 +28,8 @@ class Config(C.Structure):
 EXPORTS = ["pomcp_create", "pomcp_destroy", "pomcp_last_error", "pomcp_set_model_rocksample", "pomcp_set_world",
            "pomcp_set_root_particles", "pomcp_search", "pomcp_root_stats", "pomcp_node_stats", "pomcp_advance",
            "pomcp_root_particles", "pomcp_generate_steps", "pomcp_counters", "pomcp_root_stats_device",
-           "pomcp_reset_tree", "pomcp_debug_steplog"]
+           "pomcp_reset_tree", "pomcp_debug_steplog", "pomcp_set_preferred_actions",
+           "pomcp_root_rock_data"]
 
 
 def library_path():
@@ -71,6 +72,8 @@ def load(build_if_missing=True):
     L.pomcp_root_stats_device.argtypes = [vp, vp, vp]
     L.pomcp_reset_tree.argtypes = [vp, vp]
     L.pomcp_debug_steplog.argtypes = [vp, P(i64)]
+    L.pomcp_set_preferred_actions.argtypes = [vp, C.c_int, P(dbl)]
+    L.pomcp_root_rock_data.argtypes = [vp, P(dbl), P(i32)]
     _LIB = L
     return L
 
@@ -125,6 +128,21 @@ class Planner:
                                                      int(start_cell), _p(thr53, C.c_uint64),
                                                      _p(rewards, C.c_double)))
         self.n_actions = 5 + n_rocks
+
+    def set_preferred_actions(self, enabled, prob=None):
+        """--preferred_actions: in-tree action sets from per-node rock statistics; prob [cells][n_rocks] float64."""
+        if enabled:
+            prob = np.ascontiguousarray(prob, dtype=np.float64).reshape(-1)
+            self._ck(self.lib.pomcp_set_preferred_actions(self.h, 1, _p(prob, C.c_double)))
+        else:
+            self._ck(self.lib.pomcp_set_preferred_actions(self.h, 0, None))
+
+    def root_rock_data(self):
+        ch = np.zeros(24, dtype=np.float64)
+        gd = np.zeros(24, dtype=np.int32)
+        rc = self._ck(self.lib.pomcp_root_rock_data(self.h, _p(ch, C.c_double), _p(gd, C.c_int32)))
+        n = self.n_actions - 5
+        return None if rc else (ch[:n].copy(), gd[:n].copy())
 
     def set_world(self, actual_mask, sampled_mask):
         self._ck(self.lib.pomcp_set_world(self.h, int(actual_mask), int(sampled_mask)))

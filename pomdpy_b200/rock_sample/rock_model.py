@@ -333,17 +333,19 @@ class RockModel(Model):
             raise ValueError("map too large for the packed device state (<=256 cells, <=24 rocks)")
         cell = np.array(self.env_map, dtype=np.int8).reshape(-1)
         thr53 = np.zeros((n_cells, self.n_rocks), dtype=np.uint64)
+        prob = np.zeros((n_cells, self.n_rocks), dtype=np.float64)
         for i in range(self.n_rows):
             for j in range(self.n_cols):
                 for k, rp in enumerate(self.rock_positions):
                     d = np.sqrt(np.power(rp.j - j, 2.0) + np.power(rp.i - i, 2.0))
                     p = self.get_sensor_correctness_probability(d)
+                    prob[i * self.n_cols + j, k] = p
                     thr53[i * self.n_cols + j, k] = int(math.floor(binomial_threshold(p) * 9007199254740992.0))
         rewards = np.array([-self.illegal_move_penalty, self.exit_reward, self.good_rock_reward,
                             -self.bad_rock_penalty], dtype=np.float64)
         return dict(kind="rocksample", rows=self.n_rows, cols=self.n_cols, n_rocks=self.n_rocks,
                     n_actions=5 + self.n_rocks, cell=cell, start_cell=self.cell_index(self.start_position),
-                    thr53=thr53, rewards=rewards)
+                    thr53=thr53, prob=prob, rewards=rewards)
 
     def world_masks(self):
         """(actual_rock_mask, sampled_rock_mask): the mutable world the device model reads (A.5)."""

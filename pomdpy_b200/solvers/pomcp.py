@@ -73,8 +73,7 @@ class POMCP(Solver):
         self.seed = int(getattr(model, "seed", 1993))
         self.timeout = float(getattr(model, "action_selection_timeout", 60))
         self.max_particle_count = int(getattr(model, "max_particle_count", 2000))
-        if getattr(model, "preferred_actions", False):
-            console(2, module, "--preferred_actions: in-tree action sets are the plain legal sets on the device")
+        self.preferred = bool(getattr(model, "preferred_actions", False))
         d = _dist()
         self.world = d.get_world_size() if d else 1
         self.rank = d.get_rank() if d else 0
@@ -91,6 +90,9 @@ class POMCP(Solver):
         bag = np.fromiter((model.pack_state(model.sample_an_init_state()) for _ in range(n_start)),
                           dtype=np.uint32, count=n_start)
         self.planner.set_world(*model.world_masks())
+        if self.preferred != getattr(self.planner, "_preferred", False):      # rock_position_history.py:52-55
+            self.planner.set_preferred_actions(self.preferred, spec["prob"])
+            self.planner._preferred = self.preferred
         self.planner.set_root_particles(bag, spec["start_cell"])
         self._root_cell = spec["start_cell"]
         self._stats = None
@@ -148,7 +150,12 @@ class POMCP(Solver):
     def root_data(self):
         cell = self._root_cell
         pos = GridPosition(cell // self.model.n_cols, cell % self.model.n_cols)
-        return PositionAndRockData(self.model, pos, [RockData() for _ in range(self.model.n_rocks)], self)
+        rocks = [RockData() for _ in range(self.model.n_rocks)]
+        stats = self.planner.root_rock_data() if self.preferred else None
+        if stats is not None:
+            for rd, ch, gd in zip(rocks, stats[0], stats[1]):
+                rd.chance_good, rd.goodness_number = float(ch), int(gd)
+        return PositionAndRockData(self.model, pos, rocks, self)
 
     def _merged_root_stats(self):
         """Root statistics summed over the ranks: one all-reduce of 2*32 int64 per move."""

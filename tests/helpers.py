@@ -16,7 +16,9 @@ def golden_tables(tag):
 
 
 def oracle_model(t):
-    return oracle.Model(int(t["rows"]), int(t["cols"]), t["cell"], int(t["start_cell"]), t["thr53"], t["rewards"])
+    m = oracle.Model(int(t["rows"]), int(t["cols"]), t["cell"], int(t["start_cell"]), t["thr53"], t["rewards"])
+    m.set_prob(t["prob"])
+    return m
 
 
 def make_planner(t, **kw):

@@ -164,3 +164,30 @@ def test_product_does_not_import_the_oracle():
             if f.endswith((".py", ".cu", ".cuh", ".h")):
                 src = open(os.path.join(dirpath, f)).read()
                 assert "import oracle" not in src and "liboracle" not in src and "pomcp_oracle" not in src, f
+
+
+def test_preferred_action_heuristic_golden():
+    """create_child / generate_smart_actions (rock_position_history.py:96-137, 170-234): the oracle's per-node
+    functions and the product's host classes against node states recorded from the executed reference."""
+    from pomdpy_b200.rock_sample import PositionAndRockData, RockAction, RockData, RockModel, RockObservation
+    with open(os.path.join(GOLDEN, "smart_actions.json")) as f:
+        chains = json.load(f)["chains"]
+    models, oms = {}, {}
+    for ch in chains:
+        tag = ch["map"]
+        if tag not in models:
+            models[tag] = RockModel(dict(map_file=tag, discount=0.95, preferred_actions=True))
+            oms[tag] = oracle_model(golden_tables(tag))
+        m, om = models[tag], oms[tag]
+        K = m.n_rocks
+        data = PositionAndRockData(m, m.start_position.copy(), [RockData() for _ in range(K)], None)
+        st, cell = oracle.rockstats_init(om), om.start_cell
+        for s in ch["steps"]:
+            a, good = s["action"], bool(s["obs_good"])
+            data = data.create_child(RockAction(a), RockObservation(good, False) if a >= 4 else RockObservation())
+            st = oracle.rockstats_child(om, st, cell, a, good)
+            cell = s["cell"]
+            assert m.cell_index(data.grid_position) == cell
+            assert [r.goodness_number for r in data.all_rock_data] == s["good"] == [st.good[k] for k in range(K)]
+            assert [r.chance_good for r in data.all_rock_data] == s["chance"] == [st.chance[k] for k in range(K)]
+            assert sum(1 << x for x in data.generate_smart_actions()) == s["mask"] == oracle.smart_mask(om, st, cell)

@@ -45,3 +45,14 @@ def test_solver_surface_matches_what_agent_touches():
     assert not solver.disable_tree and len(solver.belief_tree_index.state_particles) == 2000
     solver.history.add_entry()
     assert solver.history.get_length() == 1
+
+
+def test_cli_preferred_actions_runs():
+    """The README command of the reference (README.md:85): --preferred_actions."""
+    import pomcp as cli
+    agent = cli.main(["--env", "RockSample", "--solver", "POMCP", "--max_steps", "200", "--n_epochs", "20",
+                      "--n_sims", "500", "--seed", "123", "--preferred_actions", "--verbosity", "0"])
+    er = agent.experiment_results
+    print("preferred actions: %.2f +- %.2f" % (er.discounted_return.mean, er.discounted_return.std_err()))
+    assert er.discounted_return.count == 20
+    assert -5.0 < er.discounted_return.mean < 26.0        # reference: 7.2 pooled over 40 epochs (BASELINE.md)

@@ -207,3 +207,42 @@ def test_errors_are_loud():
     with pytest.raises(native.PomcpError):
         native.Planner(tree_depth_cap=1)
     pl.close()
+
+
+@pytest.mark.parametrize("tag,seed,n_sims,sched", [("map-7-8", 51, 1000, (8, 2, 128)), ("map-15-15", 52, 20000, (64, 4, 8192))])
+def test_preferred_actions_episode_bit_exact(tag, seed, n_sims, sched):
+    """--preferred_actions (rock_position_history.py): per-node rock statistics and smart action sets on the
+    device == oracle, over several moves with belief updates (fresh and existing roots)."""
+    w0, growth, wmax = sched
+    kw = dict(seed=seed, gen_w0=w0, gen_growth=growth, gen_wmax=wmax, node_capacity=1 << 17)
+    t = golden_tables(tag)
+    actual, bag, rng = random_world_and_bag(t, seed)
+    om = oracle_model(t)
+    g = oracle.GsPOMCP(om, actual, 0, bag, seed=seed)
+    g.set_preferred(True)
+    pl = make_planner(t, **kw)
+    pl.set_preferred_actions(True, t["prob"])
+    pl.set_world(actual, 0)
+    pl.set_root_particles(bag, int(t["start_cell"]))
+    cell, rocks, sampled = int(t["start_cell"]), int(bag[0] >> 8), 0
+    for mv in range(10):
+        g.search(n_sims, move=mv, w0=w0, growth=growth, wmax=wmax)
+        pl.search(n_sims, move=mv)
+        st = _assert_same_root(g, pl)
+        assert bin(st["legal"]).count("1") < om.n_actions          # the in-tree set is restricted
+        for a in range(om.n_actions):
+            for o in (0, 1):
+                x, y = g.node_stats([(a, o)]), pl.node_stats([(a, o)])
+                assert (x is None) == (y is None)
+                if x is not None:
+                    assert x["legal"] == y["legal"] and np.array_equal(x["n"], y["n"]) and np.array_equal(x["qfix"], y["qfix"])
+        a = g.greedy(move=mv, stats=st)
+        o = om.step(cell, rocks, a, int(rng.integers(0, 1 << 53)), actual, sampled)
+        cell, rocks = o.next_cell, o.next_rocks
+        if o.terminal or not o.legal:
+            break
+        if a == 4:
+            sampled |= 1 << int(t["cell"][cell])
+        assert g.update(a, o.obs_good, sampled, move=mv) == pl.advance(a, o.obs_good, sampled, move=mv)
+        assert np.array_equal(pl.root_particles()[0], g.bag())
+    pl.close()
