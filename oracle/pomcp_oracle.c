@@ -44,7 +44,7 @@
 #define ORC_CELL_OBSTACLE (-3)
 #define ORC_QFIX_SCALE 16777216.0 /* 2^24 fixed-point scale of summed returns (gs mode) */
 #define ORC_SEQ_ALLOC_MAX 16      /* arrivals <= this: exact virtual-pull allocation; more: water-filling */
-#define ORC_BISECT_ITERS 24
+#define ORC_BISECT_ITERS 14
 
 /* ------------------------------------------------------------------------ */
 /* Philox4x32-10 (Salmon et al., SC'11) -- counter-based RNG shared by spec.  */

@@ -5,7 +5,6 @@
 // pomdpy/action_selection/action_selectors.py:6-37, pomdpy/pomdp/model.py:221-252).  See DESIGN.md.
 //
 // Build: nvcc -gencode arch=compute_100a,code=sm_100a -O3 -lineinfo -fmad=false -shared -Xcompiler -fPIC
-#include <cooperative_groups.h>
 #include <cuda_runtime.h>
 
 #include <cstddef>
@@ -18,17 +17,19 @@
 #include "../../include/pomcp_b200.h"
 #include "pomcp_device.cuh"
 
-namespace cg = cooperative_groups;
-
 #define AS POMCP_AS
 #define CHILD_LOCKED 0xFFFFFFFFu
+#define CHILD_VISITED 0x80000000u   // set on a child slot once a backup has passed through the child (N > 0)
+#define CHILD_ID(c) ((int)((c) & 0x7FFFFFFFu) - 1)
 #define SEARCH_THREADS 256
+#ifndef SEARCH_MIN_BLOCKS
 #define SEARCH_MIN_BLOCKS 4
+#endif
 #define ADV_THREADS 1024
 #define ADV_TRIES 4
 #define SEQ_ALLOC_MAX 16u      // arrivals <= this: exact virtual-pull allocation; more: water-filling
 #ifndef BISECT_ITERS
-#define BISECT_ITERS 24
+#define BISECT_ITERS 14
 #endif
 
 // ---------------------------------------------------------------------------------------------------------
@@ -40,7 +41,8 @@ struct DevState {
     uint32_t actual, sampled;
     int32_t n_bag, bag_sel;
     int32_t wl_count[4];
-    int32_t stop, pad;
+    int32_t stop;
+    uint32_t barrier;                  // arrival counter of grid_barrier (zeroed before each search)
     unsigned long long gstep;          // global level-step stamp, never reused
     long long sims_done;               // simulations completed by the last search
     long long counters[16];
@@ -56,7 +58,7 @@ struct DevState {
 struct Tree {                          // structure-of-arrays belief-tree arena
     int32_t *n;                        // [cap][AS]   visit_count of edge (node, action)
     long long *qfix;                   // [cap][AS]   sum of q in 2^-24 fixed point
-    uint32_t *child;                   // [cap][AS][2] child id + 1 keyed (action, obs_good); 0 = none
+    uint32_t *child;                   // [cap][AS][2] child id + 1 keyed (action, obs_good), bit 31 = has statistics; 0 = none
     uint32_t *legal;                   // [cap]       legal-action mask (fixed at creation)
     int32_t *cell;                     // [cap]       robot cell of the node
     unsigned long long *arrive;        // [cap]       (stamp << 32) | arrivals in the current level step
@@ -91,6 +93,24 @@ struct SearchParams {
     double ucb_c, discount;
     unsigned long long timeout_ns;     // 0 = no wall-clock guard; measured from kernel start
 };
+
+// Grid-wide barrier of the cooperative search kernel: one arrival counter that only grows (zeroed by the host before
+// each launch); block b has passed `epoch` barriers, so barrier e completes when the counter reaches (e+1)*blocks.
+// Waiting threads back off with nanosleep instead of hammering L2, which matters in the phases where a handful of
+// warps work and ~600 blocks wait.  The cooperative launch guarantees that all blocks are resident.
+__device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int nblocks, unsigned int &epoch)
+{
+    __syncthreads();
+    ++epoch;
+    if (threadIdx.x == 0) {
+        __threadfence();                                   // release this block's writes
+        atomicAdd(counter, 1u);
+        const unsigned int target = epoch * nblocks;
+        while (*((volatile unsigned int *)counter) < target) __nanosleep(32);
+        __threadfence();                                   // acquire (also invalidates this SM's L1)
+    }
+    __syncthreads();
+}
 
 __device__ __forceinline__ unsigned long long globaltimer_ns()
 {
@@ -290,7 +310,8 @@ extern "C" __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_BLOCKS)
 pomcp_search_kernel(const SearchParams p)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    cg::grid_group grid = cg::this_grid();
+    unsigned int bar_epoch = 0;
+#define GRID_SYNC() grid_barrier(&p.S->barrier, gridDim.x, bar_epoch)
     SmemModel M;
     size_t off = stage_model(smem, p.model, p.thr53, p.n_thr, M);
     double *disc = reinterpret_cast<double *>(smem + off);          // discount^t, t < max_depth
@@ -326,7 +347,7 @@ pomcp_search_kernel(const SearchParams p)
 #define PHASE_MARK(k) do { if (gtid == 0) { const unsigned long long now_ = globaltimer_ns(); tp[k] += now_ - tmark; tmark = now_; } } while (0)
     const SimCtx ctx{p, M, actual, sampled};
     int W = p.w0;
-    grid.sync();                                                    // everyone has read S before anyone writes it
+    GRID_SYNC();                                                    // everyone has read S before anyone writes it
 
     while (done < p.n_sims) {
         const int w = (int)((p.n_sims - done) < (long long)W ? (p.n_sims - done) : (long long)W);
@@ -357,7 +378,7 @@ pomcp_search_kernel(const SearchParams p)
             ++gstep; ++lsteps;
             const int ring = (int)(gstep & 3ull), ring_next = (int)((gstep + 1) & 3ull);
             const unsigned long long stamp_next = (gstep + 1) << 32;
-            grid.sync();                                             // arrivals of this level are complete
+            GRID_SYNC();                                             // arrivals of this level are complete
             if (gtid == 0 && lsteps <= 128) S->steplog[lsteps - 1][0] = (long long)(globaltimer_ns() - tmark);
             PHASE_MARK(1);
             const int nwl = *((volatile int32_t *)&S->wl_count[ring]);
@@ -381,7 +402,7 @@ pomcp_search_kernel(const SearchParams p)
                 }
             }
             if (gtid == 0 && lsteps <= 128) S->steplog[lsteps - 1][1] = (long long)(globaltimer_ns() - tmark);
-            grid.sync();
+            GRID_SYNC();
             }
             if (gtid == 0 && lsteps <= 128) { S->steplog[lsteps - 1][2] = (long long)(globaltimer_ns() - tmark) - S->steplog[lsteps - 1][1]; S->steplog[lsteps - 1][4] = nwl; }
             PHASE_MARK(2);
@@ -419,7 +440,12 @@ pomcp_search_kernel(const SearchParams p)
                             uint32_t cmask = H->legal[sr.cell]; bool have_mask = false;     // the child's action set
                             uint32_t c = p.t.child[cslot];                                  // :106
                             if (c == 0 && d + 1 < p.dcap) {                                 // :107-108 (N(X) > 0 here)
-                                c = atomicCAS(&p.t.child[cslot], 0u, CHILD_LOCKED);
+                                // one CAS per distinct child slot among the lanes that got here together
+                                const unsigned cm = __activemask();
+                                const unsigned same = __match_any_sync(cm, (unsigned long long)cslot);
+                                if (lane == __ffs((int)same) - 1) c = atomicCAS(&p.t.child[cslot], 0u, CHILD_LOCKED);
+                                c = __shfl_sync(same, c, __ffs((int)same) - 1);
+                                if (lane != __ffs((int)same) - 1 && c == 0) c = CHILD_LOCKED;   // the group leader creates it
                                 if (c == 0) {                                               // this thread creates it
                                     const unsigned am = __activemask();                     // one arena bump per warp
                                     const int rk = __popc(am & ((1u << lane) - 1u));
@@ -448,8 +474,8 @@ pomcp_search_kernel(const SearchParams p)
                                                              (int)(st & 0xFFu), a, sr.good, (int)sr.cell);
                                 virgin_step(ctx, i, sim, -1 - (int)cslot, cmask, sr.cell, sr.rocks, d + 1, c_levels);
                             } else {
-                                const int id = (int)c - 1;
-                                if (row_sum(p.t.n + (size_t)id * AS) == 0)
+                                const int id = CHILD_ID(c);
+                                if (!(c & CHILD_VISITED))                                   // no statistics yet (N = 0)
                                     virgin_step(ctx, i, sim, id, p.t.legal[id], sr.cell, sr.rocks, d + 1, c_levels);
                                 else { p.b.node[i] = id; arrive_at = id; arrive_slot = a * 2 + sr.good; }   // descend
                             }
@@ -464,10 +490,14 @@ pomcp_search_kernel(const SearchParams p)
                 if (arrive_at >= 0) {
                     const unsigned peers = __match_any_sync(amask, arrive_at);
                     if (lane == __ffs((int)peers) - 1) {
-                        const unsigned long long old = atomicMax(&p.t.arrive[arrive_at], stamp_next);
-                        if (old < stamp_next) {
-                            const int s = atomicAdd(&S->wl_count[ring_next], 1);
-                            p.b.wl_node[s] = arrive_at; p.t.slot[arrive_at] = s;
+                        // stamp the node on its first arrival of this level step (a plain L2 read first: on a busy
+                        // node almost every group finds the stamp in place and issues one fire-and-forget add)
+                        if (*((volatile unsigned long long *)&p.t.arrive[arrive_at]) < stamp_next) {
+                            const unsigned long long old = atomicMax(&p.t.arrive[arrive_at], stamp_next);
+                            if (old < stamp_next) {
+                                const int s = atomicAdd(&S->wl_count[ring_next], 1);
+                                p.b.wl_node[s] = arrive_at; p.t.slot[arrive_at] = s;
+                            }
                         }
                         atomicAdd(&p.t.arrive[arrive_at], (unsigned long long)__popc(peers));
                     }
@@ -479,7 +509,7 @@ pomcp_search_kernel(const SearchParams p)
                     const int cnt = arr1[t];
                     if (cnt == 0) continue;
                     arr1[t] = 0;
-                    const int Xc = (int)p.t.child[(size_t)root * AS * 2 + t] - 1;
+                    const int Xc = CHILD_ID(p.t.child[(size_t)root * AS * 2 + t]);
                     const unsigned long long old = atomicMax(&p.t.arrive[Xc], stamp_next);
                     if (old < stamp_next) {
                         const int sl = atomicAdd(&S->wl_count[ring_next], 1);
@@ -540,11 +570,21 @@ pomcp_search_kernel(const SearchParams p)
                     const int e = (1 + (int)(ar0 & 31) * 2 + (int)((ar0 >> 5) & 1)) * A + a;
                     atomicAdd(&acc_n[e], 1);
                     atomicAdd(reinterpret_cast<unsigned long long *>(&acc_q[e]), (unsigned long long)qi);
+                    if (depth > 2) {                                         // mark the depth-2 child of this edge
+                        int X = p.b.path_node[(size_t)p.wmax + i];
+                        if (X < 0) X = CHILD_ID(p.t.child[(size_t)(-1 - X)]);
+                        uint32_t *cs = &p.t.child[((size_t)X * AS + a) * 2 + ((ar >> 5) & 1u)];
+                        if (!(*((volatile uint32_t *)cs) & CHILD_VISITED)) atomicOr(cs, CHILD_VISITED);
+                    }
                 } else {
                     int X = p.b.path_node[(size_t)d * p.wmax + i];
-                    if (X < 0) X = (int)p.t.child[(size_t)(-1 - X)] - 1;     // id published after this sim passed
+                    if (X < 0) X = CHILD_ID(p.t.child[(size_t)(-1 - X)]);    // id published after this sim passed
                     atomicAdd(&p.t.n[(size_t)X * AS + a], 1);
                     atomicAdd(reinterpret_cast<unsigned long long *>(&p.t.qfix[(size_t)X * AS + a]), (unsigned long long)qi);
+                    if (d + 1 < depth) {                                     // the child below this edge now has statistics
+                        uint32_t *cs = &p.t.child[((size_t)X * AS + a) * 2 + ((ar >> 5) & 1u)];
+                        if (!(*((volatile uint32_t *)cs) & CHILD_VISITED)) atomicOr(cs, CHILD_VISITED);
+                    }
                 }
                 delayed = q;
             }
@@ -555,7 +595,12 @@ pomcp_search_kernel(const SearchParams p)
             if (dn == 0) continue;
             const int slot = e / A, a = e - slot * A;
             int X = root;
-            if (slot > 0) X = (int)p.t.child[(size_t)root * AS * 2 + (slot - 1)] - 1;
+            if (slot > 0) {                                          // a depth-1 node: it has statistics from now on
+                uint32_t *cs = &p.t.child[(size_t)root * AS * 2 + (slot - 1)];
+                const uint32_t cv = *((volatile uint32_t *)cs);
+                X = CHILD_ID(cv);
+                if (!(cv & CHILD_VISITED)) atomicOr(cs, CHILD_VISITED);
+            }
             atomicAdd(&p.t.n[(size_t)X * AS + a], dn);
             atomicAdd(reinterpret_cast<unsigned long long *>(&p.t.qfix[(size_t)X * AS + a]), (unsigned long long)acc_q[e]);
             acc_n[e] = 0; acc_q[e] = 0;
@@ -563,7 +608,7 @@ pomcp_search_kernel(const SearchParams p)
         done += w;
         if (W < p.wmax) { long long nw = (long long)W * p.growth; W = nw > p.wmax ? p.wmax : (int)nw; }
         if (p.timeout_ns && gtid == 0 && globaltimer_ns() - t_start > p.timeout_ns) S->stop = 1;
-        grid.sync();
+        GRID_SYNC();
         PHASE_MARK(4);
         if (p.timeout_ns && *((volatile int32_t *)&S->stop)) break;   // action_selection_timeout
     }
@@ -688,7 +733,7 @@ pomcp_advance_kernel(const AdvanceParams p)
                                           p.action, p.obs_good, (int)sr.cell);
                 p.t.legal[id] = lm;
                 status = 1;
-            } else id = (int)c - 1;
+            } else id = CHILD_ID(c);
             S->root = id; S->n_bag = accepted; S->bag_sel ^= 1;                        // :210
             S->adv_status = status; S->adv_root_cell = p.t.cell[id];
         }
@@ -1056,6 +1101,7 @@ extern "C" int pomcp_search(pomcp_handle *h, int64_t n_sims, uint32_t sim_offset
     int blocks = (int)((widest + SEARCH_THREADS - 1) / SEARCH_THREADS);
     if (blocks < 1) blocks = 1;
     if (blocks > h->coop_blocks) blocks = h->coop_blocks;
+    CK(cudaMemsetAsync(&h->dS->barrier, 0, sizeof(uint32_t), s));
     void *args[] = {&p};
     CK(cudaLaunchCooperativeKernel((void *)pomcp_search_kernel, dim3(blocks), dim3(SEARCH_THREADS), args,
                                    h->search_smem, s));
@@ -1100,7 +1146,7 @@ extern "C" int pomcp_node_stats(pomcp_handle *h, const int32_t *path_ao, int len
         uint32_t c;
         CK(cudaMemcpy(&c, h->t.child + ((size_t)X * AS + a) * 2 + o, sizeof(c), cudaMemcpyDeviceToHost));
         if (c == 0 || c == CHILD_LOCKED) return 1;
-        X = (int32_t)c - 1;
+        X = CHILD_ID(c);
     }
     int32_t nn[AS]; long long qq[AS];
     CK(cudaMemcpy(nn, h->t.n + (size_t)X * AS, sizeof(nn), cudaMemcpyDeviceToHost));

@@ -1,5 +1,5 @@
 import sys,time
-sys.path.insert(0,'/root/repo/scratch'); sys.path.insert(0,'/root/repo/oracle')
+sys.path.insert(0,'/root/repo/tools'); sys.path.insert(0,'/root/repo/oracle')
 from quality import *
 tag=sys.argv[1]; n_sims=int(sys.argv[2]); neps=int(sys.argv[3])
 om,z=load(tag)

@@ -12,3 +12,5 @@ c = pl.counters(); print(c["last_search_ns"] * 1e-6, c["level_steps"] // 3, c["a
 L = pl.steplog()
 for i in range(min(128, c["level_steps"] // 3)):
     print(i, "wait %.1f alloc %.1f wait2 %.1f expand %.1f us  nwl %d" % (L[i, 0] / 1e3, L[i, 1] / 1e3, L[i, 2] / 1e3, L[i, 3] / 1e3, L[i, 4]))
+
+print("tsec cycles [choice, step+path, child, virgin/rowsum, syncwarp, arrive]:", L[127].tolist())
