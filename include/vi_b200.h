@@ -26,7 +26,7 @@ int vi_solve_reference(int device, int S, int A, int Z, const double *T, const d
 /* Textbook projection for large |S| (BASELINE config 5):
  *   proj[a][s][o*G + g] = sum_s' T[a][s][s'] * O[a][s'][o] * gamma[g][s']
  * as |A| GEMMs [S x S] . [S x Z*G] on the fp64 tensor cores (DMMA), all pointers on the device, row-major.
- * scratch_dev holds S*Z*G doubles.  Asynchronous on `stream`. */
+ * scratch_dev holds S*Z*G doubles; S % 128 == 0 and (Z*G) % 64 == 0.  Asynchronous on `stream`. */
 int vi_project_textbook_dev(int device, int S, int A, int Z, int G, const double *T_dev, const double *O_dev,
                             const double *gamma_dev, double *scratch_dev, double *proj_dev, void *stream,
                             char *err, int errlen);

@@ -169,71 +169,100 @@ __global__ void vi_scale_kernel(int S, int Z, int G, const double *__restrict__ 
     }
 }
 
-// C[M x N] = A[M x K] . B[K x N], row-major fp64.  Block tile 64 x 64, k-step 16 through shared memory; 8 warps, each
-// owning a 16 x 32 sub-tile = 2 x 4 DMMA tiles of 8 x 8.  M, N multiples of 64 and K of 16.
-#define GT 64
-#define GK 16
+// C[M x N] = A[M x K] . B[K x N], row-major fp64, on the fp64 tensor cores.
+// Block tile 128 x 64, k-step 16, 3-stage cp.async pipeline; 8 warps as 4 (M) x 2 (N), each owning a 32 x 32 sub-tile
+// = 4 x 4 DMMA tiles (mma.sync.m8n8k4.f64: 32 accumulator doubles per thread).  Shared-memory rows are padded so that
+// the 64-bit fragment loads of each half-warp hit 16 distinct bank pairs.  M % 128 == 0, N % 64 == 0, K % 16 == 0.
+#define GBM 128
+#define GBN 64
+#define GBK 16
+#define GSTAGES 3
+#define SA_LD 20               // doubles per A row in shared memory (16 + 4 pad)
+#define SB_LD 68               // doubles per B row in shared memory (64 + 4 pad)
+
+__device__ __forceinline__ void cp_async16(void *smem, const void *gmem)
+{
+    const unsigned s = (unsigned)__cvta_generic_to_shared(smem);
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(s), "l"(gmem));
+}
+
 __global__ void __launch_bounds__(256) vi_dgemm_dmma_kernel(int M, int N, int K, const double *__restrict__ A,
                                                             const double *__restrict__ B, double *__restrict__ C)
 {
-    __shared__ double sA[GT][GK + 1];        // +1: conflict-free column reads
-    __shared__ double sB[GK][GT + 2];
+    extern __shared__ __align__(16) double gsm[];
+    double *sA = gsm;                                   // [GSTAGES][GBM][SA_LD]
+    double *sB = gsm + GSTAGES * GBM * SA_LD;           // [GSTAGES][GBK][SB_LD]
     const int tid = threadIdx.x, lane = tid & 31, warp = tid >> 5;
-    const int bm = blockIdx.y * GT, bn = blockIdx.x * GT;
-    const int wm = (warp >> 1) * 16, wn = (warp & 1) * 32;
+    const int bm = blockIdx.y * GBM, bn = blockIdx.x * GBN;
+    const int wm = (warp >> 1) * 32, wn = (warp & 1) * 32;
     const int gid = lane >> 2, tig = lane & 3;                  // mma.m8n8k4 fragment coordinates
-    double acc[2][4][2];
+    double acc[4][4][2];
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) acc[i][j][0] = acc[i][j][1] = 0.0;
-    for (int k0 = 0; k0 < K; k0 += GK) {
-        for (int e = tid; e < GT * GK; e += 256) {              // A tile: 64 rows x 16 k
-            const int r = e / GK, c = e - r * GK;
-            sA[r][c] = A[(size_t)(bm + r) * K + k0 + c];
+
+    auto load_stage = [&](int stage, int k0) {
+        double *a = sA + stage * GBM * SA_LD, *b = sB + stage * GBK * SB_LD;
+#pragma unroll
+        for (int e = 0; e < 4; ++e) {                           // A: 128 rows x 16 k = 1024 chunks of 2 doubles
+            const int ch = tid + e * 256, r = ch >> 3, c2 = (ch & 7) * 2;
+            cp_async16(a + r * SA_LD + c2, A + (size_t)(bm + r) * K + k0 + c2);
         }
-        for (int e = tid; e < GK * GT; e += 256) {              // B tile: 16 k x 64 cols
-            const int r = e / GT, c = e - r * GT;
-            sB[r][c] = B[(size_t)(k0 + r) * N + bn + c];
+#pragma unroll
+        for (int e = 0; e < 2; ++e) {                           // B: 16 k x 64 cols = 512 chunks
+            const int ch = tid + e * 256, r = ch >> 5, c2 = (ch & 31) * 2;
+            cp_async16(b + r * SB_LD + c2, B + (size_t)(k0 + r) * N + bn + c2);
         }
+        asm volatile("cp.async.commit_group;");
+    };
+
+    const int nk = K / GBK;
+    for (int s = 0; s < GSTAGES - 1; ++s) { if (s < nk) load_stage(s, s * GBK); else asm volatile("cp.async.commit_group;"); }
+    for (int kt = 0; kt < nk; ++kt) {
+        asm volatile("cp.async.wait_group %0;" ::"n"(GSTAGES - 2));
         __syncthreads();
+        const int nxt = kt + GSTAGES - 1;
+        if (nxt < nk) load_stage(nxt % GSTAGES, nxt * GBK); else asm volatile("cp.async.commit_group;");
+        const double *a = sA + (kt % GSTAGES) * GBM * SA_LD, *b = sB + (kt % GSTAGES) * GBK * SB_LD;
 #pragma unroll
-        for (int kk = 0; kk < GK; kk += 4) {
-            double a[2], b[4];
+        for (int kk = 0; kk < GBK; kk += 4) {
+            double af[4], bf[4];
 #pragma unroll
-            for (int i = 0; i < 2; ++i) a[i] = sA[wm + i * 8 + gid][kk + tig];     // A fragment: row gid, col tig
+            for (int i = 0; i < 4; ++i) af[i] = a[(wm + i * 8 + gid) * SA_LD + kk + tig];   // A fragment: row gid, col tig
 #pragma unroll
-            for (int j = 0; j < 4; ++j) b[j] = sB[kk + tig][wn + j * 8 + gid];     // B fragment: row tig, col gid
+            for (int j = 0; j < 4; ++j) bf[j] = b[(kk + tig) * SB_LD + wn + j * 8 + gid];   // B fragment: row tig, col gid
 #pragma unroll
-            for (int i = 0; i < 2; ++i)
+            for (int i = 0; i < 4; ++i)
 #pragma unroll
                 for (int j = 0; j < 4; ++j)
                     asm volatile("mma.sync.aligned.m8n8k4.row.col.f64.f64.f64.f64 {%0,%1}, {%2}, {%3}, {%0,%1};"
-                                 : "+d"(acc[i][j][0]), "+d"(acc[i][j][1]) : "d"(a[i]), "d"(b[j]));
+                                 : "+d"(acc[i][j][0]), "+d"(acc[i][j][1]) : "d"(af[i]), "d"(bf[j]));
         }
-        __syncthreads();
     }
 #pragma unroll
-    for (int i = 0; i < 2; ++i)
+    for (int i = 0; i < 4; ++i)
 #pragma unroll
         for (int j = 0; j < 4; ++j) {                           // C fragment: row gid, cols 2*tig, 2*tig+1
             const int r = bm + wm + i * 8 + gid, c = bn + wn + j * 8 + 2 * tig;
             *reinterpret_cast<double2 *>(&C[(size_t)r * N + c]) = make_double2(acc[i][j][0], acc[i][j][1]);
         }
 }
+#define DGEMM_SMEM ((GSTAGES * GBM * SA_LD + GSTAGES * GBK * SB_LD) * sizeof(double))
 
 extern "C" int vi_project_textbook_dev(int device, int S, int A, int Z, int G, const double *T_dev, const double *O_dev,
                                        const double *gamma_dev, double *scratch_dev, double *proj_dev, void *stream,
                                        char *err, int errlen)
 {
     const int N = Z * G;
-    if (S % GT || N % GT || S % GK) { snprintf(err, errlen, "S and Z*G must be multiples of 64"); return -1; }
     VCK(cudaSetDevice(device));
+    if (S % GBM || N % GBN || S % GBK) { snprintf(err, errlen, "S must be a multiple of 128 and Z*G of 64"); return -1; }
+    VCK(cudaFuncSetAttribute(vi_dgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DGEMM_SMEM));
     cudaStream_t st = (cudaStream_t)stream;
     for (int a = 0; a < A; ++a) {
         vi_scale_kernel<<<148 * 8, 256, 0, st>>>(S, Z, G, O_dev + (size_t)a * S * Z, gamma_dev, scratch_dev);
-        dim3 grid(N / GT, S / GT);
-        vi_dgemm_dmma_kernel<<<grid, 256, 0, st>>>(S, N, S, T_dev + (size_t)a * S * S, scratch_dev,
+        dim3 grid(N / GBN, S / GBM);
+        vi_dgemm_dmma_kernel<<<grid, 256, DGEMM_SMEM, st>>>(S, N, S, T_dev + (size_t)a * S * S, scratch_dev,
                                                    proj_dev + (size_t)a * S * N);
     }
     VCK(cudaGetLastError());

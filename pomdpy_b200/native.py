@@ -93,6 +93,7 @@ class Planner:
                           int(gen_growth), int(gen_wmax), 0)
         self.h = C.c_void_p()
         self.n_actions = 0
+        self._bag_hint = None
         rc = self.lib.pomcp_create(C.byref(self.cfg), int(device), C.byref(self.h))
         if rc != 0:
             msg = self.lib.pomcp_last_error(self.h).decode() if self.h else "pomcp_create failed"
@@ -149,6 +150,7 @@ class Planner:
 
     def set_root_particles(self, packed, root_cell):
         packed = np.ascontiguousarray(packed, dtype=np.uint32)
+        self._bag_hint = int(packed.size)
         self._ck(self.lib.pomcp_set_root_particles(self.h, _p(packed, C.c_uint32), int(packed.size), int(root_cell)))
 
     def search(self, n_sims, move=0, sim_offset=0, timeout_s=0.0, stream=None):
@@ -187,12 +189,19 @@ class Planner:
                                         int(max_tries), C.byref(status), C.byref(tries), C.byref(acc)))
         return dict(status=status.value, tries=tries.value, accepted=acc.value)
 
-    def root_particles(self):
-        cap = max(int(self.cfg.max_particle_count), 1 << 16)
-        out = np.zeros(cap, dtype=np.uint32)
+    def root_particles(self, fetch=True):
+        """(packed states, root cell) of the current root belief; fetch=False returns only (count, root cell)."""
         n, cell = C.c_int32(), C.c_int32()
-        self._ck(self.lib.pomcp_root_particles(self.h, _p(out, C.c_uint32), cap, C.byref(n), C.byref(cell)))
-        return out[:min(n.value, cap)].copy(), cell.value
+        if not fetch:
+            self._ck(self.lib.pomcp_root_particles(self.h, None, 0, C.byref(n), C.byref(cell)))
+            return n.value, cell.value
+        cap = int(self.cfg.max_particle_count) if self._bag_hint is None else max(self._bag_hint, 1)
+        out = np.empty(max(cap, int(self.cfg.max_particle_count)), dtype=np.uint32)
+        self._ck(self.lib.pomcp_root_particles(self.h, _p(out, C.c_uint32), out.size, C.byref(n), C.byref(cell)))
+        if n.value > out.size:                           # an initial belief larger than max_particle_count
+            out = np.empty(n.value, dtype=np.uint32)
+            self._ck(self.lib.pomcp_root_particles(self.h, _p(out, C.c_uint32), out.size, C.byref(n), C.byref(cell)))
+        return out[:n.value].copy(), cell.value
 
     def generate_steps(self, state, action, u53, actual_mask, sampled_mask):
         state = np.ascontiguousarray(state, dtype=np.uint32)

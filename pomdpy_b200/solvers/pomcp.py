@@ -206,7 +206,7 @@ class POMCP(Solver):
             return
         if res["status"] == 1:
             console(4, module, "observed child was never expanded: fresh root")
-        _, self._root_cell = self.planner.root_particles()
+        _, self._root_cell = self.planner.root_particles(fetch=False)
 
     def prune(self, belief_node=None):
         """Sibling subtrees are simply left behind in the arena (belief_tree.py:87-109 frees them)."""
