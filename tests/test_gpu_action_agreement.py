@@ -1,0 +1,85 @@
+"""Action agreement with the reference algorithm where its own choice is decisive (north star: "the chosen action
+matches on fixed seeds where reference Q-gaps exceed Monte-Carlo noise").
+
+The reference side is the oracle's "ref" mode (the reference's sequential POMCP with all its quirks, pinned bit for
+bit to the executed reference).  Situations (belief, world, position) are harvested along reference-algorithm
+episodes on RockSample(7,8) at the reference's budget (n_sims = 500).  A situation is *decisive* when 16
+independent reference searches (different random streams) all pick the same action; there the CUDA planner, at the
+same budget, must pick that action too (every one of 4 seeds)."""
+import numpy as np
+import pytest
+
+import oracle
+from helpers import golden_tables, make_planner, oracle_model
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
+
+
+def _harvest(om, t, n_episodes=12, n_sims=500):
+    K = om.n_rocks
+    out = []
+    for ep in range(n_episodes):
+        rng = np.random.default_rng(4000 + ep)
+        actual = int(rng.integers(0, 1 << K))
+        bag_rocks = rng.integers(0, 1 << K, size=2000).astype(np.uint32)
+        ref = oracle.RefPOMCP(om, actual, 0, bag_rocks, seed=4000 + ep)
+        cell, rocks, sampled = om.start_cell, int(bag_rocks[0]), 0
+        bag = (bag_rocks << np.uint32(8)) | np.uint32(cell)
+        for mv in range(25):
+            out.append(dict(actual=actual, sampled=sampled, cell=cell, bag=bag.copy()))
+            a = ref.search(n_sims)
+            o = om.step(cell, rocks, a, int(rng.integers(0, 1 << 53)), actual, sampled)
+            cell, rocks = o.next_cell, o.next_rocks
+            if o.terminal or not o.legal:
+                break
+            if a == 4:
+                sampled |= 1 << int(t["cell"][cell])
+            if ref.update(a, o.obs_good, sampled) != 0:
+                break
+            # the belief the reference holds now = the particles of its new root: regenerate an equivalent bag
+            g = oracle.GsPOMCP(om, actual, sampled, bag, root_cell=out[-1]["cell"], seed=ep * 100 + mv)
+            g.set_world(actual, 0 if a != 4 else sampled)
+            if g.update(a, o.obs_good, sampled, move=mv)["status"] == 2:
+                break
+            bag = g.bag()
+    return out
+
+
+def test_decisive_reference_actions_are_matched():
+    t = golden_tables("map-7-8")
+    om = oracle_model(t)
+    situations = _harvest(om, t)
+    decisive, agree, checked = 0, 0, []
+    pl = None
+    for si, s in enumerate(situations):
+        picks = []
+        for r in range(16):
+            picks.append(_ref_search_at(om, t, s, 9000 + 16 * si + r))
+        if len(set(picks)) != 1:
+            continue
+        decisive += 1
+        a_ref = picks[0]
+        ok = True
+        for seed in range(4):
+            pl = make_planner(t, seed=700 + seed, gen_w0=8, gen_growth=2, gen_wmax=64, node_capacity=1 << 14)
+            pl.set_world(s["actual"], s["sampled"])
+            pl.set_root_particles(s["bag"], s["cell"])
+            pl.search(500, move=si)
+            st = pl.root_stats()
+            mean = np.where(st["n"] > 0, st["qfix"] / 2.0 ** 24 / np.maximum(st["n"], 1), 0.0)
+            legal = np.array([(st["legal"] >> a) & 1 for a in range(om.n_actions)], dtype=bool)
+            mean[~legal] = -np.inf
+            ok &= int(np.argmax(mean)) == a_ref
+            pl.close()
+        agree += ok
+        checked.append((si, a_ref, ok))
+    print("situations %d, decisive for the reference %d, matched by the CUDA planner %d" % (len(situations), decisive, agree))
+    assert decisive >= 15, "too few decisive situations to say anything"
+    assert agree >= 0.9 * decisive, checked
+
+
+def _ref_search_at(om, t, s, seed):
+    """One reference-algorithm search (n_sims = 500) from the situation's belief at the situation's cell."""
+    m = oracle.Model(int(t["rows"]), int(t["cols"]), t["cell"], s["cell"], t["thr53"], t["rewards"])
+    ref = oracle.RefPOMCP(m, s["actual"], s["sampled"], (s["bag"] >> np.uint32(8)).astype(np.uint32), seed=seed)
+    return ref.search(500)
