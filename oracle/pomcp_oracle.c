@@ -788,12 +788,16 @@ static double gs_rollout(orc_gs *h, gs_sim *s, uint32_t move)
 {
     double sum = 0.0, disc = 1.0; int t = 0, terminal = 0;
     int cell = s->cell; uint32_t rocks = s->rocks;
+    uint32_t x[4] = {0, 0, 0, 0};
     while (t < h->max_depth && !terminal) {
-        uint32_t x[4]; gs_block(h, (uint32_t)(s->depth + 1 + t), s->sim, move, DOM_SIM, x);
+        /* one Philox block per two rollout steps: words (0,1) then (2,3); the first word picks the action, the
+         * second is the top 32 bits of the 53-bit sensor uniform */
+        if ((t & 1) == 0) gs_block(h, (uint32_t)(s->depth + 1 + (t >> 1)), s->sim, move, DOM_SIM, x);
+        uint32_t w0 = x[(t & 1) * 2], w1 = x[(t & 1) * 2 + 1];
         uint32_t mask = h->m->legal[cell];
-        int idx = (int)randbelow32(x[0], (uint32_t)__builtin_popcount(mask)), a = -1;
+        int idx = (int)randbelow32(w0, (uint32_t)__builtin_popcount(mask)), a = -1;
         for (int b = 0, seen = 0; b < 32; ++b) if ((mask >> b) & 1u) { if (seen == idx) { a = b; break; } ++seen; }
-        orc_step_out o; orc_step(h->m, &h->w, cell, rocks, a, u53_of(x[1], x[2]), &o);
+        orc_step_out o; orc_step(h->m, &h->w, cell, rocks, a, (uint64_t)w1 << 21, &o);
         terminal = o.terminal;
         if (o.reward != 0.0) sum += o.reward * disc;
         disc *= h->discount;

@@ -531,10 +531,17 @@ pomcp_search_kernel(const SearchParams p)
                 uint32_t cell = st & 0xFFu, rocks = st >> 8;
                 double sum = 0.0;
                 int t = 0;
+                Philox4 r{0u, 0u, 0u, 0u};
                 for (; t < p.max_depth; ++t) {
-                    const Philox4 r = philox4x32_10((uint32_t)(depth + 1 + t), sim, p.move, DOM_SIM, p.key0, p.key1);
+                    // one Philox block per two rollout steps: (x, y) then (z, w); word 0 picks the action, word 1 is
+                    // the top 32 bits of the 53-bit sensor uniform
+                    uint32_t w0, w1;
+                    if ((t & 1) == 0) {
+                        r = philox4x32_10((uint32_t)(depth + 1 + (t >> 1)), sim, p.move, DOM_SIM, p.key0, p.key1);
+                        w0 = r.x; w1 = r.y;
+                    } else { w0 = r.z; w1 = r.w; }
                     const uint32_t mask = H->legal[cell];
-                    const int a = nth_legal(H, mask, randbelow32(r.x, (uint32_t)__popc(mask)));
+                    const int a = nth_legal(H, mask, randbelow32(w0, (uint32_t)__popc(mask)));
                     int rew = REW_NONE;
                     if (a < 4) {
                         cell = (uint32_t)((int)cell + H->delta[a]);
@@ -548,7 +555,7 @@ pomcp_search_kernel(const SearchParams p)
                         const int k = a - 5;
                         if (!((sampled >> k) & 1u)) {
                             const uint32_t truth = (actual >> k) & 1u;
-                            const uint32_t correct = u53_of(r.y, r.z) <= M.thr53[cell * H->n_rocks + k];
+                            const uint32_t correct = ((uint64_t)w1 << 21) <= M.thr53[cell * H->n_rocks + k];
                             const uint32_t good = correct ? truth : (truth ^ 1u);
                             rocks = (rocks & ~(1u << k)) | (good << k);
                         }
