@@ -110,8 +110,8 @@ int pomcp_generate_steps(pomcp_handle *h, int64_t n, const uint32_t *state, cons
 /* counters: [0] tree levels, [1] rollout steps, [2] nodes created, [3] nodes in arena, [4] allocation nodes,
  * [5] generations, [6] level steps, [7] last search ns (device globaltimer), [8] sims of last search,
  * [9] kernel launches so far, [10] cooperative grid blocks, [11] threads per block,
- * [12] device-to-host bytes of one pomcp_root_stats call, [13..15] ns of the last search spent in the level-step
- * phases (count arrivals / allocate / choose+step+expand); the rest of [7] is rollout + backup */
+ * [12] device-to-host bytes of one pomcp_root_stats call, [13] / [14] ns of the last search spent waiting at the
+ * level-step barrier / allocating, [15] first failed device-side bounds check (-DPOMCP_CHECKS builds; 0 = none) */
 int pomcp_counters(pomcp_handle *h, int64_t out[16]);
 
 /* profiling aid: per level step of the last search, ns of {barrier wait, allocate (thread 0), barrier wait,

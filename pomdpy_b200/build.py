@@ -27,19 +27,25 @@ def stale():
     return any(os.path.getmtime(d) > t for d in deps)
 
 
-def build(force=False, verbose=False):
-    """Build libpomcp_b200.so next to this package; returns its path."""
-    if not force and not stale():
+CHECKS_LIB = os.path.join(HERE, "libpomcp_b200_checks.so")
+
+
+def build(force=False, verbose=False, checks=False):
+    """Build libpomcp_b200.so next to this package; returns its path.  checks=True builds the variant with
+    device-side bounds checks (-DPOMCP_CHECKS) as libpomcp_b200_checks.so."""
+    out = CHECKS_LIB if checks else LIB
+    if not force and not checks and not stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-Xptxas", "-v"] if verbose else []) + ["-o", LIB] + \
-          [os.path.join(CSRC, f) for f in SOURCES]
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-DPOMCP_CHECKS"] if checks else []) + (["-Xptxas", "-v"] if verbose else []) + \
+          ["-o", out] + [os.path.join(CSRC, f) for f in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)
     if verbose:
         print(res.stderr)
-    return LIB
+    return out
 
 
 if __name__ == "__main__":
     print(build(force=True, verbose=True))
+    print(build(force=True, checks=True))

@@ -18,6 +18,14 @@
 #include "pomcp_device.cuh"
 
 #define AS POMCP_AS
+
+// Bounds checks of the device code (compute-sanitizer is not available on the GPU pool): a -DPOMCP_CHECKS build
+// records the largest failing check code in DevState.check_failed; tests/test_gpu_debug_checks.py runs it.
+#ifdef POMCP_CHECKS
+#define DCHECK(S_, cond, code) do { if (!(cond)) atomicMax(&(S_)->check_failed, (code)); } while (0)
+#else
+#define DCHECK(S_, cond, code) do { } while (0)
+#endif
 #define CHILD_LOCKED 0xFFFFFFFFu
 #define CHILD_VISITED 0x80000000u   // set on a child slot once a backup has passed through the child (N > 0)
 #define CHILD_ID(c) ((int)((c) & 0x7FFFFFFFu) - 1)
@@ -43,6 +51,7 @@ struct DevState {
     int32_t wl_count[4];
     int32_t stop;
     uint32_t barrier;                  // arrival counter of grid_barrier (zeroed before each search)
+    int32_t check_failed, check_pad;   // POMCP_CHECKS builds: code of the first failed device-side bounds check
     unsigned long long gstep;          // global level-step stamp, never reused
     long long sims_done;               // simulations completed by the last search
     long long counters[16];
@@ -90,6 +99,7 @@ struct SearchParams {
     long long n_sims;
     uint32_t sim_offset, move, key0, key1;
     int32_t w0, growth, wmax, max_depth, dcap, n_thr;
+    long long node_cap;
     double ucb_c, discount;
     unsigned long long timeout_ns;     // 0 = no wall-clock guard; measured from kernel start
 };
@@ -287,6 +297,7 @@ __device__ __noinline__ void virgin_step(const SimCtx &c, int i, uint32_t sim, i
 {
     const SearchParams &p = c.p;
     if (d >= p.max_depth) { p.b.flag[i] = 2; p.b.depth[i] = (uint8_t)d; return; }          // solvers/pomcp.py:100
+    DCHECK(p.S, mask != 0u && d < p.dcap && cell < (uint32_t)c.M.hdr->n_cells, 11);
     const Philox4 r = philox4x32_10((uint32_t)(d + 1), sim, p.move, DOM_SIM, p.key0, p.key1);
     const int a = nth_bit(mask, randbelow32(r.x, (uint32_t)__popc(mask)));
     const StepResult sr = rs_step(c.M, cell, rocks, a, u53_of(r.y, r.z), c.actual, c.sampled);
@@ -414,6 +425,7 @@ pomcp_search_kernel(const SearchParams p)
                     const int X = p.b.node[i];
                     const int d = p.b.depth[i];
                     const uint32_t sim = p.sim_offset + (uint32_t)(done + i);
+                    DCHECK(S, X >= 0 && X < S->node_count && d < p.dcap, 21);
                     if (d >= p.max_depth) p.b.flag[i] = 2;                                  // :100
                     else {
                         const Philox4 r = philox4x32_10((uint32_t)(d + 1), sim, p.move, DOM_SIM, p.key0, p.key1);
@@ -427,7 +439,9 @@ pomcp_search_kernel(const SearchParams p)
                             a = p.b.wl_meta[s] & 255;
                             for (int bq = 0; bq < A; ++bq) if (r.x < thr[bq]) { a = bq; break; }
                         }
+                        DCHECK(S, a >= 0 && a < A && ((mask >> a) & 1u) && k >= 1u && k <= (uint32_t)w, 22);
                         const uint32_t st = p.b.state[i];
+                        DCHECK(S, (st & 0xFFu) == (uint32_t)p.t.cell[X], 23);
                         const StepResult sr = rs_step(M, st & 0xFFu, st >> 8, a, u53_of(r.y, r.z), actual, sampled);  // :104
                         ++c_levels;
                         p.b.path_node[(size_t)d * p.wmax + i] = X;
@@ -452,6 +466,7 @@ pomcp_search_kernel(const SearchParams p)
                                     int id0 = 0;
                                     if (rk == 0) id0 = atomicAdd(&S->node_count, __popc(am));
                                     const int id = __shfl_sync(am, id0, __ffs((int)am) - 1) + rk;
+                                    DCHECK(S, id > 0 && (long long)id < p.node_cap, 24);
                                     p.t.cell[id] = (int32_t)sr.cell;
                                     if (p.t.chance)                                         // create_child + smart action set
                                         cmask = child_smart_mask(H, p.t.prob, p.t.chance + (size_t)X * POMCP_RS,
@@ -496,6 +511,7 @@ pomcp_search_kernel(const SearchParams p)
                             const unsigned long long old = atomicMax(&p.t.arrive[arrive_at], stamp_next);
                             if (old < stamp_next) {
                                 const int s = atomicAdd(&S->wl_count[ring_next], 1);
+                                DCHECK(S, s < p.wmax, 25);
                                 p.b.wl_node[s] = arrive_at; p.t.slot[arrive_at] = s;
                             }
                         }
@@ -543,6 +559,7 @@ pomcp_search_kernel(const SearchParams p)
                     const uint32_t mask = H->legal[cell];
                     const int a = nth_legal(H, mask, randbelow32(w0, (uint32_t)__popc(mask)));
                     int rew = REW_NONE;
+                    DCHECK(S, a >= 0 && a < A && cell < (uint32_t)H->n_cells, 41);
                     if (a < 4) {
                         cell = (uint32_t)((int)cell + H->delta[a]);
                         if (H->cell[cell] == POMCP_CELL_GOAL) { sum += H->rew[REW_EXIT] * disc[t]; ++t; break; }
@@ -586,6 +603,7 @@ pomcp_search_kernel(const SearchParams p)
                 } else {
                     int X = p.b.path_node[(size_t)d * p.wmax + i];
                     if (X < 0) X = CHILD_ID(p.t.child[(size_t)(-1 - X)]);    // id published after this sim passed
+                    DCHECK(S, X > 0 && X < S->node_count && a < A, 31);
                     atomicAdd(&p.t.n[(size_t)X * AS + a], 1);
                     atomicAdd(reinterpret_cast<unsigned long long *>(&p.t.qfix[(size_t)X * AS + a]), (unsigned long long)qi);
                     if (d + 1 < depth) {                                     // the child below this edge now has statistics
@@ -1101,7 +1119,7 @@ extern "C" int pomcp_search(pomcp_handle *h, int64_t n_sims, uint32_t sim_offset
     p.n_sims = n_sims; p.sim_offset = sim_offset; p.move = move;
     p.key0 = (uint32_t)h->cfg.seed; p.key1 = (uint32_t)(h->cfg.seed >> 32);
     p.w0 = h->cfg.gen_w0; p.growth = h->cfg.gen_growth; p.wmax = h->cfg.gen_wmax;
-    p.max_depth = h->cfg.max_depth; p.dcap = h->cfg.tree_depth_cap; p.n_thr = h->n_thr;
+    p.max_depth = h->cfg.max_depth; p.dcap = h->cfg.tree_depth_cap; p.n_thr = h->n_thr; p.node_cap = h->cap;
     p.ucb_c = h->cfg.ucb_coefficient; p.discount = h->cfg.discount;
     p.timeout_ns = timeout_s > 0 ? (unsigned long long)(timeout_s * 1e9) : 0ull;   // checked between generations
     long long widest = n_sims < (long long)p.wmax ? n_sims : (long long)p.wmax;
@@ -1260,7 +1278,8 @@ extern "C" int pomcp_counters(pomcp_handle *h, int64_t out[16])
     out[9] = h->launches;
     out[10] = h->coop_blocks;
     out[11] = SEARCH_THREADS;
-    for (int i = 0; i < 3; ++i) out[13 + i] = st.phase_ns[1 + i];   // count / allocate / choose+step+expand
+    for (int i = 0; i < 2; ++i) out[13 + i] = st.phase_ns[1 + i];   // barrier wait / allocate
+    out[15] = st.check_failed;                                      // POMCP_CHECKS builds
     out[12] = (int64_t)(DEVSTATE_HEAD + AS * sizeof(int32_t) + AS * sizeof(long long) + sizeof(uint32_t));  // D2H bytes of pomcp_root_stats
     return 0;
 }
