@@ -35,6 +35,7 @@
 #endif
 #define ADV_THREADS 1024
 #define ADV_TRIES 4
+#define ROLL_SLICE 8            // rollout steps per slice while waiting at a barrier (even: Philox block pairs)
 #define SEQ_ALLOC_MAX 16u      // arrivals <= this: exact virtual-pull allocation; more: water-filling
 #ifndef BISECT_ITERS
 #define BISECT_ITERS 14
@@ -51,7 +52,8 @@ struct DevState {
     int32_t wl_count[4];
     int32_t stop;
     uint32_t barrier;                  // arrival counter of grid_barrier (zeroed before each search)
-    int32_t check_failed, check_pad;   // POMCP_CHECKS builds: code of the first failed device-side bounds check
+    int32_t check_failed, check_pad;
+    int32_t ro_cursor[2];              // work counters of the final rollout + backup phase (alternating per generation)   // POMCP_CHECKS builds: code of the first failed device-side bounds check
     unsigned long long gstep;          // global level-step stamp, never reused
     long long sims_done;               // simulations completed by the last search
     long long counters[16];
@@ -80,13 +82,16 @@ struct Tree {                          // structure-of-arrays belief-tree arena
 struct SimBuf {                        // per simulation-in-flight scratch, SoA over the generation
     uint32_t *state;                   // packed state cell | rocks << 8
     int32_t *node;                     // current node, or child-slot index when `pending`
-    uint8_t *flag;                     // bits 0-1 status (0 descending, 1 rollout pending, 2 done), bit 2 pending
+    uint8_t *flag;                     // status: 0 descending, 1 leaf (rollout pending / in progress), 2 done without rollout,
+                                       //         3 rollout finished
     uint8_t *depth;                    // path entries recorded
     int32_t *path_node;                // [dcap][wmax]
     uint16_t *path_ar;                 // [dcap][wmax] action | obs_good << 5 | reward id << 8
     int32_t *wl_node;                  // [wmax] worklist of nodes with arrivals in this level step
     uint32_t *wl_thr;                  // [wmax][32] cumulative action thresholds for nodes with >= 2 arrivals
     int32_t *wl_meta;                  // [wmax] last action (bits 0-7) | (N > 0) << 8
+    double *ro_sum;                    // [wmax] discounted reward sum of a rollout in progress
+    uint8_t *ro_t;                     // [wmax] rollout steps done so far (rollouts advance in slices)
 };
 
 struct SearchParams {
@@ -358,14 +363,89 @@ pomcp_search_kernel(const SearchParams p)
 #define PHASE_MARK(k) do { if (gtid == 0) { const unsigned long long now_ = globaltimer_ns(); tp[k] += now_ - tmark; tmark = now_; } } while (0)
     const SimCtx ctx{p, M, actual, sampled};
     int W = p.w0;
+    long long gen_done = 0;                                          // simulations of earlier generations (stream ids)
+
+    // Advance the rollout of leaf simulation i by at most `budget` steps (an even number, or to the end): the state
+    // of a rollout in progress lives in p.b.state / ro_sum / ro_t, so any thread may resume it.
+    auto rollout_advance = [&](int i, int budget) {
+        const uint32_t sim = p.sim_offset + (uint32_t)(gen_done + i);
+        const int depth = p.b.depth[i];
+        const uint32_t st = p.b.state[i];
+        uint32_t cell = st & 0xFFu, rocks = st >> 8;
+        double sum = p.b.ro_sum[i];
+        int t = p.b.ro_t[i];
+        const int t0 = t, t_end = (t + budget < p.max_depth) ? t + budget : p.max_depth;
+        bool finished = false;
+        Philox4 r{0u, 0u, 0u, 0u};
+        for (; t < t_end; ++t) {
+            // one Philox block per two rollout steps: (x, y) then (z, w); word 0 picks the action, word 1 is the top
+            // 32 bits of the 53-bit sensor uniform
+            uint32_t w0, w1;
+            if ((t & 1) == 0) {
+                r = philox4x32_10((uint32_t)(depth + 1 + (t >> 1)), sim, p.move, DOM_SIM, p.key0, p.key1);
+                w0 = r.x; w1 = r.y;
+            } else { w0 = r.z; w1 = r.w; }
+            const uint32_t mask = H->legal[cell];
+            const int a = nth_legal(H, mask, randbelow32(w0, (uint32_t)__popc(mask)));
+            DCHECK(S, a >= 0 && a < A && cell < (uint32_t)H->n_cells, 41);
+            if (a < 4) {
+                cell = (uint32_t)((int)cell + H->delta[a]);
+                if (H->cell[cell] == POMCP_CELL_GOAL) { sum += H->rew[REW_EXIT] * disc[t]; ++t; finished = true; break; }
+            } else if (a == 4) {
+                const int code = H->cell[cell];
+                const int rew = (((actual & rocks) >> code) & 1u) ? REW_GOOD : REW_BAD;
+                rocks &= ~(1u << code);
+                sum += H->rew[rew] * disc[t];
+            } else {
+                const int k = a - 5;
+                if (!((sampled >> k) & 1u)) {
+                    const uint32_t truth = (actual >> k) & 1u;
+                    const uint32_t correct = ((uint64_t)w1 << 21) <= M.thr53[cell * H->n_rocks + k];
+                    const uint32_t good = correct ? truth : (truth ^ 1u);
+                    rocks = (rocks & ~(1u << k)) | (good << k);
+                }
+            }
+        }
+        c_rollout += t - t0;
+        p.b.ro_sum[i] = sum;
+        if (finished || t >= p.max_depth) p.b.flag[i] = 3;
+        else { p.b.state[i] = cell | (rocks << 8); p.b.ro_t[i] = (uint8_t)t; }
+    };
+
+    // Grid barrier that works while it waits: after arriving, the block keeps advancing the rollouts of its own leaf
+    // simulations in slices of ROLL_SLICE steps until every block has arrived.
+    int gen_w = 0;                                                   // width of the current generation
+    auto grid_sync_working = [&]() {
+        __syncthreads();
+        ++bar_epoch;
+        if (threadIdx.x == 0) { __threadfence(); atomicAdd(&S->barrier, 1u); }
+        const unsigned int target = bar_epoch * gridDim.x;
+        int next_j = 0;
+        for (;;) {
+            int released = 0;
+            if (threadIdx.x == 0) released = *((volatile unsigned int *)&S->barrier) >= target;
+            if (__syncthreads_or(released)) break;
+            int worked = 0;
+            for (; gtid + next_j * T < gen_w; ++next_j) {
+                const int i = gtid + next_j * T;
+                if ((p.b.flag[i] & 3) == 1) { rollout_advance(i, ROLL_SLICE); worked = 1; break; }   // stay on i until done
+            }
+            if (!__syncthreads_or(worked)) __nanosleep(64);
+        }
+        if (threadIdx.x == 0) __threadfence();
+        __syncthreads();
+    };
+
     GRID_SYNC();                                                    // everyone has read S before anyone writes it
 
     while (done < p.n_sims) {
         const int w = (int)((p.n_sims - done) < (long long)W ? (p.n_sims - done) : (long long)W);
         ++gens;
+        gen_w = w; gen_done = done;
         // ---- start of a generation: every simulation draws a root particle (belief_node.py:47-48) ----
         const bool root_virgin = row_sum(p.t.n + (size_t)root * AS) == 0;
         const uint32_t root_mask = p.t.legal[root];
+        if (gtid == 0) S->ro_cursor[(gens + 1) & 1] = 0;            // the next generation's work counter
         if (!root_virgin && gwarp == 0) {                            // all w simulations arrive at the root
             if (lane == 0) {
                 const unsigned long long s1 = gstep + 1;
@@ -381,6 +461,7 @@ pomcp_search_kernel(const SearchParams p)
             const uint32_t sim = p.sim_offset + (uint32_t)(done + i);
             const Philox4 r = philox4x32_10(0u, sim, p.move, DOM_SIM, p.key0, p.key1);
             const uint32_t st = bag[randbelow32(r.x, (uint32_t)n_bag)];
+            p.b.ro_t[i] = 0; p.b.ro_sum[i] = 0.0;
             if (root_virgin) virgin_step(ctx, i, sim, root, root_mask, st & 0xFFu, st >> 8, 0, c_levels);
             else { p.b.state[i] = st; p.b.node[i] = root; p.b.flag[i] = 0; p.b.depth[i] = 0; }
         }
@@ -389,7 +470,7 @@ pomcp_search_kernel(const SearchParams p)
             ++gstep; ++lsteps;
             const int ring = (int)(gstep & 3ull), ring_next = (int)((gstep + 1) & 3ull);
             const unsigned long long stamp_next = (gstep + 1) << 32;
-            GRID_SYNC();                                             // arrivals of this level are complete
+            grid_sync_working();                                     // arrivals of this level are complete
             if (gtid == 0 && lsteps <= 128) S->steplog[lsteps - 1][0] = (long long)(globaltimer_ns() - tmark);
             PHASE_MARK(1);
             const int nwl = *((volatile int32_t *)&S->wl_count[ring]);
@@ -413,7 +494,7 @@ pomcp_search_kernel(const SearchParams p)
                 }
             }
             if (gtid == 0 && lsteps <= 128) S->steplog[lsteps - 1][1] = (long long)(globaltimer_ns() - tmark);
-            GRID_SYNC();
+            grid_sync_working();
             }
             if (gtid == 0 && lsteps <= 128) { S->steplog[lsteps - 1][2] = (long long)(globaltimer_ns() - tmark) - S->steplog[lsteps - 1][1]; S->steplog[lsteps - 1][4] = nwl; }
             PHASE_MARK(2);
@@ -491,7 +572,9 @@ pomcp_search_kernel(const SearchParams p)
                             } else {
                                 const int id = CHILD_ID(c);
                                 if (!(c & CHILD_VISITED))                                   // no statistics yet (N = 0)
-                                    virgin_step(ctx, i, sim, id, p.t.legal[id], sr.cell, sr.rocks, d + 1, c_levels);
+                                    // the node may have been published in this very phase by another SM: read its action
+                                    // set from L2 (ld.cg), never from a possibly stale L1 line
+                                    virgin_step(ctx, i, sim, id, __ldcg(&p.t.legal[id]), sr.cell, sr.rocks, d + 1, c_levels);
                                 else { p.b.node[i] = id; arrive_at = id; arrive_slot = a * 2 + sr.good; }   // descend
                             }
                         }
@@ -538,49 +621,19 @@ pomcp_search_kernel(const SearchParams p)
             PHASE_MARK(3);
         }
         // ---- rollout (belief_tree_solver.py:123-152, from the post-action state) + backup (:126-137) ----
-        for (int i = gtid; i < w; i += T) {
+        GRID_SYNC();              // every slice in flight has been stored: leaves are claimed by other threads below
+        // Simulations are claimed 32 at a time from a work counter: rollouts that already advanced while their
+        // owner waited at a barrier are resumed (or skipped) by whoever claims them, which balances the tail.
+        for (;;) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&S->ro_cursor[gens & 1], 32);
+            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (base >= w) break;
+            const int i = base + lane;
+            if (i >= w) continue;
+            if ((p.b.flag[i] & 3) == 1) rollout_advance(i, p.max_depth);
             const int depth = p.b.depth[i];
-            double delayed = 0.0;
-            if ((p.b.flag[i] & 3) == 1) {
-                const uint32_t sim = p.sim_offset + (uint32_t)(done + i);
-                uint32_t st = p.b.state[i];
-                uint32_t cell = st & 0xFFu, rocks = st >> 8;
-                double sum = 0.0;
-                int t = 0;
-                Philox4 r{0u, 0u, 0u, 0u};
-                for (; t < p.max_depth; ++t) {
-                    // one Philox block per two rollout steps: (x, y) then (z, w); word 0 picks the action, word 1 is
-                    // the top 32 bits of the 53-bit sensor uniform
-                    uint32_t w0, w1;
-                    if ((t & 1) == 0) {
-                        r = philox4x32_10((uint32_t)(depth + 1 + (t >> 1)), sim, p.move, DOM_SIM, p.key0, p.key1);
-                        w0 = r.x; w1 = r.y;
-                    } else { w0 = r.z; w1 = r.w; }
-                    const uint32_t mask = H->legal[cell];
-                    const int a = nth_legal(H, mask, randbelow32(w0, (uint32_t)__popc(mask)));
-                    int rew = REW_NONE;
-                    DCHECK(S, a >= 0 && a < A && cell < (uint32_t)H->n_cells, 41);
-                    if (a < 4) {
-                        cell = (uint32_t)((int)cell + H->delta[a]);
-                        if (H->cell[cell] == POMCP_CELL_GOAL) { sum += H->rew[REW_EXIT] * disc[t]; ++t; break; }
-                    } else if (a == 4) {
-                        const int code = H->cell[cell];
-                        rew = (((actual & rocks) >> code) & 1u) ? REW_GOOD : REW_BAD;
-                        rocks &= ~(1u << code);
-                        sum += H->rew[rew] * disc[t];
-                    } else {
-                        const int k = a - 5;
-                        if (!((sampled >> k) & 1u)) {
-                            const uint32_t truth = (actual >> k) & 1u;
-                            const uint32_t correct = ((uint64_t)w1 << 21) <= M.thr53[cell * H->n_rocks + k];
-                            const uint32_t good = correct ? truth : (truth ^ 1u);
-                            rocks = (rocks & ~(1u << k)) | (good << k);
-                        }
-                    }
-                }
-                c_rollout += t;
-                delayed = sum;
-            }
+            double delayed = ((p.b.flag[i] & 3) == 3) ? p.b.ro_sum[i] : 0.0;
             for (int d = depth - 1; d >= 0; --d) {
                 const uint32_t ar = p.b.path_ar[(size_t)d * p.wmax + i];
                 const int a = ar & 31;
@@ -868,6 +921,7 @@ static void free_all(pomcp_handle *h)
     cudaFree(h->t.arrive); cudaFree(h->t.slot); cudaFree(h->t.chance); cudaFree(h->t.good); cudaFree((void *)h->t.prob);
     cudaFree(h->b.state); cudaFree(h->b.node); cudaFree(h->b.flag); cudaFree(h->b.depth); cudaFree(h->b.path_node);
     cudaFree(h->b.path_ar); cudaFree(h->b.wl_node); cudaFree(h->b.wl_thr); cudaFree(h->b.wl_meta);
+    cudaFree(h->b.ro_sum); cudaFree(h->b.ro_t);
     cudaFree(h->bag[0]); cudaFree(h->bag[1]);
     if (h->stage) cudaFreeHost(h->stage);
 }
@@ -923,6 +977,8 @@ extern "C" int pomcp_create(const pomcp_config *cfg, int device, pomcp_handle **
     CK(cudaMalloc(&h->b.wl_node, wmax * sizeof(int32_t)));
     CK(cudaMalloc(&h->b.wl_thr, wmax * 32 * sizeof(uint32_t)));
     CK(cudaMalloc(&h->b.wl_meta, wmax * sizeof(int32_t)));
+    CK(cudaMalloc(&h->b.ro_sum, wmax * sizeof(double)));
+    CK(cudaMalloc(&h->b.ro_t, wmax));
     CK(cudaMallocHost(&h->stage, 1 << 16));
     return 0;
 }
@@ -1127,6 +1183,7 @@ extern "C" int pomcp_search(pomcp_handle *h, int64_t n_sims, uint32_t sim_offset
     if (blocks < 1) blocks = 1;
     if (blocks > h->coop_blocks) blocks = h->coop_blocks;
     CK(cudaMemsetAsync(&h->dS->barrier, 0, sizeof(uint32_t), s));
+    CK(cudaMemsetAsync(h->dS->ro_cursor, 0, 2 * sizeof(int32_t), s));
     void *args[] = {&p};
     CK(cudaLaunchCooperativeKernel((void *)pomcp_search_kernel, dim3(blocks), dim3(SEARCH_THREADS), args,
                                    h->search_smem, s));

@@ -50,4 +50,8 @@ def test_checks_build_trips_nothing():
     env = dict(os.environ, POMCP_B200_LIB=lib)
     res = subprocess.run([sys.executable, "-c", "ROOT = %r\n" % ROOT + SCRIPT], env=env, capture_output=True, text=True,
                          timeout=500)
+    if res.returncode != 0 or "CHECKS-OK" not in res.stdout:
+        os.makedirs(os.path.join(ROOT, "gpurun_out"), exist_ok=True)
+        with open(os.path.join(ROOT, "gpurun_out", "checks_child.log"), "a") as f:
+            f.write("==== rc %d\n%s\n%s\n" % (res.returncode, res.stdout[-3000:], res.stderr[-6000:]))
     assert res.returncode == 0 and "CHECKS-OK" in res.stdout, res.stdout[-2000:] + res.stderr[-4000:]
