@@ -161,7 +161,7 @@ __device__ __forceinline__ size_t stage_model(unsigned char *smem, const ModelHe
 // Batch-UCB allocation for a node with k >= 2 simultaneous arrivals (warp-cooperative, lane = action).
 // Water-filling of k pulls over the UCB1 indices mean + c*sqrt(ln(N+1)/n); output: 32-bit cumulative thresholds.
 // ---------------------------------------------------------------------------------------------------------
-__device__ __noinline__ void warp_allocation(const SearchParams &p, int X, uint32_t k, int lane, int A,
+__device__ __forceinline__ void warp_allocation(const SearchParams &p, int X, uint32_t k, int lane, int A,
                                              uint32_t *thr_out, int32_t *meta_out)
 {
     const unsigned full = 0xFFFFFFFFu;
@@ -226,7 +226,7 @@ __device__ __noinline__ void warp_allocation(const SearchParams &p, int X, uint3
 //   k == 1: UCB1 arg-max (action_selectors.py:6-37), uniform tie-break with the 32-bit draw x0.
 //   k >= 2: the k arrivals share the virtual-pull sequence "pull j takes the UCB1 arg-max (lowest id on ties) given
 //           the statistics plus the virtual visits of pulls 0..j-1"; this simulation takes pull j = floor(x0*k/2^32).
-__device__ __noinline__ int select_thread(const SearchParams &p, int X, uint32_t mask, int A, uint32_t x0, uint32_t k)
+__device__ __forceinline__ int select_thread(const SearchParams &p, int X, uint32_t mask, int A, uint32_t x0, uint32_t k)
 {
     const int32_t *nrow = p.t.n + (size_t)X * AS;
     const long long *qrow = p.t.qfix + (size_t)X * AS;
@@ -297,7 +297,7 @@ struct SimCtx {
 // A simulation standing at a node without statistics (N = 0): every legal action is untried, so UCB1 is a uniform
 // draw (action_selectors.py:6-37 with +inf bonuses), the node cannot be expanded (solvers/pomcp.py:107) and the
 // simulation ends in a rollout.  `node_ref` is the node id, or -1 - child_slot while the id is being published.
-__device__ __noinline__ void virgin_step(const SimCtx &c, int i, uint32_t sim, int node_ref, uint32_t mask,
+__device__ __forceinline__ void virgin_step(const SimCtx &c, int i, uint32_t sim, int node_ref, uint32_t mask,
                                          uint32_t cell, uint32_t rocks, int d, long long &c_levels)
 {
     const SearchParams &p = c.p;
