@@ -1,29 +1,100 @@
 """Return parity on the reference's own configuration (BASELINE.json configs[0]): RockSample(7,8), n_sims=500,
-max_steps=200, through the CLI -> Agent -> CUDA solver.
+max_steps=200.
 
-Reference numbers, per-epoch discounted return, no preferred actions:
-  executed reference, seeds 123-126, 40 epochs pooled ........ 14.62  (per-epoch sigma ~ 4.0 -> stderr ~ 0.63)
-  validated restatement of the reference algorithm, 60 epochs . 15.75 +- 0.51   (this repo's oracle 'ref': 15.64 +- 0.40)
-  canonical POMCP (state carried down the tree), 60 epochs .... 16.78 +- 0.49
-The device planner is the canonical variant, so the criterion is one-sided against the reference
-("not below the reference's interval") with a sanity ceiling; tolerance = 3 standard errors of the difference of
-two 120-epoch means (sigma 4.0): 3 * 4.0 * sqrt(1/120 + 1/40) = 2.2."""
+Two arms on the SAME 150 worlds (true rock states, initial beliefs, start particle, environment noise all drawn
+from one per-epoch generator):
+  reference arm -- the oracle's "ref" mode, i.e. the reference's sequential POMCP with all its quirks, pinned bit for
+                   bit to the executed reference (tests/test_cpu_oracle.py); 15.6 +- 0.4 over 60 epochs in DESIGN.md,
+                   the executed reference itself gave 14.62 pooled over 40 epochs;
+  CUDA arm      -- the planner behind the C ABI (generation schedule 8, x2, <= 64).
+The device planner is the canonical POMCP variant (state carried down the tree), for which SURVEY.md
+Appendix D measured +1.0 +- 0.5 over the reference at this budget, so the criterion is one-sided: the paired
+difference CUDA - reference must not be below -2 standard errors, and must stay under a sanity ceiling.  A second
+test drives the whole CLI -> Agent -> solver stack and checks the same number through that path."""
+import numpy as np
 import pytest
+
+import oracle
+from helpers import golden_tables, make_planner, oracle_model
 
 pytestmark = [pytest.mark.gpu, pytest.mark.timeout(900)]
 
-REFERENCE_MEAN = 14.62
-TOLERANCE = 2.2
-CEILING = 20.5          # canonical POMCP at this budget: 16.8 +- 0.5; anything above 20 would be a bug, not skill
+N_EPOCHS, N_SIMS, MAX_STEPS, DISCOUNT = 150, 500, 200, 0.95
 
 
-def test_discounted_return_matches_reference_within_ci():
+def _world(t, om, ep):
+    rng = np.random.default_rng(50_000 + ep)
+    K = om.n_rocks
+    actual = int(rng.integers(0, 1 << K))
+    bag_rocks = rng.integers(0, 1 << K, size=2000).astype(np.uint32)
+    start_rocks = int(bag_rocks[rng.integers(0, 2000)])
+    return rng, actual, bag_rocks, start_rocks
+
+
+def _episode(t, om, ep, search, update):
+    rng, actual, bag_rocks, rocks = _world(t, om, ep)
+    cell, sampled, ret, disc = om.start_cell, 0, 0.0, 1.0
+    for mv in range(MAX_STEPS):
+        a = search(mv)
+        o = om.step(cell, rocks, a, int(rng.integers(0, 1 << 53)), actual, sampled)
+        ret += disc * o.reward
+        disc *= DISCOUNT
+        cell, rocks = o.next_cell, o.next_rocks
+        if o.terminal or not o.legal:
+            break
+        if a == 4:
+            sampled |= 1 << int(t["cell"][cell])
+        if not update(a, o.obs_good, sampled, mv):
+            break
+    return ret
+
+
+def test_paired_return_vs_reference_algorithm():
+    t = golden_tables("map-7-8")
+    om = oracle_model(t)
+    ref_ret, gpu_ret = [], []
+    pl = make_planner(t, seed=2024, gen_w0=8, gen_growth=2, gen_wmax=64, node_capacity=1 << 15)
+    for ep in range(N_EPOCHS):
+        _, actual, bag_rocks, _ = _world(t, om, ep)
+        ref = oracle.RefPOMCP(om, actual, 0, bag_rocks, seed=77_000 + ep)
+        ref_ret.append(_episode(t, om, ep, lambda mv: ref.search(N_SIMS),
+                                lambda a, og, sm, mv: ref.update(a, og, sm) == 0))
+        bag = (bag_rocks << np.uint32(8)) | np.uint32(om.start_cell)
+        pl.set_world(actual, 0)
+        pl.set_root_particles(bag, om.start_cell)
+
+        def gpu_search(mv, ep=ep):
+            pl.search(N_SIMS, move=ep * 256 + mv)
+            st = pl.root_stats()
+            return oracle.GsPOMCP.greedy(_Seeded(2024, om), move=ep * 256 + mv, stats=st)
+
+        gpu_ret.append(_episode(t, om, ep, gpu_search,
+                                lambda a, og, sm, mv, ep=ep: pl.advance(a, og, sm, move=ep * 256 + mv)["status"] != 2))
+    pl.close()
+    ref_ret, gpu_ret = np.array(ref_ret), np.array(gpu_ret)
+    diff = gpu_ret - ref_ret
+    se = diff.std(ddof=1) / np.sqrt(N_EPOCHS)
+    print("reference algorithm %.2f +- %.2f | CUDA planner %.2f +- %.2f | paired difference %+.2f +- %.2f (%d epochs)"
+          % (ref_ret.mean(), ref_ret.std(ddof=1) / np.sqrt(N_EPOCHS), gpu_ret.mean(),
+             gpu_ret.std(ddof=1) / np.sqrt(N_EPOCHS), diff.mean(), se, N_EPOCHS))
+    assert 12.0 < ref_ret.mean() < 19.0                  # the reference arm reproduces the reference's level
+    assert diff.mean() > -2.0 * se, "CUDA planner below the reference's interval"
+    assert gpu_ret.mean() < 20.5                         # canonical POMCP at this budget: 16.8 +- 0.5 (Appendix D)
+
+
+class _Seeded:
+    """Just enough of GsPOMCP for its greedy(): seed and model."""
+
+    def __init__(self, seed, model):
+        self.seed, self.model = seed, model
+
+
+def test_cli_discounted_return_matches_reference_level():
     import pomcp as cli
     agent = cli.main(["--env", "RockSample", "--solver", "POMCP", "--max_steps", "200", "--n_epochs", "120",
                       "--n_sims", "500", "--seed", "123", "--verbosity", "0"])
     st = agent.experiment_results.discounted_return
+    print("CLI path: %.2f +- %.2f over %d epochs (executed reference 14.62)" % (st.mean, st.std_err(), st.count))
     assert st.count == 120
-    print("GPU planner: %.2f +- %.2f over %d epochs (reference %.2f)" % (st.mean, st.std_err(), st.count, REFERENCE_MEAN))
-    assert st.mean > REFERENCE_MEAN - TOLERANCE, "discounted return below the reference's interval"
-    assert st.mean < CEILING
-    assert 2.0 < st.std_dev() < 8.0       # per-epoch spread of the reference is ~4.0
+    assert 14.62 - 2.2 < st.mean < 20.5                  # 3 standard errors of the difference of a 120- and a 40-epoch mean
+    assert 2.0 < st.std_dev() < 8.0                      # per-epoch spread of the reference is ~4.0
