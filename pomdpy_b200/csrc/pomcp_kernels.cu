@@ -53,7 +53,10 @@ struct DevState {
     int32_t stop;
     uint32_t barrier;                  // arrival counter of grid_barrier (zeroed before each search)
     int32_t check_failed, check_pad;
-    int32_t ro_cursor[2];              // work counters of the final rollout + backup phase (alternating per generation)   // POMCP_CHECKS builds: code of the first failed device-side bounds check
+    int32_t ro_cursor[2];              // work counters of the final rollout + backup phase (alternating per generation)
+    // root edge statistics as of the end of the last search / advance / plant (one copy serves pomcp_root_stats)
+    long long res_n[AS], res_q[AS];
+    uint32_t res_legal; int32_t res_valid;   // POMCP_CHECKS builds: code of the first failed device-side bounds check
     unsigned long long gstep;          // global level-step stamp, never reused
     long long sims_done;               // simulations completed by the last search
     long long counters[16];
@@ -138,6 +141,17 @@ __device__ __forceinline__ unsigned long long globaltimer_ns()
 __device__ __forceinline__ float edge_mean(long long qfix, int n)
 {
     return ((float)qfix * (1.0f / 16777216.0f)) / (float)n;
+}
+
+// Publish the root's edge statistics in the state block (threads 0..AS-1 of one block): pomcp_root_stats is then a
+// single device-to-host copy.
+__device__ __forceinline__ void publish_root(DevState *S, const Tree &t, int root, int tid)
+{
+    if (tid < AS) {
+        S->res_n[tid] = t.n[(size_t)root * AS + tid];
+        S->res_q[tid] = t.qfix[(size_t)root * AS + tid];
+    }
+    if (tid == 0) { S->res_legal = t.legal[root]; S->res_valid = 1; }
 }
 
 // Stage the model tables into shared memory; returns the first free byte offset (16-byte aligned).
@@ -691,6 +705,7 @@ pomcp_search_kernel(const SearchParams p)
         if (p.timeout_ns && *((volatile int32_t *)&S->stop)) break;   // action_selection_timeout
     }
 
+    if (blockIdx.x == 0) publish_root(S, p.t, root, threadIdx.x);     // after the last generation's barrier
     // counters (warp-reduced) and persistent state
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
@@ -816,6 +831,8 @@ pomcp_advance_kernel(const AdvanceParams p)
             S->adv_status = status; S->adv_root_cell = p.t.cell[id];
         }
     }
+    __syncthreads();
+    publish_root(S, p.t, S->root, tid);
 }
 
 // generate_step over a batch (parity harness for rock_model.py:451-465)
@@ -856,7 +873,9 @@ __global__ void pomcp_plant_root_kernel(DevState *S, Tree t, const ModelHeader *
             legal = child_smart_mask(H, t.prob, ch, gd, t.chance, t.good, root_cell, 0, 0, root_cell);   // a = 0: no update
         }
         t.legal[0] = legal;
+        S->res_legal = legal; S->res_valid = 1;
     }
+    if (blockIdx.x == 0 && threadIdx.x < AS) { S->res_n[threadIdx.x] = 0; S->res_q[threadIdx.x] = 0; }
 }
 
 // Root edge statistics as 2*AS 64-bit integers (n[0..AS), qfix[0..AS)) in a caller-provided device buffer: the
@@ -1198,18 +1217,14 @@ extern "C" int pomcp_root_stats(pomcp_handle *h, int64_t *n, int64_t *qfix, uint
     if (!h) return -1;
     if (!h->have_root) return fail(h, "no root belief");
     CK(cudaSetDevice(h->device));
+    DevState *st = reinterpret_cast<DevState *>(h->stage);           // pinned staging: one asynchronous copy + sync
+    CK(cudaMemcpyAsync(st, h->dS, DEVSTATE_HEAD, cudaMemcpyDeviceToHost, h->last_stream));
     CK(cudaStreamSynchronize(h->last_stream));
-    DevState st;
-    CK(cudaMemcpy(&st, h->dS, DEVSTATE_HEAD, cudaMemcpyDeviceToHost));
-    h->nodes_used = st.node_count;
+    h->nodes_used = st->node_count;
     const int A = h->hmodel.n_actions;
-    int32_t nn[AS]; long long qq[AS]; uint32_t lg;
-    CK(cudaMemcpy(nn, h->t.n + (size_t)st.root * AS, sizeof(nn), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(qq, h->t.qfix + (size_t)st.root * AS, sizeof(qq), cudaMemcpyDeviceToHost));
-    CK(cudaMemcpy(&lg, h->t.legal + st.root, sizeof(lg), cudaMemcpyDeviceToHost));
-    for (int a = 0; a < A; ++a) { n[a] = nn[a]; qfix[a] = qq[a]; }
-    if (legal_mask) *legal_mask = lg;
-    if (sims_done) *sims_done = st.sims_done;
+    for (int a = 0; a < A; ++a) { n[a] = st->res_n[a]; qfix[a] = st->res_q[a]; }
+    if (legal_mask) *legal_mask = st->res_legal;
+    if (sims_done) *sims_done = st->sims_done;
     return 0;
 }
 
@@ -1337,6 +1352,6 @@ extern "C" int pomcp_counters(pomcp_handle *h, int64_t out[16])
     out[11] = SEARCH_THREADS;
     for (int i = 0; i < 2; ++i) out[13 + i] = st.phase_ns[1 + i];   // barrier wait / allocate
     out[15] = st.check_failed;                                      // POMCP_CHECKS builds
-    out[12] = (int64_t)(DEVSTATE_HEAD + AS * sizeof(int32_t) + AS * sizeof(long long) + sizeof(uint32_t));  // D2H bytes of pomcp_root_stats
+    out[12] = (int64_t)DEVSTATE_HEAD;                               // D2H bytes of pomcp_root_stats
     return 0;
 }

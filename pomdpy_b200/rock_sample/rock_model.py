@@ -151,6 +151,14 @@ class RockModel(Model):
         self.unique_rocks_sampled = []
         return RockState(self.start_position, self.sample_rocks())
 
+    def sample_init_states_packed(self, n):
+        """n draws of sample_an_init_state() in the device particle format (uint32 cell | rocks << 8), vectorised:
+        the same distribution -- start cell, i.i.d. uniform rock masks (:156-159, :175-176) -- from one numpy call."""
+        self.sampled_rock_yet = False
+        self.unique_rocks_sampled = []
+        rocks = np.random.randint(0, 1 << self.n_rocks, size=int(n)).astype(np.uint32)
+        return (rocks << np.uint32(8)) | np.uint32(self.cell_index(self.start_position))
+
     def sample_position(self):
         return GridPosition(int(np.random.randint(0, self.n_rows)), int(np.random.randint(0, self.n_cols)))
 
@@ -328,6 +336,8 @@ class RockModel(Model):
         rewards (illegal, exit, good sample, bad sample).  Thresholds are computed with the reference's own
         numpy expressions (:148-150, grid_position.py:41-42) so that device decisions equal np.random.binomial
         decisions for the same uniform."""
+        if getattr(self, "_device_spec", None) is not None:       # the tables never change after construction
+            return self._device_spec
         n_cells = self.n_rows * self.n_cols
         if n_cells > 256 or self.n_rocks > 24 or 5 + self.n_rocks > 32:
             raise ValueError("map too large for the packed device state (<=256 cells, <=24 rocks)")
@@ -343,9 +353,10 @@ class RockModel(Model):
                     thr53[i * self.n_cols + j, k] = int(math.floor(binomial_threshold(p) * 9007199254740992.0))
         rewards = np.array([-self.illegal_move_penalty, self.exit_reward, self.good_rock_reward,
                             -self.bad_rock_penalty], dtype=np.float64)
-        return dict(kind="rocksample", rows=self.n_rows, cols=self.n_cols, n_rocks=self.n_rocks,
-                    n_actions=5 + self.n_rocks, cell=cell, start_cell=self.cell_index(self.start_position),
-                    thr53=thr53, prob=prob, rewards=rewards)
+        self._device_spec = dict(kind="rocksample", rows=self.n_rows, cols=self.n_cols, n_rocks=self.n_rocks,
+                                 n_actions=5 + self.n_rocks, cell=cell, start_cell=self.cell_index(self.start_position),
+                                 thr53=thr53, prob=prob, rewards=rewards)
+        return self._device_spec
 
     def world_masks(self):
         """(actual_rock_mask, sampled_rock_mask): the mutable world the device model reads (A.5)."""

@@ -87,8 +87,11 @@ class POMCP(Solver):
         self.spec = spec
         # belief_tree_solver.py:36-38: n_start_states draws of sample_an_init_state (numpy generator)
         n_start = int(getattr(model, "n_start_states", 2000))
-        bag = np.fromiter((model.pack_state(model.sample_an_init_state()) for _ in range(n_start)),
-                          dtype=np.uint32, count=n_start)
+        if hasattr(model, "sample_init_states_packed"):
+            bag = np.ascontiguousarray(model.sample_init_states_packed(n_start), dtype=np.uint32)
+        else:
+            bag = np.fromiter((model.pack_state(model.sample_an_init_state()) for _ in range(n_start)),
+                              dtype=np.uint32, count=n_start)
         self.planner.set_world(*model.world_masks())
         if self.preferred != getattr(self.planner, "_preferred", False):      # rock_position_history.py:52-55
             self.planner.set_preferred_actions(self.preferred, spec["prob"])
