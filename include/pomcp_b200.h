@@ -118,6 +118,33 @@ int pomcp_counters(pomcp_handle *h, int64_t out[16]);
  * expand (thread 0)}, worklist nodes, 3 spare: [128][8] */
 int pomcp_debug_steplog(pomcp_handle *h, int64_t *out);
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Reference-exact mode: the reference's SEQUENTIAL POMCP with all its quirks as a
+ * single-thread kernel.  Parity, not speed: with the sequential Philox draw stream that oracle/refharness/ injects
+ * into the executed reference, root statistics, chosen action, real step and belief update equal the reference's
+ * bit for bit (pomdpy/solvers/pomcp.py:69-137, belief_tree_solver.py:42-212, action_selectors.py:6-37).
+ * log_table[N] = ln(N + 1) as numpy computes it, N < n_log.
+ * ---------------------------------------------------------------------------------------------------------- */
+typedef struct pomcp_refexact pomcp_refexact;
+int pomcp_refexact_create(int device, int rows, int cols, const int8_t *cell, int start_cell, const uint64_t *thr53,
+                          const double rewards[4], uint32_t actual_mask, const uint32_t *bag_rocks, int n_bag,
+                          int max_depth, int max_particle_count, double ucb_c, double discount, uint64_t seed,
+                          uint32_t stream_id, const double *log_table, int n_log, int64_t cap_nodes,
+                          int64_t cap_particles, pomcp_refexact **out);
+void pomcp_refexact_destroy(pomcp_refexact *h);
+const char *pomcp_refexact_last_error(const pomcp_refexact *h);
+/* POMCP.select_eps_greedy_action (solvers/pomcp.py:69-78) */
+int pomcp_refexact_search(pomcp_refexact *h, int n_sims, int32_t *action, int64_t *n, double *total, double *mean,
+                          uint32_t *legal, int64_t *N, uint64_t *draws);
+/* solver.belief_tree_index.sample_particle() (agent.py:157) */
+int pomcp_refexact_sample_root_particle(pomcp_refexact *h, int32_t *particle);
+/* model.generate_step(state, action) on the true state (agent.py:174): out = obs_good, terminal, legal, next cell,
+ * next rocks, next particle */
+int pomcp_refexact_env_step(pomcp_refexact *h, int particle, int action, int64_t out[6], double *reward, uint64_t *draws);
+/* BeliefTreeSolver.update (belief_tree_solver.py:154-212) */
+int pomcp_refexact_update(pomcp_refexact *h, int action, int obs_good, uint32_t sampled_after, int32_t *disable_tree,
+                          uint64_t *draws);
+
 #ifdef __cplusplus
 }
 #endif

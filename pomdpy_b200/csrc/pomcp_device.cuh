@@ -131,7 +131,7 @@ __device__ __forceinline__ int nth_bit(uint32_t mask, uint32_t j)
 #define POMCP_RS 24            // rock stride of the statistics arrays
 
 // Statistics of the child of node X under (a, og) -> its smart-action mask; stored for node `store_id` if >= 0.
-__device__ __noinline__ uint32_t child_smart_mask(const ModelHeader *H, const double *prob, const double *chance,
+static __device__ __noinline__ uint32_t child_smart_mask(const ModelHeader *H, const double *prob, const double *chance,
                                                   const int16_t *good, double *chance_out, int16_t *good_out,
                                                   int pcell, int a, int og, int ccell)
 {

@@ -29,7 +29,9 @@ EXPORTS = ["pomcp_create", "pomcp_destroy", "pomcp_last_error", "pomcp_set_model
            "pomcp_set_root_particles", "pomcp_search", "pomcp_root_stats", "pomcp_node_stats", "pomcp_advance",
            "pomcp_root_particles", "pomcp_generate_steps", "pomcp_counters", "pomcp_root_stats_device",
            "pomcp_reset_tree", "pomcp_debug_steplog", "pomcp_set_preferred_actions",
-           "pomcp_root_rock_data"]
+           "pomcp_root_rock_data", "pomcp_refexact_create", "pomcp_refexact_destroy", "pomcp_refexact_last_error",
+           "pomcp_refexact_search", "pomcp_refexact_sample_root_particle", "pomcp_refexact_env_step",
+           "pomcp_refexact_update"]
 
 
 def library_path():
@@ -74,6 +76,16 @@ def load(build_if_missing=True):
     L.pomcp_debug_steplog.argtypes = [vp, P(i64)]
     L.pomcp_set_preferred_actions.argtypes = [vp, C.c_int, P(dbl)]
     L.pomcp_root_rock_data.argtypes = [vp, P(dbl), P(i32)]
+    L.pomcp_refexact_create.argtypes = [C.c_int, C.c_int, C.c_int, P(C.c_int8), C.c_int, P(u64), P(dbl), u32, P(u32),
+                                        C.c_int, C.c_int, C.c_int, dbl, dbl, u64, u32, P(dbl), C.c_int, i64, i64, P(vp)]
+    L.pomcp_refexact_destroy.argtypes = [vp]
+    L.pomcp_refexact_destroy.restype = None
+    L.pomcp_refexact_last_error.argtypes = [vp]
+    L.pomcp_refexact_last_error.restype = C.c_char_p
+    L.pomcp_refexact_search.argtypes = [vp, C.c_int, P(i32), P(i64), P(dbl), P(dbl), P(u32), P(i64), P(u64)]
+    L.pomcp_refexact_sample_root_particle.argtypes = [vp, P(i32)]
+    L.pomcp_refexact_env_step.argtypes = [vp, C.c_int, C.c_int, P(i64), P(dbl), P(u64)]
+    L.pomcp_refexact_update.argtypes = [vp, C.c_int, C.c_int, u32, P(i32), P(u64)]
     _LIB = L
     return L
 
@@ -231,3 +243,76 @@ class Planner:
                  "last_search_ns", "last_search_sims", "launches", "coop_blocks", "threads_per_block",
                  "root_stats_d2h_bytes", "phase_wait_ns", "phase_alloc_ns", "check_failed")
         return dict(zip(names, c.tolist()))
+
+
+class ReferenceExact:
+    """The reference's sequential POMCP, quirks included, as a single-thread CUDA kernel (parity path; see
+    csrc/pomcp_refexact.cu).  Draws come from one sequential Philox stream keyed by `seed`."""
+
+    def __init__(self, rows, cols, cell, start_cell, thr53, rewards, actual_mask, bag_rocks, max_depth=100,
+                 max_particle_count=2000, ucb_c=3.0, discount=0.95, seed=0, stream_id=0, n_log=1 << 16,
+                 cap_nodes=1 << 16, cap_particles=1 << 22, device=0):
+        self.lib = load()
+        cell = np.ascontiguousarray(cell, dtype=np.int8).reshape(-1)
+        self.n_actions = 5 + int(cell.max()) + 1
+        thr53 = np.ascontiguousarray(thr53, dtype=np.uint64).reshape(-1)
+        rewards = np.ascontiguousarray(rewards, dtype=np.float64)
+        bag = np.ascontiguousarray(bag_rocks, dtype=np.uint32)
+        log_table = np.log(np.arange(n_log, dtype=np.float64) + 1.0)          # numpy's ln(N + 1), as the reference
+        log_table = np.array([np.log(N + 1) for N in range(n_log)], dtype=np.float64)
+        self.h = C.c_void_p()
+        rc = self.lib.pomcp_refexact_create(int(device), int(rows), int(cols), _p(cell, C.c_int8), int(start_cell),
+                                            _p(thr53, C.c_uint64), _p(rewards, C.c_double), int(actual_mask),
+                                            _p(bag, C.c_uint32), int(bag.size), int(max_depth), int(max_particle_count),
+                                            float(ucb_c), float(discount), int(seed), int(stream_id),
+                                            _p(log_table, C.c_double), int(n_log), int(cap_nodes), int(cap_particles),
+                                            C.byref(self.h))
+        if rc != 0:
+            msg = self.lib.pomcp_refexact_last_error(self.h).decode()
+            self.close()
+            raise PomcpError(msg)
+
+    def close(self):
+        if getattr(self, "h", None):
+            self.lib.pomcp_refexact_destroy(self.h)
+            self.h = C.c_void_p()
+
+    def __del__(self):
+        try:
+            self.close()
+        except Exception:
+            pass
+
+    def _ck(self, rc):
+        if rc < 0:
+            raise PomcpError(self.lib.pomcp_refexact_last_error(self.h).decode())
+        return rc
+
+    def search(self, n_sims):
+        A = self.n_actions
+        n = np.zeros(A, dtype=np.int64)
+        tot = np.zeros(A, dtype=np.float64)
+        mean = np.zeros(A, dtype=np.float64)
+        act, legal, N, draws = C.c_int32(), C.c_uint32(), C.c_int64(), C.c_uint64()
+        self._ck(self.lib.pomcp_refexact_search(self.h, int(n_sims), C.byref(act), _p(n, C.c_int64), _p(tot, C.c_double),
+                                                _p(mean, C.c_double), C.byref(legal), C.byref(N), C.byref(draws)))
+        return dict(action=act.value, n=n, total=tot, mean=mean, legal=legal.value, N=N.value, draws=draws.value)
+
+    def sample_root_particle(self):
+        p = C.c_int32()
+        self._ck(self.lib.pomcp_refexact_sample_root_particle(self.h, C.byref(p)))
+        return p.value
+
+    def env_step(self, particle, action):
+        out = np.zeros(6, dtype=np.int64)
+        rew, draws = C.c_double(), C.c_uint64()
+        self._ck(self.lib.pomcp_refexact_env_step(self.h, int(particle), int(action), _p(out, C.c_int64), C.byref(rew),
+                                                  C.byref(draws)))
+        return dict(obs_good=int(out[0]), terminal=int(out[1]), legal=int(out[2]), next_cell=int(out[3]),
+                    next_rocks=int(out[4]), particle=int(out[5]), reward=rew.value, draws=draws.value)
+
+    def update(self, action, obs_good, sampled_after):
+        dis, draws = C.c_int32(), C.c_uint64()
+        rc = self._ck(self.lib.pomcp_refexact_update(self.h, int(action), int(bool(obs_good)), int(sampled_after),
+                                                     C.byref(dis), C.byref(draws)))
+        return dict(status=rc, disable_tree=bool(dis.value), draws=draws.value)
