@@ -300,7 +300,9 @@ __device__ __forceinline__ int select_thread(const SearchParams &p, int X, uint3
 //     [expand]    every simulation chooses, steps the model, looks up / creates the child and -- if the child has
 //                 statistics -- registers its arrival there for the next level; a child without statistics
 //                 ("virgin": N = 0, e.g. just created) is finished on the spot: uniform action, step, leaf
-// (one grid barrier after each), then [rollout + backup] with commutative integer atomics.
+// with one grid barrier after each; while a block waits at such a barrier it advances the rollouts of its own leaves
+// in slices.  Then [rollout + backup]: the remaining rollouts and the backups (commutative integer atomics) are
+// claimed 32 simulations at a time from a work counter.
 // ---------------------------------------------------------------------------------------------------------
 struct SimCtx {
     const SearchParams &p;
@@ -1309,9 +1311,17 @@ extern "C" int pomcp_generate_steps(pomcp_handle *h, int64_t n, const uint32_t *
     if (!h->have_model) return fail(h, "set the model first");
     if (n <= 0) return 0;
     CK(cudaSetDevice(h->device));
-    uint32_t *ds, *dn, *dw0, *dw1; uint8_t *da, *df; uint64_t *du; double *dr;
-    CK(cudaMalloc(&ds, n * 4)); CK(cudaMalloc(&dn, n * 4)); CK(cudaMalloc(&da, n)); CK(cudaMalloc(&df, n));
-    CK(cudaMalloc(&du, n * 8)); CK(cudaMalloc(&dr, n * 8)); CK(cudaMalloc(&dw0, n * 4)); CK(cudaMalloc(&dw1, n * 4));
+    struct Scratch {                                      // device scratch, released on every exit path
+        void *p[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        ~Scratch() { for (void *q : p) cudaFree(q); }
+    } sc;
+    const size_t bytes[8] = {(size_t)n * 4, (size_t)n * 4, (size_t)n, (size_t)n, (size_t)n * 8, (size_t)n * 8, (size_t)n * 4,
+                             (size_t)n * 4};
+    for (int i = 0; i < 8; ++i) CK(cudaMalloc(&sc.p[i], bytes[i]));
+    uint32_t *ds = (uint32_t *)sc.p[0], *dn = (uint32_t *)sc.p[1], *dw0 = (uint32_t *)sc.p[6], *dw1 = (uint32_t *)sc.p[7];
+    uint8_t *da = (uint8_t *)sc.p[2], *df = (uint8_t *)sc.p[3];
+    uint64_t *du = (uint64_t *)sc.p[4];
+    double *dr = (double *)sc.p[5];
     CK(cudaMemcpy(dw0, actual, n * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(dw1, sampled, n * 4, cudaMemcpyHostToDevice));
     CK(cudaMemcpy(ds, state, n * 4, cudaMemcpyHostToDevice));
@@ -1324,7 +1334,6 @@ extern "C" int pomcp_generate_steps(pomcp_handle *h, int64_t n, const uint32_t *
     CK(cudaMemcpy(next_state, dn, n * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(flags, df, n, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(reward, dr, n * 8, cudaMemcpyDeviceToHost));
-    cudaFree(ds); cudaFree(dn); cudaFree(da); cudaFree(df); cudaFree(du); cudaFree(dr); cudaFree(dw0); cudaFree(dw1);
     return 0;
 }
 

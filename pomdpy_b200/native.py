@@ -258,7 +258,7 @@ class ReferenceExact:
         thr53 = np.ascontiguousarray(thr53, dtype=np.uint64).reshape(-1)
         rewards = np.ascontiguousarray(rewards, dtype=np.float64)
         bag = np.ascontiguousarray(bag_rocks, dtype=np.uint32)
-        log_table = np.log(np.arange(n_log, dtype=np.float64) + 1.0)          # numpy's ln(N + 1), as the reference
+        # ln(N + 1) exactly as the reference evaluates it: np.log on a Python int, one scalar at a time
         log_table = np.array([np.log(N + 1) for N in range(n_log)], dtype=np.float64)
         self.h = C.c_void_p()
         rc = self.lib.pomcp_refexact_create(int(device), int(rows), int(cols), _p(cell, C.c_int8), int(start_cell),
