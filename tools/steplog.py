@@ -13,4 +13,4 @@ L = pl.steplog()
 for i in range(min(128, c["level_steps"] // 3)):
     print(i, "wait %.1f alloc %.1f wait2 %.1f expand %.1f us  nwl %d" % (L[i, 0] / 1e3, L[i, 1] / 1e3, L[i, 2] / 1e3, L[i, 3] / 1e3, L[i, 4]))
 
-print("tsec cycles [choice, step+path, child, virgin/rowsum, syncwarp, arrive]:", L[127].tolist())
+print("tsec cycles [choice, step+path, child, leaf-or-descend, syncwarp, arrive, load-sim, load-node]:", L[127].tolist())
