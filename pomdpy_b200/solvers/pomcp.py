@@ -106,9 +106,18 @@ class POMCP(Solver):
     # ---- plumbing -------------------------------------------------------------------------------------
     def _acquire_planner(self, agent):
         model = self.model
-        wmax = int(getattr(model, "gen_wmax", 0)) or max(32, min(1 << 18, self.sims_per_rank // 4 or 1))
-        w0 = int(getattr(model, "gen_w0", 0)) or max(1, min(1024, wmax // 16))
-        growth = int(getattr(model, "gen_growth", 0)) or 2
+        # Generation schedule (simulations in flight): small budgets keep the waves narrow (quality first: at
+        # n_sims = 500 widths up to 64 match the sequential planner's return, 128 starts to cost); large budgets use
+        # the throughput schedule of bench.py (x4 growth up to half the budget; return at 1e6 simulations per move
+        # is insensitive to it, profiles/r01_schedule_sweep.txt).
+        if self.sims_per_rank <= 4096:
+            auto = (max(1, min(1024, (self.sims_per_rank // 4 or 1) // 16)), 2, max(32, self.sims_per_rank // 4 or 1))
+        else:
+            wm = min(1 << 19, self.sims_per_rank // 2)
+            auto = (max(1, wm // 128), 4, wm)
+        w0 = int(getattr(model, "gen_w0", 0)) or auto[0]
+        growth = int(getattr(model, "gen_growth", 0)) or auto[1]
+        wmax = max(int(getattr(model, "gen_wmax", 0)) or auto[2], w0)
         max_steps = int(getattr(model, "max_steps", 200))
         cap = int(getattr(model, "node_capacity", 0)) or \
             int(min(1 << 24, max(1 << 14, self.sims_per_rank * min(max_steps, 8) + 64)))
