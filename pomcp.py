@@ -45,6 +45,7 @@ def build_parser():
     p.add_argument("--gen_w0", default=0, type=int, help="first generation width of the device search (0 = auto)")
     p.add_argument("--gen_growth", default=0, type=int, help="generation growth factor (0 = auto)")
     p.add_argument("--gen_wmax", default=0, type=int, help="max simulations in flight (0 = auto)")
+    p.add_argument("--concurrent_epochs", default=0, type=int, help="run this many epochs at once on the GPU (0 = serial)")
     p.set_defaults(preferred_actions=False, use_tf=False, save=False)
     return p
 
@@ -74,6 +75,16 @@ def main(argv=None):
         env = RockModel(args)
         if util.VERBOSITY >= 3:
             env.draw_env()
+        lanes = args.pop("concurrent_epochs", 0)
+        if lanes and lanes > 1 and world == 1:
+            from pomdpy_b200.batch import BatchedAgent
+            from pomdpy_b200.util import console
+            agent = BatchedAgent(env, lanes)
+            mean, err = agent.run(args["n_epochs"])
+            console(2, "agent", "epochs: " + str(args["n_epochs"]))
+            console(2, "agent", "ave discounted return/step: " + str(mean) + " +- " + str(err))
+            console(2, "agent", "ave time/epoch: " + str(agent.wall_seconds / max(1, args["n_epochs"])))
+            return agent
         agent = Agent(env, POMCP)
         agent.discounted_return()
         return agent

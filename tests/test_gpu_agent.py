@@ -56,3 +56,18 @@ def test_cli_preferred_actions_runs():
     print("preferred actions: %.2f +- %.2f" % (er.discounted_return.mean, er.discounted_return.std_err()))
     assert er.discounted_return.count == 20
     assert -5.0 < er.discounted_return.mean < 26.0        # reference: 7.2 pooled over 40 epochs
+
+
+def test_batched_epochs_match_serial_level_and_are_faster():
+    """Episode-level batching (pomdpy_b200/batch.py): 256 epochs on 32 concurrent lanes."""
+    import time
+    import pomcp as cli
+    t0 = time.time()
+    agent = cli.main(["--env", "RockSample", "--solver", "POMCP", "--n_epochs", "256", "--n_sims", "500", "--seed", "123",
+                      "--verbosity", "0", "--concurrent_epochs", "32"])
+    dt = time.time() - t0
+    st = agent.discounted_return
+    print("batched: %.2f +- %.2f over %d epochs, %.1f ms/epoch (%.0f epochs/s)" % (st.mean, st.std_err(), st.count,
+                                                                                  1e3 * agent.wall_seconds / 256, 256 / agent.wall_seconds))
+    assert st.count == 256 and 14.62 - 2.0 < st.mean < 20.5
+    assert agent.total_sims >= 256 * 500 and dt < 60
