@@ -20,6 +20,7 @@ extern "C" {
 #define POMCP_MAX_ACTIONS 32   /* |A| = 5 + n_rocks <= 32: one warp lane per action */
 #define POMCP_MAX_CELLS 256
 #define POMCP_MAX_ROCKS 24
+#define POMCP_MAX_OBS 32       /* tabular models: |Z| <= 32 observations */
 #define POMCP_QFIX_SCALE 16777216.0 /* root statistics carry sum(q) as a 2^-24 fixed-point integer */
 
 typedef struct pomcp_handle pomcp_handle;
@@ -51,6 +52,16 @@ const char *pomcp_last_error(const pomcp_handle *h);
  * {illegal, exit, good sample, bad sample}. */
 int pomcp_set_model_rocksample(pomcp_handle *h, int rows, int cols, const int8_t *cell, int start_cell,
                                const uint64_t *thr53, const double rewards[4]);
+
+/* Any model given by explicit matrices -- what the reference's Model ABC exposes through get_transition_matrix /
+ * get_observation_matrix / get_reward_matrix (pomdpy/pomdp/model.py:133-160, examples/tiger/tiger_model.py:102-139) --
+ * as 32-bit cumulative thresholds: Tc[a][s][s'] = min(floor(2^32 * sum_{j<=s'} T[a][s][j]), 2^32 - 1) and
+ * Oc[a][s'][z] likewise (every row must end at 0xFFFFFFFF); R[a][s]; term_action_mask marks the actions that end an
+ * episode (Tiger: opening a door), term_state[s'] the absorbing states (may be NULL).  A packed state is the state
+ * index; observations are indices 0..n_obs-1 (the obs_good argument of pomcp_advance / pomcp_node_stats). */
+int pomcp_set_model_tabular(pomcp_handle *h, int n_states, int n_actions, int n_obs, const uint32_t *Tc,
+                            const uint32_t *Oc, const double *R, uint32_t term_action_mask,
+                            const uint8_t *term_state);
 
 /* --preferred_actions (pomcp.py:30-31; examples/rock_sample/rock_position_history.py:52-55, 96-137, 170-234): nodes
  * carry per-rock statistics and their in-tree action set is generate_smart_actions(); prob is the sensor
@@ -106,6 +117,11 @@ int pomcp_root_particles(pomcp_handle *h, uint32_t *out, int capacity, int32_t *
 int pomcp_generate_steps(pomcp_handle *h, int64_t n, const uint32_t *state, const uint8_t *action,
                          const uint64_t *u53, const uint32_t *actual_mask, const uint32_t *sampled_mask,
                          uint32_t *next_state, uint8_t *flags, double *reward);
+
+/* generate_step of the tabular model for a batch: state, action and two 32-bit draws per item (w1 -> next state,
+ * w2 -> observation) -> next state, observation, reward, terminal flag.  Host arrays. */
+int pomcp_tabular_steps(pomcp_handle *h, int64_t n, const uint32_t *state, const uint8_t *action, const uint32_t *w1,
+                        const uint32_t *w2, uint32_t *next_state, int32_t *obs, double *reward, uint8_t *terminal);
 
 /* counters: [0] tree levels, [1] rollout steps, [2] nodes created, [3] nodes in arena, [4] allocation nodes,
  * [5] generations, [6] level steps, [7] last search ns (device globaltimer), [8] sims of last search,

@@ -77,6 +77,12 @@ def lib():
         L.orc_gs_root_cell.argtypes = [vp]
         L.orc_gs_set_preferred.argtypes = [vp, i32]
         L.orc_model_set_prob.argtypes = [vp, P(dbl)]
+        L.orc_tab_create.restype = vp
+        L.orc_tab_create.argtypes = [i32, i32, i32, P(u32), P(u32), P(dbl), u32, P(C.c_uint8)]
+        L.orc_tab_destroy.argtypes = [vp]
+        L.orc_tab_step.argtypes = [vp, i32, i32, u32, u32, i32, P(i32), P(i32), P(dbl), P(i32)]
+        L.orc_gs_create_tab.restype = vp
+        L.orc_gs_create_tab.argtypes = [vp, P(u32), i32, i32, i32, dbl, dbl, u64]
         L.orc_rockstats_init.argtypes = [vp, vp]
         L.orc_rockstats_child.argtypes = [vp, vp, i32, i32, i32, vp]
         L.orc_smart_mask.restype = u32
@@ -136,6 +142,37 @@ class Model:
         o = StepOut()
         lib().orc_step(self.h, _p(w, C.c_uint32), int(cell), int(rocks), int(action), int(u53), C.byref(o))
         return o
+
+
+class TabularModel:
+    """Tabular POMDP tables: cumulative 32-bit thresholds Tc[a][s][s'], Oc[a][s'][z], rewards R[a][s], the mask of
+    actions that end the episode and per-state terminal flags."""
+
+    def __init__(self, Tc, Oc, R, term_action_mask=0, term_state=None):
+        self.Tc = np.ascontiguousarray(Tc, dtype=np.uint32)
+        self.Oc = np.ascontiguousarray(Oc, dtype=np.uint32)
+        self.R = np.ascontiguousarray(R, dtype=np.float64)
+        self.n_actions, self.n_states, _ = self.Tc.shape
+        self.n_obs = self.Oc.shape[2]
+        self.start_cell = 0
+        ts = np.zeros(self.n_states, dtype=np.uint8) if term_state is None else \
+            np.ascontiguousarray(term_state, dtype=np.uint8)
+        self.h = lib().orc_tab_create(self.n_states, self.n_actions, self.n_obs, _p(self.Tc, C.c_uint32),
+                                      _p(self.Oc, C.c_uint32), _p(self.R, C.c_double), int(term_action_mask),
+                                      _p(ts, C.c_uint8))
+        if not self.h:
+            raise ValueError("tabular model outside the oracle's limits")
+
+    def __del__(self):
+        if getattr(self, "h", None):
+            lib().orc_tab_destroy(self.h)
+            self.h = None
+
+    def step(self, s, a, w1, w2, with_obs=True):
+        nxt, obs, term, rew = C.c_int32(), C.c_int32(), C.c_int32(), C.c_double()
+        lib().orc_tab_step(self.h, int(s), int(a), int(w1), int(w2), int(bool(with_obs)), C.byref(nxt),
+                           C.byref(obs), C.byref(rew), C.byref(term))
+        return nxt.value, obs.value, rew.value, term.value
 
 
 class RockStats(C.Structure):
@@ -229,8 +266,13 @@ class GsPOMCP:
         self.seed = int(seed)
         b = np.ascontiguousarray(bag_packed, dtype=np.uint32)
         rc = model.start_cell if root_cell is None else int(root_cell)
-        self.h = lib().orc_gs_create(model.h, int(actual_mask), int(sampled_mask), _p(b, C.c_uint32), len(b), rc,
-                                     int(max_depth), int(dcap), float(ucb_c), float(discount), self.seed)
+        self.tabular = isinstance(model, TabularModel)
+        if self.tabular:
+            self.h = lib().orc_gs_create_tab(model.h, _p(b, C.c_uint32), len(b), int(max_depth), int(dcap),
+                                             float(ucb_c), float(discount), self.seed)
+        else:
+            self.h = lib().orc_gs_create(model.h, int(actual_mask), int(sampled_mask), _p(b, C.c_uint32), len(b), rc,
+                                         int(max_depth), int(dcap), float(ucb_c), float(discount), self.seed)
 
     def __del__(self):
         if getattr(self, "h", None):
@@ -283,7 +325,7 @@ class GsPOMCP:
     def update(self, action, obs_good, sampled_mask_after, move=0, need=2000, max_tries=None):
         status, tries = C.c_int32(), C.c_int64()
         mt = int(max_tries if max_tries is not None else 256 * need)
-        got = lib().orc_gs_update(self.h, int(action), int(bool(obs_good)), int(sampled_mask_after), int(move),
+        got = lib().orc_gs_update(self.h, int(action), int(obs_good), int(sampled_mask_after), int(move),
                                   int(need), mt, C.byref(status), C.byref(tries))
         return dict(accepted=int(got), status=status.value, tries=tries.value)
 

@@ -575,17 +575,68 @@ float orc_det_logf_u32(uint32_t x)
     return (float)e * 0.693145751953125f + ((float)e * 1.42860682030941723212e-6f + lnm);
 }
 
+/* ------------------------------------------------------------------------------------------------------------
+ * Tabular POMDP (the reference's Model ABC with explicit matrices, e.g. examples/tiger/tiger_model.py:102-139):
+ * T[a][s][s'], O[a][s'][z], R[a][s], as 32-bit cumulative thresholds floor(cumsum * 2^32) (last entry 0xFFFFFFFF).
+ * A draw w picks the first index k with cdf[k] > min(w, 2^32 - 2): zero-probability entries are never picked.
+ * An episode ends after an action of term_action_mask (Tiger: opening a door) or on entering a term_state.
+ * ---------------------------------------------------------------------------------------------------------- */
+#define ORC_ZS_MAX 32
+typedef struct {
+    int32_t S, A, Z, ZS;                 /* ZS: observation stride of the child table (power of two >= Z) */
+    uint32_t term_action_mask;
+    uint32_t *Tc, *Oc; double *R; uint8_t *term_state;
+} orc_tab;
+
+orc_tab *orc_tab_create(int S, int A, int Z, const uint32_t *Tc, const uint32_t *Oc, const double *R,
+                        uint32_t term_action_mask, const uint8_t *term_state)
+{
+    if (S < 1 || A < 1 || A > ORC_MAX_ACTIONS || Z < 1 || Z > ORC_ZS_MAX) return NULL;
+    orc_tab *m = (orc_tab *)calloc(1, sizeof(orc_tab));
+    m->S = S; m->A = A; m->Z = Z; m->ZS = 2; while (m->ZS < Z) m->ZS *= 2;
+    m->term_action_mask = term_action_mask;
+    size_t nt = (size_t)A * S * S, no = (size_t)A * S * Z;
+    m->Tc = (uint32_t *)malloc(4 * nt); memcpy(m->Tc, Tc, 4 * nt);
+    m->Oc = (uint32_t *)malloc(4 * no); memcpy(m->Oc, Oc, 4 * no);
+    m->R = (double *)malloc(8 * (size_t)A * S); memcpy(m->R, R, 8 * (size_t)A * S);
+    m->term_state = (uint8_t *)calloc((size_t)S, 1);
+    if (term_state) memcpy(m->term_state, term_state, (size_t)S);
+    return m;
+}
+void orc_tab_destroy(orc_tab *m) { if (!m) return; free(m->Tc); free(m->Oc); free(m->R); free(m->term_state); free(m); }
+
+static int tab_sample(const uint32_t *cdf, int n, uint32_t w)
+{
+    if (w == 0xFFFFFFFFu) w = 0xFFFFFFFEu;
+    int lo = 0, hi = n - 1;
+    while (lo < hi) { int mid = (lo + hi) >> 1; if (cdf[mid] > w) hi = mid; else lo = mid + 1; }
+    return lo;
+}
+
+/* generate_step of a tabular model: w1 draws the next state, w2 the observation (not drawn in rollouts) */
+void orc_tab_step(const orc_tab *m, int s, int a, uint32_t w1, uint32_t w2, int with_obs,
+                  int32_t *next, int32_t *obs, double *reward, int32_t *terminal)
+{
+    int ns = tab_sample(m->Tc + ((size_t)a * m->S + s) * m->S, m->S, w1);
+    *next = ns;
+    *obs = with_obs ? tab_sample(m->Oc + ((size_t)a * m->S + ns) * m->Z, m->Z, w2) : 0;
+    *reward = m->R[(size_t)a * m->S + s];
+    *terminal = (int)((m->term_action_mask >> a) & 1u) | (int)m->term_state[ns];
+}
+
 typedef struct {
     int32_t cell; uint32_t legal;
     int64_t n[ORC_MAX_ACTIONS];
     int64_t qfix[ORC_MAX_ACTIONS];             /* sum of llrint(q * 2^24) */
-    int32_t child[ORC_MAX_ACTIONS][2];
     orc_rockstats st;                          /* only meaningful with preferred actions */
 } gs_node;
 
 typedef struct {
-    const orc_model *m; orc_world w;
+    const orc_model *m; orc_world w;           /* RockSample ... */
+    const orc_tab *tm;                         /* ... or a tabular model (m == NULL) */
+    int32_t A, ZS;                             /* action count, observation stride of the child table */
     gs_node *nodes; int32_t n_nodes, cap_nodes; int32_t root;
+    int32_t *child;                            /* [cap_nodes][32][ZS] child ids keyed (action, observation), -1 = none */
     uint32_t *bag; int32_t n_bag;              /* packed states: cell | rocks << 8 */
     int32_t max_depth, dcap; double ucb_c, discount;
     uint32_t key[2];
@@ -594,16 +645,43 @@ typedef struct {
     int32_t preferred;                         /* --preferred_actions: in-tree action sets from the rock statistics */
 } orc_gs;
 
+/* Model dispatch of the gs planner.  A packed state is cell | rocks << 8 (RockSample) or the state index (tabular);
+ * a node's tag is what its action set depends on: the robot cell (RockSample), nothing (tabular: 0). */
+typedef struct { uint32_t next; int32_t tag; int32_t obs; double reward; int32_t terminal; } gs_step_out;
+
+static uint32_t gs_tag_legal(const orc_gs *h, int32_t tag)
+{ return h->m ? h->m->legal[tag] : (h->A >= 32 ? 0xFFFFFFFFu : ((1u << h->A) - 1u)); }
+static int32_t gs_state_tag(const orc_gs *h, uint32_t st) { return h->m ? (int32_t)(st & 0xFFu) : 0; }
+
+static void gs_step(const orc_gs *h, uint32_t st, int a, uint32_t w1, uint32_t w2, int rollout, gs_step_out *o)
+{
+    if (h->m) {
+        orc_step_out r;
+        orc_step(h->m, &h->w, (int)(st & 0xFFu), st >> 8, a, rollout ? (uint64_t)w1 << 21 : u53_of(w1, w2), &r);
+        o->next = (uint32_t)r.next_cell | (r.next_rocks << 8); o->tag = r.next_cell; o->obs = r.obs_good ? 1 : 0;
+        o->reward = r.reward; o->terminal = r.terminal;
+    } else {
+        int32_t ns;
+        orc_tab_step(h->tm, (int)st, a, w1, w2, !rollout, &ns, &o->obs, &o->reward, &o->terminal);
+        o->next = (uint32_t)ns; o->tag = 0;
+    }
+}
+
+static int32_t *gs_child(const orc_gs *h, int32_t X, int a, int o)
+{ return &h->child[((size_t)X * ORC_MAX_ACTIONS + (size_t)a) * (size_t)h->ZS + (size_t)o]; }
+
 static int32_t gs_new_node(orc_gs *h, int32_t cell)
 {
     if (h->n_nodes == h->cap_nodes) {
         h->cap_nodes = h->cap_nodes ? h->cap_nodes * 2 : 1024;
         h->nodes = (gs_node *)realloc(h->nodes, sizeof(gs_node) * (size_t)h->cap_nodes);
+        h->child = (int32_t *)realloc(h->child, sizeof(int32_t) * (size_t)h->cap_nodes * ORC_MAX_ACTIONS * (size_t)h->ZS);
     }
     gs_node *nd = &h->nodes[h->n_nodes];
     memset(nd, 0, sizeof(*nd));
-    nd->cell = cell; nd->legal = h->m->legal[cell];
-    for (int a = 0; a < ORC_MAX_ACTIONS; ++a) nd->child[a][0] = nd->child[a][1] = -1;
+    nd->cell = cell; nd->legal = gs_tag_legal(h, cell);
+    int32_t *c = gs_child(h, h->n_nodes, 0, 0);
+    for (int i = 0; i < ORC_MAX_ACTIONS * h->ZS; ++i) c[i] = -1;
     return h->n_nodes++;
 }
 
@@ -613,6 +691,7 @@ orc_gs *orc_gs_create(const orc_model *m, uint32_t actual_mask, uint32_t sampled
 {
     orc_gs *h = (orc_gs *)calloc(1, sizeof(orc_gs));
     h->m = m; h->w.actual_mask = actual_mask; h->w.sampled_mask = sampled_mask;
+    h->A = m->n_actions; h->ZS = 2;
     h->max_depth = max_depth; h->dcap = dcap; h->ucb_c = ucb_c; h->discount = discount;
     h->key[0] = (uint32_t)seed; h->key[1] = (uint32_t)(seed >> 32);
     h->bag = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(n_bag > 0 ? n_bag : 1));
@@ -620,7 +699,20 @@ orc_gs *orc_gs_create(const orc_model *m, uint32_t actual_mask, uint32_t sampled
     h->root = gs_new_node(h, root_cell);
     return h;
 }
-void orc_gs_destroy(orc_gs *h) { if (!h) return; free(h->nodes); free(h->bag); free(h); }
+/* The same planner over a tabular model; bag_packed holds state indices. */
+orc_gs *orc_gs_create_tab(const orc_tab *tm, const uint32_t *bag_packed, int n_bag,
+                          int max_depth, int dcap, double ucb_c, double discount, uint64_t seed)
+{
+    orc_gs *h = (orc_gs *)calloc(1, sizeof(orc_gs));
+    h->tm = tm; h->A = tm->A; h->ZS = tm->ZS;
+    h->max_depth = max_depth; h->dcap = dcap; h->ucb_c = ucb_c; h->discount = discount;
+    h->key[0] = (uint32_t)seed; h->key[1] = (uint32_t)(seed >> 32);
+    h->bag = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)(n_bag > 0 ? n_bag : 1));
+    memcpy(h->bag, bag_packed, sizeof(uint32_t) * (size_t)n_bag); h->n_bag = n_bag;
+    h->root = gs_new_node(h, 0);
+    return h;
+}
+void orc_gs_destroy(orc_gs *h) { if (!h) return; free(h->nodes); free(h->child); free(h->bag); free(h); }
 void orc_gs_set_world(orc_gs *h, uint32_t actual, uint32_t sampled) { h->w.actual_mask = actual; h->w.sampled_mask = sampled; }
 
 /* --preferred_actions (rock_position_history.py:52-55): call right after orc_gs_create; the root gets fresh
@@ -672,7 +764,7 @@ static float butterfly_sum32(const float v[32])
  * 32-bit draw x takes the first action a with x < thr[a], or `*last` if there is none. */
 static void gs_allocation(const orc_gs *h, const gs_node *nd, int64_t k, uint32_t thr[32], int *last)
 {
-    int A = h->m->n_actions;
+    int A = h->A;
     int64_t N = 0; int untried = 0, nlegal = 0;
     float v[32]; const float cf = (float)h->ucb_c;
     for (int a = 0; a < 32; ++a) v[a] = 0.0f;
@@ -739,7 +831,7 @@ static int nth_set_bit(uint32_t mask, uint32_t j)
  * Untried actions score +inf (solvers/pomcp.py:64-65): with at least k of them the draw is uniform over them. */
 static int gs_select(const orc_gs *h, const gs_node *nd, uint32_t x0, int64_t k)
 {
-    int A = h->m->n_actions; const float cf = (float)h->ucb_c;
+    int A = h->A; const float cf = (float)h->ucb_c;
     int64_t N = 0; uint32_t untried = 0;
     for (int a = 0; a < A; ++a) if ((nd->legal >> a) & 1u) { N += nd->n[a]; if (nd->n[a] == 0) untried |= 1u << a; }
     uint32_t nu = (uint32_t)__builtin_popcount(untried);
@@ -776,7 +868,7 @@ static int gs_select(const orc_gs *h, const gs_node *nd, uint32_t x0, int64_t k)
 
 typedef struct {
     uint32_t sim;          /* global simulation index (stream id) */
-    int32_t cell; uint32_t rocks;
+    uint32_t st;           /* packed state */
     int32_t node, depth;   /* current node / number of path entries */
     int32_t status;        /* 0 descending, 1 leaf: rollout pending, 2 done (terminal or horizon) */
     int32_t *pnode; uint8_t *pact; double *prew;
@@ -787,21 +879,21 @@ typedef struct {
 static double gs_rollout(orc_gs *h, gs_sim *s, uint32_t move)
 {
     double sum = 0.0, disc = 1.0; int t = 0, terminal = 0;
-    int cell = s->cell; uint32_t rocks = s->rocks;
+    uint32_t st = s->st;
     uint32_t x[4] = {0, 0, 0, 0};
     while (t < h->max_depth && !terminal) {
         /* one Philox block per two rollout steps: words (0,1) then (2,3); the first word picks the action, the
-         * second is the top 32 bits of the 53-bit sensor uniform */
+         * second drives the model (RockSample: top 32 bits of the 53-bit sensor uniform; tabular: next state) */
         if ((t & 1) == 0) gs_block(h, (uint32_t)(s->depth + 1 + (t >> 1)), s->sim, move, DOM_SIM, x);
         uint32_t w0 = x[(t & 1) * 2], w1 = x[(t & 1) * 2 + 1];
-        uint32_t mask = h->m->legal[cell];
+        uint32_t mask = gs_tag_legal(h, gs_state_tag(h, st));
         int idx = (int)randbelow32(w0, (uint32_t)__builtin_popcount(mask)), a = -1;
         for (int b = 0, seen = 0; b < 32; ++b) if ((mask >> b) & 1u) { if (seen == idx) { a = b; break; } ++seen; }
-        orc_step_out o; orc_step(h->m, &h->w, cell, rocks, a, (uint64_t)w1 << 21, &o);
+        gs_step_out o; gs_step(h, st, a, w1, 0u, 1, &o);
         terminal = o.terminal;
         if (o.reward != 0.0) sum += o.reward * disc;
         disc *= h->discount;
-        cell = o.next_cell; rocks = o.next_rocks;
+        st = o.next;
         ++t; h->n_rollout_steps++;
     }
     return sum;
@@ -812,7 +904,6 @@ static double gs_rollout(orc_gs *h, gs_sim *s, uint32_t move)
 int orc_gs_search(orc_gs *h, int64_t n_sims, uint32_t sim_offset, uint32_t move, int w0, int growth, int wmax)
 {
     if (w0 < 1) w0 = 1; if (growth < 1) growth = 1; if (wmax < w0) wmax = w0;
-    int A = h->m->n_actions; (void)A;
     int dcap = h->dcap;
     int64_t done = 0; int64_t W = w0;
     gs_sim *S = (gs_sim *)calloc((size_t)wmax, sizeof(gs_sim));
@@ -828,8 +919,7 @@ int orc_gs_search(orc_gs *h, int64_t n_sims, uint32_t sim_offset, uint32_t move,
             s->sim = sim_offset + (uint32_t)(done + i);
             s->pnode = pn + i * dcap; s->pact = pa + i * dcap; s->prew = pr + i * dcap;
             uint32_t x[4]; gs_block(h, 0, s->sim, move, DOM_SIM, x);
-            uint32_t st = h->bag[randbelow32(x[0], (uint32_t)h->n_bag)];
-            s->cell = (int32_t)(st & 0xFFu); s->rocks = st >> 8;
+            s->st = h->bag[randbelow32(x[0], (uint32_t)h->n_bag)];
             s->node = h->root; s->depth = 0; s->status = 0; s->delayed = 0.0;
         }
         for (;;) {                                  /* level steps */
@@ -871,19 +961,19 @@ int orc_gs_search(orc_gs *h, int64_t n_sims, uint32_t sim_offset, uint32_t move,
                     a = alloc_last[X];
                     for (int b = 0; b < 32; ++b) if (x[0] < thr[b]) { a = b; break; }
                 }
-                orc_step_out o; orc_step(h->m, &h->w, s->cell, s->rocks, a, u53_of(x[1], x[2]), &o);
+                gs_step_out o; gs_step(h, s->st, a, x[1], x[2], 0, &o);
                 h->n_levels++;
                 s->pnode[d] = X; s->pact[d] = (uint8_t)a; s->prew[d] = o.reward; s->depth = d + 1;
                 if (s->depth > h->max_tree_depth) h->max_tree_depth = s->depth;
-                int og = o.obs_good ? 1 : 0;
-                int32_t child = nd->child[a][og];
+                int og = o.obs;
+                int32_t child = *gs_child(h, X, a, og);
                 int64_t Nx = 0; for (int b = 0; b < 32; ++b) Nx += nd->n[b];
                 if (child < 0 && !o.terminal && Nx > 0 && d + 1 < dcap) {   /* solvers/pomcp.py:107 */
-                    child = gs_new_node(h, o.next_cell); nd = &h->nodes[X];
+                    child = gs_new_node(h, o.tag); nd = &h->nodes[X];
                     gs_init_child(h, child, X, a, og);
-                    nd->child[a][og] = child; h->n_created++;
+                    *gs_child(h, X, a, og) = child; h->n_created++;
                 }
-                s->cell = o.next_cell; s->rocks = o.next_rocks;
+                s->st = o.next;
                 if (o.terminal) { s->status = 2; s->delayed = 0.0; }
                 else if (child >= 0) { s->node = child; }
                 else s->status = 1;
@@ -916,7 +1006,7 @@ int orc_gs_search(orc_gs *h, int64_t n_sims, uint32_t sim_offset, uint32_t move,
 void orc_gs_root_stats(const orc_gs *h, int64_t *n, int64_t *qfix, uint32_t *legal)
 {
     const gs_node *nd = &h->nodes[h->root];
-    for (int a = 0; a < h->m->n_actions; ++a) { n[a] = nd->n[a]; qfix[a] = nd->qfix[a]; }
+    for (int a = 0; a < h->A; ++a) { n[a] = nd->n[a]; qfix[a] = nd->qfix[a]; }
     *legal = nd->legal;
 }
 void orc_gs_counters(const orc_gs *h, int64_t out[8])
@@ -929,9 +1019,9 @@ void orc_gs_counters(const orc_gs *h, int64_t out[8])
 int orc_gs_node_stats(const orc_gs *h, const int32_t *path_ao, int len, int64_t *n, int64_t *qfix, uint32_t *legal, int32_t *cell)
 {
     int32_t X = h->root;
-    for (int i = 0; i < len; ++i) { X = h->nodes[X].child[path_ao[2 * i]][path_ao[2 * i + 1]]; if (X < 0) return 1; }
+    for (int i = 0; i < len; ++i) { X = *gs_child(h, X, path_ao[2 * i], path_ao[2 * i + 1]); if (X < 0) return 1; }
     const gs_node *nd = &h->nodes[X];
-    for (int a = 0; a < h->m->n_actions; ++a) { n[a] = nd->n[a]; qfix[a] = nd->qfix[a]; }
+    for (int a = 0; a < h->A; ++a) { n[a] = nd->n[a]; qfix[a] = nd->qfix[a]; }
     *legal = nd->legal; *cell = nd->cell;
     return 0;
 }
@@ -958,25 +1048,26 @@ int orc_gs_greedy(const int64_t *n, const int64_t *qfix, uint32_t legal, int n_a
 int64_t orc_gs_update(orc_gs *h, int action, int obs_good, uint32_t sampled_mask_after, uint32_t move,
                       int need, int64_t max_tries, int32_t *status, int64_t *tries_used)
 {
+    const int obs = h->m ? (obs_good ? 1 : 0) : obs_good;      /* tabular: the observation index */
     h->w.sampled_mask = sampled_mask_after;
     uint32_t *nb = (uint32_t *)malloc(sizeof(uint32_t) * (size_t)need);
     int64_t got = 0, t = 0;
     for (; t < max_tries && got < need; ++t) {
         uint32_t x[4]; gs_block(h, (uint32_t)t, (uint32_t)(t >> 32), move, DOM_UPDATE, x);
         uint32_t st = h->bag[randbelow32(x[0], (uint32_t)h->n_bag)];
-        orc_step_out o; orc_step(h->m, &h->w, (int)(st & 0xFFu), st >> 8, action, u53_of(x[1], x[2]), &o);
-        if ((o.obs_good ? 1 : 0) == (obs_good ? 1 : 0)) nb[got++] = (uint32_t)o.next_cell | (o.next_rocks << 8);
+        gs_step_out o; gs_step(h, st, action, x[1], x[2], 0, &o);
+        if (o.obs == obs) nb[got++] = o.next;
     }
     *tries_used = t;
     if (got == 0) { free(nb); *status = 2; return 0; }
     /* child position: make_next_position on the node's cell (rock_position_history.py:96-99) */
-    gs_node *root = &h->nodes[h->root];
-    int32_t child = root->child[action][obs_good ? 1 : 0];
+    int32_t child = *gs_child(h, h->root, action, obs);
     *status = 0;
     if (child < 0) {
-        orc_step_out o; orc_step(h->m, &h->w, root->cell, 0, action, 0, &o);
-        child = gs_new_node(h, o.next_cell); *status = 1;
-        gs_init_child(h, child, h->root, action, obs_good ? 1 : 0);
+        int32_t tag = 0;
+        if (h->m) { orc_step_out o; orc_step(h->m, &h->w, h->nodes[h->root].cell, 0, action, 0, &o); tag = o.next_cell; }
+        child = gs_new_node(h, tag); *status = 1;
+        gs_init_child(h, child, h->root, action, obs);
     }
     h->root = child;
     free(h->bag); h->bag = nb; h->n_bag = (int32_t)got;

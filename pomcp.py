@@ -12,7 +12,7 @@ import numpy as np
 
 def build_parser():
     p = argparse.ArgumentParser(description="Set the run parameters.")
-    p.add_argument("--env", type=str, help="Specify the env to solve {RockSample}")
+    p.add_argument("--env", type=str, help="Specify the env to solve {RockSample} (additive: Tiger)")
     p.add_argument("--solver", default="POMCP", type=str, help="Specify the solver to use {POMCP}")
     p.add_argument("--seed", default=1993, type=int, help="Specify the random seed for numpy.random")
     p.add_argument("--use_tf", dest="use_tf", action="store_true", help="Set if using TensorFlow")
@@ -86,6 +86,12 @@ def main(argv=None):
             console(2, "agent", "ave time/epoch: " + str(agent.wall_seconds / max(1, args["n_epochs"])))
             return agent
         agent = Agent(env, POMCP)
+        agent.discounted_return()
+        return agent
+    if args["env"] == "Tiger":           # additive: the reference's Tiger matrices under the CUDA planner
+        from pomdpy_b200.tabular import tiger
+        args.pop("concurrent_epochs", None)
+        agent = Agent(tiger(args), POMCP)
         agent.discounted_return()
         return agent
     print("Unknown env {}".format(args["env"]))

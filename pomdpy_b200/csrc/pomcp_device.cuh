@@ -107,6 +107,33 @@ __device__ __forceinline__ StepResult rs_step(const SmemModel &M, uint32_t cell,
     return r;
 }
 
+// ---------------------------------------------------------------------------------------------------------
+// Tabular POMDP (the reference's Model ABC with explicit matrices, e.g. examples/tiger/tiger_model.py:102-139):
+// T[a][s][s'], O[a][s'][z] as 32-bit cumulative thresholds floor(cumsum * 2^32) (last entry 0xFFFFFFFF), R[a][s].
+// The tables stay in global memory (L1/L2 resident for small models); a packed state is the state index.
+// ---------------------------------------------------------------------------------------------------------
+struct TabHeader {
+    int32_t S, A, Z, ZS;        // ZS: observation stride of the child table (power of two >= max(Z, 2))
+    uint32_t term_action_mask;  // actions that end the episode (Tiger: opening a door)
+    int32_t stage_d1;           // depth-1 edges fit the per-block shared-memory staging
+    int32_t pad0, pad1;
+};
+struct TabTables {
+    const uint32_t *Tc;         // [A][S][S]
+    const uint32_t *Oc;         // [A][S][Z]  (row: action, next state)
+    const double *R;            // [A][S]
+    const uint8_t *term_state;  // [S]
+};
+
+// first index k with cdf[k] > min(w, 2^32 - 2): zero-probability entries are never drawn
+__device__ __forceinline__ int tab_sample(const uint32_t *cdf, int n, uint32_t w)
+{
+    if (w == 0xFFFFFFFFu) w = 0xFFFFFFFEu;
+    int lo = 0, hi = n - 1;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(cdf + mid) > w) hi = mid; else lo = mid + 1; }
+    return lo;
+}
+
 // index of the j-th (0-based) set bit of a legal mask whose bits >= 5 are all set up to n_actions
 __device__ __forceinline__ int nth_legal(const ModelHeader *H, uint32_t mask, uint32_t j)
 {

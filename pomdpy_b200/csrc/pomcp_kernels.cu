@@ -72,9 +72,10 @@ struct DevState {
 struct Tree {                          // structure-of-arrays belief-tree arena
     int32_t *n;                        // [cap][AS]   visit_count of edge (node, action)
     long long *qfix;                   // [cap][AS]   sum of q in 2^-24 fixed point
-    uint32_t *child;                   // [cap][AS][2] child id + 1 keyed (action, obs_good), bit 31 = has statistics; 0 = none
+    uint32_t *child;                   // [cap][AS][ZS] child id + 1 keyed (action, observation), bit 31 = has statistics;
+                                       //              0 = none.  ZS = 2 for RockSample (obs_good)
     uint32_t *legal;                   // [cap]       legal-action mask (fixed at creation)
-    int32_t *cell;                     // [cap]       robot cell of the node
+    int32_t *cell;                     // [cap]       tag of the node: robot cell (RockSample), 0 (tabular)
     unsigned long long *arrive;        // [cap]       (stamp << 32) | arrivals in the current level step
     int32_t *slot;                     // [cap]       worklist slot of the node in the current level step
     double *chance;                    // [cap][24]   --preferred_actions: chance_good per rock (null otherwise)
@@ -89,7 +90,8 @@ struct SimBuf {                        // per simulation-in-flight scratch, SoA 
                                        //         3 rollout finished
     uint8_t *depth;                    // path entries recorded
     int32_t *path_node;                // [dcap][wmax]
-    uint16_t *path_ar;                 // [dcap][wmax] action | obs_good << 5 | reward id << 8
+    uint16_t *path_ar;                 // [dcap][wmax] action | obs_good << 5 | reward id << 8   (tabular: action | obs << 5)
+    double *path_rew;                  // [dcap][wmax] tabular models: the step reward (null for RockSample)
     int32_t *wl_node;                  // [wmax] worklist of nodes with arrivals in this level step
     uint32_t *wl_thr;                  // [wmax][32] cumulative action thresholds for nodes with >= 2 arrivals
     int32_t *wl_meta;                  // [wmax] last action (bits 0-7) | (N > 0) << 8
@@ -101,6 +103,8 @@ struct SearchParams {
     DevState *S;
     const ModelHeader *model;
     const uint64_t *thr53;
+    TabHeader tab;                     // tabular models (KIND 1); unused by RockSample
+    TabTables tt;
     Tree t;
     SimBuf b;
     const uint32_t *bag[2];
@@ -110,6 +114,137 @@ struct SearchParams {
     long long node_cap;
     double ucb_c, discount;
     unsigned long long timeout_ns;     // 0 = no wall-clock guard; measured from kernel start
+};
+
+// ---------------------------------------------------------------------------------------------------------
+// Model policies.  The planner kernels are templates over KIND: 0 = RockSample (tables staged in shared memory, the
+// reference's flagship and the benchmark), 1 = tabular POMDP (tables in global memory).  A policy provides the
+// generative step, the action set of a node tag and the rollout inner loop; everything else is model-agnostic.
+// ---------------------------------------------------------------------------------------------------------
+struct StepOut { uint32_t next, tag; int obs, rew, terminal; double reward; };
+
+template <int KIND> struct Mdl;
+
+template <> struct Mdl<0> {
+    struct Ctx { SmemModel M; uint32_t actual, sampled; };
+    static __device__ __forceinline__ size_t stage(unsigned char *smem, const ModelHeader *gm, const uint64_t *gthr,
+                                                   int n_thr, const TabHeader &, const TabTables &, Ctx &c)
+    {   // stage the model tables into shared memory; returns the first free byte offset (16-byte aligned)
+        const int nw = (int)(sizeof(ModelHeader) / 4);
+        uint32_t *dst = reinterpret_cast<uint32_t *>(smem);
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(gm);
+        for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
+        size_t off = (sizeof(ModelHeader) + 15) & ~size_t(15);
+        uint64_t *thr = reinterpret_cast<uint64_t *>(smem + off);
+        for (int i = threadIdx.x; i < n_thr; i += blockDim.x) thr[i] = gthr[i];
+        off += ((size_t)n_thr * 8 + 15) & ~size_t(15);
+        c.M.hdr = reinterpret_cast<const ModelHeader *>(smem);
+        c.M.thr53 = thr;
+        return off;
+    }
+    static __device__ __forceinline__ int n_actions(const Ctx &c, const ModelHeader *gm) { return gm->n_actions; }
+    static __device__ __forceinline__ int zs(const Ctx &) { return 2; }
+    static __device__ __forceinline__ bool stage_d1(const Ctx &) { return true; }
+    static __device__ __forceinline__ uint32_t state_tag(uint32_t st) { return st & 0xFFu; }
+    static __device__ __forceinline__ uint32_t tag_legal(const Ctx &c, uint32_t tag) { return c.M.hdr->legal[tag]; }
+    static __device__ __forceinline__ bool tag_ok(const Ctx &c, uint32_t tag) { return tag < (uint32_t)c.M.hdr->n_cells; }
+    static __device__ __forceinline__ StepOut step(const Ctx &c, uint32_t st, int a, uint32_t wy, uint32_t wz)
+    {
+        const StepResult sr = rs_step(c.M, st & 0xFFu, st >> 8, a, u53_of(wy, wz), c.actual, c.sampled);
+        return StepOut{sr.cell | (sr.rocks << 8), sr.cell, sr.good, sr.rew, sr.terminal, 0.0};
+    }
+    static __device__ __forceinline__ uint16_t path_code(int a, const StepOut &o)
+    { return (uint16_t)(a | (o.obs << 5) | (o.rew << 8)); }
+    static __device__ __forceinline__ int path_obs(uint32_t ar) { return (int)((ar >> 5) & 1u); }
+    static __device__ __forceinline__ double path_reward(const Ctx &c, uint32_t ar, const double *) { return c.M.hdr->rew[ar >> 8]; }
+    // Rollout steps t .. t_end-1 from packed state st (uniform legal actions); true when the episode ended.
+    // One Philox block per two steps: (x, y) then (z, w); word 0 picks the action, word 1 is the top 32 bits of the
+    // 53-bit sensor uniform.
+    static __device__ __forceinline__ bool rollout(const Ctx &c, DevState *S, uint32_t sim, uint32_t move, uint32_t key0,
+                                                   uint32_t key1, int depth, const double *disc, uint32_t &st, int &t,
+                                                   int t_end, double &sum)
+    {
+        const ModelHeader *H = c.M.hdr;
+        uint32_t cell = st & 0xFFu, rocks = st >> 8;
+        const uint32_t actual = c.actual, sampled = c.sampled;
+        bool finished = false;
+        Philox4 r{0u, 0u, 0u, 0u};
+        for (; t < t_end; ++t) {
+            uint32_t w0, w1;
+            if ((t & 1) == 0) {
+                r = philox4x32_10((uint32_t)(depth + 1 + (t >> 1)), sim, move, DOM_SIM, key0, key1);
+                w0 = r.x; w1 = r.y;
+            } else { w0 = r.z; w1 = r.w; }
+            const uint32_t mask = H->legal[cell];
+            const int a = nth_legal(H, mask, randbelow32(w0, (uint32_t)__popc(mask)));
+            DCHECK(S, a >= 0 && a < H->n_actions && cell < (uint32_t)H->n_cells, 41);
+            if (a < 4) {
+                cell = (uint32_t)((int)cell + H->delta[a]);
+                if (H->cell[cell] == POMCP_CELL_GOAL) { sum += H->rew[REW_EXIT] * disc[t]; ++t; finished = true; break; }
+            } else if (a == 4) {
+                const int code = H->cell[cell];
+                const int rew = (((actual & rocks) >> code) & 1u) ? REW_GOOD : REW_BAD;
+                rocks &= ~(1u << code);
+                sum += H->rew[rew] * disc[t];
+            } else {
+                const int k = a - 5;
+                if (!((sampled >> k) & 1u)) {
+                    const uint32_t truth = (actual >> k) & 1u;
+                    const uint32_t correct = ((uint64_t)w1 << 21) <= c.M.thr53[cell * H->n_rocks + k];
+                    const uint32_t good = correct ? truth : (truth ^ 1u);
+                    rocks = (rocks & ~(1u << k)) | (good << k);
+                }
+            }
+        }
+        st = cell | (rocks << 8);
+        return finished;
+    }
+};
+
+template <> struct Mdl<1> {
+    struct Ctx { TabHeader h; TabTables t; };
+    static __device__ __forceinline__ size_t stage(unsigned char *, const ModelHeader *, const uint64_t *, int,
+                                                   const TabHeader &h, const TabTables &t, Ctx &c)
+    { c.h = h; c.t = t; return 0; }
+    static __device__ __forceinline__ int n_actions(const Ctx &c, const ModelHeader *) { return c.h.A; }
+    static __device__ __forceinline__ int zs(const Ctx &c) { return c.h.ZS; }
+    static __device__ __forceinline__ bool stage_d1(const Ctx &c) { return c.h.stage_d1 != 0; }
+    static __device__ __forceinline__ uint32_t state_tag(uint32_t) { return 0u; }
+    static __device__ __forceinline__ uint32_t tag_legal(const Ctx &c, uint32_t)
+    { return c.h.A >= 32 ? 0xFFFFFFFFu : ((1u << c.h.A) - 1u); }
+    static __device__ __forceinline__ bool tag_ok(const Ctx &, uint32_t tag) { return tag == 0u; }
+    static __device__ __forceinline__ StepOut step(const Ctx &c, uint32_t st, int a, uint32_t wy, uint32_t wz)
+    {
+        const size_t row = (size_t)a * c.h.S + st;
+        const int ns = tab_sample(c.t.Tc + row * c.h.S, c.h.S, wy);
+        const int ob = tab_sample(c.t.Oc + ((size_t)a * c.h.S + ns) * c.h.Z, c.h.Z, wz);
+        const int term = (int)((c.h.term_action_mask >> a) & 1u) | (int)__ldg(c.t.term_state + ns);
+        return StepOut{(uint32_t)ns, 0u, ob, 0, term, __ldg(c.t.R + row)};
+    }
+    static __device__ __forceinline__ uint16_t path_code(int a, const StepOut &o) { return (uint16_t)(a | (o.obs << 5)); }
+    static __device__ __forceinline__ int path_obs(uint32_t ar) { return (int)(ar >> 5); }
+    static __device__ __forceinline__ double path_reward(const Ctx &, uint32_t, const double *rew) { return *rew; }
+    // word 0 picks the action (all actions are legal), word 1 the next state; observations are not drawn
+    static __device__ __forceinline__ bool rollout(const Ctx &c, DevState *, uint32_t sim, uint32_t move, uint32_t key0,
+                                                   uint32_t key1, int depth, const double *disc, uint32_t &st, int &t,
+                                                   int t_end, double &sum)
+    {
+        Philox4 r{0u, 0u, 0u, 0u};
+        for (; t < t_end; ++t) {
+            uint32_t w0, w1;
+            if ((t & 1) == 0) {
+                r = philox4x32_10((uint32_t)(depth + 1 + (t >> 1)), sim, move, DOM_SIM, key0, key1);
+                w0 = r.x; w1 = r.y;
+            } else { w0 = r.z; w1 = r.w; }
+            const int a = (int)randbelow32(w0, (uint32_t)c.h.A);
+            const size_t row = (size_t)a * c.h.S + st;
+            const double rew = __ldg(c.t.R + row);
+            st = (uint32_t)tab_sample(c.t.Tc + row * c.h.S, c.h.S, w1);
+            if (rew != 0.0) sum += rew * disc[t];
+            if (((c.h.term_action_mask >> a) & 1u) | __ldg(c.t.term_state + st)) { ++t; return true; }
+        }
+        return false;
+    }
 };
 
 // Grid-wide barrier of the cooperative search kernel: one arrival counter that only grows (zeroed by the host before
@@ -152,23 +287,6 @@ __device__ __forceinline__ void publish_root(DevState *S, const Tree &t, int roo
         S->res_q[tid] = t.qfix[(size_t)root * AS + tid];
     }
     if (tid == 0) { S->res_legal = t.legal[root]; S->res_valid = 1; }
-}
-
-// Stage the model tables into shared memory; returns the first free byte offset (16-byte aligned).
-__device__ __forceinline__ size_t stage_model(unsigned char *smem, const ModelHeader *gm, const uint64_t *gthr,
-                                              int n_thr, SmemModel &M)
-{
-    const int nw = (int)(sizeof(ModelHeader) / 4);
-    uint32_t *dst = reinterpret_cast<uint32_t *>(smem);
-    const uint32_t *src = reinterpret_cast<const uint32_t *>(gm);
-    for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
-    size_t off = (sizeof(ModelHeader) + 15) & ~size_t(15);
-    uint64_t *thr = reinterpret_cast<uint64_t *>(smem + off);
-    for (int i = threadIdx.x; i < n_thr; i += blockDim.x) thr[i] = gthr[i];
-    off += ((size_t)n_thr * 8 + 15) & ~size_t(15);
-    M.hdr = reinterpret_cast<const ModelHeader *>(smem);
-    M.thr53 = thr;
-    return off;
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -304,30 +422,31 @@ __device__ __forceinline__ int select_thread(const SearchParams &p, int X, uint3
 // in slices.  Then [rollout + backup]: the remaining rollouts and the backups (commutative integer atomics) are
 // claimed 32 simulations at a time from a work counter.
 // ---------------------------------------------------------------------------------------------------------
-struct SimCtx {
+template <int KIND> struct SimCtx {
     const SearchParams &p;
-    const SmemModel &M;
-    uint32_t actual, sampled;
+    const typename Mdl<KIND>::Ctx &m;
 };
 
 // A simulation standing at a node without statistics (N = 0): every legal action is untried, so UCB1 is a uniform
 // draw (action_selectors.py:6-37 with +inf bonuses), the node cannot be expanded (solvers/pomcp.py:107) and the
 // simulation ends in a rollout.  `node_ref` is the node id, or -1 - child_slot while the id is being published.
-__device__ __forceinline__ void virgin_step(const SimCtx &c, int i, uint32_t sim, int node_ref, uint32_t mask,
-                                         uint32_t cell, uint32_t rocks, int d, long long &c_levels)
+template <int KIND>
+__device__ __forceinline__ void virgin_step(const SimCtx<KIND> &c, int i, uint32_t sim, int node_ref, uint32_t mask,
+                                            uint32_t st, int d, long long &c_levels)
 {
     const SearchParams &p = c.p;
     if (d >= p.max_depth) { p.b.flag[i] = 2; p.b.depth[i] = (uint8_t)d; return; }          // solvers/pomcp.py:100
-    DCHECK(p.S, mask != 0u && d < p.dcap && cell < (uint32_t)c.M.hdr->n_cells, 11);
+    DCHECK(p.S, mask != 0u && d < p.dcap && Mdl<KIND>::tag_ok(c.m, Mdl<KIND>::state_tag(st)), 11);
     const Philox4 r = philox4x32_10((uint32_t)(d + 1), sim, p.move, DOM_SIM, p.key0, p.key1);
     const int a = nth_bit(mask, randbelow32(r.x, (uint32_t)__popc(mask)));
-    const StepResult sr = rs_step(c.M, cell, rocks, a, u53_of(r.y, r.z), c.actual, c.sampled);
+    const StepOut so = Mdl<KIND>::step(c.m, st, a, r.y, r.z);
     ++c_levels;
     p.b.path_node[(size_t)d * p.wmax + i] = node_ref;
-    p.b.path_ar[(size_t)d * p.wmax + i] = (uint16_t)(a | (sr.good << 5) | (sr.rew << 8));
+    p.b.path_ar[(size_t)d * p.wmax + i] = Mdl<KIND>::path_code(a, so);
+    if (KIND == 1) p.b.path_rew[(size_t)d * p.wmax + i] = so.reward;
     p.b.depth[i] = (uint8_t)(d + 1);
-    p.b.state[i] = sr.cell | (sr.rocks << 8);
-    p.b.flag[i] = sr.terminal ? 2 : 1;
+    p.b.state[i] = so.next;
+    p.b.flag[i] = so.terminal ? 2 : 1;
 }
 
 __device__ __forceinline__ int row_sum(const int32_t *nrow)
@@ -338,28 +457,29 @@ __device__ __forceinline__ int row_sum(const int32_t *nrow)
     return N;
 }
 
-extern "C" __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_BLOCKS)
-pomcp_search_kernel(const SearchParams p)
+template <int KIND>
+__device__ __forceinline__ void search_body(const SearchParams &p, unsigned char *smem)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
+    using MD = Mdl<KIND>;
     unsigned int bar_epoch = 0;
 #define GRID_SYNC() grid_barrier(&p.S->barrier, gridDim.x, bar_epoch)
-    SmemModel M;
-    size_t off = stage_model(smem, p.model, p.thr53, p.n_thr, M);
+    typename MD::Ctx mc;
+    size_t off = MD::stage(smem, p.model, p.thr53, p.n_thr, p.tab, p.tt, mc);
     double *disc = reinterpret_cast<double *>(smem + off);          // discount^t, t < max_depth
     off += ((size_t)p.max_depth * 8 + 15) & ~size_t(15);
-    const int A = p.model->n_actions;
-    const int n_acc = (1 + 2 * A) * A;                               // root + depth-1 edges staged per block
+    const int A = MD::n_actions(mc, p.model);
+    const int ZS = MD::zs(mc);                                       // observation stride of the child table
+    const bool stage_d1 = MD::stage_d1(mc);                          // depth-1 edges staged per block too
+    const int n_acc = stage_d1 ? (1 + ZS * A) * A : A;               // root (+ depth-1) edges staged per block
     long long *acc_q = reinterpret_cast<long long *>(smem + off);
     off += (size_t)n_acc * 8;
     int *acc_n = reinterpret_cast<int *>(smem + off);
     off += (size_t)n_acc * 4;
     int *arr1 = reinterpret_cast<int *>(smem + off);               // arrivals at the root's children, per block
-    for (int i = threadIdx.x; i < 2 * A; i += blockDim.x) arr1[i] = 0;
+    for (int i = threadIdx.x; i < ZS * A; i += blockDim.x) arr1[i] = 0;
     if (threadIdx.x == 0) { double d = 1.0; for (int t = 0; t < p.max_depth; ++t) { disc[t] = d; d *= p.discount; } }
     for (int i = threadIdx.x; i < n_acc; i += blockDim.x) { acc_q[i] = 0; acc_n[i] = 0; }
     __syncthreads();
-    const ModelHeader *H = M.hdr;
 
     DevState *S = p.S;
     const int T = gridDim.x * blockDim.x;
@@ -368,7 +488,7 @@ pomcp_search_kernel(const SearchParams p)
     const int gwarp = gtid >> 5, nwarps = T >> 5;
     const int vwarp = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;   // warp index that walks the blocks first
     const int root = S->root;
-    const uint32_t actual = S->actual, sampled = S->sampled;
+    if constexpr (KIND == 0) { mc.actual = S->actual; mc.sampled = S->sampled; }
     const uint32_t *bag = p.bag[S->bag_sel];
     const int n_bag = S->n_bag;
     unsigned long long gstep = S->gstep;
@@ -377,7 +497,7 @@ pomcp_search_kernel(const SearchParams p)
     long long done = 0, gens = 0, lsteps = 0;
     unsigned long long tp[6] = {0, 0, 0, 0, 0, 0}, tmark = t_start;   // phase clocks (gtid 0 only)
 #define PHASE_MARK(k) do { if (gtid == 0) { const unsigned long long now_ = globaltimer_ns(); tp[k] += now_ - tmark; tmark = now_; } } while (0)
-    const SimCtx ctx{p, M, actual, sampled};
+    const SimCtx<KIND> ctx{p, mc};
     int W = p.w0;
     long long gen_done = 0;                                          // simulations of earlier generations (stream ids)
 
@@ -386,46 +506,15 @@ pomcp_search_kernel(const SearchParams p)
     auto rollout_advance = [&](int i, int budget) {
         const uint32_t sim = p.sim_offset + (uint32_t)(gen_done + i);
         const int depth = p.b.depth[i];
-        const uint32_t st = p.b.state[i];
-        uint32_t cell = st & 0xFFu, rocks = st >> 8;
+        uint32_t st = p.b.state[i];
         double sum = p.b.ro_sum[i];
         int t = p.b.ro_t[i];
         const int t0 = t, t_end = (t + budget < p.max_depth) ? t + budget : p.max_depth;
-        bool finished = false;
-        Philox4 r{0u, 0u, 0u, 0u};
-        for (; t < t_end; ++t) {
-            // one Philox block per two rollout steps: (x, y) then (z, w); word 0 picks the action, word 1 is the top
-            // 32 bits of the 53-bit sensor uniform
-            uint32_t w0, w1;
-            if ((t & 1) == 0) {
-                r = philox4x32_10((uint32_t)(depth + 1 + (t >> 1)), sim, p.move, DOM_SIM, p.key0, p.key1);
-                w0 = r.x; w1 = r.y;
-            } else { w0 = r.z; w1 = r.w; }
-            const uint32_t mask = H->legal[cell];
-            const int a = nth_legal(H, mask, randbelow32(w0, (uint32_t)__popc(mask)));
-            DCHECK(S, a >= 0 && a < A && cell < (uint32_t)H->n_cells, 41);
-            if (a < 4) {
-                cell = (uint32_t)((int)cell + H->delta[a]);
-                if (H->cell[cell] == POMCP_CELL_GOAL) { sum += H->rew[REW_EXIT] * disc[t]; ++t; finished = true; break; }
-            } else if (a == 4) {
-                const int code = H->cell[cell];
-                const int rew = (((actual & rocks) >> code) & 1u) ? REW_GOOD : REW_BAD;
-                rocks &= ~(1u << code);
-                sum += H->rew[rew] * disc[t];
-            } else {
-                const int k = a - 5;
-                if (!((sampled >> k) & 1u)) {
-                    const uint32_t truth = (actual >> k) & 1u;
-                    const uint32_t correct = ((uint64_t)w1 << 21) <= M.thr53[cell * H->n_rocks + k];
-                    const uint32_t good = correct ? truth : (truth ^ 1u);
-                    rocks = (rocks & ~(1u << k)) | (good << k);
-                }
-            }
-        }
+        const bool finished = MD::rollout(mc, S, sim, p.move, p.key0, p.key1, depth, disc, st, t, t_end, sum);
         c_rollout += t - t0;
         p.b.ro_sum[i] = sum;
         if (finished || t >= p.max_depth) p.b.flag[i] = 3;
-        else { p.b.state[i] = cell | (rocks << 8); p.b.ro_t[i] = (uint8_t)t; }
+        else { p.b.state[i] = st; p.b.ro_t[i] = (uint8_t)t; }
     };
 
     // Grid barrier that works while it waits: after arriving, the block keeps advancing the rollouts of its own leaf
@@ -478,7 +567,7 @@ pomcp_search_kernel(const SearchParams p)
             const Philox4 r = philox4x32_10(0u, sim, p.move, DOM_SIM, p.key0, p.key1);
             const uint32_t st = bag[randbelow32(r.x, (uint32_t)n_bag)];
             p.b.ro_t[i] = 0; p.b.ro_sum[i] = 0.0;
-            if (root_virgin) virgin_step(ctx, i, sim, root, root_mask, st & 0xFFu, st >> 8, 0, c_levels);
+            if (root_virgin) virgin_step<KIND>(ctx, i, sim, root, root_mask, st, 0, c_levels);
             else { p.b.state[i] = st; p.b.node[i] = root; p.b.flag[i] = 0; p.b.depth[i] = 0; }
         }
         PHASE_MARK(0);
@@ -538,17 +627,18 @@ pomcp_search_kernel(const SearchParams p)
                         }
                         DCHECK(S, a >= 0 && a < A && ((mask >> a) & 1u) && k >= 1u && k <= (uint32_t)w, 22);
                         const uint32_t st = p.b.state[i];
-                        DCHECK(S, (st & 0xFFu) == (uint32_t)p.t.cell[X], 23);
-                        const StepResult sr = rs_step(M, st & 0xFFu, st >> 8, a, u53_of(r.y, r.z), actual, sampled);  // :104
+                        DCHECK(S, MD::state_tag(st) == (uint32_t)p.t.cell[X], 23);
+                        const StepOut so = MD::step(mc, st, a, r.y, r.z);                   // :104
                         ++c_levels;
                         p.b.path_node[(size_t)d * p.wmax + i] = X;
-                        p.b.path_ar[(size_t)d * p.wmax + i] = (uint16_t)(a | (sr.good << 5) | (sr.rew << 8));
+                        p.b.path_ar[(size_t)d * p.wmax + i] = MD::path_code(a, so);
+                        if (KIND == 1) p.b.path_rew[(size_t)d * p.wmax + i] = so.reward;
                         p.b.depth[i] = (uint8_t)(d + 1);
-                        p.b.state[i] = sr.cell | (sr.rocks << 8);
-                        if (sr.terminal) p.b.flag[i] = 2;
+                        p.b.state[i] = so.next;
+                        if (so.terminal) p.b.flag[i] = 2;
                         else {
-                            const size_t cslot = ((size_t)X * AS + a) * 2 + sr.good;
-                            uint32_t cmask = H->legal[sr.cell]; bool have_mask = false;     // the child's action set
+                            const size_t cslot = ((size_t)X * AS + a) * ZS + so.obs;
+                            uint32_t cmask = MD::tag_legal(mc, so.tag); bool have_mask = false;   // the child's action set
                             uint32_t c = p.t.child[cslot];                                  // :106
                             if (c == 0 && d + 1 < p.dcap) {                                 // :107-108 (N(X) > 0 here)
                                 // one CAS per distinct child slot among the lanes that got here together
@@ -564,13 +654,13 @@ pomcp_search_kernel(const SearchParams p)
                                     if (rk == 0) id0 = atomicAdd(&S->node_count, __popc(am));
                                     const int id = __shfl_sync(am, id0, __ffs((int)am) - 1) + rk;
                                     DCHECK(S, id > 0 && (long long)id < p.node_cap, 24);
-                                    p.t.cell[id] = (int32_t)sr.cell;
-                                    if (p.t.chance)                                         // create_child + smart action set
-                                        cmask = child_smart_mask(H, p.t.prob, p.t.chance + (size_t)X * POMCP_RS,
+                                    p.t.cell[id] = (int32_t)so.tag;
+                                    if constexpr (KIND == 0) if (p.t.chance)                // create_child + smart action set
+                                        cmask = child_smart_mask(mc.M.hdr, p.t.prob, p.t.chance + (size_t)X * POMCP_RS,
                                                                  p.t.good + (size_t)X * POMCP_RS,
                                                                  p.t.chance + (size_t)id * POMCP_RS,
                                                                  p.t.good + (size_t)id * POMCP_RS, (int)(st & 0xFFu), a,
-                                                                 sr.good, (int)sr.cell);
+                                                                 so.obs, (int)so.tag);
                                     p.t.legal[id] = cmask;
                                     __threadfence();                                        // node fields before its id
                                     atomicExch(&p.t.child[cslot], (uint32_t)id + 1u);
@@ -580,24 +670,24 @@ pomcp_search_kernel(const SearchParams p)
                             }
                             if (c == 0) p.b.flag[i] = 1;                                    // depth cap: leaf (:119)
                             else if (c == CHILD_LOCKED) {                                   // created in this step
-                                if (p.t.chance && !have_mask)                               // id not published yet: derive the set
-                                    cmask = child_smart_mask(H, p.t.prob, p.t.chance + (size_t)X * POMCP_RS,
+                                if constexpr (KIND == 0) if (p.t.chance && !have_mask)      // id not published yet: derive the set
+                                    cmask = child_smart_mask(mc.M.hdr, p.t.prob, p.t.chance + (size_t)X * POMCP_RS,
                                                              p.t.good + (size_t)X * POMCP_RS, nullptr, nullptr,
-                                                             (int)(st & 0xFFu), a, sr.good, (int)sr.cell);
-                                virgin_step(ctx, i, sim, -1 - (int)cslot, cmask, sr.cell, sr.rocks, d + 1, c_levels);
+                                                             (int)(st & 0xFFu), a, so.obs, (int)so.tag);
+                                virgin_step<KIND>(ctx, i, sim, -1 - (int)cslot, cmask, so.next, d + 1, c_levels);
                             } else {
                                 const int id = CHILD_ID(c);
                                 if (!(c & CHILD_VISITED))                                   // no statistics yet (N = 0)
                                     // the node may have been published in this very phase by another SM: read its action
                                     // set from L2 (ld.cg), never from a possibly stale L1 line
-                                    virgin_step(ctx, i, sim, id, __ldcg(&p.t.legal[id]), sr.cell, sr.rocks, d + 1, c_levels);
-                                else { p.b.node[i] = id; arrive_at = id; arrive_slot = a * 2 + sr.good; }   // descend
+                                    virgin_step<KIND>(ctx, i, sim, id, __ldcg(&p.t.legal[id]), so.next, d + 1, c_levels);
+                                else { p.b.node[i] = id; arrive_at = id; arrive_slot = a * ZS + so.obs; }   // descend
                             }
                         }
                     }
                 }
                 __syncwarp();
-                // arrivals for the next level.  From the root: counted per block in shared memory (<= 2|A| children);
+                // arrivals for the next level.  From the root: counted per block in shared memory (<= ZS|A| children);
                 // deeper: aggregated per warp and node (match.any), one atomic per group
                 if (level == 0) { if (arrive_at >= 0) atomicAdd(&arr1[arrive_slot], 1); continue; }
                 const unsigned amask = __ballot_sync(0xFFFFFFFFu, arrive_at >= 0);
@@ -620,11 +710,11 @@ pomcp_search_kernel(const SearchParams p)
             }
             if (level == 0) {                                        // publish this block's arrivals at the root's children
                 __syncthreads();
-                for (int t = threadIdx.x; t < 2 * A; t += blockDim.x) {
+                for (int t = threadIdx.x; t < ZS * A; t += blockDim.x) {
                     const int cnt = arr1[t];
                     if (cnt == 0) continue;
                     arr1[t] = 0;
-                    const int Xc = CHILD_ID(p.t.child[(size_t)root * AS * 2 + t]);
+                    const int Xc = CHILD_ID(p.t.child[(size_t)root * AS * ZS + t]);
                     const unsigned long long old = atomicMax(&p.t.arrive[Xc], stamp_next);
                     if (old < stamp_next) {
                         const int sl = atomicAdd(&S->wl_count[ring_next], 1);
@@ -653,20 +743,25 @@ pomcp_search_kernel(const SearchParams p)
             for (int d = depth - 1; d >= 0; --d) {
                 const uint32_t ar = p.b.path_ar[(size_t)d * p.wmax + i];
                 const int a = ar & 31;
-                const double q = H->rew[ar >> 8] + p.discount * delayed;
+                const double q = MD::path_reward(mc, ar, KIND == 1 ? p.b.path_rew + (size_t)d * p.wmax + i : nullptr) +
+                                 p.discount * delayed;
                 const long long qi = __double2ll_rn(q * POMCP_QFIX_SCALE);
                 if (d == 0) {
                     atomicAdd(&acc_n[a], 1);
                     atomicAdd(reinterpret_cast<unsigned long long *>(&acc_q[a]), (unsigned long long)qi);
-                } else if (d == 1) {
+                    if (!stage_d1 && depth > 1) {                            // the depth-1 child has statistics from now on
+                        uint32_t *cs = &p.t.child[((size_t)root * AS + a) * ZS + MD::path_obs(ar)];
+                        if (!(*((volatile uint32_t *)cs) & CHILD_VISITED)) atomicOr(cs, CHILD_VISITED);
+                    }
+                } else if (d == 1 && stage_d1) {
                     const uint32_t ar0 = p.b.path_ar[i];
-                    const int e = (1 + (int)(ar0 & 31) * 2 + (int)((ar0 >> 5) & 1)) * A + a;
+                    const int e = (1 + (int)(ar0 & 31) * ZS + MD::path_obs(ar0)) * A + a;
                     atomicAdd(&acc_n[e], 1);
                     atomicAdd(reinterpret_cast<unsigned long long *>(&acc_q[e]), (unsigned long long)qi);
                     if (depth > 2) {                                         // mark the depth-2 child of this edge
                         int X = p.b.path_node[(size_t)p.wmax + i];
                         if (X < 0) X = CHILD_ID(p.t.child[(size_t)(-1 - X)]);
-                        uint32_t *cs = &p.t.child[((size_t)X * AS + a) * 2 + ((ar >> 5) & 1u)];
+                        uint32_t *cs = &p.t.child[((size_t)X * AS + a) * ZS + MD::path_obs(ar)];
                         if (!(*((volatile uint32_t *)cs) & CHILD_VISITED)) atomicOr(cs, CHILD_VISITED);
                     }
                 } else {
@@ -676,7 +771,7 @@ pomcp_search_kernel(const SearchParams p)
                     atomicAdd(&p.t.n[(size_t)X * AS + a], 1);
                     atomicAdd(reinterpret_cast<unsigned long long *>(&p.t.qfix[(size_t)X * AS + a]), (unsigned long long)qi);
                     if (d + 1 < depth) {                                     // the child below this edge now has statistics
-                        uint32_t *cs = &p.t.child[((size_t)X * AS + a) * 2 + ((ar >> 5) & 1u)];
+                        uint32_t *cs = &p.t.child[((size_t)X * AS + a) * ZS + MD::path_obs(ar)];
                         if (!(*((volatile uint32_t *)cs) & CHILD_VISITED)) atomicOr(cs, CHILD_VISITED);
                     }
                 }
@@ -690,7 +785,7 @@ pomcp_search_kernel(const SearchParams p)
             const int slot = e / A, a = e - slot * A;
             int X = root;
             if (slot > 0) {                                          // a depth-1 node: it has statistics from now on
-                uint32_t *cs = &p.t.child[(size_t)root * AS * 2 + (slot - 1)];
+                uint32_t *cs = &p.t.child[(size_t)root * AS * ZS + (slot - 1)];
                 const uint32_t cv = *((volatile uint32_t *)cs);
                 X = CHILD_ID(cv);
                 if (!(cv & CHILD_VISITED)) atomicOr(cs, CHILD_VISITED);
@@ -734,6 +829,20 @@ pomcp_search_kernel(const SearchParams p)
     }
 }
 
+extern "C" __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_BLOCKS)
+pomcp_search_kernel(const SearchParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    search_body<0>(p, smem);
+}
+
+extern "C" __global__ void __launch_bounds__(SEARCH_THREADS, SEARCH_MIN_BLOCKS)
+pomcp_search_tab_kernel(const SearchParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    search_body<1>(p, smem);
+}
+
 // ---------------------------------------------------------------------------------------------------------
 // K2: belief update -- batched rejection sampling with an order-preserving (stream-compacted) survivor set,
 // then the re-root.  One block: a belief is only max_particle_count (2000) states.
@@ -742,6 +851,8 @@ struct AdvanceParams {
     DevState *S;
     const ModelHeader *model;
     const uint64_t *thr53;
+    TabHeader tab;
+    TabTables tt;
     Tree t;
     uint32_t *bag[2];
     int32_t action, obs_good, need, n_thr;
@@ -749,19 +860,20 @@ struct AdvanceParams {
     long long max_tries;
 };
 
-extern "C" __global__ void __launch_bounds__(ADV_THREADS)
-pomcp_advance_kernel(const AdvanceParams p)
+template <int KIND>
+__device__ __forceinline__ void advance_body(const AdvanceParams &p, unsigned char *smem)
 {
-    extern __shared__ __align__(16) unsigned char smem[];
-    SmemModel M;
-    size_t off = stage_model(smem, p.model, p.thr53, p.n_thr, M);
+    using MD = Mdl<KIND>;
+    typename MD::Ctx mc;
+    size_t off = MD::stage(smem, p.model, p.thr53, p.n_thr, p.tab, p.tt, mc);
+    const int ZS = MD::zs(mc);
     int *warp_tot = reinterpret_cast<int *>(smem + off);             // [32] + [2] broadcast cells
     __shared__ long long sh_tries;
     DevState *S = p.S;
     const int tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
     const int root = S->root;
-    const uint32_t actual = S->actual;
     const uint32_t sampled = p.sampled_after;                        // belief_tree_solver.py:165 model.update first
+    if constexpr (KIND == 0) { mc.actual = S->actual; mc.sampled = sampled; }
     const uint32_t *old_bag = p.bag[S->bag_sel];
     uint32_t *new_bag = p.bag[S->bag_sel ^ 1];
     const int n_old = S->n_bag;
@@ -777,9 +889,9 @@ pomcp_advance_kernel(const AdvanceParams p)
             if (t < p.max_tries) {                                   // model.py:242-251
                 const Philox4 x = philox4x32_10((uint32_t)t, (uint32_t)(t >> 32), p.move, DOM_UPDATE, p.key0, p.key1);
                 const uint32_t st = old_bag[randbelow32(x.x, (uint32_t)n_old)];
-                const StepResult sr = rs_step(M, st & 0xFFu, st >> 8, p.action, u53_of(x.y, x.z), actual, sampled);
-                ns[r] = sr.cell | (sr.rocks << 8);
-                if (sr.good == p.obs_good) acc |= 1u << r;
+                const StepOut so = MD::step(mc, st, p.action, x.y, x.z);
+                ns[r] = so.next;
+                if (so.obs == p.obs_good) acc |= 1u << r;
             }
         }
         int cnt = __popc(acc), incl = cnt;                            // block-wide exclusive scan of cnt
@@ -815,17 +927,19 @@ pomcp_advance_kernel(const AdvanceParams p)
         S->sampled = sampled;                                        // belief_tree_solver.py:165 happens first
         if (accepted == 0) { S->adv_status = 2; S->adv_root_cell = p.t.cell[root]; }
         else {
-            uint32_t c = p.t.child[((size_t)root * AS + p.action) * 2 + p.obs_good];   // belief_tree_solver.py:167
+            uint32_t c = p.t.child[((size_t)root * AS + p.action) * ZS + p.obs_good];  // belief_tree_solver.py:167
             int status = 0, id;
             if (c == 0) {                                            // never expanded: fresh node at the next position
                 id = S->node_count++;
-                const StepResult sr = rs_step(M, (uint32_t)p.t.cell[root], 0u, p.action, 0ull, actual, sampled);
-                p.t.cell[id] = (int32_t)sr.cell;
-                uint32_t lm = M.hdr->legal[sr.cell];
-                if (p.t.chance)
-                    lm = child_smart_mask(M.hdr, p.t.prob, p.t.chance + (size_t)root * POMCP_RS, p.t.good + (size_t)root * POMCP_RS,
+                uint32_t tag = 0u;                                   // tag of the node at the next position
+                if constexpr (KIND == 0)
+                    tag = rs_step(mc.M, (uint32_t)p.t.cell[root], 0u, p.action, 0ull, mc.actual, sampled).cell;
+                p.t.cell[id] = (int32_t)tag;
+                uint32_t lm = MD::tag_legal(mc, tag);
+                if constexpr (KIND == 0) if (p.t.chance)
+                    lm = child_smart_mask(mc.M.hdr, p.t.prob, p.t.chance + (size_t)root * POMCP_RS, p.t.good + (size_t)root * POMCP_RS,
                                           p.t.chance + (size_t)id * POMCP_RS, p.t.good + (size_t)id * POMCP_RS, p.t.cell[root],
-                                          p.action, p.obs_good, (int)sr.cell);
+                                          p.action, p.obs_good, (int)tag);
                 p.t.legal[id] = lm;
                 status = 1;
             } else id = CHILD_ID(c);
@@ -837,6 +951,18 @@ pomcp_advance_kernel(const AdvanceParams p)
     publish_root(S, p.t, S->root, tid);
 }
 
+extern "C" __global__ void __launch_bounds__(ADV_THREADS) pomcp_advance_kernel(const AdvanceParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    advance_body<0>(p, smem);
+}
+
+extern "C" __global__ void __launch_bounds__(ADV_THREADS) pomcp_advance_tab_kernel(const AdvanceParams p)
+{
+    extern __shared__ __align__(16) unsigned char smem[];
+    advance_body<1>(p, smem);
+}
+
 // generate_step over a batch (parity harness for rock_model.py:451-465)
 extern "C" __global__ void pomcp_step_batch_kernel(const ModelHeader *model, const uint64_t *thr53, int n_thr,
                                                    long long n, const uint32_t *state, const uint8_t *action,
@@ -845,8 +971,9 @@ extern "C" __global__ void pomcp_step_batch_kernel(const ModelHeader *model, con
                                                    double *reward)
 {
     extern __shared__ __align__(16) unsigned char smem[];
-    SmemModel M;
-    stage_model(smem, model, thr53, n_thr, M);
+    Mdl<0>::Ctx mc;
+    Mdl<0>::stage(smem, model, thr53, n_thr, TabHeader{}, TabTables{}, mc);
+    const SmemModel &M = mc.M;
     __syncthreads();
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
         const uint32_t st = state[i];
@@ -854,6 +981,18 @@ extern "C" __global__ void pomcp_step_batch_kernel(const ModelHeader *model, con
         next_state[i] = sr.cell | (sr.rocks << 8);
         flags[i] = (uint8_t)(sr.good | (sr.empty << 1) | (sr.terminal << 2) | (sr.legal << 3));
         reward[i] = M.hdr->rew[sr.rew];
+    }
+}
+
+// generate_step of the tabular model over a batch (parity harness)
+__global__ void pomcp_tab_step_batch_kernel(TabHeader th, TabTables tt, long long n, const uint32_t *state,
+                                            const uint8_t *action, const uint32_t *w1, const uint32_t *w2,
+                                            uint32_t *next_state, int32_t *obs, double *reward, uint8_t *terminal)
+{
+    Mdl<1>::Ctx mc{th, tt};
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < n; i += (long long)gridDim.x * blockDim.x) {
+        const StepOut so = Mdl<1>::step(mc, state[i], action[i], w1[i], w2[i]);
+        next_state[i] = so.next; obs[i] = so.obs; reward[i] = so.reward; terminal[i] = (uint8_t)so.terminal;
     }
 }
 
@@ -904,6 +1043,11 @@ struct pomcp_handle {
     ModelHeader *dmodel = nullptr;
     uint64_t *dthr = nullptr;
     int n_thr = 0;
+    int kind = 0;                   // 0 RockSample, 1 tabular
+    int zs = 2;                     // observation stride of the child table
+    int n_actions = 0;
+    TabHeader tab{};
+    TabTables tt{};
     bool have_model = false, have_root = false;
     Tree t{};
     SimBuf b{};
@@ -942,7 +1086,8 @@ static void free_all(pomcp_handle *h)
     cudaFree(h->t.arrive); cudaFree(h->t.slot); cudaFree(h->t.chance); cudaFree(h->t.good); cudaFree((void *)h->t.prob);
     cudaFree(h->b.state); cudaFree(h->b.node); cudaFree(h->b.flag); cudaFree(h->b.depth); cudaFree(h->b.path_node);
     cudaFree(h->b.path_ar); cudaFree(h->b.wl_node); cudaFree(h->b.wl_thr); cudaFree(h->b.wl_meta);
-    cudaFree(h->b.ro_sum); cudaFree(h->b.ro_t);
+    cudaFree(h->b.ro_sum); cudaFree(h->b.ro_t); cudaFree(h->b.path_rew);
+    cudaFree((void *)h->tt.Tc); cudaFree((void *)h->tt.Oc); cudaFree((void *)h->tt.R); cudaFree((void *)h->tt.term_state);
     cudaFree(h->bag[0]); cudaFree(h->bag[1]);
     if (h->stage) cudaFreeHost(h->stage);
 }
@@ -1004,6 +1149,27 @@ extern "C" int pomcp_create(const pomcp_config *cfg, int device, pomcp_handle **
     return 0;
 }
 
+// Drop the device tables of a tabular model (a handle can be re-targeted at another model).
+static int release_tabular(pomcp_handle *h)
+{
+    cudaFree((void *)h->tt.Tc); cudaFree((void *)h->tt.Oc); cudaFree((void *)h->tt.R); cudaFree((void *)h->tt.term_state);
+    h->tt = TabTables{};
+    return 0;
+}
+
+// (Re)allocate the child table for an observation stride of `zs` slots per (node, action).
+static int set_child_stride(pomcp_handle *h, int zs)
+{
+    if (zs != h->zs) {
+        CK(cudaDeviceSynchronize());
+        cudaFree(h->t.child); h->t.child = nullptr;
+        CK(cudaMalloc(&h->t.child, (size_t)h->cap * AS * (size_t)zs * sizeof(uint32_t)));
+        CK(cudaMemset(h->t.child, 0, (size_t)h->cap * AS * (size_t)zs * sizeof(uint32_t)));
+        h->zs = zs;
+    }
+    return 0;
+}
+
 extern "C" int pomcp_set_model_rocksample(pomcp_handle *h, int rows, int cols, const int8_t *cell, int start_cell,
                                           const uint64_t *thr53, const double rewards[4])
 {
@@ -1043,6 +1209,9 @@ extern "C" int pomcp_set_model_rocksample(pomcp_handle *h, int rows, int cols, c
     CK(cudaMalloc(&h->dthr, (size_t)h->n_thr * sizeof(uint64_t)));
     CK(cudaMemcpy(h->dthr, thr53, (size_t)h->n_thr * sizeof(uint64_t), cudaMemcpyHostToDevice));
     CK(cudaMemcpy(h->dmodel, &m, sizeof(m), cudaMemcpyHostToDevice));
+    if (release_tabular(h)) return -1;
+    h->kind = 0; h->n_actions = m.n_actions;
+    if (set_child_stride(h, 2)) return -1;
     // launch geometry of the cooperative search kernel
     const int A = m.n_actions;
     size_t smem = ((sizeof(ModelHeader) + 15) & ~size_t(15)) + (((size_t)h->n_thr * 8 + 15) & ~size_t(15)) +
@@ -1057,7 +1226,62 @@ extern "C" int pomcp_set_model_rocksample(pomcp_handle *h, int rows, int cols, c
     CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
     if (per_sm < 1) return fail(h, "search kernel does not fit on an SM");
     h->coop_blocks = per_sm * sms;
-    h->have_model = true;
+    h->have_model = true; h->have_root = false;
+    return 0;
+}
+
+extern "C" int pomcp_set_model_tabular(pomcp_handle *h, int n_states, int n_actions, int n_obs, const uint32_t *Tc,
+                                       const uint32_t *Oc, const double *R, uint32_t term_action_mask,
+                                       const uint8_t *term_state)
+{
+    if (!h) return -1;
+    CK(cudaSetDevice(h->device));
+    if (n_states < 1 || n_states > (1 << 16)) return fail(h, "n_states out of range [1, 65536]");
+    if (n_actions < 1 || n_actions > POMCP_MAX_ACTIONS) return fail(h, "n_actions out of range [1, 32]");
+    if (n_obs < 1 || n_obs > POMCP_MAX_OBS) return fail(h, "n_obs out of range [1, 32]");
+    if (!Tc || !Oc || !R) return fail(h, "null model table");
+    const size_t S = (size_t)n_states, A = (size_t)n_actions, Z = (size_t)n_obs;
+    for (size_t r = 0; r < A * S; ++r) {                    // every cumulative row must end saturated
+        if (Tc[r * S + S - 1] != 0xFFFFFFFFu) return fail(h, "transition row does not end at 0xFFFFFFFF");
+        if (Oc[r * Z + Z - 1] != 0xFFFFFFFFu) return fail(h, "observation row does not end at 0xFFFFFFFF");
+    }
+    CK(cudaDeviceSynchronize());
+    if (release_tabular(h)) return -1;
+    uint32_t *dT, *dO; double *dR; uint8_t *dterm;
+    CK(cudaMalloc(&dT, A * S * S * 4)); h->tt.Tc = dT;
+    CK(cudaMalloc(&dO, A * S * Z * 4)); h->tt.Oc = dO;
+    CK(cudaMalloc(&dR, A * S * 8)); h->tt.R = dR;
+    CK(cudaMalloc(&dterm, S)); h->tt.term_state = dterm;
+    CK(cudaMemcpy(dT, Tc, A * S * S * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dO, Oc, A * S * Z * 4, cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(dR, R, A * S * 8, cudaMemcpyHostToDevice));
+    if (term_state) CK(cudaMemcpy(dterm, term_state, S, cudaMemcpyHostToDevice));
+    else CK(cudaMemset(dterm, 0, S));
+    int zs = 2; while (zs < n_obs) zs *= 2;
+    TabHeader &t = h->tab;
+    memset(&t, 0, sizeof(t));
+    t.S = n_states; t.A = n_actions; t.Z = n_obs; t.ZS = zs; t.term_action_mask = term_action_mask;
+    t.stage_d1 = ((size_t)(1 + zs * n_actions) * n_actions * 12 <= (size_t)(24 << 10)) ? 1 : 0;
+    h->kind = 1; h->n_actions = n_actions;
+    memset(&h->hmodel, 0, sizeof(h->hmodel));
+    h->hmodel.n_actions = n_actions; h->hmodel.n_cells = 1;
+    h->hmodel.legal[0] = n_actions >= 32 ? 0xFFFFFFFFu : ((1u << n_actions) - 1u);
+    CK(cudaMemcpy(h->dmodel, &h->hmodel, sizeof(h->hmodel), cudaMemcpyHostToDevice));
+    if (set_child_stride(h, zs)) return -1;
+    if (!h->b.path_rew)
+        CK(cudaMalloc(&h->b.path_rew, (size_t)h->cfg.gen_wmax * (size_t)h->cfg.tree_depth_cap * sizeof(double)));
+    const size_t n_acc = t.stage_d1 ? (size_t)(1 + zs * n_actions) * n_actions : (size_t)n_actions;
+    size_t smem = (((size_t)h->cfg.max_depth * 8 + 15) & ~size_t(15)) + n_acc * 12 + (size_t)zs * n_actions * 4 + 16;
+    if (smem < 512) smem = 512;                              // the belief update keeps 34 ints there
+    h->search_smem = smem;
+    CK(cudaFuncSetAttribute(pomcp_search_tab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    CK(cudaFuncSetAttribute(pomcp_advance_tab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    int per_sm = 0, sms = 0;
+    CK(cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, pomcp_search_tab_kernel, SEARCH_THREADS, smem));
+    CK(cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, h->device));
+    if (per_sm < 1) return fail(h, "search kernel does not fit on an SM");
+    h->coop_blocks = per_sm * sms;
+    h->have_model = true; h->have_root = false;
     return 0;
 }
 
@@ -1065,6 +1289,7 @@ extern "C" int pomcp_set_preferred_actions(pomcp_handle *h, int enabled, const d
 {
     if (!h) return -1;
     if (!h->have_model) return fail(h, "set the model first");
+    if (h->kind != 0) return enabled ? fail(h, "preferred actions are a RockSample heuristic") : 0;
     CK(cudaSetDevice(h->device));
     CK(cudaDeviceSynchronize());
     cudaFree(h->t.chance); cudaFree(h->t.good); cudaFree((void *)h->t.prob);
@@ -1113,7 +1338,7 @@ static int clear_arena(pomcp_handle *h, cudaStream_t s)
     if (n) {
         CK(cudaMemsetAsync(h->t.n, 0, n * AS * sizeof(int32_t), s));
         CK(cudaMemsetAsync(h->t.qfix, 0, n * AS * sizeof(long long), s));
-        CK(cudaMemsetAsync(h->t.child, 0, n * AS * 2 * sizeof(uint32_t), s));
+        CK(cudaMemsetAsync(h->t.child, 0, n * AS * (size_t)h->zs * sizeof(uint32_t), s));
         // `arrive` keeps its stamps: they are never reused (gstep only grows)
     }
     h->zeroed_upto = 0;
@@ -1137,6 +1362,8 @@ extern "C" int pomcp_set_root_particles(pomcp_handle *h, const uint32_t *packed,
     if (!h->have_model) return fail(h, "set the model first");
     if (n < 1) return fail(h, "empty belief");
     if (root_cell < 0 || root_cell >= h->hmodel.n_cells) return fail(h, "root cell outside the grid");
+    if (h->kind == 1)
+        for (int i = 0; i < n; ++i) if (packed[i] >= (uint32_t)h->tab.S) return fail(h, "particle outside the state space");
     CK(cudaSetDevice(h->device));
     const int need = n > h->cfg.max_particle_count ? n : h->cfg.max_particle_count;
     if (need > h->bag_cap) {
@@ -1192,6 +1419,7 @@ extern "C" int pomcp_search(pomcp_handle *h, int64_t n_sims, uint32_t sim_offset
     SearchParams p;
     memset(&p, 0, sizeof(p));
     p.S = h->dS; p.model = h->dmodel; p.thr53 = h->dthr; p.t = h->t; p.b = h->b;
+    p.tab = h->tab; p.tt = h->tt;
     p.bag[0] = h->bag[0]; p.bag[1] = h->bag[1];
     p.n_sims = n_sims; p.sim_offset = sim_offset; p.move = move;
     p.key0 = (uint32_t)h->cfg.seed; p.key1 = (uint32_t)(h->cfg.seed >> 32);
@@ -1206,8 +1434,8 @@ extern "C" int pomcp_search(pomcp_handle *h, int64_t n_sims, uint32_t sim_offset
     CK(cudaMemsetAsync(&h->dS->barrier, 0, sizeof(uint32_t), s));
     CK(cudaMemsetAsync(h->dS->ro_cursor, 0, 2 * sizeof(int32_t), s));
     void *args[] = {&p};
-    CK(cudaLaunchCooperativeKernel((void *)pomcp_search_kernel, dim3(blocks), dim3(SEARCH_THREADS), args,
-                                   h->search_smem, s));
+    CK(cudaLaunchCooperativeKernel(h->kind == 0 ? (void *)pomcp_search_kernel : (void *)pomcp_search_tab_kernel,
+                                   dim3(blocks), dim3(SEARCH_THREADS), args, h->search_smem, s));
     ++h->launches;
     h->nodes_used += n_sims;
     h->zeroed_upto = h->nodes_used;
@@ -1223,7 +1451,7 @@ extern "C" int pomcp_root_stats(pomcp_handle *h, int64_t *n, int64_t *qfix, uint
     CK(cudaMemcpyAsync(st, h->dS, DEVSTATE_HEAD, cudaMemcpyDeviceToHost, h->last_stream));
     CK(cudaStreamSynchronize(h->last_stream));
     h->nodes_used = st->node_count;
-    const int A = h->hmodel.n_actions;
+    const int A = h->n_actions;
     for (int a = 0; a < A; ++a) { n[a] = st->res_n[a]; qfix[a] = st->res_q[a]; }
     if (legal_mask) *legal_mask = st->res_legal;
     if (sims_done) *sims_done = st->sims_done;
@@ -1241,16 +1469,16 @@ extern "C" int pomcp_node_stats(pomcp_handle *h, const int32_t *path_ao, int len
     CK(cudaMemcpy(&X, &h->dS->root, sizeof(X), cudaMemcpyDeviceToHost));
     for (int i = 0; i < len; ++i) {
         const int a = path_ao[2 * i], o = path_ao[2 * i + 1];
-        if (a < 0 || a >= h->hmodel.n_actions || o < 0 || o > 1) return fail(h, "bad path entry");
+        if (a < 0 || a >= h->n_actions || o < 0 || o >= h->zs) return fail(h, "bad path entry");
         uint32_t c;
-        CK(cudaMemcpy(&c, h->t.child + ((size_t)X * AS + a) * 2 + o, sizeof(c), cudaMemcpyDeviceToHost));
+        CK(cudaMemcpy(&c, h->t.child + ((size_t)X * AS + a) * (size_t)h->zs + o, sizeof(c), cudaMemcpyDeviceToHost));
         if (c == 0 || c == CHILD_LOCKED) return 1;
         X = CHILD_ID(c);
     }
     int32_t nn[AS]; long long qq[AS];
     CK(cudaMemcpy(nn, h->t.n + (size_t)X * AS, sizeof(nn), cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(qq, h->t.qfix + (size_t)X * AS, sizeof(qq), cudaMemcpyDeviceToHost));
-    for (int a = 0; a < h->hmodel.n_actions; ++a) { n[a] = nn[a]; qfix[a] = qq[a]; }
+    for (int a = 0; a < h->n_actions; ++a) { n[a] = nn[a]; qfix[a] = qq[a]; }
     if (legal_mask) CK(cudaMemcpy(legal_mask, h->t.legal + X, sizeof(uint32_t), cudaMemcpyDeviceToHost));
     if (cell) CK(cudaMemcpy(cell, h->t.cell + X, sizeof(int32_t), cudaMemcpyDeviceToHost));
     return 0;
@@ -1261,19 +1489,22 @@ extern "C" int pomcp_advance(pomcp_handle *h, int action, int obs_good, uint32_t
 {
     if (!h) return -1;
     if (!h->have_root) return fail(h, "no root belief");
-    if (action < 0 || action >= h->hmodel.n_actions) return fail(h, "action out of range");
+    if (action < 0 || action >= h->n_actions) return fail(h, "action out of range");
+    if (h->kind == 1 ? (obs_good < 0 || obs_good >= h->tab.Z) : (obs_good < 0)) return fail(h, "observation out of range");
     CK(cudaSetDevice(h->device));
     if (h->nodes_used + 2 > h->cap) return fail(h, "node arena full");
     AdvanceParams p;
     memset(&p, 0, sizeof(p));
     p.S = h->dS; p.model = h->dmodel; p.thr53 = h->dthr; p.t = h->t;
+    p.tab = h->tab; p.tt = h->tt;
     p.bag[0] = h->bag[0]; p.bag[1] = h->bag[1];
-    p.action = action; p.obs_good = obs_good ? 1 : 0; p.need = h->cfg.max_particle_count; p.n_thr = h->n_thr;
+    p.action = action; p.obs_good = h->kind == 1 ? obs_good : (obs_good ? 1 : 0); p.need = h->cfg.max_particle_count; p.n_thr = h->n_thr;
     p.sampled_after = sampled_after; p.move = move;
     p.key0 = (uint32_t)h->cfg.seed; p.key1 = (uint32_t)(h->cfg.seed >> 32);
     p.max_tries = max_tries > 0 ? max_tries : 256ll * p.need;
     cudaStream_t s = h->last_stream;
-    pomcp_advance_kernel<<<1, ADV_THREADS, h->search_smem, s>>>(p);
+    if (h->kind == 0) pomcp_advance_kernel<<<1, ADV_THREADS, h->search_smem, s>>>(p);
+    else pomcp_advance_tab_kernel<<<1, ADV_THREADS, h->search_smem, s>>>(p);
     CK(cudaGetLastError());
     ++h->launches;
     CK(cudaStreamSynchronize(s));
@@ -1309,6 +1540,7 @@ extern "C" int pomcp_generate_steps(pomcp_handle *h, int64_t n, const uint32_t *
 {
     if (!h) return -1;
     if (!h->have_model) return fail(h, "set the model first");
+    if (h->kind != 0) return fail(h, "pomcp_generate_steps is the RockSample harness; use pomcp_tabular_steps");
     if (n <= 0) return 0;
     CK(cudaSetDevice(h->device));
     struct Scratch {                                      // device scratch, released on every exit path
@@ -1334,6 +1566,40 @@ extern "C" int pomcp_generate_steps(pomcp_handle *h, int64_t n, const uint32_t *
     CK(cudaMemcpy(next_state, dn, n * 4, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(flags, df, n, cudaMemcpyDeviceToHost));
     CK(cudaMemcpy(reward, dr, n * 8, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+extern "C" int pomcp_tabular_steps(pomcp_handle *h, int64_t n, const uint32_t *state, const uint8_t *action,
+                                   const uint32_t *w1, const uint32_t *w2, uint32_t *next_state, int32_t *obs,
+                                   double *reward, uint8_t *terminal)
+{
+    if (!h) return -1;
+    if (!h->have_model || h->kind != 1) return fail(h, "set a tabular model first");
+    if (n <= 0) return 0;
+    for (int64_t i = 0; i < n; ++i)
+        if (state[i] >= (uint32_t)h->tab.S || action[i] >= h->tab.A) return fail(h, "state or action out of range");
+    CK(cudaSetDevice(h->device));
+    struct Scratch {                                      // device scratch, released on every exit path
+        void *p[8] = {nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr, nullptr};
+        ~Scratch() { for (void *q : p) cudaFree(q); }
+    } sc;
+    const size_t bytes[8] = {(size_t)n * 4, (size_t)n, (size_t)n * 4, (size_t)n * 4, (size_t)n * 4, (size_t)n * 4,
+                             (size_t)n * 8, (size_t)n};
+    for (int i = 0; i < 8; ++i) CK(cudaMalloc(&sc.p[i], bytes[i]));
+    CK(cudaMemcpy(sc.p[0], state, bytes[0], cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(sc.p[1], action, bytes[1], cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(sc.p[2], w1, bytes[2], cudaMemcpyHostToDevice));
+    CK(cudaMemcpy(sc.p[3], w2, bytes[3], cudaMemcpyHostToDevice));
+    int blocks = (int)((n + 255) / 256); if (blocks > 1184) blocks = 1184;
+    pomcp_tab_step_batch_kernel<<<blocks, 256>>>(h->tab, h->tt, n, (const uint32_t *)sc.p[0], (const uint8_t *)sc.p[1],
+                                                 (const uint32_t *)sc.p[2], (const uint32_t *)sc.p[3], (uint32_t *)sc.p[4],
+                                                 (int32_t *)sc.p[5], (double *)sc.p[6], (uint8_t *)sc.p[7]);
+    CK(cudaGetLastError());
+    ++h->launches;
+    CK(cudaMemcpy(next_state, sc.p[4], bytes[4], cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(obs, sc.p[5], bytes[5], cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(reward, sc.p[6], bytes[6], cudaMemcpyDeviceToHost));
+    CK(cudaMemcpy(terminal, sc.p[7], bytes[7], cudaMemcpyDeviceToHost));
     return 0;
 }
 

@@ -31,7 +31,7 @@ EXPORTS = ["pomcp_create", "pomcp_destroy", "pomcp_last_error", "pomcp_set_model
            "pomcp_reset_tree", "pomcp_debug_steplog", "pomcp_set_preferred_actions",
            "pomcp_root_rock_data", "pomcp_refexact_create", "pomcp_refexact_destroy", "pomcp_refexact_last_error",
            "pomcp_refexact_search", "pomcp_refexact_sample_root_particle", "pomcp_refexact_env_step",
-           "pomcp_refexact_update"]
+           "pomcp_refexact_update", "pomcp_set_model_tabular", "pomcp_tabular_steps"]
 
 
 def library_path():
@@ -61,6 +61,9 @@ def load(build_if_missing=True):
     L.pomcp_last_error.argtypes = [vp]
     L.pomcp_last_error.restype = C.c_char_p
     L.pomcp_set_model_rocksample.argtypes = [vp, C.c_int, C.c_int, P(C.c_int8), C.c_int, P(u64), P(dbl)]
+    L.pomcp_set_model_tabular.argtypes = [vp, C.c_int, C.c_int, C.c_int, P(u32), P(u32), P(dbl), u32, P(C.c_uint8)]
+    L.pomcp_tabular_steps.argtypes = [vp, i64, P(u32), P(C.c_uint8), P(u32), P(u32), P(u32), P(i32), P(dbl),
+                                      P(C.c_uint8)]
     L.pomcp_set_world.argtypes = [vp, u32, u32]
     L.pomcp_set_root_particles.argtypes = [vp, P(u32), C.c_int, C.c_int]
     L.pomcp_search.argtypes = [vp, i64, u32, u32, dbl, vp]
@@ -105,6 +108,7 @@ class Planner:
                           int(gen_growth), int(gen_wmax), 0)
         self.h = C.c_void_p()
         self.n_actions = 0
+        self.tabular = False
         self._bag_hint = None
         rc = self.lib.pomcp_create(C.byref(self.cfg), int(device), C.byref(self.h))
         if rc != 0:
@@ -141,6 +145,38 @@ class Planner:
                                                      int(start_cell), _p(thr53, C.c_uint64),
                                                      _p(rewards, C.c_double)))
         self.n_actions = 5 + n_rocks
+        self.tabular = False
+
+    def set_model_tabular(self, Tc, Oc, R, term_action_mask=0, term_state=None):
+        """Tabular POMDP: cumulative thresholds Tc[a][s][s'], Oc[a][s'][z] (uint32, rows end at 0xFFFFFFFF), rewards
+        R[a][s]; see pomdpy_b200.tabular.cumulative_thresholds."""
+        Tc = np.ascontiguousarray(Tc, dtype=np.uint32)
+        Oc = np.ascontiguousarray(Oc, dtype=np.uint32)
+        R = np.ascontiguousarray(R, dtype=np.float64)
+        A, S, S2 = Tc.shape
+        if S2 != S or Oc.shape[:2] != (A, S) or R.shape != (A, S):
+            raise ValueError("expected Tc[A][S][S], Oc[A][S][Z], R[A][S]")
+        ts = None if term_state is None else np.ascontiguousarray(term_state, dtype=np.uint8)
+        if ts is not None and ts.shape != (S,):
+            raise ValueError("term_state must be [S]")
+        self._ck(self.lib.pomcp_set_model_tabular(self.h, S, A, Oc.shape[2], _p(Tc, C.c_uint32), _p(Oc, C.c_uint32),
+                                                  _p(R, C.c_double), int(term_action_mask),
+                                                  None if ts is None else _p(ts, C.c_uint8)))
+        self.n_actions = A
+        self.tabular = True
+
+    def tabular_steps(self, state, action, w1, w2):
+        state = np.ascontiguousarray(state, dtype=np.uint32)
+        action = np.ascontiguousarray(action, dtype=np.uint8)
+        w1 = np.ascontiguousarray(w1, dtype=np.uint32)
+        w2 = np.ascontiguousarray(w2, dtype=np.uint32)
+        n = state.size
+        ns, ob = np.zeros(n, dtype=np.uint32), np.zeros(n, dtype=np.int32)
+        rw, tm = np.zeros(n, dtype=np.float64), np.zeros(n, dtype=np.uint8)
+        self._ck(self.lib.pomcp_tabular_steps(self.h, n, _p(state, C.c_uint32), _p(action, C.c_uint8),
+                                              _p(w1, C.c_uint32), _p(w2, C.c_uint32), _p(ns, C.c_uint32),
+                                              _p(ob, C.c_int32), _p(rw, C.c_double), _p(tm, C.c_uint8)))
+        return ns, ob, rw, tm
 
     def set_preferred_actions(self, enabled, prob=None):
         """--preferred_actions: in-tree action sets from per-node rock statistics; prob [cells][n_rocks] float64."""
@@ -160,7 +196,7 @@ class Planner:
     def set_world(self, actual_mask, sampled_mask):
         self._ck(self.lib.pomcp_set_world(self.h, int(actual_mask), int(sampled_mask)))
 
-    def set_root_particles(self, packed, root_cell):
+    def set_root_particles(self, packed, root_cell=0):
         packed = np.ascontiguousarray(packed, dtype=np.uint32)
         self._bag_hint = int(packed.size)
         self._ck(self.lib.pomcp_set_root_particles(self.h, _p(packed, C.c_uint32), int(packed.size), int(root_cell)))
@@ -195,9 +231,10 @@ class Planner:
             return None
         return dict(n=n, qfix=q, legal=legal.value, cell=cell.value)
 
-    def advance(self, action, obs_good, sampled_mask_after, move=0, max_tries=0):
+    def advance(self, action, obs_good, sampled_mask_after=0, move=0, max_tries=0):
         status, tries, acc = C.c_int32(), C.c_int64(), C.c_int32()
-        self._ck(self.lib.pomcp_advance(self.h, int(action), int(bool(obs_good)), int(sampled_mask_after), int(move),
+        obs = int(obs_good) if self.tabular else int(bool(obs_good))     # tabular: the observation index
+        self._ck(self.lib.pomcp_advance(self.h, int(action), obs, int(sampled_mask_after), int(move),
                                         int(max_tries), C.byref(status), C.byref(tries), C.byref(acc)))
         return dict(status=status.value, tries=tries.value, accepted=acc.value)
 

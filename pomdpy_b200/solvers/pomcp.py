@@ -92,12 +92,16 @@ class POMCP(Solver):
         else:
             bag = np.fromiter((model.pack_state(model.sample_an_init_state()) for _ in range(n_start)),
                               dtype=np.uint32, count=n_start)
-        self.planner.set_world(*model.world_masks())
-        if self.preferred != getattr(self.planner, "_preferred", False):      # rock_position_history.py:52-55
-            self.planner.set_preferred_actions(self.preferred, spec["prob"])
-            self.planner._preferred = self.preferred
-        self.planner.set_root_particles(bag, spec["start_cell"])
-        self._root_cell = spec["start_cell"]
+        self.tabular = spec.get("kind", "rocksample") == "tabular"
+        if self.tabular:
+            self.preferred = False                                            # a RockSample heuristic
+        else:
+            self.planner.set_world(*model.world_masks())
+            if self.preferred != getattr(self.planner, "_preferred", False):  # rock_position_history.py:52-55
+                self.planner.set_preferred_actions(self.preferred, spec["prob"])
+                self.planner._preferred = self.preferred
+        self.planner.set_root_particles(bag, spec.get("start_cell", 0))
+        self._root_cell = spec.get("start_cell", 0)
         self._stats = None
         self.belief_tree_index = BeliefNodeView(self)
         self.sims_done = 0
@@ -140,8 +144,11 @@ class POMCP(Solver):
                             discount=float(model.discount), seed=self.seed, node_capacity=cap, gen_w0=w0,
                             gen_growth=growth, gen_wmax=wmax, device=device)
         spec = model.device_spec()
-        pl.set_model_rocksample(spec["rows"], spec["cols"], spec["cell"], spec["start_cell"], spec["thr53"],
-                                spec["rewards"])
+        if spec.get("kind", "rocksample") == "tabular":
+            pl.set_model_tabular(spec["Tc"], spec["Oc"], spec["R"], spec["term_action_mask"], spec["term_state"])
+        else:
+            pl.set_model_rocksample(spec["rows"], spec["cols"], spec["cell"], spec["start_cell"], spec["thr53"],
+                                    spec["rewards"])
         agent._pomcp_planner = (key, pl)
         return pl
 
@@ -160,6 +167,8 @@ class POMCP(Solver):
         return self._stats
 
     def root_data(self):
+        if self.tabular:
+            return None                                  # create_root_historical_data() of a tabular model
         cell = self._root_cell
         pos = GridPosition(cell // self.model.n_cols, cell % self.model.n_cols)
         rocks = [RockData() for _ in range(self.model.n_rocks)]
@@ -208,8 +217,9 @@ class POMCP(Solver):
         refill the belief by rejection sampling (on the device).  On failure: disable_tree, no exception."""
         self.model.update(step_result)                                           # :165
         _, sampled = self.model.world_masks()
-        res = self.planner.advance(step_result.action.bin_number, bool(step_result.observation.is_good), sampled,
-                                   move=self.move)
+        obs = step_result.observation
+        res = self.planner.advance(step_result.action.bin_number,
+                                   int(obs.bin_number) if self.tabular else bool(obs.is_good), sampled, move=self.move)
         self._stats = None
         self.move_in_epoch += 1
         if res["status"] == 2:

@@ -1,0 +1,164 @@
+"""GPU parity of the tabular-model planner: the CUDA kernels, through the C ABI, against the
+CPU oracle -- bit-exact root / inner-node statistics and beliefs -- on Tiger and on random POMDPs that exercise both
+the shared-memory staging of depth-1 edges and the global-atomic path (|A|*|Z| too large to stage)."""
+import numpy as np
+import pytest
+
+import oracle
+from pomdpy_b200 import native
+from pomdpy_b200.tabular import random_pomdp, tiger
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+MODELS = {
+    "tiger": lambda: tiger(),
+    "rand-32-6-8": lambda: random_pomdp(32, 6, 8, seed=1),          # depth-1 edges staged in shared memory
+    "rand-64-16-32": lambda: random_pomdp(64, 16, 32, seed=2),      # (1 + 32*16)*16 edges: not staged
+    "rand-300-32-3": lambda: random_pomdp(300, 32, 3, seed=3),      # all 32 action lanes
+}
+
+
+def _pair(name, seed=0, n_bag=2000, **kw):
+    m = MODELS[name]()
+    om = oracle.TabularModel(m.Tc, m.Oc, m.R, m.term_action_mask, m.term_state)
+    bag = m.sample_init_states_packed(n_bag, np.random.RandomState(seed))
+    g = oracle.GsPOMCP(om, 0, 0, bag, max_depth=kw.get("max_depth", 100), dcap=kw.get("tree_depth_cap", 64),
+                       ucb_c=kw.get("ucb_coefficient", 3.0), discount=kw.get("discount", 0.95), seed=kw.get("seed", 0))
+    pl = native.Planner(**kw)
+    pl.set_model_tabular(m.Tc, m.Oc, m.R, m.term_action_mask, m.term_state)
+    pl.set_root_particles(bag)
+    return m, om, g, pl
+
+
+def _same(a, b):
+    assert a["legal"] == b["legal"]
+    assert np.array_equal(a["n"], b["n"]), (a["n"], b["n"])
+    assert np.array_equal(a["qfix"], b["qfix"]), (a["qfix"], b["qfix"])
+
+
+@pytest.mark.parametrize("name", list(MODELS))
+def test_tabular_generate_step_matches_oracle(name):
+    m = MODELS[name]()
+    om = oracle.TabularModel(m.Tc, m.Oc, m.R, m.term_action_mask, m.term_state)
+    pl = native.Planner()
+    pl.set_model_tabular(m.Tc, m.Oc, m.R, m.term_action_mask, m.term_state)
+    rng = np.random.RandomState(5)
+    n = 4000
+    s = rng.randint(0, m.num_states, size=n).astype(np.uint32)
+    a = rng.randint(0, m.num_actions, size=n).astype(np.uint8)
+    w = rng.randint(0, 1 << 32, size=(2, n), dtype=np.uint64).astype(np.uint32)
+    w[0, :8] = [0, 0xFFFFFFFF, 0xFFFFFFFE, 1 << 31, (1 << 31) - 1, 1, 2, 3]
+    w[1, 8:16] = [0, 0xFFFFFFFF, 0xFFFFFFFE, 1 << 31, (1 << 31) - 1, 1, 2, 3]
+    ns, ob, rw, tm = pl.tabular_steps(s, a, w[0], w[1])
+    for i in range(n):
+        assert (int(ns[i]), int(ob[i]), float(rw[i]), int(tm[i])) == om.step(int(s[i]), int(a[i]), int(w[0, i]), int(w[1, i]))
+    pl.close()
+
+
+CASES = [
+    # model, n_sims, (w0, growth, wmax), planner kwargs
+    ("tiger", 300, (1, 1, 1), {}),
+    ("tiger", 20000, (32, 2, 2048), dict(ucb_coefficient=30.0)),
+    ("tiger", 50000, (64, 4, 16384), dict(ucb_coefficient=30.0, seed=7)),
+    ("rand-32-6-8", 500, (1, 1, 1), dict(max_depth=30)),
+    ("rand-32-6-8", 30000, (32, 2, 4096), dict(max_depth=30, ucb_coefficient=10.0)),
+    ("rand-64-16-32", 30000, (32, 2, 4096), dict(max_depth=20, ucb_coefficient=10.0)),
+    ("rand-64-16-32", 3000, (8, 2, 64), dict(max_depth=20, tree_depth_cap=4)),
+    ("rand-300-32-3", 40000, (64, 4, 8192), dict(max_depth=25, ucb_coefficient=8.0, discount=0.9)),
+]
+
+
+@pytest.mark.parametrize("name,n_sims,sched,kw", CASES)
+def test_tabular_search_bit_exact(name, n_sims, sched, kw):
+    w0, growth, wmax = sched
+    m, om, g, pl = _pair(name, gen_w0=w0, gen_growth=growth, gen_wmax=wmax, node_capacity=1 << 17, **kw)
+    g.search(n_sims, w0=w0, growth=growth, wmax=wmax)
+    pl.search(n_sims)
+    a, b = g.root_stats(), pl.root_stats()
+    _same(a, b)
+    assert int(b["n"].sum()) == n_sims
+    gc, pc = g.counters(), pl.counters()
+    for k in ("levels", "rollout_steps", "created", "nodes", "generations"):
+        assert gc[k] == pc[k], (k, gc[k], pc[k])
+    # inner nodes: every (action, observation) child of the root and one grandchild layer
+    checked = 0
+    for act in range(m.num_actions):
+        for z in range(m.num_observations):
+            x, y = g.node_stats([(act, z)]), pl.node_stats([(act, z)])
+            assert (x is None) == (y is None)
+            if x is None:
+                continue
+            _same(x, y)
+            checked += 1
+            for a2 in range(min(m.num_actions, 3)):
+                x2, y2 = g.node_stats([(act, z), (a2, 0)]), pl.node_stats([(act, z), (a2, 0)])
+                assert (x2 is None) == (y2 is None)
+                if x2 is not None:
+                    _same(x2, y2)
+    assert checked > 0 or n_sims < 10
+    pl.close()
+
+
+@pytest.mark.parametrize("name,kw", [("tiger", dict(ucb_coefficient=30.0)), ("rand-32-6-8", dict(max_depth=30)),
+                                     ("rand-64-16-32", dict(max_depth=20))])
+def test_tabular_search_update_loop_bit_exact(name, kw):
+    """Several real steps: search, greedy action, belief update with a sampled observation, re-root."""
+    m, om, g, pl = _pair(name, gen_w0=32, gen_growth=2, gen_wmax=2048, node_capacity=1 << 17, max_particle_count=1500,
+                         **kw)
+    rng = np.random.RandomState(11)
+    state = int(rng.randint(m.num_states))
+    for move in range(5):
+        g.search(6000, move=move, w0=32, growth=2, wmax=2048)
+        pl.search(6000, move=move)
+        a, b = g.root_stats(), pl.root_stats()
+        _same(a, b)
+        act = g.greedy(move, a)
+        if name == "tiger":
+            act = 0                                              # keep listening: opening ends the episode
+        ns, z, _, _ = om.step(state, act, int(rng.randint(1 << 32)), int(rng.randint(1 << 32)))
+        state = ns
+        u = g.update(act, z, 0, move=move, need=1500)
+        v = pl.advance(act, z, 0, move=move)
+        assert (u["status"], u["tries"], u["accepted"]) == (v["status"], v["tries"], v["accepted"])
+        if u["status"] == 2:
+            break
+        bag, _ = pl.root_particles()
+        assert np.array_equal(bag, g.bag())
+        _same(g.root_stats(), pl.root_stats())
+    pl.close()
+
+
+def test_tabular_argument_errors():
+    m = tiger()
+    pl = native.Planner()
+    bad = m.Tc.copy()
+    bad[0, 0, -1] = 5
+    with pytest.raises(native.PomcpError):
+        pl.set_model_tabular(bad, m.Oc, m.R, m.term_action_mask, m.term_state)
+    pl.set_model_tabular(m.Tc, m.Oc, m.R, m.term_action_mask, m.term_state)
+    with pytest.raises(native.PomcpError):
+        pl.set_root_particles(np.array([0, 1, 2], dtype=np.uint32))      # state 2 does not exist
+    pl.set_root_particles(np.array([0, 1], dtype=np.uint32))
+    with pytest.raises(native.PomcpError):
+        pl.advance(0, 2)                                                 # observation 2 does not exist
+    with pytest.raises(native.PomcpError):
+        pl.set_preferred_actions(True, np.zeros(4))
+    pl.close()
+
+
+def test_tiger_agent_episodes():
+    """The reference's Agent loop (agent.py:150-213) on Tiger through the CUDA solver: listens first, then opens; the
+    mean discounted return beats both opening at once (-5) and never opening."""
+    from pomdpy_b200 import Agent
+    from pomdpy_b200.solvers import POMCP
+    args = dict(max_steps=30, n_epochs=60, n_sims=4000, seed=5, ucb_coefficient=30.0, discount=0.95, max_depth=30,
+                max_particle_count=1000, n_start_states=1000, epsilon_start=0.5, epsilon_minimum=0.1,
+                epsilon_decay=0.95, action_selection_timeout=60, timeout=3600, preferred_actions=False,
+                save=False, test=10, env="Tiger", solver="POMCP")
+    np.random.seed(5)
+    agent = Agent(tiger(args), POMCP)
+    agent.discounted_return()
+    er = agent.experiment_results
+    mean = er.discounted_return.mean
+    print("tiger: discounted return %.2f +- %.2f over %d epochs" % (mean, er.discounted_return.std_err(), args["n_epochs"]))
+    assert mean > 0.0
