@@ -162,3 +162,32 @@ def test_tiger_agent_episodes():
     mean = er.discounted_return.mean
     print("tiger: discounted return %.2f +- %.2f over %d epochs" % (mean, er.discounted_return.std_err(), args["n_epochs"]))
     assert mean > 0.0
+
+
+def test_pomcp_agrees_with_value_iteration_on_tiger():
+    """The two device solvers on the same matrices (continuing Tiger, horizon 6): the POMCP kernel's greedy action at
+    clear-cut beliefs equals the action of the value-iteration kernel's alpha vectors, and its root value at the
+    uniform belief approaches the exact one from below."""
+    from pomdpy_b200 import vi
+    from pomdpy_b200.tabular import TabularModel
+    from pomdpy_b200.tiger.tiger_model import TigerModel as TM
+    T, O, R = TM.get_transition_matrix(), TM.get_observation_matrix(), TM.get_reward_matrix()
+    H = 6
+    alpha, acts = vi.solve_reference(T, O, R, 0.95, H)
+    m = TabularModel({}, T, O, R, [0.5, 0.5], name="TigerContinuing")
+    pl = native.Planner(max_depth=H, ucb_coefficient=30.0, seed=1, gen_w0=64, gen_growth=2, gen_wmax=4096,
+                        node_capacity=1 << 18)
+    pl.set_model_tabular(m.Tc, m.Oc, m.R, 0, None)
+    for p0 in (0.5, 0.03, 0.97, 0.3, 0.7):
+        b = np.array([p0, 1.0 - p0])
+        best = int(np.argmax(alpha @ b))
+        n0 = int(round(2000 * p0))
+        pl.set_root_particles(np.array([0] * n0 + [1] * (2000 - n0), dtype=np.uint32))
+        pl.search(100000)
+        st = pl.root_stats()
+        q = st["qfix"] / np.maximum(st["n"], 1) / native.QFIX_SCALE
+        assert int(np.argmax(q)) == int(acts[best]), (p0, q, acts[best])
+        if p0 == 0.5:
+            exact = float((alpha @ b).max())
+            assert exact - 1.0 < q.max() <= exact + 0.05, (q.max(), exact)
+    pl.close()
