@@ -30,14 +30,16 @@ def stale():
 CHECKS_LIB = os.path.join(HERE, "libpomcp_b200_checks.so")
 
 
-def build(force=False, verbose=False, checks=False):
+def build(force=False, verbose=False, checks=False, defines=(), out=None):
     """Build libpomcp_b200.so next to this package; returns its path.  checks=True builds the variant with
-    device-side bounds checks (-DPOMCP_CHECKS) as libpomcp_b200_checks.so."""
-    out = CHECKS_LIB if checks else LIB
-    if not force and not checks and not stale():
+    device-side bounds checks (-DPOMCP_CHECKS) as libpomcp_b200_checks.so; `defines` + `out` build an experiment
+    variant (e.g. defines=("POMCP_TSEC",) for the expand-phase section timers) to load through POMCP_B200_LIB."""
+    variant = checks or bool(defines)
+    out = out or (CHECKS_LIB if checks else LIB)
+    if not force and not variant and not stale():
         return LIB
-    cmd = [_nvcc()] + NVCC_FLAGS + (["-DPOMCP_CHECKS"] if checks else []) + (["-Xptxas", "-v"] if verbose else []) + \
-          ["-o", out] + [os.path.join(CSRC, f) for f in SOURCES]
+    cmd = [_nvcc()] + NVCC_FLAGS + (["-DPOMCP_CHECKS"] if checks else []) + ["-D" + d for d in defines] + \
+          (["-Xptxas", "-v"] if verbose else []) + ["-o", out] + [os.path.join(CSRC, f) for f in SOURCES]
     res = subprocess.run(cmd, capture_output=True, text=True)
     if res.returncode != 0:
         raise RuntimeError("nvcc failed:\n" + res.stdout + res.stderr)

@@ -26,6 +26,17 @@
 #else
 #define DCHECK(S_, cond, code) do { } while (0)
 #endif
+// Section timers of the expand phase (-DPOMCP_TSEC diagnostic build only): per-thread clock64 deltas, summed over the
+// grid into steplog[127][0..7] at the end of the search.
+#ifdef POMCP_TSEC
+#define TSEC_DECL long long tsec_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tsec_prev_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tsec_t_ = 0
+#define TSEC_START() (tsec_t_ = clock64())
+#define TSEC(k) do { const long long n_ = clock64(); tsec_[k] += n_ - tsec_t_; tsec_t_ = n_; } while (0)
+#else
+#define TSEC_DECL
+#define TSEC_START() do { } while (0)
+#define TSEC(k) do { } while (0)
+#endif
 #define CHILD_LOCKED 0xFFFFFFFFu
 #define CHILD_VISITED 0x80000000u   // set on a child slot once a backup has passed through the child (N > 0)
 #define CHILD_ID(c) ((int)((c) & 0x7FFFFFFFu) - 1)
@@ -93,8 +104,9 @@ struct SimBuf {                        // per simulation-in-flight scratch, SoA 
     uint16_t *path_ar;                 // [dcap][wmax] action | obs_good << 5 | reward id << 8   (tabular: action | obs << 5)
     double *path_rew;                  // [dcap][wmax] tabular models: the step reward (null for RockSample)
     int32_t *wl_node;                  // [wmax] worklist of nodes with arrivals in this level step
-    uint32_t *wl_thr;                  // [wmax][32] cumulative action thresholds for nodes with >= 2 arrivals
-    int32_t *wl_meta;                  // [wmax] last action (bits 0-7) | (N > 0) << 8
+    uint32_t *wl_thr;                  // [wmax][32] plan data: action mask (kind 0) | <= 16 pull bytes (kind 1) |
+                                       //            cumulative action thresholds (kind 2)
+    int32_t *wl_meta;                  // [wmax] plan of the node: kind << 16 | arrivals (kind 1) << 8 | last action (kind 2)
     double *ro_sum;                    // [wmax] discounted reward sum of a rollout in progress
     uint8_t *ro_t;                     // [wmax] rollout steps done so far (rollouts advance in slices)
 };
@@ -351,64 +363,90 @@ __device__ __forceinline__ void warp_allocation(const SearchParams &p, int X, ui
     const float f = (x / V) * 4294967296.0f;
     thr_out[lane] = f >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)f;
     const unsigned pos = __ballot_sync(full, v > 0.0f);
-    if (lane == 0) *meta_out = (31 - __clz((int)pos)) | ((N > 0) ? 256 : 0);
+    if (lane == 0) *meta_out = (31 - __clz((int)pos)) | (2 << 16);                  // PLAN_THRESHOLDS
 }
 
-// Action of one simulation at a node with k <= SEQ_ALLOC_MAX arrivals (thread-level; statistics are read-only).
-//   k == 1: UCB1 arg-max (action_selectors.py:6-37), uniform tie-break with the 32-bit draw x0.
-//   k >= 2: the k arrivals share the virtual-pull sequence "pull j takes the UCB1 arg-max (lowest id on ties) given
-//           the statistics plus the virtual visits of pulls 0..j-1"; this simulation takes pull j = floor(x0*k/2^32).
-__device__ __forceinline__ int select_thread(const SearchParams &p, int X, uint32_t mask, int A, uint32_t x0, uint32_t k)
+// Action plan of a node with k <= SEQ_ALLOC_MAX arrivals (warp-cooperative, lane = action; statistics are read-only
+// within a generation, so the plan is computed once per node and level step instead of once per simulation).
+//   kind 0  uniform draw over an action mask:  at least k untried actions (n == 0 scores +inf, pomcp.py:64-65), or
+//           k == 1: the UCB1 arg-max set (action_selectors.py:6-37; the draw breaks ties), or c = 0: the best means
+//   kind 1  the k arrivals share the virtual-pull sequence "pull j takes the UCB1 arg-max (lowest id on ties) given
+//           the statistics plus the virtual visits of pulls 0..j-1"; a simulation takes pull j = floor(x0*k/2^32)
+#define PLAN_MASK 0
+#define PLAN_PULLS 1
+#define PLAN_THRESHOLDS 2
+__device__ __forceinline__ void warp_plan_few(const SearchParams &p, int X, uint32_t k, int lane, int A,
+                                              uint32_t *out, int32_t *meta_out)
 {
-    const int32_t *nrow = p.t.n + (size_t)X * AS;
-    const long long *qrow = p.t.qfix + (size_t)X * AS;
-    int N = 0; uint32_t untried = 0;
+    const unsigned full = 0xFFFFFFFFu;
+    const uint32_t mask = p.t.legal[X];
+    const bool legal = lane < A && ((mask >> lane) & 1u);
+    const int n = legal ? p.t.n[(size_t)X * AS + lane] : 0;
+    const long long qf = legal ? p.t.qfix[(size_t)X * AS + lane] : 0;
+    int N = n;
 #pragma unroll
-    for (int q = 0; q < AS / 4; ++q) {
-        const int4 v4 = reinterpret_cast<const int4 *>(nrow)[q];
-        const uint32_t m4 = (mask >> (4 * q)) & 15u;
-        if (m4 & 1u) { N += v4.x; if (v4.x == 0) untried |= 1u << (4 * q); }
-        if (m4 & 2u) { N += v4.y; if (v4.y == 0) untried |= 2u << (4 * q); }
-        if (m4 & 4u) { N += v4.z; if (v4.z == 0) untried |= 4u << (4 * q); }
-        if (m4 & 8u) { N += v4.w; if (v4.w == 0) untried |= 8u << (4 * q); }
+    for (int off = 16; off >= 1; off >>= 1) N += __shfl_xor_sync(full, N, off);
+    const unsigned untried = __ballot_sync(full, legal && n == 0);
+    if ((uint32_t)__popc(untried) >= k) {
+        if (lane == 0) { out[0] = untried; *meta_out = PLAN_MASK << 16; }
+        return;
     }
-    const uint32_t n_untried = (uint32_t)__popc(untried);
-    if (n_untried >= k) return nth_bit(untried, randbelow32(x0, n_untried));   // n == 0 scores +inf (pomcp.py:64-65)
     const float L = det_logf_u32((uint32_t)N + 1u);
     const float cf = (float)p.ucb_c;
-    if (k == 1) {
-        float best = -INFINITY; uint32_t ties = 0;
-        for (int a = 0; a < A; ++a) {
-            if (!((mask >> a) & 1u)) continue;
-            const int na = nrow[a];
-            const float s = edge_mean(qrow[a], na) + cf * sqrtf(L / (float)na);
-            if (s > best) { best = s; ties = 1u << a; }
-            else if (s == best) ties |= 1u << a;
-        }
-        return nth_bit(ties, randbelow32(x0, (uint32_t)__popc(ties)));
+    if (k == 1) {                                                    // no untried action here: every legal n > 0
+        const float sc = legal ? edge_mean(qf, n) + cf * sqrtf(L / (float)n) : -INFINITY;
+        float best = sc;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) best = fmaxf(best, __shfl_xor_sync(full, best, off));
+        const unsigned ties = __ballot_sync(full, legal && sc == best);
+        if (lane == 0) { out[0] = ties; *meta_out = PLAN_MASK << 16; }
+        return;
     }
     const float c2L = (cf * cf) * L;
-    float sc[AS]; uint8_t va[AS];
-    float qmax = -INFINITY; uint32_t qties = 0;
-    for (int a = 0; a < A; ++a) {
-        va[a] = 0; sc[a] = -INFINITY;
-        if (!((mask >> a) & 1u)) continue;
-        const int na = nrow[a];
-        const float qb = na == 0 ? 0.0f : edge_mean(qrow[a], na);
-        if (qb > qmax) { qmax = qb; qties = 1u << a; } else if (qb == qmax) qties |= 1u << a;
-        sc[a] = na == 0 ? INFINITY : qb + cf * sqrtf(L / (float)na);
+    const float qb = n == 0 ? 0.0f : edge_mean(qf, n);
+    if (!(c2L > 0.0f)) {
+        float qmax = legal ? qb : -INFINITY;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) qmax = fmaxf(qmax, __shfl_xor_sync(full, qmax, off));
+        const unsigned qties = __ballot_sync(full, legal && qb == qmax);
+        if (lane == 0) { out[0] = qties; *meta_out = PLAN_MASK << 16; }
+        return;
     }
-    if (!(c2L > 0.0f)) return nth_bit(qties, randbelow32(x0, (uint32_t)__popc(qties)));
-    const uint32_t j = randbelow32(x0, k);
-    for (uint32_t pull = 0;; ++pull) {
-        int w = 0; float bs = sc[0];
-        for (int a = 1; a < A; ++a) if (sc[a] > bs) { bs = sc[a]; w = a; }
-        if (pull == j) return w;
-        const int na = nrow[w];
-        const float qb = na == 0 ? 0.0f : edge_mean(qrow[w], na);
-        va[w] += 1;
-        sc[w] = qb + cf * sqrtf(L / (float)(na + (int)va[w]));
+    float sc = legal ? (n == 0 ? INFINITY : qb + cf * sqrtf(L / (float)n)) : -INFINITY;
+    int va = 0;
+    uint32_t seq[4] = {0u, 0u, 0u, 0u};
+    for (uint32_t pull = 0; pull < k; ++pull) {
+        float bs = sc;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) bs = fmaxf(bs, __shfl_xor_sync(full, bs, off));
+        const int w = __ffs((int)__ballot_sync(full, sc == bs)) - 1;
+        seq[pull >> 2] |= (uint32_t)w << (8 * (pull & 3u));
+        if (lane == w) { va += 1; sc = qb + cf * sqrtf(L / (float)(n + va)); }
     }
+    if (lane < 4) out[lane] = seq[lane];
+    if (lane == 0) *meta_out = (PLAN_PULLS << 16) | (int32_t)(k << 8);
+}
+
+// Plan of node X for its k arrivals of this level step (one warp).
+__device__ __forceinline__ void warp_plan(const SearchParams &p, int X, uint32_t k, int lane, int A,
+                                          uint32_t *out, int32_t *meta_out)
+{
+    if (k > SEQ_ALLOC_MAX) warp_allocation(p, X, k, lane, A, out, meta_out);
+    else warp_plan_few(p, X, k, lane, A, out, meta_out);
+}
+
+// The action of one simulation from its node's plan and its 32-bit draw x0.
+__device__ __forceinline__ int plan_action(const uint32_t *plan, int32_t meta, uint32_t x0, int A)
+{
+    const int kind = meta >> 16;
+    if (kind == PLAN_THRESHOLDS) {
+        int a = meta & 255;
+        for (int bq = 0; bq < A; ++bq) if (x0 < plan[bq]) { a = bq; break; }
+        return a;
+    }
+    if (kind == PLAN_MASK) { const uint32_t m = plan[0]; return nth_bit(m, randbelow32(x0, (uint32_t)__popc(m))); }
+    const uint32_t j = randbelow32(x0, (uint32_t)(meta >> 8) & 255u);
+    return (int)((plan[j >> 2] >> (8 * (j & 3u))) & 255u);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -498,6 +536,7 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
     unsigned long long tp[6] = {0, 0, 0, 0, 0, 0}, tmark = t_start;   // phase clocks (gtid 0 only)
 #define PHASE_MARK(k) do { if (gtid == 0) { const unsigned long long now_ = globaltimer_ns(); tp[k] += now_ - tmark; tmark = now_; } } while (0)
     const SimCtx<KIND> ctx{p, mc};
+    TSEC_DECL;
     int W = p.w0;
     long long gen_done = 0;                                          // simulations of earlier generations (stream ids)
 
@@ -557,10 +596,8 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                 p.t.arrive[root] = (s1 << 32) | (unsigned long long)(unsigned)w;
                 p.t.slot[root] = 0; p.b.wl_node[0] = root; S->wl_count[(int)(s1 & 3ull)] = 1;
             }
-            if ((uint32_t)w > SEQ_ALLOC_MAX) {                       // its allocation is known now: no extra phase
-                warp_allocation(p, root, (uint32_t)w, lane, A, p.b.wl_thr, p.b.wl_meta);
-                if (lane == 0) ++c_alloc;
-            }
+            warp_plan(p, root, (uint32_t)w, lane, A, p.b.wl_thr, p.b.wl_meta);   // known now: no extra phase
+            if (lane == 0 && (uint32_t)w > SEQ_ALLOC_MAX) ++c_alloc;
         }
         for (int i = gtid; i < w; i += T) {
             const uint32_t sim = p.sim_offset + (uint32_t)(done + i);
@@ -581,21 +618,22 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
             const int nwl = *((volatile int32_t *)&S->wl_count[ring]);
             if (gtid == 0) S->wl_count[ring_next] = 0;
             if (nwl == 0) break;
-            // [allocate] every warp inspects 32 worklist entries at once (strided by the warp count, so that the
-            // early, busy entries spread over all warps) and serves those with > SEQ_ALLOC_MAX arrivals
+            // [allocate] one warp per worklist node computes the node's action plan for its arrivals: every warp
+            // inspects 32 entries at once (strided by the warp count, so that the early, busy entries spread out)
             if (level > 0) {
             for (int base = 0; base < nwl; base += nwarps * 32) {
                 const int e = base + lane * nwarps + vwarp;
                 int X = 0; uint32_t k = 0;
                 if (e < nwl) { X = p.b.wl_node[e]; k = (uint32_t)p.t.arrive[X]; }
-                unsigned todo = __ballot_sync(0xFFFFFFFFu, k > SEQ_ALLOC_MAX);
+                unsigned todo = __ballot_sync(0xFFFFFFFFu, e < nwl);
                 while (todo) {
                     const int src = __ffs((int)todo) - 1;
                     todo &= todo - 1;
                     const int es = base + src * nwarps + vwarp;
-                    warp_allocation(p, __shfl_sync(0xFFFFFFFFu, X, src), __shfl_sync(0xFFFFFFFFu, k, src), lane, A,
-                                    p.b.wl_thr + (size_t)es * 32, p.b.wl_meta + es);
-                    if (lane == 0) ++c_alloc;
+                    const uint32_t ks = __shfl_sync(0xFFFFFFFFu, k, src);
+                    warp_plan(p, __shfl_sync(0xFFFFFFFFu, X, src), ks, lane, A, p.b.wl_thr + (size_t)es * 32,
+                              p.b.wl_meta + es);
+                    if (lane == 0 && ks > SEQ_ALLOC_MAX) ++c_alloc;
                 }
             }
             if (gtid == 0 && lsteps <= 128) S->steplog[lsteps - 1][1] = (long long)(globaltimer_ns() - tmark);
@@ -607,6 +645,7 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
             for (int base = gtid - lane; base < w; base += T) {
                 const int i = base + lane;
                 int arrive_at = -1, arrive_slot = 0;                 // non-virgin child this simulation descends to
+                TSEC_START();
                 if (i < w && (p.b.flag[i] & 3) == 0) {
                     const int X = p.b.node[i];
                     const int d = p.b.depth[i];
@@ -615,17 +654,11 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                     if (d >= p.max_depth) p.b.flag[i] = 2;                                  // :100
                     else {
                         const Philox4 r = philox4x32_10((uint32_t)(d + 1), sim, p.move, DOM_SIM, p.key0, p.key1);
-                        const uint32_t mask = p.t.legal[X];
-                        const uint32_t k = (uint32_t)p.t.arrive[X];
-                        int a;
-                        if (k <= SEQ_ALLOC_MAX) a = select_thread(p, X, mask, A, r.x, k);
-                        else {
-                            const int s = p.t.slot[X];
-                            const uint32_t *thr = p.b.wl_thr + (size_t)s * 32;
-                            a = p.b.wl_meta[s] & 255;
-                            for (int bq = 0; bq < A; ++bq) if (r.x < thr[bq]) { a = bq; break; }
-                        }
-                        DCHECK(S, a >= 0 && a < A && ((mask >> a) & 1u) && k >= 1u && k <= (uint32_t)w, 22);
+                        const int s = p.t.slot[X];
+                        TSEC(0);                                     // load sim + node header (+ Philox)
+                        const int a = plan_action(p.b.wl_thr + (size_t)s * 32, p.b.wl_meta[s], r.x, A);
+                        DCHECK(S, s >= 0 && s < p.wmax && a >= 0 && a < A && ((p.t.legal[X] >> a) & 1u), 22);
+                        TSEC(1);                                     // choice
                         const uint32_t st = p.b.state[i];
                         DCHECK(S, MD::state_tag(st) == (uint32_t)p.t.cell[X], 23);
                         const StepOut so = MD::step(mc, st, a, r.y, r.z);                   // :104
@@ -635,6 +668,7 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                         if (KIND == 1) p.b.path_rew[(size_t)d * p.wmax + i] = so.reward;
                         p.b.depth[i] = (uint8_t)(d + 1);
                         p.b.state[i] = so.next;
+                        TSEC(2);                                     // step + path stores
                         if (so.terminal) p.b.flag[i] = 2;
                         else {
                             const size_t cslot = ((size_t)X * AS + a) * ZS + so.obs;
@@ -668,6 +702,7 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                                     c = CHILD_LOCKED; have_mask = true;
                                 }
                             }
+                            TSEC(3);                                                        // child lookup / creation
                             if (c == 0) p.b.flag[i] = 1;                                    // depth cap: leaf (:119)
                             else if (c == CHILD_LOCKED) {                                   // created in this step
                                 if constexpr (KIND == 0) if (p.t.chance && !have_mask)      // id not published yet: derive the set
@@ -686,7 +721,9 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                         }
                     }
                 }
+                TSEC(4);                                             // leaf (virgin step) or descend
                 __syncwarp();
+                TSEC(5);
                 // arrivals for the next level.  From the root: counted per block in shared memory (<= ZS|A| children);
                 // deeper: aggregated per warp and node (match.any), one atomic per group
                 if (level == 0) { if (arrive_at >= 0) atomicAdd(&arr1[arrive_slot], 1); continue; }
@@ -707,6 +744,7 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                         atomicAdd(&p.t.arrive[arrive_at], (unsigned long long)__popc(peers));
                     }
                 }
+                TSEC(6);                                             // arrival registration
             }
             if (level == 0) {                                        // publish this block's arrivals at the root's children
                 __syncthreads();
@@ -724,6 +762,16 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                 }
             }
             if (gtid == 0 && lsteps <= 128) S->steplog[lsteps - 1][3] = (long long)(globaltimer_ns() - tmark);
+#ifdef POMCP_TSEC
+            if (lsteps <= 63) {                                      // per level step: rows 64.. of the step log
+                for (int k = 0; k < 8; ++k) {
+                    long long v = tsec_[k] - tsec_prev_[k];
+                    tsec_prev_[k] = tsec_[k];
+                    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+                    if (lane == 0 && v) atomicAdd(reinterpret_cast<unsigned long long *>(&S->steplog[63 + lsteps][k]), (unsigned long long)v);
+                }
+            }
+#endif
             PHASE_MARK(3);
         }
         // ---- rollout (belief_tree_solver.py:123-152, from the post-action state) + backup (:126-137) ----
@@ -817,6 +865,13 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
         atomicAdd(reinterpret_cast<unsigned long long *>(&S->counters[2]), (unsigned long long)c_created);
         atomicAdd(reinterpret_cast<unsigned long long *>(&S->counters[4]), (unsigned long long)c_alloc);
     }
+#ifdef POMCP_TSEC
+    for (int k = 0; k < 8; ++k) {
+        long long v = tsec_[k];
+        for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long *>(&S->steplog[127][k]), (unsigned long long)v);
+    }
+#endif
     if (gtid == 0) {
         S->gstep = gstep;
         S->sims_done = done;

@@ -6,11 +6,13 @@ t = golden_tables("map-15-15"); actual, bag, _ = random_world_and_bag(t, 41)
 w0, g, wmax = [int(x) for x in sys.argv[1:4]]
 pl = make_planner(t, seed=1, gen_w0=w0, gen_growth=g, gen_wmax=wmax, node_capacity=1 << 22)
 pl.set_world(actual, 0)
-for rep in range(3):
+for rep in range(1):
     pl.set_root_particles(bag, int(t["start_cell"])); pl.search(1000000, move=rep); pl.root_stats()
-c = pl.counters(); print(c["last_search_ns"] * 1e-6, c["level_steps"] // 3, c["alloc_nodes"] // 3)
+c = pl.counters(); print(c["last_search_ns"] * 1e-6, c["level_steps"], c["alloc_nodes"])
 L = pl.steplog()
-for i in range(min(128, c["level_steps"] // 3)):
-    print(i, "wait %.1f alloc %.1f wait2 %.1f expand %.1f us  nwl %d" % (L[i, 0] / 1e3, L[i, 1] / 1e3, L[i, 2] / 1e3, L[i, 3] / 1e3, L[i, 4]))
+for i in range(min(63, c["level_steps"])):
+    print(i, "wait %.1f alloc %.1f wait2 %.1f expand %.1f us  nwl %d" % (L[i, 0] / 1e3, L[i, 1] / 1e3, L[i, 2] / 1e3, L[i, 3] / 1e3, L[i, 4]),
+          " tsec Mcyc [load choice step child leaf sync arrive]:", [round(float(x) / 1e6, 1) for x in L[64 + i, :7]])
 
-print("tsec cycles [choice, step+path, child, leaf-or-descend, syncwarp, arrive, load-sim, load-node]:", L[127].tolist())
+tot = float(L[127, :7].sum()) or 1.0
+print("tsec share [load, choice, step, child, leaf-or-descend, syncwarp, arrive]:", [round(float(x) / tot, 3) for x in L[127, :7]], "total Gcycles", tot / 1e9)
