@@ -811,10 +811,13 @@ static void gs_allocation(const orc_gs *h, const gs_node *nd, int64_t k, uint32_
     }
     float V = x[31];
     *last = 0;
+    uint32_t run = 0;                      /* running maximum over the actions with positive weight: thresholds are
+                                            * non-decreasing and an action without weight is never drawn */
     for (int a = 0; a < 32; ++a) {
         float f = (x[a] / V) * 4294967296.0f;
-        thr[a] = f >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)f;
-        if (v[a] > 0.0f) *last = a;
+        uint32_t t = f >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)f;
+        if (v[a] > 0.0f) { *last = a; if (t > run) run = t; }
+        thr[a] = run;
     }
 }
 

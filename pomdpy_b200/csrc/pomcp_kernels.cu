@@ -47,6 +47,8 @@
 #define ADV_THREADS 1024
 #define ADV_TRIES 4
 #define ROLL_SLICE 8            // rollout steps per slice while waiting at a barrier (even: Philox block pairs)
+#define ARR_HT 1024            // per-block arrival table (shared memory): slots of {node id, arrivals in this level step}
+#define ARR_PROBES 8
 #define SEQ_ALLOC_MAX 16u      // arrivals <= this: exact virtual-pull allocation; more: water-filling
 #ifndef BISECT_ITERS
 #define BISECT_ITERS 14
@@ -361,7 +363,15 @@ __device__ __forceinline__ void warp_allocation(const SearchParams &p, int X, ui
     }
     const float V = __shfl_sync(full, x, 31);
     const float f = (x / V) * 4294967296.0f;
-    thr_out[lane] = f >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)f;
+    // running maximum over the actions with positive weight: non-decreasing thresholds, and an action without
+    // weight repeats its predecessor's (prefix sums of different lanes round differently), so it is never drawn
+    uint32_t th = v > 0.0f ? (f >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)f) : 0u;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t y = __shfl_up_sync(full, th, off);
+        if (lane >= off && y > th) th = y;
+    }
+    thr_out[lane] = th;
     const unsigned pos = __ballot_sync(full, v > 0.0f);
     if (lane == 0) *meta_out = (31 - __clz((int)pos)) | (2 << 16);                  // PLAN_THRESHOLDS
 }
@@ -439,10 +449,10 @@ __device__ __forceinline__ void warp_plan(const SearchParams &p, int X, uint32_t
 __device__ __forceinline__ int plan_action(const uint32_t *plan, int32_t meta, uint32_t x0, int A)
 {
     const int kind = meta >> 16;
-    if (kind == PLAN_THRESHOLDS) {
-        int a = meta & 255;
-        for (int bq = 0; bq < A; ++bq) if (x0 < plan[bq]) { a = bq; break; }
-        return a;
+    if (kind == PLAN_THRESHOLDS) {                       // first action whose threshold exceeds x0 (bisection)
+        int lo = 0, hi = A;
+        while (lo < hi) { const int mid = (lo + hi) >> 1; if (x0 < plan[mid]) hi = mid; else lo = mid + 1; }
+        return lo < A ? lo : (meta & 255);
     }
     if (kind == PLAN_MASK) { const uint32_t m = plan[0]; return nth_bit(m, randbelow32(x0, (uint32_t)__popc(m))); }
     const uint32_t j = randbelow32(x0, (uint32_t)(meta >> 8) & 255u);
@@ -515,6 +525,10 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
     off += (size_t)n_acc * 4;
     int *arr1 = reinterpret_cast<int *>(smem + off);               // arrivals at the root's children, per block
     for (int i = threadIdx.x; i < ZS * A; i += blockDim.x) arr1[i] = 0;
+    off += ((size_t)ZS * A * 4 + 15) & ~size_t(15);
+    uint32_t *ht_key = reinterpret_cast<uint32_t *>(smem + off);    // arrivals at deeper nodes, per block (hash table)
+    int *ht_cnt = reinterpret_cast<int *>(smem + off + ARR_HT * 4);
+    for (int i = threadIdx.x; i < ARR_HT; i += blockDim.x) { ht_key[i] = 0u; ht_cnt[i] = 0; }
     if (threadIdx.x == 0) { double d = 1.0; for (int t = 0; t < p.max_depth; ++t) { disc[t] = d; d *= p.discount; } }
     for (int i = threadIdx.x; i < n_acc; i += blockDim.x) { acc_q[i] = 0; acc_n[i] = 0; }
     __syncthreads();
@@ -612,6 +626,19 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
             ++gstep; ++lsteps;
             const int ring = (int)(gstep & 3ull), ring_next = (int)((gstep + 1) & 3ull);
             const unsigned long long stamp_next = (gstep + 1) << 32;
+            // cnt arrivals at node Xn for the next level step: stamp the node and enter it in the worklist on its first
+            // arrival (a plain L2 read first: a busy node is almost always stamped already), then one fire-and-forget add
+            auto register_arrivals = [&](int Xn, uint32_t cnt) {
+                if (*((volatile unsigned long long *)&p.t.arrive[Xn]) < stamp_next) {
+                    const unsigned long long old = atomicMax(&p.t.arrive[Xn], stamp_next);
+                    if (old < stamp_next) {
+                        const int sl = atomicAdd(&S->wl_count[ring_next], 1);
+                        DCHECK(S, sl < p.wmax, 25);
+                        p.b.wl_node[sl] = Xn; p.t.slot[Xn] = sl;
+                    }
+                }
+                atomicAdd(&p.t.arrive[Xn], (unsigned long long)cnt);
+            };
             grid_sync_working();                                     // arrivals of this level are complete
             if (gtid == 0 && lsteps <= 128) S->steplog[lsteps - 1][0] = (long long)(globaltimer_ns() - tmark);
             PHASE_MARK(1);
@@ -724,41 +751,39 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                 TSEC(4);                                             // leaf (virgin step) or descend
                 __syncwarp();
                 TSEC(5);
-                // arrivals for the next level.  From the root: counted per block in shared memory (<= ZS|A| children);
-                // deeper: aggregated per warp and node (match.any), one atomic per group
-                if (level == 0) { if (arrive_at >= 0) atomicAdd(&arr1[arrive_slot], 1); continue; }
-                const unsigned amask = __ballot_sync(0xFFFFFFFFu, arrive_at >= 0);
+                // arrivals for the next level are counted per block in shared memory -- from the root in a table
+                // indexed by child slot (<= ZS|A| children), deeper in a small hash table keyed by node id -- and
+                // published once per block and node after the loop: a busy node sees one atomic per block, not one per
+                // warp, and no simulation waits for the round trip
                 if (arrive_at >= 0) {
-                    const unsigned peers = __match_any_sync(amask, arrive_at);
-                    if (lane == __ffs((int)peers) - 1) {
-                        // stamp the node on its first arrival of this level step (a plain L2 read first: on a busy
-                        // node almost every group finds the stamp in place and issues one fire-and-forget add)
-                        if (*((volatile unsigned long long *)&p.t.arrive[arrive_at]) < stamp_next) {
-                            const unsigned long long old = atomicMax(&p.t.arrive[arrive_at], stamp_next);
-                            if (old < stamp_next) {
-                                const int s = atomicAdd(&S->wl_count[ring_next], 1);
-                                DCHECK(S, s < p.wmax, 25);
-                                p.b.wl_node[s] = arrive_at; p.t.slot[arrive_at] = s;
-                            }
+                    if (level == 0) atomicAdd(&arr1[arrive_slot], 1);
+                    else {
+                        uint32_t hq = ((uint32_t)arrive_at * 2654435761u) >> 22;
+                        int probe = 0;
+                        for (; probe < ARR_PROBES; ++probe, hq = (hq + 1u) & (ARR_HT - 1)) {
+                            const uint32_t prev = atomicCAS(&ht_key[hq], 0u, (uint32_t)arrive_at);
+                            if (prev == 0u || prev == (uint32_t)arrive_at) { atomicAdd(&ht_cnt[hq], 1); break; }
                         }
-                        atomicAdd(&p.t.arrive[arrive_at], (unsigned long long)__popc(peers));
+                        if (probe == ARR_PROBES) register_arrivals(arrive_at, 1u);      // table crowded: publish directly
                     }
                 }
                 TSEC(6);                                             // arrival registration
             }
-            if (level == 0) {                                        // publish this block's arrivals at the root's children
-                __syncthreads();
+            __syncthreads();                                         // publish this block's arrivals
+            if (level == 0) {
                 for (int t = threadIdx.x; t < ZS * A; t += blockDim.x) {
                     const int cnt = arr1[t];
                     if (cnt == 0) continue;
                     arr1[t] = 0;
-                    const int Xc = CHILD_ID(p.t.child[(size_t)root * AS * ZS + t]);
-                    const unsigned long long old = atomicMax(&p.t.arrive[Xc], stamp_next);
-                    if (old < stamp_next) {
-                        const int sl = atomicAdd(&S->wl_count[ring_next], 1);
-                        p.b.wl_node[sl] = Xc; p.t.slot[Xc] = sl;
-                    }
-                    atomicAdd(&p.t.arrive[Xc], (unsigned long long)(unsigned)cnt);
+                    register_arrivals(CHILD_ID(p.t.child[(size_t)root * AS * ZS + t]), (uint32_t)cnt);
+                }
+            } else {
+                for (int t = threadIdx.x; t < ARR_HT; t += blockDim.x) {
+                    const uint32_t key = ht_key[t];
+                    if (key == 0u) continue;
+                    const int cnt = ht_cnt[t];
+                    ht_key[t] = 0u; ht_cnt[t] = 0;
+                    register_arrivals((int)key, (uint32_t)cnt);
                 }
             }
             if (gtid == 0 && lsteps <= 128) S->steplog[lsteps - 1][3] = (long long)(globaltimer_ns() - tmark);
@@ -1270,7 +1295,7 @@ extern "C" int pomcp_set_model_rocksample(pomcp_handle *h, int rows, int cols, c
     // launch geometry of the cooperative search kernel
     const int A = m.n_actions;
     size_t smem = ((sizeof(ModelHeader) + 15) & ~size_t(15)) + (((size_t)h->n_thr * 8 + 15) & ~size_t(15)) +
-                  (((size_t)h->cfg.max_depth * 8 + 15) & ~size_t(15)) + (size_t)(1 + 2 * A) * A * 12 + (size_t)2 * A * 4 + 16;
+                  (((size_t)h->cfg.max_depth * 8 + 15) & ~size_t(15)) + (size_t)(1 + 2 * A) * A * 12 + (((size_t)2 * A * 4 + 15) & ~size_t(15)) + (size_t)ARR_HT * 8 + 16;
     h->search_smem = smem;
     CK(cudaFuncSetAttribute(pomcp_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(pomcp_search_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1326,7 +1351,7 @@ extern "C" int pomcp_set_model_tabular(pomcp_handle *h, int n_states, int n_acti
     if (!h->b.path_rew)
         CK(cudaMalloc(&h->b.path_rew, (size_t)h->cfg.gen_wmax * (size_t)h->cfg.tree_depth_cap * sizeof(double)));
     const size_t n_acc = t.stage_d1 ? (size_t)(1 + zs * n_actions) * n_actions : (size_t)n_actions;
-    size_t smem = (((size_t)h->cfg.max_depth * 8 + 15) & ~size_t(15)) + n_acc * 12 + (size_t)zs * n_actions * 4 + 16;
+    size_t smem = (((size_t)h->cfg.max_depth * 8 + 15) & ~size_t(15)) + n_acc * 12 + (((size_t)zs * n_actions * 4 + 15) & ~size_t(15)) + (size_t)ARR_HT * 8 + 16;
     if (smem < 512) smem = 512;                              // the belief update keeps 34 ints there
     h->search_smem = smem;
     CK(cudaFuncSetAttribute(pomcp_search_tab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
