@@ -49,6 +49,9 @@
 #define ROLL_SLICE 8            // rollout steps per slice while waiting at a barrier (even: Philox block pairs)
 #define ARR_HT 1024            // per-block arrival table (shared memory): slots of {node id, arrivals in this level step}
 #define ARR_PROBES 8
+#define PLAN_MASK 0            // kinds of a node's action plan (warp_plan)
+#define PLAN_PULLS 1
+#define PLAN_THRESHOLDS 2
 #define SEQ_ALLOC_MAX 16u      // arrivals <= this: exact virtual-pull allocation; more: water-filling
 #ifndef BISECT_ITERS
 #define BISECT_ITERS 14
@@ -90,7 +93,9 @@ struct Tree {                          // structure-of-arrays belief-tree arena
     uint32_t *legal;                   // [cap]       legal-action mask (fixed at creation)
     int32_t *cell;                     // [cap]       tag of the node: robot cell (RockSample), 0 (tabular)
     unsigned long long *arrive;        // [cap]       (stamp << 32) | arrivals in the current level step
-    int32_t *slot;                     // [cap]       worklist slot of the node in the current level step
+    uint4 *plan;                       // [cap][2]    action plan of the node for the current level step:
+                                       //             {kind << 16 | arrivals << 8 | last action, worklist slot, -, -},
+                                       //             {action mask (kind 0) | <= 16 pull bytes (kind 1)}; kind 2: thresholds in wl_thr[slot]
     double *chance;                    // [cap][24]   --preferred_actions: chance_good per rock (null otherwise)
     int16_t *good;                     // [cap][24]   --preferred_actions: goodness number per rock
     const double *prob;                // [cells][n_rocks] sensor correctness probability
@@ -106,9 +111,7 @@ struct SimBuf {                        // per simulation-in-flight scratch, SoA 
     uint16_t *path_ar;                 // [dcap][wmax] action | obs_good << 5 | reward id << 8   (tabular: action | obs << 5)
     double *path_rew;                  // [dcap][wmax] tabular models: the step reward (null for RockSample)
     int32_t *wl_node;                  // [wmax] worklist of nodes with arrivals in this level step
-    uint32_t *wl_thr;                  // [wmax][32] plan data: action mask (kind 0) | <= 16 pull bytes (kind 1) |
-                                       //            cumulative action thresholds (kind 2)
-    int32_t *wl_meta;                  // [wmax] plan of the node: kind << 16 | arrivals (kind 1) << 8 | last action (kind 2)
+    uint32_t *wl_thr;                  // [wmax][32] cumulative action thresholds of worklist nodes with a kind-2 plan
     double *ro_sum;                    // [wmax] discounted reward sum of a rollout in progress
     uint8_t *ro_t;                     // [wmax] rollout steps done so far (rollouts advance in slices)
 };
@@ -144,9 +147,10 @@ template <> struct Mdl<0> {
     static __device__ __forceinline__ size_t stage(unsigned char *smem, const ModelHeader *gm, const uint64_t *gthr,
                                                    int n_thr, const TabHeader &, const TabTables &, Ctx &c)
     {   // stage the model tables into shared memory; returns the first free byte offset (16-byte aligned)
-        const int nw = (int)(sizeof(ModelHeader) / 4);
-        uint32_t *dst = reinterpret_cast<uint32_t *>(smem);
-        const uint32_t *src = reinterpret_cast<const uint32_t *>(gm);
+        static_assert(sizeof(ModelHeader) % 16 == 0, "ModelHeader is staged in 16-byte pieces");
+        const int nw = (int)(sizeof(ModelHeader) / 16);
+        uint4 *dst = reinterpret_cast<uint4 *>(smem);
+        const uint4 *src = reinterpret_cast<const uint4 *>(gm);
         for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
         size_t off = (sizeof(ModelHeader) + 15) & ~size_t(15);
         uint64_t *thr = reinterpret_cast<uint64_t *>(smem + off);
@@ -308,7 +312,7 @@ __device__ __forceinline__ void publish_root(DevState *S, const Tree &t, int roo
 // Water-filling of k pulls over the UCB1 indices mean + c*sqrt(ln(N+1)/n); output: 32-bit cumulative thresholds.
 // ---------------------------------------------------------------------------------------------------------
 __device__ __forceinline__ void warp_allocation(const SearchParams &p, int X, uint32_t k, int lane, int A,
-                                             uint32_t *thr_out, int32_t *meta_out)
+                                                uint32_t *thr_out, int slot)
 {
     const unsigned full = 0xFFFFFFFFu;
     const uint32_t mask = p.t.legal[X];
@@ -373,7 +377,16 @@ __device__ __forceinline__ void warp_allocation(const SearchParams &p, int X, ui
     }
     thr_out[lane] = th;
     const unsigned pos = __ballot_sync(full, v > 0.0f);
-    if (lane == 0) *meta_out = (31 - __clz((int)pos)) | (2 << 16);                  // PLAN_THRESHOLDS
+    // every G-th threshold goes into the node's plan record: a simulation finds its group of G actions there and
+    // needs one more (16-byte aligned row) access for the thresholds inside the group
+    const int G = (A + 5) / 6;
+    uint32_t cg[6];
+#pragma unroll
+    for (int g = 0; g < 6; ++g) { const int src = g * G + G - 1; cg[g] = __shfl_sync(full, th, src < 31 ? src : 31); }
+    if (lane == 0) {
+        p.t.plan[(size_t)X * 2] = make_uint4((uint32_t)((31 - __clz((int)pos)) | (PLAN_THRESHOLDS << 16)), (uint32_t)slot, cg[4], cg[5]);
+        p.t.plan[(size_t)X * 2 + 1] = make_uint4(cg[0], cg[1], cg[2], cg[3]);
+    }
 }
 
 // Action plan of a node with k <= SEQ_ALLOC_MAX arrivals (warp-cooperative, lane = action; statistics are read-only
@@ -382,11 +395,7 @@ __device__ __forceinline__ void warp_allocation(const SearchParams &p, int X, ui
 //           k == 1: the UCB1 arg-max set (action_selectors.py:6-37; the draw breaks ties), or c = 0: the best means
 //   kind 1  the k arrivals share the virtual-pull sequence "pull j takes the UCB1 arg-max (lowest id on ties) given
 //           the statistics plus the virtual visits of pulls 0..j-1"; a simulation takes pull j = floor(x0*k/2^32)
-#define PLAN_MASK 0
-#define PLAN_PULLS 1
-#define PLAN_THRESHOLDS 2
-__device__ __forceinline__ void warp_plan_few(const SearchParams &p, int X, uint32_t k, int lane, int A,
-                                              uint32_t *out, int32_t *meta_out)
+__device__ __forceinline__ void warp_plan_few(const SearchParams &p, int X, uint32_t k, int lane, int A, int slot)
 {
     const unsigned full = 0xFFFFFFFFu;
     const uint32_t mask = p.t.legal[X];
@@ -398,7 +407,7 @@ __device__ __forceinline__ void warp_plan_few(const SearchParams &p, int X, uint
     for (int off = 16; off >= 1; off >>= 1) N += __shfl_xor_sync(full, N, off);
     const unsigned untried = __ballot_sync(full, legal && n == 0);
     if ((uint32_t)__popc(untried) >= k) {
-        if (lane == 0) { out[0] = untried; *meta_out = PLAN_MASK << 16; }
+        if (lane == 0) { p.t.plan[(size_t)X * 2] = make_uint4(PLAN_MASK << 16, (uint32_t)slot, 0u, 0u); p.t.plan[(size_t)X * 2 + 1].x = untried; }
         return;
     }
     const float L = det_logf_u32((uint32_t)N + 1u);
@@ -409,7 +418,7 @@ __device__ __forceinline__ void warp_plan_few(const SearchParams &p, int X, uint
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) best = fmaxf(best, __shfl_xor_sync(full, best, off));
         const unsigned ties = __ballot_sync(full, legal && sc == best);
-        if (lane == 0) { out[0] = ties; *meta_out = PLAN_MASK << 16; }
+        if (lane == 0) { p.t.plan[(size_t)X * 2] = make_uint4(PLAN_MASK << 16, (uint32_t)slot, 0u, 0u); p.t.plan[(size_t)X * 2 + 1].x = ties; }
         return;
     }
     const float c2L = (cf * cf) * L;
@@ -419,7 +428,7 @@ __device__ __forceinline__ void warp_plan_few(const SearchParams &p, int X, uint
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) qmax = fmaxf(qmax, __shfl_xor_sync(full, qmax, off));
         const unsigned qties = __ballot_sync(full, legal && qb == qmax);
-        if (lane == 0) { out[0] = qties; *meta_out = PLAN_MASK << 16; }
+        if (lane == 0) { p.t.plan[(size_t)X * 2] = make_uint4(PLAN_MASK << 16, (uint32_t)slot, 0u, 0u); p.t.plan[(size_t)X * 2 + 1].x = qties; }
         return;
     }
     float sc = legal ? (n == 0 ? INFINITY : qb + cf * sqrtf(L / (float)n)) : -INFINITY;
@@ -433,30 +442,41 @@ __device__ __forceinline__ void warp_plan_few(const SearchParams &p, int X, uint
         seq[pull >> 2] |= (uint32_t)w << (8 * (pull & 3u));
         if (lane == w) { va += 1; sc = qb + cf * sqrtf(L / (float)(n + va)); }
     }
-    if (lane < 4) out[lane] = seq[lane];
-    if (lane == 0) *meta_out = (PLAN_PULLS << 16) | (int32_t)(k << 8);
+    if (lane == 0) {
+        p.t.plan[(size_t)X * 2] = make_uint4((PLAN_PULLS << 16) | (k << 8), (uint32_t)slot, 0u, 0u);
+        p.t.plan[(size_t)X * 2 + 1] = make_uint4(seq[0], seq[1], seq[2], seq[3]);
+    }
 }
 
 // Plan of node X for its k arrivals of this level step (one warp).
-__device__ __forceinline__ void warp_plan(const SearchParams &p, int X, uint32_t k, int lane, int A,
-                                          uint32_t *out, int32_t *meta_out)
+__device__ __forceinline__ void warp_plan(const SearchParams &p, int X, uint32_t k, int lane, int A, int slot)
 {
-    if (k > SEQ_ALLOC_MAX) warp_allocation(p, X, k, lane, A, out, meta_out);
-    else warp_plan_few(p, X, k, lane, A, out, meta_out);
+    if (k > SEQ_ALLOC_MAX) warp_allocation(p, X, k, lane, A, p.b.wl_thr + (size_t)slot * 32, slot);
+    else warp_plan_few(p, X, k, lane, A, slot);
 }
 
 // The action of one simulation from its node's plan and its 32-bit draw x0.
-__device__ __forceinline__ int plan_action(const uint32_t *plan, int32_t meta, uint32_t x0, int A)
+__device__ __forceinline__ int plan_action(const SearchParams &p, int X, uint32_t x0, int A)
 {
-    const int kind = meta >> 16;
-    if (kind == PLAN_THRESHOLDS) {                       // first action whose threshold exceeds x0 (bisection)
-        int lo = 0, hi = A;
-        while (lo < hi) { const int mid = (lo + hi) >> 1; if (x0 < plan[mid]) hi = mid; else lo = mid + 1; }
-        return lo < A ? lo : (meta & 255);
+    const uint4 head = p.t.plan[(size_t)X * 2], data = p.t.plan[(size_t)X * 2 + 1];
+    const int meta = (int)head.x, kind = meta >> 16;
+    if (kind == PLAN_THRESHOLDS) {                       // first action whose threshold exceeds x0
+        const int G = (A + 5) / 6;                       // thresholds are non-decreasing: find the group of G ...
+        const int g = x0 < data.x ? 0 : x0 < data.y ? 1 : x0 < data.z ? 2 : x0 < data.w ? 3 : x0 < head.z ? 4 :
+                      x0 < head.w ? 5 : 6;
+        if (g == 6) return meta & 255;
+        const uint32_t *thr = p.b.wl_thr + (size_t)head.y * 32 + g * G;
+        uint32_t tq[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) tq[q] = (q < G && g * G + q < 32) ? thr[q] : 0xFFFFFFFFu;   // ... then the action
+#pragma unroll
+        for (int q = 0; q < 6; ++q) if (x0 < tq[q]) return g * G + q;
+        return meta & 255;
     }
-    if (kind == PLAN_MASK) { const uint32_t m = plan[0]; return nth_bit(m, randbelow32(x0, (uint32_t)__popc(m))); }
+    if (kind == PLAN_MASK) return nth_bit(data.x, randbelow32(x0, (uint32_t)__popc(data.x)));
     const uint32_t j = randbelow32(x0, (uint32_t)(meta >> 8) & 255u);
-    return (int)((plan[j >> 2] >> (8 * (j & 3u))) & 255u);
+    const uint32_t word = (j >> 2) == 0 ? data.x : (j >> 2) == 1 ? data.y : (j >> 2) == 2 ? data.z : data.w;
+    return (int)((word >> (8 * (j & 3u))) & 255u);
 }
 
 // ---------------------------------------------------------------------------------------------------------
@@ -608,9 +628,9 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
             if (lane == 0) {
                 const unsigned long long s1 = gstep + 1;
                 p.t.arrive[root] = (s1 << 32) | (unsigned long long)(unsigned)w;
-                p.t.slot[root] = 0; p.b.wl_node[0] = root; S->wl_count[(int)(s1 & 3ull)] = 1;
+                p.b.wl_node[0] = root; S->wl_count[(int)(s1 & 3ull)] = 1;
             }
-            warp_plan(p, root, (uint32_t)w, lane, A, p.b.wl_thr, p.b.wl_meta);   // known now: no extra phase
+            warp_plan(p, root, (uint32_t)w, lane, A, 0);                 // known now: no extra phase
             if (lane == 0 && (uint32_t)w > SEQ_ALLOC_MAX) ++c_alloc;
         }
         for (int i = gtid; i < w; i += T) {
@@ -634,7 +654,7 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                     if (old < stamp_next) {
                         const int sl = atomicAdd(&S->wl_count[ring_next], 1);
                         DCHECK(S, sl < p.wmax, 25);
-                        p.b.wl_node[sl] = Xn; p.t.slot[Xn] = sl;
+                        p.b.wl_node[sl] = Xn;
                     }
                 }
                 atomicAdd(&p.t.arrive[Xn], (unsigned long long)cnt);
@@ -658,8 +678,7 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                     todo &= todo - 1;
                     const int es = base + src * nwarps + vwarp;
                     const uint32_t ks = __shfl_sync(0xFFFFFFFFu, k, src);
-                    warp_plan(p, __shfl_sync(0xFFFFFFFFu, X, src), ks, lane, A, p.b.wl_thr + (size_t)es * 32,
-                              p.b.wl_meta + es);
+                    warp_plan(p, __shfl_sync(0xFFFFFFFFu, X, src), ks, lane, A, es);
                     if (lane == 0 && ks > SEQ_ALLOC_MAX) ++c_alloc;
                 }
             }
@@ -681,10 +700,9 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                     if (d >= p.max_depth) p.b.flag[i] = 2;                                  // :100
                     else {
                         const Philox4 r = philox4x32_10((uint32_t)(d + 1), sim, p.move, DOM_SIM, p.key0, p.key1);
-                        const int s = p.t.slot[X];
-                        TSEC(0);                                     // load sim + node header (+ Philox)
-                        const int a = plan_action(p.b.wl_thr + (size_t)s * 32, p.b.wl_meta[s], r.x, A);
-                        DCHECK(S, s >= 0 && s < p.wmax && a >= 0 && a < A && ((p.t.legal[X] >> a) & 1u), 22);
+                        TSEC(0);                                     // load sim (+ Philox)
+                        const int a = plan_action(p, X, r.x, A);
+                        DCHECK(S, a >= 0 && a < A && ((p.t.legal[X] >> a) & 1u), 22);
                         TSEC(1);                                     // choice
                         const uint32_t st = p.b.state[i];
                         DCHECK(S, MD::state_tag(st) == (uint32_t)p.t.cell[X], 23);
@@ -723,8 +741,12 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                                                                  p.t.good + (size_t)id * POMCP_RS, (int)(st & 0xFFu), a,
                                                                  so.obs, (int)so.tag);
                                     p.t.legal[id] = cmask;
-                                    __threadfence();                                        // node fields before its id
-                                    atomicExch(&p.t.child[cslot], (uint32_t)id + 1u);
+                                    // The id may be picked up by another SM in this very phase.  Without preferred
+                                    // actions such a reader derives the action set from its own state and touches no
+                                    // field of the node before the next grid barrier; with them it reads legal[id]:
+                                    // node fields before the id
+                                    if (KIND == 0 && p.t.chance) __threadfence();
+                                    __stcg(&p.t.child[cslot], (uint32_t)id + 1u);
                                     ++c_created;
                                     c = CHILD_LOCKED; have_mask = true;
                                 }
@@ -739,10 +761,13 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                                 virgin_step<KIND>(ctx, i, sim, -1 - (int)cslot, cmask, so.next, d + 1, c_levels);
                             } else {
                                 const int id = CHILD_ID(c);
-                                if (!(c & CHILD_VISITED))                                   // no statistics yet (N = 0)
-                                    // the node may have been published in this very phase by another SM: read its action
-                                    // set from L2 (ld.cg), never from a possibly stale L1 line
-                                    virgin_step<KIND>(ctx, i, sim, id, __ldcg(&p.t.legal[id]), so.next, d + 1, c_levels);
+                                if (!(c & CHILD_VISITED)) {                                 // no statistics yet (N = 0)
+                                    // the node may have been published in this very phase by another SM: with
+                                    // preferred actions its action set is read from L2 (ld.cg), never from a possibly
+                                    // stale L1 line; otherwise it follows from the simulation's own state
+                                    if (KIND == 0 && p.t.chance) cmask = __ldcg(&p.t.legal[id]);
+                                    virgin_step<KIND>(ctx, i, sim, id, cmask, so.next, d + 1, c_levels);
+                                }
                                 else { p.b.node[i] = id; arrive_at = id; arrive_slot = a * ZS + so.obs; }   // descend
                             }
                         }
@@ -1163,9 +1188,9 @@ static void free_all(pomcp_handle *h)
 {
     cudaFree(h->dS); cudaFree(h->dmodel); cudaFree(h->dthr);
     cudaFree(h->t.n); cudaFree(h->t.qfix); cudaFree(h->t.child); cudaFree(h->t.legal); cudaFree(h->t.cell);
-    cudaFree(h->t.arrive); cudaFree(h->t.slot); cudaFree(h->t.chance); cudaFree(h->t.good); cudaFree((void *)h->t.prob);
+    cudaFree(h->t.arrive); cudaFree(h->t.plan); cudaFree(h->t.chance); cudaFree(h->t.good); cudaFree((void *)h->t.prob);
     cudaFree(h->b.state); cudaFree(h->b.node); cudaFree(h->b.flag); cudaFree(h->b.depth); cudaFree(h->b.path_node);
-    cudaFree(h->b.path_ar); cudaFree(h->b.wl_node); cudaFree(h->b.wl_thr); cudaFree(h->b.wl_meta);
+    cudaFree(h->b.path_ar); cudaFree(h->b.wl_node); cudaFree(h->b.wl_thr);
     cudaFree(h->b.ro_sum); cudaFree(h->b.ro_t); cudaFree(h->b.path_rew);
     cudaFree((void *)h->tt.Tc); cudaFree((void *)h->tt.Oc); cudaFree((void *)h->tt.R); cudaFree((void *)h->tt.term_state);
     cudaFree(h->bag[0]); cudaFree(h->bag[1]);
@@ -1209,7 +1234,7 @@ extern "C" int pomcp_create(const pomcp_config *cfg, int device, pomcp_handle **
     CK(cudaMalloc(&h->t.legal, cap * sizeof(uint32_t)));
     CK(cudaMalloc(&h->t.cell, cap * sizeof(int32_t)));
     CK(cudaMalloc(&h->t.arrive, cap * sizeof(unsigned long long)));
-    CK(cudaMalloc(&h->t.slot, cap * sizeof(int32_t)));
+    CK(cudaMalloc(&h->t.plan, cap * 2 * sizeof(uint4)));
     CK(cudaMemset(h->t.n, 0, cap * AS * sizeof(int32_t)));
     CK(cudaMemset(h->t.qfix, 0, cap * AS * sizeof(long long)));
     CK(cudaMemset(h->t.child, 0, cap * AS * 2 * sizeof(uint32_t)));
@@ -1222,7 +1247,6 @@ extern "C" int pomcp_create(const pomcp_config *cfg, int device, pomcp_handle **
     CK(cudaMalloc(&h->b.path_ar, wmax * dcap * sizeof(uint16_t)));
     CK(cudaMalloc(&h->b.wl_node, wmax * sizeof(int32_t)));
     CK(cudaMalloc(&h->b.wl_thr, wmax * 32 * sizeof(uint32_t)));
-    CK(cudaMalloc(&h->b.wl_meta, wmax * sizeof(int32_t)));
     CK(cudaMalloc(&h->b.ro_sum, wmax * sizeof(double)));
     CK(cudaMalloc(&h->b.ro_t, wmax));
     CK(cudaMallocHost(&h->stage, 1 << 16));
