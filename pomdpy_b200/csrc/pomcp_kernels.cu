@@ -29,7 +29,7 @@
 // Section timers of the expand phase (-DPOMCP_TSEC diagnostic build only): per-thread clock64 deltas, summed over the
 // grid into steplog[127][0..7] at the end of the search.
 #ifdef POMCP_TSEC
-#define TSEC_DECL long long tsec_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tsec_prev_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tsec_t_ = 0
+#define TSEC_DECL long long tsec_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tsec_prev_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tsec_t_ = 0, tsec_bk_ = 0
 #define TSEC_START() (tsec_t_ = clock64())
 #define TSEC(k) do { const long long n_ = clock64(); tsec_[k] += n_ - tsec_t_; tsec_t_ = n_; } while (0)
 #else
@@ -47,7 +47,9 @@
 #define ADV_THREADS 1024
 #define ADV_TRIES 4
 #define ROLL_SLICE 8            // rollout steps per slice while waiting at a barrier (even: Philox block pairs)
+#ifndef ARR_HT
 #define ARR_HT 1024            // per-block arrival table (shared memory): slots of {node id, arrivals in this level step}
+#endif
 #define ARR_PROBES 8
 #define PLAN_MASK 0            // kinds of a node's action plan (warp_plan)
 #define PLAN_PULLS 1
@@ -783,7 +785,7 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                 if (arrive_at >= 0) {
                     if (level == 0) atomicAdd(&arr1[arrive_slot], 1);
                     else {
-                        uint32_t hq = ((uint32_t)arrive_at * 2654435761u) >> 22;
+                        uint32_t hq = (((uint32_t)arrive_at * 2654435761u) >> 16) & (ARR_HT - 1);
                         int probe = 0;
                         for (; probe < ARR_PROBES; ++probe, hq = (hq + 1u) & (ARR_HT - 1)) {
                             const uint32_t prev = atomicCAS(&ht_key[hq], 0u, (uint32_t)arrive_at);
@@ -835,7 +837,9 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
             if (base >= w) break;
             const int i = base + lane;
             if (i >= w) continue;
+            TSEC_START();
             if ((p.b.flag[i] & 3) == 1) rollout_advance(i, p.max_depth);
+            TSEC(7);                                                 // final phase: rollouts
             const int depth = p.b.depth[i];
             double delayed = ((p.b.flag[i] & 3) == 3) ? p.b.ro_sum[i] : 0.0;
             for (int d = depth - 1; d >= 0; --d) {
@@ -875,6 +879,9 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                 }
                 delayed = q;
             }
+#ifdef POMCP_TSEC
+            { const long long n_ = clock64(); tsec_bk_ += n_ - tsec_t_; }   // final phase: backup
+#endif
         }
         __syncthreads();
         for (int e = threadIdx.x; e < n_acc; e += blockDim.x) {      // flush the staged root / depth-1 edges
@@ -916,6 +923,11 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
         atomicAdd(reinterpret_cast<unsigned long long *>(&S->counters[4]), (unsigned long long)c_alloc);
     }
 #ifdef POMCP_TSEC
+    {
+        long long v = tsec_bk_;
+        for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long *>(&S->steplog[125][0]), (unsigned long long)v);
+    }
     for (int k = 0; k < 8; ++k) {
         long long v = tsec_[k];
         for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
@@ -931,6 +943,7 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
         S->counters[7] = (long long)(globaltimer_ns() - t_start);
         S->counters[8] = done;
         for (int k = 0; k < 6; ++k) S->phase_ns[k] = (long long)tp[k];
+        for (int k = 0; k < 6; ++k) S->steplog[126][k] = (long long)tp[k];   // profiling aid: phase totals of this search
     }
 }
 

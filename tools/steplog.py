@@ -16,3 +16,5 @@ for i in range(min(63, c["level_steps"])):
 
 tot = float(L[127, :7].sum()) or 1.0
 print("tsec share [load, choice, step, child, leaf-or-descend, syncwarp, arrive]:", [round(float(x) / tot, 3) for x in L[127, :7]], "total Gcycles", tot / 1e9)
+print("phase totals us [gen start, barrier wait (working), allocate + barrier, expand, rollout + backup + flush]:", [round(float(x) / 1e3, 1) for x in L[126, :5]])
+print("final phase Gcycles over all threads: rollouts %.2f backup %.2f (expand sections total %.2f)" % (L[127, 7] / 1e9, L[125, 0] / 1e9, L[127, :7].sum() / 1e9))
