@@ -1567,7 +1567,8 @@ extern "C" int pomcp_root_stats(pomcp_handle *h, int64_t *n, int64_t *qfix, uint
     DevState *st = reinterpret_cast<DevState *>(h->stage);           // pinned staging: one asynchronous copy + sync
     CK(cudaMemcpyAsync(st, h->dS, DEVSTATE_HEAD, cudaMemcpyDeviceToHost, h->last_stream));
     CK(cudaStreamSynchronize(h->last_stream));
-    h->nodes_used = st->node_count;
+    h->nodes_used = st->node_count;                                  // exact now (the copy is ordered after the search):
+    h->zeroed_upto = st->node_count;                                 // the next tree reset clears only what was touched
     const int A = h->n_actions;
     for (int a = 0; a < A; ++a) { n[a] = st->res_n[a]; qfix[a] = st->res_q[a]; }
     if (legal_mask) *legal_mask = st->res_legal;
