@@ -129,6 +129,7 @@ struct SearchParams {
     const uint32_t *bag[2];
     long long n_sims;
     uint32_t sim_offset, move, key0, key1;
+    uint32_t ks[20];                   // Philox key schedule: ks[2r], ks[2r+1] = (key0 + r*0x9E3779B9, key1 + r*0xBB67AE85)
     int32_t w0, growth, wmax, max_depth, dcap, n_thr;
     long long node_cap;
     double ucb_c, discount;
@@ -180,8 +181,8 @@ template <> struct Mdl<0> {
     // Rollout steps t .. t_end-1 from packed state st (uniform legal actions); true when the episode ended.
     // One Philox block per two steps: (x, y) then (z, w); word 0 picks the action, word 1 is the top 32 bits of the
     // 53-bit sensor uniform.
-    static __device__ __forceinline__ bool rollout(const Ctx &c, DevState *S, uint32_t sim, uint32_t move, uint32_t key0,
-                                                   uint32_t key1, int depth, const double *disc, uint32_t &st, int &t,
+    static __device__ __forceinline__ bool rollout(const Ctx &c, DevState *S, uint32_t sim, uint32_t move,
+                                                   const uint32_t *ks, int depth, const double *disc, uint32_t &st, int &t,
                                                    int t_end, double &sum)
     {
         const ModelHeader *H = c.M.hdr;
@@ -192,7 +193,7 @@ template <> struct Mdl<0> {
         for (; t < t_end; ++t) {
             uint32_t w0, w1;
             if ((t & 1) == 0) {
-                r = philox4x32_10((uint32_t)(depth + 1 + (t >> 1)), sim, move, DOM_SIM, key0, key1);
+                r = philox4x32_10_ks((uint32_t)(depth + 1 + (t >> 1)), sim, move, DOM_SIM, ks);
                 w0 = r.x; w1 = r.y;
             } else { w0 = r.z; w1 = r.w; }
             const uint32_t mask = H->legal[cell];
@@ -245,15 +246,15 @@ template <> struct Mdl<1> {
     static __device__ __forceinline__ int path_obs(uint32_t ar) { return (int)(ar >> 5); }
     static __device__ __forceinline__ double path_reward(const Ctx &, uint32_t, const double *rew) { return *rew; }
     // word 0 picks the action (all actions are legal), word 1 the next state; observations are not drawn
-    static __device__ __forceinline__ bool rollout(const Ctx &c, DevState *, uint32_t sim, uint32_t move, uint32_t key0,
-                                                   uint32_t key1, int depth, const double *disc, uint32_t &st, int &t,
+    static __device__ __forceinline__ bool rollout(const Ctx &c, DevState *, uint32_t sim, uint32_t move,
+                                                   const uint32_t *ks, int depth, const double *disc, uint32_t &st, int &t,
                                                    int t_end, double &sum)
     {
         Philox4 r{0u, 0u, 0u, 0u};
         for (; t < t_end; ++t) {
             uint32_t w0, w1;
             if ((t & 1) == 0) {
-                r = philox4x32_10((uint32_t)(depth + 1 + (t >> 1)), sim, move, DOM_SIM, key0, key1);
+                r = philox4x32_10_ks((uint32_t)(depth + 1 + (t >> 1)), sim, move, DOM_SIM, ks);
                 w0 = r.x; w1 = r.y;
             } else { w0 = r.z; w1 = r.w; }
             const int a = (int)randbelow32(w0, (uint32_t)c.h.A);
@@ -585,7 +586,7 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
         double sum = p.b.ro_sum[i];
         int t = p.b.ro_t[i];
         const int t0 = t, t_end = (t + budget < p.max_depth) ? t + budget : p.max_depth;
-        const bool finished = MD::rollout(mc, S, sim, p.move, p.key0, p.key1, depth, disc, st, t, t_end, sum);
+        const bool finished = MD::rollout(mc, S, sim, p.move, p.ks, depth, disc, st, t, t_end, sum);
         c_rollout += t - t0;
         p.b.ro_sum[i] = sum;
         if (finished || t >= p.max_depth) p.b.flag[i] = 3;
@@ -1540,6 +1541,7 @@ extern "C" int pomcp_search(pomcp_handle *h, int64_t n_sims, uint32_t sim_offset
     p.bag[0] = h->bag[0]; p.bag[1] = h->bag[1];
     p.n_sims = n_sims; p.sim_offset = sim_offset; p.move = move;
     p.key0 = (uint32_t)h->cfg.seed; p.key1 = (uint32_t)(h->cfg.seed >> 32);
+    for (uint32_t r = 0; r < 10; ++r) { p.ks[2 * r] = p.key0 + r * 0x9E3779B9u; p.ks[2 * r + 1] = p.key1 + r * 0xBB67AE85u; }
     p.w0 = h->cfg.gen_w0; p.growth = h->cfg.gen_growth; p.wmax = h->cfg.gen_wmax;
     p.max_depth = h->cfg.max_depth; p.dcap = h->cfg.tree_depth_cap; p.n_thr = h->n_thr; p.node_cap = h->cap;
     p.ucb_c = h->cfg.ucb_coefficient; p.discount = h->cfg.discount;
