@@ -1138,6 +1138,24 @@ __global__ void pomcp_plant_root_kernel(DevState *S, Tree t, const ModelHeader *
     if (blockIdx.x == 0 && threadIdx.x < AS) { S->res_n[threadIdx.x] = 0; S->res_q[threadIdx.x] = 0; }
 }
 
+// Zero the statistics and child tables of the arena prefix that earlier searches touched.  The exact node count is
+// read on the device (the host only knows an upper bound unless it has read the state block back), so a tree reset
+// clears what was used, not what could have been used.
+__global__ void pomcp_clear_arena_kernel(const DevState *S, Tree t, int zs, long long upper)
+{
+    long long n = S->node_count;
+    if (n > upper) n = upper;
+    const long long n4 = n * (AS * 4 / 16), q4 = n * (AS * 8 / 16), c4 = n * ((long long)AS * zs * 4 / 16);
+    const uint4 z = make_uint4(0u, 0u, 0u, 0u);
+    uint4 *pn = reinterpret_cast<uint4 *>(t.n), *pq = reinterpret_cast<uint4 *>(t.qfix), *pc = reinterpret_cast<uint4 *>(t.child);
+    const long long stride = (long long)gridDim.x * blockDim.x;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < q4; i += stride) {
+        pq[i] = z;
+        if (i < n4) pn[i] = z;
+    }
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < c4; i += stride) pc[i] = z;
+}
+
 // Root edge statistics as 2*AS 64-bit integers (n[0..AS), qfix[0..AS)) in a caller-provided device buffer: the
 // operand of the root-parallel merge (one all-reduce(sum) over NVLink per move).
 __global__ void pomcp_root_stats_kernel(const DevState *S, Tree t, long long *out)
@@ -1452,12 +1470,13 @@ extern "C" int pomcp_set_world(pomcp_handle *h, uint32_t actual, uint32_t sample
 // Zero the part of the arena that earlier searches touched.
 static int clear_arena(pomcp_handle *h, cudaStream_t s)
 {
-    const size_t n = (size_t)h->zeroed_upto;
-    if (n) {
-        CK(cudaMemsetAsync(h->t.n, 0, n * AS * sizeof(int32_t), s));
-        CK(cudaMemsetAsync(h->t.qfix, 0, n * AS * sizeof(long long), s));
-        CK(cudaMemsetAsync(h->t.child, 0, n * AS * (size_t)h->zs * sizeof(uint32_t), s));
-        // `arrive` keeps its stamps: they are never reused (gstep only grows)
+    const long long n = h->zeroed_upto < h->cap ? h->zeroed_upto : h->cap;
+    if (n > 0) {                                             // `arrive` keeps its stamps: they are never reused
+        long long blocks = (n * (AS * 8 / 16) + 255) / 256;
+        if (blocks > 148 * 8) blocks = 148 * 8;
+        pomcp_clear_arena_kernel<<<(int)blocks, 256, 0, s>>>(h->dS, h->t, h->zs, n);
+        CK(cudaGetLastError());
+        ++h->launches;
     }
     h->zeroed_upto = 0;
     return 0;
