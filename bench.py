@@ -179,6 +179,10 @@ def run_b200(args):
     host_bag_np = host_bag.numpy().view(np.uint32)
     pl.set_root_particles(host_bag_np, spec["start_cell"])
     stream = torch.cuda.current_stream().cuda_stream
+    fused = None
+    if world > 1 and os.environ.get("POMCP_FUSED_MERGE", "1") != "0":
+        from pomdpy_b200 import dist as dist_mod
+        fused = dist_mod.try_fused_merge(pl)             # merge inside the search kernel (NVLink peer stores)
     stats = torch.zeros(64, dtype=torch.int64, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")         # > 126 MB L2
 
@@ -194,9 +198,10 @@ def run_b200(args):
         pl.search(n_sims, move=i, sim_offset=rank * n_sims, stream=stream)
         if ev:
             ev[1].record()
-        pl.root_stats_device(stats.data_ptr(), stream)
-        if world > 1:
-            dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+        if fused is None:
+            pl.root_stats_device(stats.data_ptr(), stream)
+            if world > 1:
+                dist.all_reduce(stats, op=dist.ReduceOp.SUM)
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
@@ -217,9 +222,9 @@ def run_b200(args):
     c1 = pl.counters()
     step_ms = sum(a.elapsed_time(b) for a, b in ev_step)
     kern_ms = sum(a.elapsed_time(b) for a, b in ev_kern) / args.steps
-    merged = stats.cpu().numpy()
     A = spec["n_actions"]
-    assert int(merged[:A].sum()) == n_sims * world, "root visit counts do not add up to the simulations run"
+    merged = stats.cpu().numpy()[:A] if fused is None else pl.merged_root_stats()["n"]
+    assert int(merged.sum()) == n_sims * world, "root visit counts do not add up to the simulations run"
 
     # ---- end to end through the C ABI with host buffers --------------------------------------------------
     barrier()
@@ -227,7 +232,9 @@ def run_b200(args):
     for i in range(args.steps):
         pl.set_root_particles(host_bag_np, spec["start_cell"])                     # H2D from pinned memory
         pl.search(n_sims, move=1000 + i, sim_offset=rank * n_sims, stream=stream)
-        if world > 1:
+        if fused is not None:
+            res = pl.merged_root_stats()                                           # D2H of the in-kernel merge
+        elif world > 1:
             pl.root_stats_device(stats.data_ptr(), stream)
             dist.all_reduce(stats, op=dist.ReduceOp.SUM)
             res = stats.cpu()                                                      # D2H
@@ -272,6 +279,9 @@ def run_b200(args):
                        "discount": 0.95, "generation_schedule": [w0, growth, wmax],
                        "l2": "flushed between timed steps (256 MiB device write, untimed)",
                        "step": "fresh tree + search + root-statistics merge",
+                       "merge": ("none (1 GPU)" if world == 1 else
+                                 "fused into the search kernel: peer stores over NVLink, no collective call" if fused
+                                 else "NCCL all-reduce of 64 int64"),
                        "tree_levels_per_sim": L, "rollout_steps_per_sim": R,
                        "generate_steps_per_s": (d["levels"] + d["rollout_steps"]) * world / (step_ms * 1e-3)},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -284,7 +294,7 @@ def run_b200(args):
                          "issue_slot_utilisation_pct": prof.get("issue_active_pct"),
                          "thread_instructions_per_generate_step": prof.get("thread_inst_per_generate_step")},
             "e2e": {"value": sims / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": int(bag.nbytes),
-                    "d2h_bytes_per_step": int(c1["root_stats_d2h_bytes"] if world == 1 else 64 * 8)},
+                    "d2h_bytes_per_step": int(c1["root_stats_d2h_bytes"] if (world == 1 or fused is not None) else 64 * 8)},
             "gpu_launches": int(d["launches"]),
             "clocks": clocks,
         }

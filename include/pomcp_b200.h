@@ -20,6 +20,7 @@ extern "C" {
 #define POMCP_MAX_ACTIONS 32   /* |A| = 5 + n_rocks <= 32: one warp lane per action */
 #define POMCP_MAX_CELLS 256
 #define POMCP_MAX_ROCKS 24
+#define POMCP_MAX_PEERS 8      /* root-parallel merge inside the search kernel: the GPUs of one NVSwitch box */
 #define POMCP_MAX_OBS 32       /* tabular models: |Z| <= 32 observations */
 #define POMCP_QFIX_SCALE 16777216.0 /* root statistics carry sum(q) as a 2^-24 fixed-point integer */
 
@@ -94,6 +95,16 @@ int pomcp_root_stats(pomcp_handle *h, int64_t *n, int64_t *qfix, uint32_t *legal
 /* Root statistics into a caller-provided DEVICE buffer of 64 int64 (n[0..32), qfix[0..32)), asynchronous on
  * `stream`: the operand of the root-parallel merge (all-reduce(sum) across ranks before solvers/pomcp.py:78). */
 int pomcp_root_stats_device(pomcp_handle *h, int64_t *dev_out, void *stream);
+
+/* Root-parallel search with the merge fused into the search kernel.  peer_buffers[r] is rank r's exchange
+ * buffer (POMCP_MERGE_BYTES, zero-initialised, 16-byte aligned) as mapped into THIS process -- e.g. the buffer_ptrs of
+ * a torch symmetric-memory rendezvous, or cudaIpcOpenMemHandle pointers.  From then on every pomcp_search pushes the
+ * rank's 64 root words to all peers over NVLink, waits for theirs and sums; all ranks must search in lockstep.
+ * pomcp_merged_root_stats returns the sums (the operand of the greedy choice, solvers/pomcp.py:78); pomcp_root_stats
+ * keeps returning the local tree's.  world <= 1 switches the exchange off. */
+#define POMCP_MERGE_BYTES ((2 * POMCP_MAX_PEERS * 64 + 2 * POMCP_MAX_PEERS) * 8)
+int pomcp_set_peer_merge(pomcp_handle *h, int world, int rank, const uint64_t *peer_buffers);
+int pomcp_merged_root_stats(pomcp_handle *h, int64_t *n, int64_t *qfix, uint32_t *legal_mask, int64_t *sims_done);
 
 /* Fresh tree over the current root belief (BeliefTree.reset + initialize, belief_tree.py:19-49), asynchronous. */
 int pomcp_reset_tree(pomcp_handle *h, void *stream);

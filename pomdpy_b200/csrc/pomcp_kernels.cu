@@ -74,7 +74,10 @@ struct DevState {
     int32_t ro_cursor[2];              // work counters of the final rollout + backup phase (alternating per generation)
     // root edge statistics as of the end of the last search / advance / plant (one copy serves pomcp_root_stats)
     long long res_n[AS], res_q[AS];
-    uint32_t res_legal; int32_t res_valid;   // POMCP_CHECKS builds: code of the first failed device-side bounds check
+    uint32_t res_legal; int32_t res_valid;
+    // root edge statistics summed over the ranks of a root-parallel search (fused merge in the search kernel's tail)
+    long long mrg_n[AS], mrg_q[AS];
+    unsigned long long mrg_seq;        // sequence number of the merge that filled mrg_*; 0 = the exchange timed out
     unsigned long long gstep;          // global level-step stamp, never reused
     long long sims_done;               // simulations completed by the last search
     long long counters[16];
@@ -134,7 +137,17 @@ struct SearchParams {
     long long node_cap;
     double ucb_c, discount;
     unsigned long long timeout_ns;     // 0 = no wall-clock guard; measured from kernel start
+    // root-parallel merge over NVLink peer memory (world <= 8 GPUs of one box): every rank's exchange buffer, mapped
+    // into this process; layout MERGE_* below
+    unsigned long long peer_buf[POMCP_MAX_PEERS];
+    int32_t world, rank;
+    unsigned long long merge_seq;
 };
+
+// Exchange buffer of one rank (int64 words): slots[2][POMCP_MAX_PEERS][64] then flags[2][POMCP_MAX_PEERS].  Set
+// `seq & 1` is used by merge number seq, so a peer that is already one search ahead writes the other set.
+#define MERGE_SLOT_WORDS (2 * POMCP_MAX_PEERS * 64)
+#define MERGE_WORDS (MERGE_SLOT_WORDS + 2 * POMCP_MAX_PEERS)
 
 // ---------------------------------------------------------------------------------------------------------
 // Model policies.  The planner kernels are templates over KIND: 0 = RockSample (tables staged in shared memory, the
@@ -909,6 +922,44 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
     }
 
     if (blockIdx.x == 0) publish_root(S, p.t, root, threadIdx.x);     // after the last generation's barrier
+    // ---- fused root merge: instead of a separate all-reduce, block 0 pushes this rank's 64 root words
+    // into every peer's exchange buffer with peer stores over NVLink, raises its flag there, waits for the peers'
+    // flags in its own buffer and sums.  Integer operands: every rank gets the same sums in any order.
+    if (p.world > 1 && blockIdx.x == 0) {
+        __syncthreads();                                             // res_n / res_q are in place
+        const int par = (int)(p.merge_seq & 1ull);
+        for (int idx = threadIdx.x; idx < 64 * p.world; idx += blockDim.x) {
+            const int peer = idx >> 6, wq = idx & 63;
+            const long long v = wq < AS ? S->res_n[wq] : S->res_q[wq - AS];
+            long long *dst = reinterpret_cast<long long *>(p.peer_buf[peer]);
+            dst[(size_t)(par * POMCP_MAX_PEERS + p.rank) * 64 + wq] = v;
+        }
+        __threadfence_system();                                      // data before the flags, system-wide
+        __syncthreads();
+        long long *mine = reinterpret_cast<long long *>(p.peer_buf[p.rank]);
+        int ok = 1;
+        if (threadIdx.x < p.world) {
+            volatile unsigned long long *flag = reinterpret_cast<volatile unsigned long long *>(p.peer_buf[threadIdx.x]) +
+                                                MERGE_SLOT_WORDS + par * POMCP_MAX_PEERS + p.rank;
+            *flag = p.merge_seq;
+            volatile unsigned long long *own = reinterpret_cast<volatile unsigned long long *>(mine) + MERGE_SLOT_WORDS +
+                                               par * POMCP_MAX_PEERS + threadIdx.x;
+            const unsigned long long t0 = globaltimer_ns();
+            while (*own < p.merge_seq) {                             // peer threadIdx.x has delivered merge `seq`
+                __nanosleep(200);
+                if (globaltimer_ns() - t0 > 2000000000ull) { ok = 0; break; }   // a peer never searched: give up
+            }
+        }
+        ok = __syncthreads_and(ok);
+        __threadfence_system();
+        if (threadIdx.x < 64) {
+            long long sum = 0;
+            for (int r = 0; r < p.world; ++r)
+                sum += *((volatile long long *)&mine[(size_t)(par * POMCP_MAX_PEERS + r) * 64 + threadIdx.x]);
+            if (threadIdx.x < AS) S->mrg_n[threadIdx.x] = sum; else S->mrg_q[threadIdx.x - AS] = sum;
+        }
+        if (threadIdx.x == 0) S->mrg_seq = ok ? p.merge_seq : 0ull;
+    }
     // counters (warp-reduced) and persistent state
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
@@ -1199,6 +1250,9 @@ struct pomcp_handle {
     int coop_blocks = 0;
     size_t search_smem = 0;
     long long launches = 0;
+    int world = 1, rank = 0;        // fused root merge (pomcp_set_peer_merge)
+    unsigned long long peer_buf[POMCP_MAX_PEERS] = {0, 0, 0, 0, 0, 0, 0, 0};
+    unsigned long long merge_seq = 0;
     void *stage = nullptr;          // pinned host staging
     cudaStream_t last_stream = nullptr;
 };
@@ -1565,6 +1619,11 @@ extern "C" int pomcp_search(pomcp_handle *h, int64_t n_sims, uint32_t sim_offset
     p.max_depth = h->cfg.max_depth; p.dcap = h->cfg.tree_depth_cap; p.n_thr = h->n_thr; p.node_cap = h->cap;
     p.ucb_c = h->cfg.ucb_coefficient; p.discount = h->cfg.discount;
     p.timeout_ns = timeout_s > 0 ? (unsigned long long)(timeout_s * 1e9) : 0ull;   // checked between generations
+    p.world = h->world; p.rank = h->rank;
+    if (h->world > 1) {
+        for (int r = 0; r < h->world; ++r) p.peer_buf[r] = h->peer_buf[r];
+        p.merge_seq = ++h->merge_seq;
+    }
     long long widest = n_sims < (long long)p.wmax ? n_sims : (long long)p.wmax;
     int blocks = (int)((widest + SEARCH_THREADS - 1) / SEARCH_THREADS);
     if (blocks < 1) blocks = 1;
@@ -1592,6 +1651,38 @@ extern "C" int pomcp_root_stats(pomcp_handle *h, int64_t *n, int64_t *qfix, uint
     h->zeroed_upto = st->node_count;                                 // the next tree reset clears only what was touched
     const int A = h->n_actions;
     for (int a = 0; a < A; ++a) { n[a] = st->res_n[a]; qfix[a] = st->res_q[a]; }
+    if (legal_mask) *legal_mask = st->res_legal;
+    if (sims_done) *sims_done = st->sims_done;
+    return 0;
+}
+
+extern "C" int pomcp_set_peer_merge(pomcp_handle *h, int world, int rank, const uint64_t *peer_buffers)
+{
+    if (!h) return -1;
+    if (world <= 1) { h->world = 1; h->rank = 0; return 0; }
+    if (world > POMCP_MAX_PEERS || rank < 0 || rank >= world || !peer_buffers) return fail(h, "bad peer-merge arguments");
+    for (int r = 0; r < world; ++r) {
+        if (!peer_buffers[r] || (peer_buffers[r] & 15u)) return fail(h, "peer buffer null or misaligned");
+        h->peer_buf[r] = peer_buffers[r];
+    }
+    h->world = world; h->rank = rank; h->merge_seq = 0;
+    return 0;
+}
+
+extern "C" int pomcp_merged_root_stats(pomcp_handle *h, int64_t *n, int64_t *qfix, uint32_t *legal_mask,
+                                       int64_t *sims_done)
+{
+    if (!h) return -1;
+    if (!h->have_root) return fail(h, "no root belief");
+    if (h->world <= 1) return pomcp_root_stats(h, n, qfix, legal_mask, sims_done);
+    CK(cudaSetDevice(h->device));
+    DevState *st = reinterpret_cast<DevState *>(h->stage);
+    CK(cudaMemcpyAsync(st, h->dS, DEVSTATE_HEAD, cudaMemcpyDeviceToHost, h->last_stream));
+    CK(cudaStreamSynchronize(h->last_stream));
+    h->nodes_used = st->node_count;
+    h->zeroed_upto = st->node_count;
+    if (h->merge_seq == 0 || st->mrg_seq != h->merge_seq) return fail(h, "root merge: a peer did not deliver its statistics");
+    for (int a = 0; a < h->n_actions; ++a) { n[a] = st->mrg_n[a]; qfix[a] = st->mrg_q[a]; }
     if (legal_mask) *legal_mask = st->res_legal;
     if (sims_done) *sims_done = st->sims_done;
     return 0;

@@ -43,3 +43,46 @@ def merge_device(planner, n_actions, stream=None):
     dist.all_reduce(buf, op=dist.ReduceOp.SUM)
     host = buf.cpu().numpy()
     return host[:n_actions].copy(), host[32:32 + n_actions].copy()
+
+
+class FusedMerge(object):
+    """Exchange buffers for the merge that runs inside the search kernel (include/pomcp_b200.h, pomcp_set_peer_merge):
+    one symmetric-memory allocation per rank, every rank's buffer mapped into every process (NVLink peer access), so
+    the kernel's tail can push its 64 root words to all peers and sum theirs without a separate collective."""
+
+    def __init__(self, planner, group=None):
+        import torch
+        import torch.distributed as dist
+        import torch.distributed._symmetric_memory as symm_mem
+        from . import native
+        group = group or dist.group.WORLD
+        self.world, self.rank = dist.get_world_size(group), dist.get_rank(group)
+        if self.world > 8:
+            raise RuntimeError("the fused merge serves the <= 8 GPUs of one box")
+        words = native.MERGE_BYTES // 8
+        self.buf = symm_mem.empty((words,), dtype=torch.int64, device=torch.device("cuda", torch.cuda.current_device()))
+        self.buf.zero_()
+        self.handle = symm_mem.rendezvous(self.buf, group)
+        torch.cuda.synchronize()
+        dist.barrier(group)                              # every buffer is zero before anyone's kernel writes a flag
+        planner.set_peer_merge(self.world, self.rank, [int(p) for p in self.handle.buffer_ptrs])
+        self.planner = planner
+
+
+def try_fused_merge(planner):
+    """FusedMerge if the process group is NCCL on CUDA and symmetric memory can be set up, else None (the caller
+    then merges with merge_device).  The decision is collective: either every rank gets one or none does."""
+    import torch
+    import torch.distributed as dist
+    ok, fm = 1, None
+    try:
+        fm = FusedMerge(planner)
+    except Exception:
+        ok = 0
+    flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
+    dist.all_reduce(flag, op=dist.ReduceOp.MIN)
+    if int(flag.item()) == 0:
+        if fm is not None:
+            planner.set_peer_merge(1, 0, [])
+        return None
+    return fm

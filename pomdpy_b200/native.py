@@ -10,6 +10,7 @@ import numpy as np
 from . import build as _build
 
 QFIX_SCALE = float(1 << 24)
+MERGE_BYTES = (2 * 8 * 64 + 2 * 8) * 8       # POMCP_MERGE_BYTES of include/pomcp_b200.h
 MAX_ACTIONS = 32
 _LIB = None
 
@@ -31,7 +32,8 @@ EXPORTS = ["pomcp_create", "pomcp_destroy", "pomcp_last_error", "pomcp_set_model
            "pomcp_reset_tree", "pomcp_debug_steplog", "pomcp_set_preferred_actions",
            "pomcp_root_rock_data", "pomcp_refexact_create", "pomcp_refexact_destroy", "pomcp_refexact_last_error",
            "pomcp_refexact_search", "pomcp_refexact_sample_root_particle", "pomcp_refexact_env_step",
-           "pomcp_refexact_update", "pomcp_set_model_tabular", "pomcp_tabular_steps"]
+           "pomcp_refexact_update", "pomcp_set_model_tabular", "pomcp_tabular_steps",
+           "pomcp_set_peer_merge", "pomcp_merged_root_stats"]
 
 
 def library_path():
@@ -64,6 +66,8 @@ def load(build_if_missing=True):
     L.pomcp_set_model_tabular.argtypes = [vp, C.c_int, C.c_int, C.c_int, P(u32), P(u32), P(dbl), u32, P(C.c_uint8)]
     L.pomcp_tabular_steps.argtypes = [vp, i64, P(u32), P(C.c_uint8), P(u32), P(u32), P(u32), P(i32), P(dbl),
                                       P(C.c_uint8)]
+    L.pomcp_set_peer_merge.argtypes = [vp, C.c_int, C.c_int, P(u64)]
+    L.pomcp_merged_root_stats.argtypes = [vp, P(i64), P(i64), P(u32), P(i64)]
     L.pomcp_set_world.argtypes = [vp, u32, u32]
     L.pomcp_set_root_particles.argtypes = [vp, P(u32), C.c_int, C.c_int]
     L.pomcp_search.argtypes = [vp, i64, u32, u32, dbl, vp]
@@ -218,6 +222,21 @@ class Planner:
         legal, done = C.c_uint32(), C.c_int64()
         self._ck(self.lib.pomcp_root_stats(self.h, _p(n, C.c_int64), _p(q, C.c_int64), C.byref(legal),
                                            C.byref(done)))
+        return dict(n=n, qfix=q, legal=legal.value, sims_done=done.value)
+
+    def set_peer_merge(self, world, rank, peer_buffers):
+        """Fuse the root-parallel merge into the search kernel: peer_buffers[r] = device address of rank r's exchange
+        buffer (MERGE_BYTES, zeroed) as mapped into this process.  world <= 1 switches it off."""
+        ptrs = np.ascontiguousarray(list(peer_buffers) + [0] * (8 - len(peer_buffers)), dtype=np.uint64)
+        self._ck(self.lib.pomcp_set_peer_merge(self.h, int(world), int(rank), _p(ptrs, C.c_uint64)))
+
+    def merged_root_stats(self):
+        """Root statistics summed over the ranks by the last search (set_peer_merge); raises if a peer was missing."""
+        n = np.zeros(self.n_actions, dtype=np.int64)
+        q = np.zeros(self.n_actions, dtype=np.int64)
+        legal, done = C.c_uint32(), C.c_int64()
+        self._ck(self.lib.pomcp_merged_root_stats(self.h, _p(n, C.c_int64), _p(q, C.c_int64), C.byref(legal),
+                                                  C.byref(done)))
         return dict(n=n, qfix=q, legal=legal.value, sims_done=done.value)
 
     def node_stats(self, path):

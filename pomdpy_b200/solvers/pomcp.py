@@ -14,6 +14,7 @@ kernel over a device-resident structure-of-arrays belief tree (pomcp_search), up
 rejection-sampling belief update (pomcp_advance).  With torch.distributed initialised the search is
 root-parallel: every rank grows its own tree with its share of the budget and the root statistics are summed
 with one all-reduce before the greedy choice (solvers/pomcp.py:78).  There is no CPU fallback."""
+import os
 import time
 
 import numpy as np
@@ -149,6 +150,15 @@ class POMCP(Solver):
         else:
             pl.set_model_rocksample(spec["rows"], spec["cols"], spec["cell"], spec["start_cell"], spec["thr53"],
                                     spec["rewards"])
+        if self.world > 1:                                   # root-parallel: fuse the merge into the search kernel
+            d = _dist()
+            try:
+                import torch
+                fused = torch.cuda.is_available() and d.get_backend() == "nccl" and \
+                    os.environ.get("POMCP_FUSED_MERGE", "1") != "0"
+            except Exception:
+                fused = False
+            pl._fused_merge = dist_mod.try_fused_merge(pl) if fused else None
         agent._pomcp_planner = (key, pl)
         return pl
 
@@ -180,6 +190,8 @@ class POMCP(Solver):
 
     def _merged_root_stats(self):
         """Root statistics summed over the ranks: one all-reduce of 2*32 int64 per move."""
+        if self.world > 1 and getattr(self.planner, "_fused_merge", None) is not None:
+            return self.planner.merged_root_stats()          # summed inside the search kernel over NVLink peer memory
         local = self.planner.root_stats()
         if self.world == 1:
             return local
