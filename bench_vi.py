@@ -81,6 +81,47 @@ def synthetic(S=4096, A=16, Z=64, G=64):
                                    "peak_source": "nominal fp64 tensor (DMMA) rate of B200; no measured fp64 peak in MEASURED_PEAKS.json"}}))
 
 
+def synthetic_backup(S=4096, A=16, Z=64, G=64, P=1024):
+    """Config 5 end to end: one point-based backup of |Gamma| = 64 vectors at 1024 belief points."""
+    import torch
+    from pomdpy_b200 import vi
+    rng = np.random.default_rng(123)
+    T = rng.dirichlet(np.ones(S), size=(A, S))
+    O = rng.dirichlet(np.ones(Z), size=(A, S))
+    R = rng.uniform(-1, 1, size=(A, S))
+    gamma = rng.uniform(-1, 1, size=(G, S))
+    B = rng.dirichlet(np.ones(S) * 0.05, size=P)
+    Td, Od, Rd, Gd, Bd = (torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (T, O, R, gamma, B))
+    alpha, act, w = vi.point_based_backup(Td, Od, Rd, Gd, Bd, 0.95, keep_work=True)      # warm-up
+    torch.cuda.synchronize()
+    ev = [torch.cuda.Event(enable_timing=True) for _ in range(2)]
+    ev[0].record()
+    for _ in range(3):
+        alpha, act = vi.point_based_backup(Td, Od, Rd, Gd, Bd, 0.95)
+    ev[1].record()
+    torch.cuda.synchronize()
+    ms = ev[0].elapsed_time(ev[1]) / 3
+    flop = 2.0 * A * S * S * Z * G + 2.0 * A * P * S * Z * G
+    # spot check against float64 numpy: scores and new vectors of a few belief points (projection rows are checked above)
+    pts = rng.integers(0, P, size=4)
+    proj = w["proj"]
+    score = w["score"].reshape(A, P, Z, G)[:, pts].cpu().numpy()
+    want_score = np.einsum("ps,asc->apc", B[pts], proj.cpu().numpy()).reshape(A, len(pts), Z, G)
+    err_score = float(np.abs(score - want_score).max() / np.abs(want_score).max())
+    gbest, gact, galpha = w["best"].cpu().numpy(), w["action"].cpu().numpy(), w["alpha"].cpu().numpy()
+    err_alpha = 0.0
+    for p in pts:
+        a = int(gact[p])
+        cols = np.arange(Z) * G + gbest[a, p]
+        want = R[a] + 0.95 * proj[a][:, torch.from_numpy(cols).cuda()].sum(dim=1).cpu().numpy()
+        err_alpha = max(err_alpha, float(np.abs(galpha[p] - want).max() / np.abs(want).max()))
+    print(json.dumps({"metric": "vi_point_based_backup_ms", "value": ms, "unit": "ms", "higher_is_better": False,
+                      "config": {"S": S, "A": A, "O": Z, "Gamma": G, "belief_points": P},
+                      "tflops_fp64_gemm_part": flop / (ms * 1e-3) / 1e12, "vectors_after_prune": int(len(alpha)),
+                      "max_rel_err_scores_vs_float64_numpy": err_score, "max_rel_err_alpha_vs_float64_numpy": err_alpha}))
+
+
 if __name__ == "__main__":
     tiger()
     synthetic()
+    synthetic_backup()

@@ -31,6 +31,21 @@ int vi_project_textbook_dev(int device, int S, int A, int Z, int G, const double
                             const double *gamma_dev, double *scratch_dev, double *proj_dev, void *stream,
                             char *err, int errlen);
 
+/* Point-based backup for large |S| (the cross-sum of the exact backup taken at P belief points), all pointers on the
+ * device, row-major fp64, asynchronous on `stream`:
+ *   g*(a,p,o) = argmax_g b_p . proj[a][:, o, g]      (proj as above; scores by DMMA GEMMs [P x S] . [S x Z*G])
+ *   a*(p)     = argmax_a b_p . R[a] + discount * sum_o max_g b_p . proj[a][:, o, g]
+ *   alpha_p   = R[a*] + discount * sum_o proj[a*][:, o, g*(a*,p,o)]         -> alpha_dev [P][S], action_dev [P]
+ * followed, if `prune`, by the pointwise-dominance prune (delta 1e-10) into pruned_dev / pruned_action_dev / *n_out_dev.
+ * Work buffers: scratch [S*Z*G], proj [A*S*Z*G], score [A*P*Z*G] doubles, best [A*P*Z], keep [P] int32, value [A*P].
+ * S % 128 == 0, P % 128 == 0, (Z*G) % 64 == 0. */
+int vi_point_based_backup_dev(int device, int S, int A, int Z, int G, int P, const double *T_dev, const double *O_dev,
+                              const double *R_dev, const double *gamma_dev, const double *beliefs_dev, double discount,
+                              double *scratch_dev, double *proj_dev, double *score_dev, int32_t *best_dev,
+                              double *value_dev, double *alpha_dev, int32_t *action_dev, int prune, double *pruned_dev,
+                              int32_t *pruned_action_dev, int32_t *keep_dev, int32_t *n_out_dev, void *stream,
+                              char *err, int errlen);
+
 #ifdef __cplusplus
 }
 #endif

@@ -94,3 +94,21 @@ def canonical_set(vecs, actions, delta=DELTA):
 def textbook_projection(gamma, T, O):
     """proj[a, o, g, s] = sum_s' T[a, s, s'] * O[a, s', o] * gamma[g, s']   (float64 einsum)."""
     return np.einsum("ast,ato,gt->aogs", T, O, gamma, optimize=True)
+
+
+def point_based_backup(T, O, R, gamma, beliefs, discount):
+    """float64 restatement of vi_point_based_backup_dev (include/vi_b200.h): returns alpha [P][S], action [P],
+    best [A][P][Z], value [A][P], score [A][P][Z][G]."""
+    proj = textbook_projection(gamma, T, O)                       # [a][o][g][s]
+    score = np.einsum("ps,aogs->apog", beliefs, proj, optimize=True)
+    best = score.argmax(axis=3)                                   # first maximiser
+    value = beliefs @ R.T                                         # [p][a]
+    value = value.T + discount * score.max(axis=3).sum(axis=2)    # [a][p]
+    action = value.argmax(axis=0)
+    P, S = beliefs.shape
+    Z = O.shape[2]
+    alpha = np.empty((P, S))
+    for p in range(P):
+        a = action[p]
+        alpha[p] = R[a] + discount * proj[a, np.arange(Z), best[a, p], :].sum(axis=0)
+    return alpha, action, best, value, score

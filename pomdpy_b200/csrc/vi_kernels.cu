@@ -268,3 +268,103 @@ extern "C" int vi_project_textbook_dev(int device, int S, int A, int Z, int G, c
     VCK(cudaGetLastError());
     return 0;
 }
+
+// ---------------------------------------------------------------------------------------------------------
+// Point-based backup for large |S| (the cross-sum of the exact backup, taken at belief points):
+//   proj[a][s][o,g]  = sum_s' T[a][s][s'] O[a][s'][o] gamma_g[s']               (DMMA GEMMs, above)
+//   score[a][p][o,g] = b_p . proj[a][:, o,g]                                    (DMMA GEMMs: B [P x S] . proj[a])
+//   g*(a,p,o) = argmax_g score (lowest g on ties);   v[a][p] = b_p . R[a] + discount * sum_o score[a][p][o, g*]
+//   a*(p) = argmax_a v (lowest a on ties);   alpha_p = R[a*] + discount * sum_o proj[a*][:, o, g*(a*,p,o)]
+// one new vector per belief point, then the pointwise-dominance prune.  All fp64, sums over o in index order.
+// ---------------------------------------------------------------------------------------------------------
+__global__ void __launch_bounds__(256) vi_pb_choose_kernel(int S, int Z, int G, int P, const double *__restrict__ score,
+                                                           const double *__restrict__ R, const double *__restrict__ B,
+                                                           double discount, int32_t *__restrict__ best,
+                                                           double *__restrict__ value)
+{
+    extern __shared__ double pb_sm[];                          // [Z] best scores, then [8] warp partials
+    const int a = blockIdx.y, p = blockIdx.x, tid = threadIdx.x, lane = tid & 31, wid = tid >> 5;
+    const double *sc = score + ((size_t)a * P + p) * (size_t)Z * G;
+    for (int o = wid; o < Z; o += 8) {                         // one warp per observation: arg-max over g
+        double bv = -INFINITY; int bg = 0;
+        for (int g = lane; g < G; g += 32) { const double v = sc[(size_t)o * G + g]; if (v > bv) { bv = v; bg = g; } }
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) {
+            const double ov = __shfl_xor_sync(0xFFFFFFFFu, bv, off);
+            const int og = __shfl_xor_sync(0xFFFFFFFFu, bg, off);
+            if (ov > bv || (ov == bv && og < bg)) { bv = ov; bg = og; }
+        }
+        if (lane == 0) { pb_sm[o] = bv; best[((size_t)a * P + p) * Z + o] = bg; }
+    }
+    double part = 0.0;                                         // b_p . R[a]
+    for (int s = tid; s < S; s += 256) part += B[(size_t)p * S + s] * R[(size_t)a * S + s];
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) part += __shfl_xor_sync(0xFFFFFFFFu, part, off);
+    if (lane == 0) pb_sm[Z + wid] = part;
+    __syncthreads();
+    if (tid == 0) {
+        double br = 0.0, fut = 0.0;
+        for (int w = 0; w < 8; ++w) br += pb_sm[Z + w];
+        for (int o = 0; o < Z; ++o) fut += pb_sm[o];
+        value[(size_t)a * P + p] = br + discount * fut;
+    }
+}
+
+__global__ void vi_pb_pick_kernel(int A, int P, const double *__restrict__ value, int32_t *__restrict__ action)
+{
+    const int p = blockIdx.x * blockDim.x + threadIdx.x;
+    if (p >= P) return;
+    double bv = -INFINITY; int ba = 0;
+    for (int a = 0; a < A; ++a) { const double v = value[(size_t)a * P + p]; if (v > bv) { bv = v; ba = a; } }
+    action[p] = ba;
+}
+
+__global__ void __launch_bounds__(256) vi_pb_alpha_kernel(int S, int Z, int G, int P, const double *__restrict__ proj,
+                                                          const double *__restrict__ R, const int32_t *__restrict__ best,
+                                                          const int32_t *__restrict__ action, double discount,
+                                                          double *__restrict__ alpha)
+{
+    extern __shared__ int pb_cols[];                           // [Z] column o*G + g* of the chosen action
+    const int p = blockIdx.y, a = action[p];
+    for (int o = threadIdx.x; o < Z; o += blockDim.x) pb_cols[o] = o * G + best[((size_t)a * P + p) * Z + o];
+    __syncthreads();
+    const int s = blockIdx.x * blockDim.x + threadIdx.x;
+    if (s >= S) return;
+    const double *row = proj + ((size_t)a * S + s) * (size_t)Z * G;
+    double fut = 0.0;
+    for (int o = 0; o < Z; ++o) fut += row[pb_cols[o]];
+    alpha[(size_t)p * S + s] = R[(size_t)a * S + s] + discount * fut;
+}
+
+extern "C" int vi_point_based_backup_dev(int device, int S, int A, int Z, int G, int P, const double *T_dev,
+                                         const double *O_dev, const double *R_dev, const double *gamma_dev,
+                                         const double *beliefs_dev, double discount, double *scratch_dev,
+                                         double *proj_dev, double *score_dev, int32_t *best_dev, double *value_dev,
+                                         double *alpha_dev, int32_t *action_dev, int prune, double *pruned_dev,
+                                         int32_t *pruned_action_dev, int32_t *keep_dev, int32_t *n_out_dev, void *stream,
+                                         char *err, int errlen)
+{
+    const int N = Z * G;
+    VCK(cudaSetDevice(device));
+    if (P % GBM) { snprintf(err, errlen, "the number of belief points must be a multiple of 128"); return -1; }
+    if (Z > 2048) { snprintf(err, errlen, "|Z| > 2048"); return -1; }
+    int rc = vi_project_textbook_dev(device, S, A, Z, G, T_dev, O_dev, gamma_dev, scratch_dev, proj_dev, stream, err, errlen);
+    if (rc) return rc;
+    cudaStream_t st = (cudaStream_t)stream;
+    for (int a = 0; a < A; ++a) {                              // score[a] = B . proj[a]
+        dim3 grid(N / GBN, P / GBM);
+        vi_dgemm_dmma_kernel<<<grid, 256, DGEMM_SMEM, st>>>(P, N, S, beliefs_dev, proj_dev + (size_t)a * S * N,
+                                                   score_dev + (size_t)a * P * N);
+    }
+    vi_pb_choose_kernel<<<dim3(P, A), 256, (Z + 8) * sizeof(double), st>>>(S, Z, G, P, score_dev, R_dev, beliefs_dev,
+                                                                             discount, best_dev, value_dev);
+    vi_pb_pick_kernel<<<(P + 255) / 256, 256, 0, st>>>(A, P, value_dev, action_dev);
+    vi_pb_alpha_kernel<<<dim3((S + 255) / 256, P), 256, Z * sizeof(int), st>>>(S, Z, G, P, proj_dev, R_dev, best_dev,
+                                                                               action_dev, discount, alpha_dev);
+    if (prune) {
+        vi_prune_kernel<<<(P + 127) / 128, 128, 0, st>>>(S, P, alpha_dev, 1e-10, keep_dev);
+        vi_compact_kernel<<<1, 1024, 0, st>>>(S, P, alpha_dev, action_dev, keep_dev, pruned_dev, pruned_action_dev, n_out_dev);
+    }
+    VCK(cudaGetLastError());
+    return 0;
+}

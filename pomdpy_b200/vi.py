@@ -37,6 +37,9 @@ def _lib():
                                          C.c_int, P(dbl), P(i32), P(i32), C.c_char_p, C.c_int]
         L.vi_project_textbook_dev.argtypes = [C.c_int, C.c_int, C.c_int, C.c_int, C.c_int, C.c_void_p, C.c_void_p,
                                               C.c_void_p, C.c_void_p, C.c_void_p, C.c_void_p, C.c_char_p, C.c_int]
+        vp = C.c_void_p
+        L.vi_point_based_backup_dev.argtypes = [C.c_int] * 6 + [vp] * 5 + [dbl] + [vp] * 7 + [C.c_int] + [vp] * 5 + \
+                                               [C.c_char_p, C.c_int]
         L._vi_ready = True
     return L
 
@@ -78,6 +81,38 @@ def project_textbook(T, O, gamma, device=0):
     if rc != 0:
         raise native.PomcpError(err.value.decode() or "vi_project_textbook_dev failed")
     return proj
+
+
+def point_based_backup(T, O, R, gamma, beliefs, discount, prune=True, device=0, keep_work=False):
+    """One point-based backup of `gamma` at the belief points (torch CUDA float64 tensors; |S| and the number of points
+    multiples of 128, |O|*|Gamma| a multiple of 64): the textbook projection and the belief scores on the fp64 tensor
+    cores, one new alpha vector per belief point, pointwise-dominance prune.  Returns (alpha [n][S], action [n]) and,
+    with keep_work, the dict of intermediate tensors (unpruned vectors, choices, values)."""
+    import torch
+    A, S, _ = T.shape
+    Z, G, P = O.shape[2], gamma.shape[0], beliefs.shape[0]
+    for t in (T, O, R, gamma, beliefs):
+        assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+    dev, N = T.device, Z * G
+    f64 = lambda *shape: torch.empty(shape, dtype=torch.float64, device=dev)
+    i32 = lambda *shape: torch.empty(shape, dtype=torch.int32, device=dev)
+    w = dict(scratch=f64(S * N), proj=f64(A, S, N), score=f64(A, P, N), best=i32(A, P, Z), value=f64(A, P),
+             alpha=f64(P, S), action=i32(P), pruned=f64(P, S), pruned_action=i32(P), keep=i32(P), n_out=i32(1))
+    err = C.create_string_buffer(256)
+    rc = _lib().vi_point_based_backup_dev(
+        int(device), S, A, Z, G, P, T.data_ptr(), O.data_ptr(), R.data_ptr(), gamma.data_ptr(), beliefs.data_ptr(),
+        float(discount), w["scratch"].data_ptr(), w["proj"].data_ptr(), w["score"].data_ptr(), w["best"].data_ptr(),
+        w["value"].data_ptr(), w["alpha"].data_ptr(), w["action"].data_ptr(), int(bool(prune)), w["pruned"].data_ptr(),
+        w["pruned_action"].data_ptr(), w["keep"].data_ptr(), w["n_out"].data_ptr(),
+        C.c_void_p(torch.cuda.current_stream().cuda_stream), err, 256)
+    if rc != 0:
+        raise native.PomcpError(err.value.decode() or "vi_point_based_backup_dev failed")
+    if prune:
+        n = int(w["n_out"].item())
+        out = (w["pruned"][:n], w["pruned_action"][:n])
+    else:
+        out = (w["alpha"], w["action"])
+    return out + (w,) if keep_work else out
 
 
 class ValueIteration(Solver):

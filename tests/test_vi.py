@@ -100,3 +100,76 @@ def test_gpu_vi_cli_runs(capsys):
     agent = cli.main(["--env", "Tiger", "--solver", "ValueIteration", "--planning_horizon", "8", "--n_epochs", "1",
                       "--max_steps", "10", "--seed", "123", "--verbosity", "1"])
     assert agent.experiment_results.discounted_return.count == 1
+
+
+@pytest.mark.gpu
+def test_gpu_point_based_backup_vs_oracle():
+    """vi_point_based_backup_dev (DMMA projection + belief scores, choices, new vectors, prune) against the float64
+    numpy restatement: values within 1e-9 relative, every choice optimal to 1e-9 and identical wherever the oracle's
+    margin exceeds 1e-6, every vector the exact backup of its choices, the pruned set's envelope unchanged."""
+    import torch
+    from pomdpy_b200 import vi
+    rng = np.random.default_rng(5)
+    S, A, Z, G, P, disc = 256, 4, 8, 16, 128, 0.95
+    T = rng.dirichlet(np.ones(S) * 0.3, size=(A, S))
+    O = rng.dirichlet(np.ones(Z), size=(A, S))
+    R = rng.uniform(-1, 1, size=(A, S))
+    gamma = rng.uniform(-5, 5, size=(G, S))
+    B = rng.dirichlet(np.ones(S) * 0.2, size=P)
+    cu = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    alpha, act, w = vi.point_based_backup(cu(T), cu(O), cu(R), cu(gamma), cu(B), disc, prune=True, keep_work=True)
+    torch.cuda.synchronize()
+    o_alpha, o_act, o_best, o_value, o_score = vi_oracle.point_based_backup(T, O, R, gamma, B, disc)
+    g_value, g_best = w["value"].cpu().numpy(), w["best"].cpu().numpy()
+    g_alpha, g_act = w["alpha"].cpu().numpy(), w["action"].cpu().numpy()
+    g_score = w["score"].cpu().numpy().reshape(A, P, Z, G)
+    scale = np.abs(o_score).max()
+    assert np.abs(g_score - o_score).max() <= 1e-9 * scale                       # DMMA scores == float64 einsum
+    assert np.abs(g_value - o_value).max() <= 1e-9 * np.abs(o_value).max()
+    # choices: optimal to rounding, and identical where the oracle's margin is clear
+    chosen = np.take_along_axis(o_score, g_best[..., None].astype(np.int64), axis=3)[..., 0]
+    assert (o_score.max(axis=3) - chosen).max() <= 1e-9 * scale
+    srt = np.sort(o_score, axis=3)
+    clear = (srt[..., -1] - srt[..., -2]) > 1e-6 * scale
+    assert np.array_equal(g_best[clear], o_best[clear]) and clear.mean() > 0.9
+    v_srt = np.sort(o_value, axis=0)
+    clear_a = (v_srt[-1] - v_srt[-2]) > 1e-6 * np.abs(o_value).max()
+    assert np.array_equal(g_act[clear_a], o_act[clear_a])
+    # every new vector is the exact backup of the choices the device made
+    proj = vi_oracle.textbook_projection(gamma, T, O)
+    for p in range(P):
+        a = int(g_act[p])
+        want = R[a] + disc * proj[a, np.arange(Z), g_best[a, p], :].sum(axis=0)
+        assert np.abs(g_alpha[p] - want).max() <= 1e-9 * np.abs(want).max()
+    # value at the belief points never decreases through the prune; same envelope as the oracle's vectors
+    alpha, act = alpha.cpu().numpy(), act.cpu().numpy()
+    assert 1 <= len(alpha) <= P and set(act.tolist()) <= set(range(A))
+    env_g, env_all, env_o = (B @ alpha.T).max(axis=1), (B @ g_alpha.T).max(axis=1), (B @ o_alpha.T).max(axis=1)
+    assert np.abs(env_g - env_all).max() <= 1e-9 * np.abs(env_all).max()
+    assert np.abs(env_g - env_o).max() <= 1e-9 * np.abs(env_o).max()
+    # a backup never loses value at its own belief point: b_p . alpha_p equals the chosen action's value
+    own = np.einsum("ps,ps->p", B, g_alpha)
+    assert np.abs(own - g_value[g_act, np.arange(P)]).max() <= 1e-9 * np.abs(own).max()
+
+
+def test_oracle_point_based_backup_is_the_one_step_lookahead():
+    """The alpha-vector form of the point-based backup equals the Bayes-filter form of the Bellman backup:
+    max_a [ b.R_a + discount * sum_o P(o | b, a) * V(b'_{a,o}) ],  V = max_g gamma_g . b'."""
+    rng = np.random.default_rng(2)
+    S, A, Z, G, P, disc = 7, 3, 4, 5, 9, 0.9
+    T = rng.dirichlet(np.ones(S), size=(A, S))
+    O = rng.dirichlet(np.ones(Z), size=(A, S))
+    R = rng.uniform(-1, 1, size=(A, S))
+    gamma = rng.uniform(-3, 3, size=(G, S))
+    B = rng.dirichlet(np.ones(S), size=P)
+    alpha, act, best, value, score = vi_oracle.point_based_backup(T, O, R, gamma, B, disc)
+    for p in range(P):
+        look = np.zeros(A)
+        for a in range(A):
+            joint = (B[p] @ T[a])[:, None] * O[a]                 # [s'][o] = P(s', o | b, a)
+            po = joint.sum(axis=0)
+            fut = sum(po[o] * (gamma @ (joint[:, o] / po[o])).max() for o in range(Z) if po[o] > 0)
+            look[a] = B[p] @ R[a] + disc * fut
+        assert np.allclose(look, value[:, p], rtol=1e-12, atol=1e-12)
+        assert act[p] == int(np.argmax(look))
+        assert np.isclose(alpha[p] @ B[p], look.max(), rtol=1e-12)
