@@ -66,7 +66,9 @@ int pomcp_set_model_tabular(pomcp_handle *h, int n_states, int n_actions, int n_
 
 /* --preferred_actions (pomcp.py:30-31; examples/rock_sample/rock_position_history.py:52-55, 96-137, 170-234): nodes
  * carry per-rock statistics and their in-tree action set is generate_smart_actions(); prob is the sensor
- * correctness probability [cell][n_rocks] (rock_model.py:148-150).  Call after the model, before the root belief. */
+ * correctness probability [cell][n_rocks] (rock_model.py:148-150).  Call after the model, before the root belief.
+ * enabled = 2 (additive; the reference has no such policy): the rollouts draw from generate_smart_actions of their own
+ * history as well -- the leaf's statistics, updated with every (action, observation) the rollout generates. */
 int pomcp_set_preferred_actions(pomcp_handle *h, int enabled, const double *prob);
 
 /* RockData of the current root (rock_position_history.py:14-26): chance_good[n_rocks], goodness_number[n_rocks];

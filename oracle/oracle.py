@@ -282,8 +282,9 @@ class GsPOMCP:
     def set_world(self, actual, sampled):
         lib().orc_gs_set_world(self.h, int(actual), int(sampled))
 
-    def set_preferred(self, enabled=True):
-        lib().orc_gs_set_preferred(self.h, int(bool(enabled)))
+    def set_preferred(self, enabled=True, rollouts=False):
+        """rollouts=True: the rollout policy draws from generate_smart_actions of the rollout's own history too."""
+        lib().orc_gs_set_preferred(self.h, (2 if rollouts else 1) if enabled else 0)
 
     def search(self, n_sims, move=0, sim_offset=0, w0=1, growth=1, wmax=1):
         lib().orc_gs_search(self.h, int(n_sims), int(sim_offset), int(move), int(w0), int(growth), int(wmax))

@@ -643,6 +643,7 @@ typedef struct {
     int64_t n_levels, n_rollout_steps, n_created, n_alloc_nodes, n_generations;
     int32_t max_tree_depth;
     int32_t preferred;                         /* --preferred_actions: in-tree action sets from the rock statistics */
+    int32_t preferred_rollout;                 /* rollouts follow generate_smart_actions of the rollout's own history */
 } orc_gs;
 
 /* Model dispatch of the gs planner.  A packed state is cell | rocks << 8 (RockSample) or the state index (tabular);
@@ -719,10 +720,11 @@ void orc_gs_set_world(orc_gs *h, uint32_t actual, uint32_t sampled) { h->w.actua
  * statistics (rock_model.py:302-304) and its action set becomes generate_smart_actions(). */
 void orc_gs_set_preferred(orc_gs *h, int enabled)
 {
-    h->preferred = enabled;
+    h->preferred_rollout = enabled == 2;       /* 2: the rollout policy uses the heuristic too */
+    h->preferred = enabled != 0;
     gs_node *r = &h->nodes[h->root];
     orc_rockstats_init(h->m, &r->st);
-    r->legal = enabled ? orc_smart_mask(h->m, &r->st, r->cell) : h->m->legal[r->cell];
+    r->legal = h->preferred ? orc_smart_mask(h->m, &r->st, r->cell) : h->m->legal[r->cell];
 }
 
 /* data.create_child + create_action_mapping for a new node (belief_node.py:96-124) */
@@ -875,6 +877,7 @@ typedef struct {
     int32_t node, depth;   /* current node / number of path entries */
     int32_t status;        /* 0 descending, 1 leaf: rollout pending, 2 done (terminal or horizon) */
     int32_t *pnode; uint8_t *pact; double *prew;
+    int32_t last_obs;      /* observation of the last tree step (start of the rollout's history) */
     double delayed;
 } gs_sim;
 
@@ -884,15 +887,24 @@ static double gs_rollout(orc_gs *h, gs_sim *s, uint32_t move)
     double sum = 0.0, disc = 1.0; int t = 0, terminal = 0;
     uint32_t st = s->st;
     uint32_t x[4] = {0, 0, 0, 0};
+    /* preferred-action rollout: the rollout keeps the rock statistics of its own history -- the leaf node's, updated
+     * with every (action, observation) it generates (rock_position_history.py:96-137) -- and draws uniformly from
+     * generate_smart_actions (:170-234) instead of the legal set */
+    orc_rockstats rst; int pref = h->m && h->preferred_rollout;
+    if (pref) {
+        const gs_node *ln = &h->nodes[s->pnode[s->depth - 1]];
+        orc_rockstats_child(h->m, &ln->st, ln->cell, s->pact[s->depth - 1], s->last_obs, &rst);
+    }
     while (t < h->max_depth && !terminal) {
         /* one Philox block per two rollout steps: words (0,1) then (2,3); the first word picks the action, the
          * second drives the model (RockSample: top 32 bits of the 53-bit sensor uniform; tabular: next state) */
         if ((t & 1) == 0) gs_block(h, (uint32_t)(s->depth + 1 + (t >> 1)), s->sim, move, DOM_SIM, x);
         uint32_t w0 = x[(t & 1) * 2], w1 = x[(t & 1) * 2 + 1];
-        uint32_t mask = gs_tag_legal(h, gs_state_tag(h, st));
+        uint32_t mask = pref ? orc_smart_mask(h->m, &rst, (int)(st & 0xFFu)) : gs_tag_legal(h, gs_state_tag(h, st));
         int idx = (int)randbelow32(w0, (uint32_t)__builtin_popcount(mask)), a = -1;
         for (int b = 0, seen = 0; b < 32; ++b) if ((mask >> b) & 1u) { if (seen == idx) { a = b; break; } ++seen; }
         gs_step_out o; gs_step(h, st, a, w1, 0u, 1, &o);
+        if (pref) { orc_rockstats nx; orc_rockstats_child(h->m, &rst, (int)(st & 0xFFu), a, o.obs, &nx); rst = nx; }
         terminal = o.terminal;
         if (o.reward != 0.0) sum += o.reward * disc;
         disc *= h->discount;
@@ -966,7 +978,7 @@ int orc_gs_search(orc_gs *h, int64_t n_sims, uint32_t sim_offset, uint32_t move,
                 }
                 gs_step_out o; gs_step(h, s->st, a, x[1], x[2], 0, &o);
                 h->n_levels++;
-                s->pnode[d] = X; s->pact[d] = (uint8_t)a; s->prew[d] = o.reward; s->depth = d + 1;
+                s->pnode[d] = X; s->pact[d] = (uint8_t)a; s->prew[d] = o.reward; s->depth = d + 1; s->last_obs = o.obs;
                 if (s->depth > h->max_tree_depth) h->max_tree_depth = s->depth;
                 int og = o.obs;
                 int32_t child = *gs_child(h, X, a, og);

@@ -40,6 +40,8 @@ def build_parser():
     p.add_argument("--max_depth", default=100, type=int, help="Max depth for a DFS of the belief search tree in MCTS")
     p.add_argument("--action_selection_timeout", default=60, type=int, help="Max num of secs for action selection")
     # additive flags (not in the reference)
+    p.add_argument("--preferred_rollouts", action="store_true",
+                   help="with --preferred_actions: rollouts draw from the smart actions of their own history too")
     p.add_argument("--map_file", default=None, type=str, help="RockSample map name or path (default map-7-8)")
     p.add_argument("--verbosity", default=2, type=int, help="console verbosity 0..4 (reference prints at 3)")
     p.add_argument("--gen_w0", default=0, type=int, help="first generation width of the device search (0 = auto)")

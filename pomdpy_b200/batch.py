@@ -51,7 +51,7 @@ class BatchedAgent(object):
             pl.set_model_rocksample(spec["rows"], spec["cols"], spec["cell"], spec["start_cell"], spec["thr53"],
                                     spec["rewards"])
             if getattr(m, "preferred_actions", False):
-                pl.set_preferred_actions(True, spec["prob"])
+                pl.set_preferred_actions(True, spec["prob"], rollouts=bool(getattr(m, "preferred_rollouts", False)))
             lane_model = copy.copy(m)                      # shares the tables, owns the per-epoch world
             lanes.append(_Lane(lane_model, pl, torch.cuda.Stream()))
         return lanes, spec

@@ -142,6 +142,7 @@ struct SearchParams {
     unsigned long long peer_buf[POMCP_MAX_PEERS];
     int32_t world, rank;
     unsigned long long merge_seq;
+    int32_t pref_rollout, pad_pr;      // --preferred_actions with preferred rollouts (RockSample)
 };
 
 // Exchange buffer of one rank (int64 words): slots[2][POMCP_MAX_PEERS][64] then flags[2][POMCP_MAX_PEERS].  Set
@@ -232,6 +233,40 @@ template <> struct Mdl<0> {
         }
         st = cell | (rocks << 8);
         return finished;
+    }
+    // Preferred-action rollout: the rollout carries the rock statistics of its own history -- the
+    // leaf's, updated with every (action, observation) it generates (rock_position_history.py:96-137) -- and draws
+    // uniformly from generate_smart_actions (:170-234) instead of the legal set.  ch / gd: the statistics after the
+    // last tree step; mask: the smart-action set there.  Runs to the end (no slices).
+    struct PrefOut { uint32_t st; int t; double sum; int finished; };
+    static __device__ __noinline__ PrefOut rollout_preferred(SmemModel M, uint32_t actual, uint32_t sampled,
+                                                             const double *prob, const double *leaf_chance,
+                                                             const int16_t *leaf_good, int leaf_cell, int leaf_action,
+                                                             int leaf_obs, uint32_t sim, uint32_t move, uint32_t key0,
+                                                             uint32_t key1, int depth, const double *disc, uint32_t st,
+                                                             int t, int t_end, double sum)
+    {   // everything by value: a reference to the caller's locals (or to the kernel parameters) would push them into
+        // local memory on the hot path as well
+        const ModelHeader *H = M.hdr;
+        double ch[POMCP_RS]; int16_t gd[POMCP_RS];
+        uint32_t mask = child_smart_mask(H, prob, leaf_chance, leaf_good, ch, gd, leaf_cell, leaf_action, leaf_obs,
+                                         (int)(st & 0xFFu));
+        Philox4 r{0u, 0u, 0u, 0u};
+        for (; t < t_end; ++t) {
+            uint32_t w0, w1;
+            if ((t & 1) == 0) {
+                r = philox4x32_10((uint32_t)(depth + 1 + (t >> 1)), sim, move, DOM_SIM, key0, key1);
+                w0 = r.x; w1 = r.y;
+            } else { w0 = r.z; w1 = r.w; }
+            const int a = nth_bit(mask, randbelow32(w0, (uint32_t)__popc(mask)));
+            const StepResult sr = rs_step(M, st & 0xFFu, st >> 8, a, (uint64_t)w1 << 21, actual, sampled);
+            const double rew = H->rew[sr.rew];
+            if (rew != 0.0) sum += rew * disc[t];
+            mask = child_smart_mask(H, prob, ch, gd, ch, gd, (int)(st & 0xFFu), a, sr.good, (int)sr.cell);
+            st = sr.cell | (sr.rocks << 8);
+            if (sr.terminal) return PrefOut{st, t + 1, sum, 1};
+        }
+        return PrefOut{st, t, sum, 0};
     }
 };
 
@@ -599,7 +634,19 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
         double sum = p.b.ro_sum[i];
         int t = p.b.ro_t[i];
         const int t0 = t, t_end = (t + budget < p.max_depth) ? t + budget : p.max_depth;
-        const bool finished = MD::rollout(mc, S, sim, p.move, p.ks, depth, disc, st, t, t_end, sum);
+        bool finished;
+        if constexpr (KIND == 0) {
+            if (p.pref_rollout) {                                    // only called with the full budget (final phase)
+                int X = p.b.path_node[(size_t)(depth - 1) * p.wmax + i];
+                if (X < 0) X = CHILD_ID(p.t.child[(size_t)(-1 - X)]);
+                const uint32_t ar = p.b.path_ar[(size_t)(depth - 1) * p.wmax + i];
+                const typename Mdl<0>::PrefOut po =
+                    Mdl<0>::rollout_preferred(mc.M, mc.actual, mc.sampled, p.t.prob, p.t.chance + (size_t)X * POMCP_RS,
+                                              p.t.good + (size_t)X * POMCP_RS, p.t.cell[X], (int)(ar & 31u), MD::path_obs(ar),
+                                              sim, p.move, p.key0, p.key1, depth, disc, st, t, t_end, sum);
+                st = po.st; t = po.t; sum = po.sum; finished = po.finished != 0;
+            } else finished = MD::rollout(mc, S, sim, p.move, p.ks, depth, disc, st, t, t_end, sum);
+        } else finished = MD::rollout(mc, S, sim, p.move, p.ks, depth, disc, st, t, t_end, sum);
         c_rollout += t - t0;
         p.b.ro_sum[i] = sum;
         if (finished || t >= p.max_depth) p.b.flag[i] = 3;
@@ -622,7 +669,7 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
             int worked = 0;
             for (; gtid + next_j * T < gen_w; ++next_j) {
                 const int i = gtid + next_j * T;
-                if ((p.b.flag[i] & 3) == 1) { rollout_advance(i, ROLL_SLICE); worked = 1; break; }   // stay on i until done
+                if ((p.b.flag[i] & 3) == 1 && !p.pref_rollout) { rollout_advance(i, ROLL_SLICE); worked = 1; break; }   // stay on i until done
             }
             if (!__syncthreads_or(worked)) __nanosleep(64);
         }
@@ -1250,6 +1297,7 @@ struct pomcp_handle {
     int coop_blocks = 0;
     size_t search_smem = 0;
     long long launches = 0;
+    int pref_rollout = 0;           // preferred actions also steer the rollouts (pomcp_set_preferred_actions(2, ...))
     int world = 1, rank = 0;        // fused root merge (pomcp_set_peer_merge)
     unsigned long long peer_buf[POMCP_MAX_PEERS] = {0, 0, 0, 0, 0, 0, 0, 0};
     unsigned long long merge_seq = 0;
@@ -1485,6 +1533,7 @@ extern "C" int pomcp_set_preferred_actions(pomcp_handle *h, int enabled, const d
     cudaFree(h->t.chance); cudaFree(h->t.good); cudaFree((void *)h->t.prob);
     h->t.chance = nullptr; h->t.good = nullptr; h->t.prob = nullptr;
     h->have_root = false;                                    // the tree must be re-planted
+    h->pref_rollout = enabled == 2;
     if (!enabled) return 0;
     if (!prob) return fail(h, "preferred actions need the sensor probability table");
     double *dp;
@@ -1619,6 +1668,7 @@ extern "C" int pomcp_search(pomcp_handle *h, int64_t n_sims, uint32_t sim_offset
     p.max_depth = h->cfg.max_depth; p.dcap = h->cfg.tree_depth_cap; p.n_thr = h->n_thr; p.node_cap = h->cap;
     p.ucb_c = h->cfg.ucb_coefficient; p.discount = h->cfg.discount;
     p.timeout_ns = timeout_s > 0 ? (unsigned long long)(timeout_s * 1e9) : 0ull;   // checked between generations
+    p.pref_rollout = h->pref_rollout;
     p.world = h->world; p.rank = h->rank;
     if (h->world > 1) {
         for (int r = 0; r < h->world; ++r) p.peer_buf[r] = h->peer_buf[r];

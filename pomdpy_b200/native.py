@@ -182,11 +182,12 @@ class Planner:
                                               _p(ob, C.c_int32), _p(rw, C.c_double), _p(tm, C.c_uint8)))
         return ns, ob, rw, tm
 
-    def set_preferred_actions(self, enabled, prob=None):
-        """--preferred_actions: in-tree action sets from per-node rock statistics; prob [cells][n_rocks] float64."""
+    def set_preferred_actions(self, enabled, prob=None, rollouts=False):
+        """--preferred_actions: in-tree action sets from per-node rock statistics; prob [cells][n_rocks] float64.
+        rollouts=True: the rollout policy draws from the smart actions of the rollout's own history as well."""
         if enabled:
             prob = np.ascontiguousarray(prob, dtype=np.float64).reshape(-1)
-            self._ck(self.lib.pomcp_set_preferred_actions(self.h, 1, _p(prob, C.c_double)))
+            self._ck(self.lib.pomcp_set_preferred_actions(self.h, 2 if rollouts else 1, _p(prob, C.c_double)))
         else:
             self._ck(self.lib.pomcp_set_preferred_actions(self.h, 0, None))
 

@@ -98,9 +98,10 @@ class POMCP(Solver):
             self.preferred = False                                            # a RockSample heuristic
         else:
             self.planner.set_world(*model.world_masks())
-            if self.preferred != getattr(self.planner, "_preferred", False):  # rock_position_history.py:52-55
-                self.planner.set_preferred_actions(self.preferred, spec["prob"])
-                self.planner._preferred = self.preferred
+            mode = (2 if getattr(model, "preferred_rollouts", False) else 1) if self.preferred else 0
+            if mode != getattr(self.planner, "_preferred", 0):                # rock_position_history.py:52-55
+                self.planner.set_preferred_actions(self.preferred, spec["prob"], rollouts=mode == 2)
+                self.planner._preferred = mode
         self.planner.set_root_particles(bag, spec.get("start_cell", 0))
         self._root_cell = spec.get("start_cell", 0)
         self._stats = None

@@ -36,7 +36,8 @@ def test_pomcp_cli_flags_match_reference():
     with open(os.path.join(GOLDEN, "cli_flags.json")) as f:
         g = json.load(f)
     assert len(g["pomcp"]) == 22
-    _check(cli.build_parser(), g["pomcp"], {"--map_file", "--verbosity", "--gen_w0", "--gen_growth", "--gen_wmax", "--concurrent_epochs"})
+    _check(cli.build_parser(), g["pomcp"], {"--map_file", "--verbosity", "--gen_w0", "--gen_growth", "--gen_wmax", "--concurrent_epochs",
+                                             "--preferred_rollouts"})
 
 
 def test_vi_cli_flags_match_reference():

@@ -71,3 +71,15 @@ def test_batched_epochs_match_serial_level_and_are_faster():
                                                                                   1e3 * agent.wall_seconds / 256, 256 / agent.wall_seconds))
     assert st.count == 256 and 14.62 - 2.0 < st.mean < 20.5
     assert agent.total_sims >= 256 * 500 and dt < 60
+
+
+def test_cli_preferred_rollouts_improve_return():
+    """Additive --preferred_rollouts: the rollout policy uses the smart actions of the rollout's own history.  On the
+    reference's configuration the return rises well above the tree-only heuristic's (~21) and the plain planner's (~16)."""
+    import pomcp as cli
+    agent = cli.main(["--env", "RockSample", "--solver", "POMCP", "--max_steps", "200", "--n_epochs", "30",
+                      "--n_sims", "500", "--seed", "123", "--preferred_actions", "--preferred_rollouts",
+                      "--verbosity", "0"])
+    er = agent.experiment_results
+    print("preferred rollouts: %.2f +- %.2f" % (er.discounted_return.mean, er.discounted_return.std_err()))
+    assert er.discounted_return.mean > 16.0

@@ -209,19 +209,26 @@ def test_errors_are_loud():
     pl.close()
 
 
-@pytest.mark.parametrize("tag,seed,n_sims,sched", [("map-7-8", 51, 1000, (8, 2, 128)), ("map-15-15", 52, 20000, (64, 4, 8192))])
-def test_preferred_actions_episode_bit_exact(tag, seed, n_sims, sched):
+@pytest.mark.parametrize("tag,seed,n_sims,sched,rollouts", [("map-7-8", 51, 1000, (8, 2, 128), False),
+                                                            ("map-15-15", 52, 20000, (64, 4, 8192), False),
+                                                            ("map-7-8", 53, 1000, (8, 2, 128), True),
+                                                            ("map-11-11", 54, 6000, (1, 1, 1), True),
+                                                            ("map-15-15", 55, 20000, (64, 4, 8192), True)])
+def test_preferred_actions_episode_bit_exact(tag, seed, n_sims, sched, rollouts):
     """--preferred_actions (rock_position_history.py): per-node rock statistics and smart action sets on the
-    device == oracle, over several moves with belief updates (fresh and existing roots)."""
+    device == oracle, over several moves with belief updates (fresh and existing roots); with `rollouts` the rollout
+    policy follows the heuristic on the rollout's own history as well."""
     w0, growth, wmax = sched
+    if rollouts and n_sims == 6000:
+        n_sims = 600                                        # strictly sequential case: keep the oracle quick
     kw = dict(seed=seed, gen_w0=w0, gen_growth=growth, gen_wmax=wmax, node_capacity=1 << 17)
     t = golden_tables(tag)
     actual, bag, rng = random_world_and_bag(t, seed)
     om = oracle_model(t)
     g = oracle.GsPOMCP(om, actual, 0, bag, seed=seed)
-    g.set_preferred(True)
+    g.set_preferred(True, rollouts=rollouts)
     pl = make_planner(t, **kw)
-    pl.set_preferred_actions(True, t["prob"])
+    pl.set_preferred_actions(True, t["prob"], rollouts=rollouts)
     pl.set_world(actual, 0)
     pl.set_root_particles(bag, int(t["start_cell"]))
     cell, rocks, sampled = int(t["start_cell"]), int(bag[0] >> 8), 0
