@@ -191,3 +191,84 @@ def test_pomcp_agrees_with_value_iteration_on_tiger():
             exact = float((alpha @ b).max())
             assert exact - 1.0 < q.max() <= exact + 0.05, (q.max(), exact)
     pl.close()
+
+
+def _custom_pair(T, O, R, b0, term_actions=(), term_states=(), n_bag=500, **kw):
+    from pomdpy_b200.tabular import TabularModel
+    m = TabularModel({}, T, O, R, b0, terminal_actions=term_actions, terminal_states=term_states)
+    om = oracle.TabularModel(m.Tc, m.Oc, m.R, m.term_action_mask, m.term_state)
+    bag = m.sample_init_states_packed(n_bag, np.random.RandomState(0))
+    g = oracle.GsPOMCP(om, 0, 0, bag, max_depth=kw.get("max_depth", 100), dcap=kw.get("tree_depth_cap", 64),
+                       ucb_c=kw.get("ucb_coefficient", 3.0), discount=kw.get("discount", 0.95), seed=kw.get("seed", 0))
+    pl = native.Planner(**kw)
+    pl.set_model_tabular(m.Tc, m.Oc, m.R, m.term_action_mask, m.term_state)
+    pl.set_root_particles(bag)
+    return m, om, g, pl
+
+
+def test_tabular_edge_models_bit_exact():
+    """Degenerate shapes: absorbing terminal states with deterministic (zero-probability-laden) transitions, a single
+    observation, a single action, a single state."""
+    rng = np.random.RandomState(3)
+    # a 6-state chain: action 0 moves right, action 1 stays; state 5 is absorbing and terminal; reward on arrival
+    S = 6
+    T = np.zeros((2, S, S))
+    for s in range(S):
+        T[0, s, min(s + 1, S - 1)] = 1.0
+        T[1, s, s] = 0.7
+        T[1, s, max(s - 1, 0)] += 0.3
+    O = np.zeros((2, S, 3))
+    O[:, :, 0], O[:, :, 1], O[:, :, 2] = 0.5, 0.5, 0.0                           # observation 2 never occurs
+    R = np.zeros((2, S))
+    R[0, 4] = 10.0
+    R[1, :] = -0.5
+    cases = [dict(T=T, O=O, R=R, b0=np.array([0.6, 0.4, 0, 0, 0, 0.0]), term_states=(5,)),
+             dict(T=rng.dirichlet(np.ones(9), size=(4, 9)), O=np.ones((4, 9, 1)), R=rng.randn(4, 9), b0=np.ones(9) / 9),
+             dict(T=rng.dirichlet(np.ones(5), size=(1, 5)), O=rng.dirichlet(np.ones(4), size=(1, 5)), R=rng.randn(1, 5),
+                  b0=np.ones(5) / 5),
+             dict(T=np.ones((3, 1, 1)), O=rng.dirichlet(np.ones(2), size=(3, 1)), R=np.array([[1.0], [2.0], [-1.0]]),
+                  b0=np.ones(1))]
+    for c in cases:
+        m, om, g, pl = _custom_pair(c["T"], c["O"], c["R"], c["b0"], term_states=c.get("term_states", ()),
+                                    gen_w0=16, gen_growth=2, gen_wmax=1024, node_capacity=1 << 16, max_depth=40)
+        for move in range(3):
+            g.search(5000, move=move, w0=16, growth=2, wmax=1024)
+            pl.search(5000, move=move)
+            a, b = g.root_stats(), pl.root_stats()
+            _same(a, b)
+            act = g.greedy(move, a)
+            u, v = g.update(act, 0, 0, move=move, need=2000), pl.advance(act, 0, 0, move=move)
+            assert (u["status"], u["tries"], u["accepted"]) == (v["status"], v["tries"], v["accepted"])
+            if u["status"] == 2:
+                break
+            assert np.array_equal(pl.root_particles()[0], g.bag())
+        pl.close()
+    # an observation that cannot occur empties the belief: status 2 on both sides, no exception
+    c = cases[0]
+    m, om, g, pl = _custom_pair(c["T"], c["O"], c["R"], c["b0"], term_states=(5,), gen_w0=16, gen_growth=2,
+                                gen_wmax=1024, node_capacity=1 << 16, max_depth=40)
+    g.search(1000, w0=16, growth=2, wmax=1024)
+    pl.search(1000)
+    u, v = g.update(1, 2, 0, need=2000, max_tries=20000), pl.advance(1, 2, 0, max_tries=20000)
+    assert u["status"] == 2 and v["status"] == 2 and v["accepted"] == 0 and v["tries"] == u["tries"] == 20000
+    pl.close()
+
+
+def test_tabular_large_state_space_and_capacity_reset():
+    """|S| = 2048 (binary search over 8 KB rows in global memory) and a search that does not fit the arena (the tree
+    is dropped, the belief kept: status 1, as for RockSample)."""
+    m = random_pomdp(2048, 2, 4, seed=8, sparsity=0.99)
+    om = oracle.TabularModel(m.Tc, m.Oc, m.R, m.term_action_mask, m.term_state)
+    bag = m.sample_init_states_packed(1000, np.random.RandomState(1))
+    g = oracle.GsPOMCP(om, 0, 0, bag, max_depth=30, seed=4)
+    pl = native.Planner(max_depth=30, seed=4, gen_w0=32, gen_growth=2, gen_wmax=2048, node_capacity=30000)
+    pl.set_model_tabular(m.Tc, m.Oc, m.R, m.term_action_mask, m.term_state)
+    pl.set_root_particles(bag)
+    g.search(20000, w0=32, growth=2, wmax=2048)
+    assert pl.search(20000) == 0
+    _same(g.root_stats(), pl.root_stats())
+    assert pl.search(20000, move=1) == 1                      # 20000 + 20000 nodes could exceed 30000: fresh tree
+    g2 = oracle.GsPOMCP(om, 0, 0, bag, max_depth=30, seed=4)
+    g2.search(20000, move=1, w0=32, growth=2, wmax=2048)
+    _same(g2.root_stats(), pl.root_stats())
+    pl.close()
