@@ -73,11 +73,15 @@ def main(argv=None):
     np.random.seed(args["seed"])
     if args["solver"] != "POMCP":
         raise ValueError("solver not supported")
-    if args["env"] == "RockSample":
-        env = RockModel(args)
-        if util.VERBOSITY >= 3:
-            env.draw_env()
+    if args["env"] in ("RockSample", "Tiger"):       # Tiger: additive, the reference's matrices under the CUDA planner
         lanes = args.pop("concurrent_epochs", 0)
+        if args["env"] == "Tiger":
+            from pomdpy_b200.tabular import tiger
+            env = tiger(args)
+        else:
+            env = RockModel(args)
+            if util.VERBOSITY >= 3:
+                env.draw_env()
         if lanes and lanes > 1 and world == 1:
             from pomdpy_b200.batch import BatchedAgent
             from pomdpy_b200.util import console
@@ -88,12 +92,6 @@ def main(argv=None):
             console(2, "agent", "ave time/epoch: " + str(agent.wall_seconds / max(1, args["n_epochs"])))
             return agent
         agent = Agent(env, POMCP)
-        agent.discounted_return()
-        return agent
-    if args["env"] == "Tiger":           # additive: the reference's Tiger matrices under the CUDA planner
-        from pomdpy_b200.tabular import tiger
-        args.pop("concurrent_epochs", None)
-        agent = Agent(tiger(args), POMCP)
         agent.discounted_return()
         return agent
     print("Unknown env {}".format(args["env"]))

@@ -28,6 +28,7 @@ class _Lane(object):
 class BatchedAgent(object):
     def __init__(self, model, lanes=32):
         self.model = model
+        self.tabular = model.device_spec().get("kind", "rocksample") == "tabular"
         self.lanes = int(lanes)
         self.discounted_return = Statistic("discounted return")
         self.undiscounted_return = Statistic("undiscounted return")
@@ -48,9 +49,12 @@ class BatchedAgent(object):
                                 discount=float(m.discount), seed=int(getattr(m, "seed", 1993)),
                                 node_capacity=max(1 << 12, n_sims * 8 + 64), gen_w0=max(1, min(1024, wmax // 16)),
                                 gen_growth=2, gen_wmax=wmax)
-            pl.set_model_rocksample(spec["rows"], spec["cols"], spec["cell"], spec["start_cell"], spec["thr53"],
-                                    spec["rewards"])
-            if getattr(m, "preferred_actions", False):
+            if self.tabular:
+                pl.set_model_tabular(spec["Tc"], spec["Oc"], spec["R"], spec["term_action_mask"], spec["term_state"])
+            else:
+                pl.set_model_rocksample(spec["rows"], spec["cols"], spec["cell"], spec["start_cell"], spec["thr53"],
+                                        spec["rewards"])
+            if not self.tabular and getattr(m, "preferred_actions", False):
                 pl.set_preferred_actions(True, spec["prob"], rollouts=bool(getattr(m, "preferred_rollouts", False)))
             lane_model = copy.copy(m)                      # shares the tables, owns the per-epoch world
             lanes.append(_Lane(lane_model, pl, torch.cuda.Stream()))
@@ -58,11 +62,13 @@ class BatchedAgent(object):
 
     def _start_epoch(self, lane, epoch, spec):
         m = lane.model
-        m.unique_rocks_sampled = []
+        if not self.tabular:
+            m.unique_rocks_sampled = []
         m.reset_for_epoch()                                # agent.py:135,143: the true world (numpy generator)
-        bag = np.ascontiguousarray(m.sample_init_states_packed(int(m.n_start_states)), dtype=np.uint32)
-        lane.planner.set_world(*m.world_masks())
-        lane.planner.set_root_particles(bag, spec["start_cell"])
+        bag = np.ascontiguousarray(m.sample_init_states_packed(int(getattr(m, "n_start_states", 2000))), dtype=np.uint32)
+        if not self.tabular:
+            lane.planner.set_world(*m.world_masks())
+        lane.planner.set_root_particles(bag, spec.get("start_cell", 0))
         idx = philox.randbelow(int(getattr(m, "seed", 1993)), len(bag), 0, 0, epoch << 12, philox.DOM_AGENT)
         lane.state = m.unpack_state(bag[idx])              # agent.py:157
         lane.epoch, lane.step, lane.ret, lane.dret, lane.disc, lane.active = epoch, 0, 0.0, 0.0, 1.0, True
@@ -98,7 +104,8 @@ class BatchedAgent(object):
                 if not res.is_terminal or not legal:       # agent.py:186
                     ln.model.update(res)
                     _, sampled = ln.model.world_masks()
-                    if ln.planner.advance(a, bool(res.observation.is_good), sampled, move=ln.move)["status"] == 2:
+                    obs = int(res.observation.bin_number) if self.tabular else bool(res.observation.is_good)
+                    if ln.planner.advance(a, obs, sampled, move=ln.move)["status"] == 2:
                         done = True                        # disable_tree: the serial path would finish with rollouts
                 if done:
                     self.discounted_return.add(ln.dret)

@@ -272,3 +272,16 @@ def test_tabular_large_state_space_and_capacity_reset():
     g2.search(20000, move=1, w0=32, growth=2, wmax=2048)
     _same(g2.root_stats(), pl.root_stats())
     pl.close()
+
+
+def test_tiger_batched_epochs():
+    """Episode-level batching (--concurrent_epochs) on a tabular model: same level of return as the serial Agent."""
+    from pomdpy_b200.batch import BatchedAgent
+    args = dict(max_steps=30, n_epochs=96, n_sims=4000, seed=5, ucb_coefficient=30.0, discount=0.95, max_depth=30,
+                max_particle_count=1000, n_start_states=1000, preferred_actions=False)
+    np.random.seed(6)
+    agent = BatchedAgent(tiger(args), lanes=16)
+    mean, err = agent.run(args["n_epochs"])
+    print("tiger batched: %.2f +- %.2f over %d epochs, %.1f ms/epoch" % (mean, err, args["n_epochs"],
+                                                                      1e3 * agent.wall_seconds / args["n_epochs"]))
+    assert agent.discounted_return.count == 96 and mean > 0.0
