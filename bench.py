@@ -30,9 +30,9 @@ import numpy as np  # noqa: E402
 
 MAP = "map-15-15"
 N_SIMS = 1_000_000
-SCHEDULE = (16384, 4, 1 << 19)          # generation widths: 16384, 65536, 262144, 524288 (+ the rest) simulations in flight;
+SCHEDULE = (32768, 4, 1 << 19)          # generation widths: 32768, 131072, 524288 (+ the rest) simulations in flight;
                                         # return at 1e6 simulations per move does not depend on the first width
-                                        # (profiles/r01_schedule_sweep.txt)
+                                        # (160 paired episodes per width, 4096 ... 65536: profiles/r01_schedule_sweep.txt)
 REF_SAMPLE_SIMS = 100_000               # per core and step, reference arm
 METRIC = "pomcp_sims_per_sec_rocksample_15_15"
 

@@ -6,7 +6,7 @@ tag = sys.argv[1] if len(sys.argv) > 1 else "map-15-15"
 n_sims = int(sys.argv[2]) if len(sys.argv) > 2 else 1000000
 t = golden_tables(tag)
 actual, bag, _ = random_world_and_bag(t, 41)
-for (w0, g, wmax) in [(1024, 2, 1 << 17), (1024, 2, 1 << 18), (4096, 4, 1 << 19), (16384, 4, 1 << 19), (1 << 18, 1, 1 << 18), (1 << 20, 1, 1 << 20)]:
+for (w0, g, wmax) in [(1024, 2, 1 << 17), (1024, 2, 1 << 18), (4096, 4, 1 << 19), (16384, 4, 1 << 19), (32768, 4, 1 << 19), (1 << 18, 1, 1 << 18), (1 << 20, 1, 1 << 20)]:
     pl = make_planner(t, seed=1, gen_w0=w0, gen_growth=g, gen_wmax=wmax, node_capacity=1 << 22)
     pl.set_world(actual, 0)
     ts = []
