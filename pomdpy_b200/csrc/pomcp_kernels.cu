@@ -203,19 +203,14 @@ template <> struct Mdl<0> {
         uint32_t cell = st & 0xFFu, rocks = st >> 8;
         const uint32_t actual = c.actual, sampled = c.sampled;
         bool finished = false;
-        Philox4 r{0u, 0u, 0u, 0u};
-        for (; t < t_end; ++t) {
-            uint32_t w0, w1;
-            if ((t & 1) == 0) {
-                r = philox4x32_10_ks((uint32_t)(depth + 1 + (t >> 1)), sim, move, DOM_SIM, ks);
-                w0 = r.x; w1 = r.y;
-            } else { w0 = r.z; w1 = r.w; }
+        // one step with the draws (w0, w1); true when the episode ended
+        auto step = [&](uint32_t w0, uint32_t w1) -> bool {
             const uint32_t mask = H->legal[cell];
             const int a = nth_legal(H, mask, randbelow32(w0, (uint32_t)__popc(mask)));
             DCHECK(S, a >= 0 && a < H->n_actions && cell < (uint32_t)H->n_cells, 41);
             if (a < 4) {
                 cell = (uint32_t)((int)cell + H->delta[a]);
-                if (H->cell[cell] == POMCP_CELL_GOAL) { sum += H->rew[REW_EXIT] * disc[t]; ++t; finished = true; break; }
+                if (H->cell[cell] == POMCP_CELL_GOAL) { sum += H->rew[REW_EXIT] * disc[t]; return true; }
             } else if (a == 4) {
                 const int code = H->cell[cell];
                 const int rew = (((actual & rocks) >> code) & 1u) ? REW_GOOD : REW_BAD;
@@ -230,6 +225,15 @@ template <> struct Mdl<0> {
                     rocks = (rocks & ~(1u << k)) | (good << k);
                 }
             }
+            return false;
+        };
+        // t is even on entry (slices are even, a finished rollout is never resumed): two steps per Philox block
+        while (t < t_end) {
+            const Philox4 r = philox4x32_10_ks((uint32_t)(depth + 1 + (t >> 1)), sim, move, DOM_SIM, ks);
+            if (step(r.x, r.y)) { ++t; finished = true; break; }
+            if (++t >= t_end) break;                                 // odd horizon
+            if (step(r.z, r.w)) { ++t; finished = true; break; }
+            ++t;
         }
         st = cell | (rocks << 8);
         return finished;
