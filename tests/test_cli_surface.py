@@ -86,3 +86,24 @@ def test_history_and_results_bookkeeping():
     assert RockAction(7).to_string() == "CHECK" and RockAction(7).rock_no == 2
     assert RockObservation().to_string() == "EMPTY" and RockObservation(True, False) == RockObservation(True, None)
     assert hash(RockObservation(True, False)) == 1 and RockObservation(False, False) == RockObservation(False, True)
+
+
+def test_bench_reference_arm_prints_the_contract_line():
+    """`bench.py --impl reference` (the CPU arm the driver runs beside the CUDA one) needs no GPU: one JSON line with
+    the metric of BASELINE.json, impl = reference, the cpu_baseline description and an e2e object."""
+    import json
+    import os
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    res = subprocess.run([sys.executable, os.path.join(root, "bench.py"), "--impl", "reference", "--steps", "1",
+                          "--warmup", "0"], capture_output=True, text=True, timeout=300)
+    assert res.returncode == 0, res.stderr[-2000:]
+    line = json.loads(res.stdout.strip().splitlines()[-1])
+    with open(os.path.join(root, "BASELINE.json")) as f:
+        base = json.load(f)
+    assert line["impl"] == "reference" and line["unit"] == "sims/s" and line["higher_is_better"] is True
+    assert line["metric"].startswith("pomcp_sims_per_sec") and "sims/sec" in base["metric"]
+    assert line["value"] > 1e4 and line["cpu_baseline"]["kind"] == "port" and line["cpu_baseline"]["cores"] >= 1
+    assert line["e2e"]["value"] == line["value"] and line["e2e"]["h2d_bytes_per_step"] == 0
+    assert line["gpu_launches"] == 0
