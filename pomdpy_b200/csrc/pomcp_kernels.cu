@@ -598,12 +598,14 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
     off += (size_t)n_acc * 8;
     int *acc_n = reinterpret_cast<int *>(smem + off);
     off += (size_t)n_acc * 4;
+    off = (off + 15) & ~size_t(15);                                  // the tables below hold 64-bit words
     int *arr1 = reinterpret_cast<int *>(smem + off);               // arrivals at the root's children, per block
     for (int i = threadIdx.x; i < ZS * A; i += blockDim.x) arr1[i] = 0;
     off += ((size_t)ZS * A * 4 + 15) & ~size_t(15);
     uint32_t *ht_key = reinterpret_cast<uint32_t *>(smem + off);    // arrivals at deeper nodes, per block (hash table)
     int *ht_cnt = reinterpret_cast<int *>(smem + off + ARR_HT * 4);
-    for (int i = threadIdx.x; i < ARR_HT; i += blockDim.x) { ht_key[i] = 0u; ht_cnt[i] = 0; }
+    long long *ht_q = reinterpret_cast<long long *>(smem + off + ARR_HT * 8);   // backup phase: return sums per edge
+    for (int i = threadIdx.x; i < ARR_HT; i += blockDim.x) { ht_key[i] = 0u; ht_cnt[i] = 0; ht_q[i] = 0; }
     if (threadIdx.x == 0) { double d = 1.0; for (int t = 0; t < p.max_depth; ++t) { disc[t] = d; d *= p.discount; } }
     for (int i = threadIdx.x; i < n_acc; i += blockDim.x) { acc_q[i] = 0; acc_n[i] = 0; }
     __syncthreads();
@@ -901,48 +903,107 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
             base = __shfl_sync(0xFFFFFFFFu, base, 0);
             if (base >= w) break;
             const int i = base + lane;
-            if (i >= w) continue;
+            const bool have = i < w;
             TSEC_START();
-            if ((p.b.flag[i] & 3) == 1) rollout_advance(i, p.max_depth);
+            if (have && (p.b.flag[i] & 3) == 1) rollout_advance(i, p.max_depth);
             TSEC(7);                                                 // final phase: rollouts
-            const int depth = p.b.depth[i];
-            double delayed = ((p.b.flag[i] & 3) == 3) ? p.b.ro_sum[i] : 0.0;
-            for (int d = depth - 1; d >= 0; --d) {
-                const uint32_t ar = p.b.path_ar[(size_t)d * p.wmax + i];
-                const int a = ar & 31;
-                const double q = MD::path_reward(mc, ar, KIND == 1 ? p.b.path_rew + (size_t)d * p.wmax + i : nullptr) +
-                                 p.discount * delayed;
-                const long long qi = __double2ll_rn(q * POMCP_QFIX_SCALE);
-                if (d == 0) {
-                    atomicAdd(&acc_n[a], 1);
-                    atomicAdd(reinterpret_cast<unsigned long long *>(&acc_q[a]), (unsigned long long)qi);
-                    if (!stage_d1 && depth > 1) {                            // the depth-1 child has statistics from now on
-                        uint32_t *cs = &p.t.child[((size_t)root * AS + a) * ZS + MD::path_obs(ar)];
-                        if (!(*((volatile uint32_t *)cs) & CHILD_VISITED)) atomicOr(cs, CHILD_VISITED);
-                    }
-                } else if (d == 1 && stage_d1) {
-                    const uint32_t ar0 = p.b.path_ar[i];
-                    const int e = (1 + (int)(ar0 & 31) * ZS + MD::path_obs(ar0)) * A + a;
-                    atomicAdd(&acc_n[e], 1);
-                    atomicAdd(reinterpret_cast<unsigned long long *>(&acc_q[e]), (unsigned long long)qi);
-                    if (depth > 2) {                                         // mark the depth-2 child of this edge
-                        int X = p.b.path_node[(size_t)p.wmax + i];
-                        if (X < 0) X = CHILD_ID(p.t.child[(size_t)(-1 - X)]);
-                        uint32_t *cs = &p.t.child[((size_t)X * AS + a) * ZS + MD::path_obs(ar)];
-                        if (!(*((volatile uint32_t *)cs) & CHILD_VISITED)) atomicOr(cs, CHILD_VISITED);
-                    }
-                } else {
-                    int X = p.b.path_node[(size_t)d * p.wmax + i];
-                    if (X < 0) X = CHILD_ID(p.t.child[(size_t)(-1 - X)]);    // id published after this sim passed
-                    DCHECK(S, X > 0 && X < S->node_count && a < A, 31);
-                    atomicAdd(&p.t.n[(size_t)X * AS + a], 1);
-                    atomicAdd(reinterpret_cast<unsigned long long *>(&p.t.qfix[(size_t)X * AS + a]), (unsigned long long)qi);
-                    if (d + 1 < depth) {                                     // the child below this edge now has statistics
-                        uint32_t *cs = &p.t.child[((size_t)X * AS + a) * ZS + MD::path_obs(ar)];
-                        if (!(*((volatile uint32_t *)cs) & CHILD_VISITED)) atomicOr(cs, CHILD_VISITED);
+            // Backup (solvers/pomcp.py:126-137), level by level from the deepest path entry of the warp: at level d the
+            // active lanes usually update the SAME edge (inside an episode the re-rooted tree is a long chain), so the
+            // warp first checks for a common edge and then issues one update for all of them.  Updates go to the
+            // per-block tables in shared memory -- root and depth-1 edges by index, deeper edges into the hash table
+            // keyed by edge -- which are flushed once per block after the loop: a hot edge sees one global atomic per
+            // block instead of one per simulation.  Integer sums: any order gives the same result.
+            const int depth = have ? (int)p.b.depth[i] : 0;
+            double delayed = (have && (p.b.flag[i] & 3) == 3) ? p.b.ro_sum[i] : 0.0;
+            int dmax = depth;
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) dmax = max(dmax, __shfl_xor_sync(0xFFFFFFFFu, dmax, off));
+            for (int d = dmax - 1; d >= 0; --d) {
+                const bool act = d < depth;
+                uint32_t key = 0u;                                   // 1 + staged index, or 0x80000000 | edge index
+                long long qi = 0;
+                if (act) {
+                    const uint32_t ar = p.b.path_ar[(size_t)d * p.wmax + i];
+                    const int a = ar & 31;
+                    const double q = MD::path_reward(mc, ar, KIND == 1 ? p.b.path_rew + (size_t)d * p.wmax + i : nullptr) +
+                                     p.discount * delayed;
+                    qi = __double2ll_rn(q * POMCP_QFIX_SCALE);
+                    delayed = q;
+                    if (d == 0) {
+                        key = 1u + (uint32_t)a;
+                        if (!stage_d1 && depth > 1) {                        // the depth-1 child has statistics from now on
+                            uint32_t *cs = &p.t.child[((size_t)root * AS + a) * ZS + MD::path_obs(ar)];
+                            if (!(*((volatile uint32_t *)cs) & CHILD_VISITED)) atomicOr(cs, CHILD_VISITED);
+                        }
+                    } else {
+                        int X = p.b.path_node[(size_t)d * p.wmax + i];
+                        if (d == 1 && stage_d1) {
+                            const uint32_t ar0 = p.b.path_ar[i];
+                            key = 1u + (uint32_t)((1 + (int)(ar0 & 31) * ZS + MD::path_obs(ar0)) * A + a);
+                        } else {
+                            if (X < 0) X = CHILD_ID(p.t.child[(size_t)(-1 - X)]);   // id published after this sim passed
+                            DCHECK(S, X > 0 && X < S->node_count && a < A, 31);
+                            key = 0x80000000u | (uint32_t)(X * AS + a);
+                        }
+                        if (d + 1 < depth) {                                 // the child below this edge now has statistics
+                            if (X < 0) X = CHILD_ID(p.t.child[(size_t)(-1 - X)]);
+                            uint32_t *cs = &p.t.child[((size_t)X * AS + a) * ZS + MD::path_obs(ar)];
+                            if (!(*((volatile uint32_t *)cs) & CHILD_VISITED)) atomicOr(cs, CHILD_VISITED);
+                        }
                     }
                 }
-                delayed = q;
+                // up to three rounds of "the first pending lane's edge, for every lane that shares it" (a chain level has
+                // one or two nodes), aggregated into the block tables; what is left updates on its own, deeper edges
+                // directly in the arena (a diverse warp gains nothing from hashing)
+                bool pending = act;
+                unsigned alone = 0u;                                     // lanes found to share their edge with nobody
+#pragma unroll
+                for (int round = 0; round < 3; ++round) {
+                    const unsigned todo = __ballot_sync(0xFFFFFFFFu, pending) & ~alone;
+                    if (todo == 0u) break;
+                    const int leader = __ffs((int)todo) - 1;
+                    const uint32_t lkey = __shfl_sync(0xFFFFFFFFu, key, leader);
+                    const bool in_grp = pending && key == lkey;
+                    const unsigned grp = __ballot_sync(0xFFFFFFFFu, in_grp);
+                    if (__popc(grp) < 2) { alone |= grp; continue; }         // nothing to share: leave it to the tail
+                    long long sum = in_grp ? qi : 0;
+#pragma unroll
+                    for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, off);
+                    if (lane == leader) {
+                        const int cnt = __popc(grp);
+                        if (!(lkey & 0x80000000u)) {
+                            atomicAdd(&acc_n[lkey - 1u], cnt);
+                            atomicAdd(reinterpret_cast<unsigned long long *>(&acc_q[lkey - 1u]), (unsigned long long)sum);
+                        } else {
+                            uint32_t hq = ((lkey * 2654435761u) >> 16) & (ARR_HT - 1);
+                            int probe = 0;
+                            for (; probe < ARR_PROBES; ++probe, hq = (hq + 1u) & (ARR_HT - 1)) {
+                                const uint32_t prev = atomicCAS(&ht_key[hq], 0u, lkey);
+                                if (prev == 0u || prev == lkey) {
+                                    atomicAdd(&ht_cnt[hq], cnt);
+                                    atomicAdd(reinterpret_cast<unsigned long long *>(&ht_q[hq]), (unsigned long long)sum);
+                                    break;
+                                }
+                            }
+                            if (probe == ARR_PROBES) {                       // table crowded: update the arena directly
+                                const size_t e = lkey & 0x7FFFFFFFu;
+                                atomicAdd(&p.t.n[e], cnt);
+                                atomicAdd(reinterpret_cast<unsigned long long *>(&p.t.qfix[e]), (unsigned long long)sum);
+                            }
+                        }
+                    }
+                    if (in_grp) pending = false;
+                }
+                if (pending) {
+                    if (!(key & 0x80000000u)) {
+                        atomicAdd(&acc_n[key - 1u], 1);
+                        atomicAdd(reinterpret_cast<unsigned long long *>(&acc_q[key - 1u]), (unsigned long long)qi);
+                    } else {
+                        const size_t e = key & 0x7FFFFFFFu;
+                        atomicAdd(&p.t.n[e], 1);
+                        atomicAdd(reinterpret_cast<unsigned long long *>(&p.t.qfix[e]), (unsigned long long)qi);
+                    }
+                }
             }
 #ifdef POMCP_TSEC
             { const long long n_ = clock64(); tsec_bk_ += n_ - tsec_t_; }   // final phase: backup
@@ -963,6 +1024,14 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
             atomicAdd(&p.t.n[(size_t)X * AS + a], dn);
             atomicAdd(reinterpret_cast<unsigned long long *>(&p.t.qfix[(size_t)X * AS + a]), (unsigned long long)acc_q[e]);
             acc_n[e] = 0; acc_q[e] = 0;
+        }
+        for (int t = threadIdx.x; t < ARR_HT; t += blockDim.x) {    // ... and the deeper edges of the hash table
+            const uint32_t key = ht_key[t];
+            if (key == 0u) continue;
+            const size_t e = key & 0x7FFFFFFFu;
+            atomicAdd(&p.t.n[e], ht_cnt[t]);
+            atomicAdd(reinterpret_cast<unsigned long long *>(&p.t.qfix[e]), (unsigned long long)ht_q[t]);
+            ht_key[t] = 0u; ht_cnt[t] = 0; ht_q[t] = 0;
         }
         done += w;
         if (W < p.wmax) { long long nw = (long long)W * p.growth; W = nw > p.wmax ? p.wmax : (int)nw; }
@@ -1457,7 +1526,7 @@ extern "C" int pomcp_set_model_rocksample(pomcp_handle *h, int rows, int cols, c
     // launch geometry of the cooperative search kernel
     const int A = m.n_actions;
     size_t smem = ((sizeof(ModelHeader) + 15) & ~size_t(15)) + (((size_t)h->n_thr * 8 + 15) & ~size_t(15)) +
-                  (((size_t)h->cfg.max_depth * 8 + 15) & ~size_t(15)) + (size_t)(1 + 2 * A) * A * 12 + (((size_t)2 * A * 4 + 15) & ~size_t(15)) + (size_t)ARR_HT * 8 + 16;
+                  (((size_t)h->cfg.max_depth * 8 + 15) & ~size_t(15)) + (size_t)(1 + 2 * A) * A * 12 + (((size_t)2 * A * 4 + 15) & ~size_t(15)) + (size_t)ARR_HT * 16 + 32;
     h->search_smem = smem;
     CK(cudaFuncSetAttribute(pomcp_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(pomcp_search_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1513,7 +1582,7 @@ extern "C" int pomcp_set_model_tabular(pomcp_handle *h, int n_states, int n_acti
     if (!h->b.path_rew)
         CK(cudaMalloc(&h->b.path_rew, (size_t)h->cfg.gen_wmax * (size_t)h->cfg.tree_depth_cap * sizeof(double)));
     const size_t n_acc = t.stage_d1 ? (size_t)(1 + zs * n_actions) * n_actions : (size_t)n_actions;
-    size_t smem = (((size_t)h->cfg.max_depth * 8 + 15) & ~size_t(15)) + n_acc * 12 + (((size_t)zs * n_actions * 4 + 15) & ~size_t(15)) + (size_t)ARR_HT * 8 + 16;
+    size_t smem = (((size_t)h->cfg.max_depth * 8 + 15) & ~size_t(15)) + n_acc * 12 + (((size_t)zs * n_actions * 4 + 15) & ~size_t(15)) + (size_t)ARR_HT * 16 + 32;
     if (smem < 512) smem = 512;                              // the belief update keeps 34 ints there
     h->search_smem = smem;
     CK(cudaFuncSetAttribute(pomcp_search_tab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

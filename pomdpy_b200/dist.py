@@ -64,9 +64,14 @@ class FusedMerge(object):
         self.buf.zero_()
         self.handle = symm_mem.rendezvous(self.buf, group)
         torch.cuda.synchronize()
-        dist.barrier(group)                              # every buffer is zero before anyone's kernel writes a flag
-        planner.set_peer_merge(self.world, self.rank, [int(p) for p in self.handle.buffer_ptrs])
-        self.planner = planner
+        self.planner, self.group = planner, group
+
+    def activate(self):
+        """Collective: call on every rank once all of them hold a FusedMerge (try_fused_merge checks that first)."""
+        import torch.distributed as dist
+        dist.barrier(self.group)                         # every buffer is zero before anyone's kernel writes a flag
+        self.planner.set_peer_merge(self.world, self.rank, [int(p) for p in self.handle.buffer_ptrs])
+        return self
 
 
 def try_fused_merge(planner):
@@ -82,7 +87,5 @@ def try_fused_merge(planner):
     flag = torch.tensor([ok], dtype=torch.int32, device="cuda")
     dist.all_reduce(flag, op=dist.ReduceOp.MIN)
     if int(flag.item()) == 0:
-        if fm is not None:
-            planner.set_peer_merge(1, 0, [])
         return None
-    return fm
+    return fm.activate()
