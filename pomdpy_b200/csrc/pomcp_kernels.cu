@@ -115,7 +115,7 @@ struct SimBuf {                        // per simulation-in-flight scratch, SoA 
     int32_t *path_node;                // [dcap][wmax]
     uint16_t *path_ar;                 // [dcap][wmax] action | obs_good << 5 | reward id << 8   (tabular: action | obs << 5)
     double *path_rew;                  // [dcap][wmax] tabular models: the step reward (null for RockSample)
-    int32_t *wl_node;                  // [wmax] worklist of nodes with arrivals in this level step
+    int32_t *wl_node;                  // [2][wmax] worklist of nodes with arrivals in this level step (set = step parity)
     uint32_t *wl_thr;                  // [wmax][32] cumulative action thresholds of worklist nodes with a kind-2 plan
     double *ro_sum;                    // [wmax] discounted reward sum of a rollout in progress
     uint8_t *ro_t;                     // [wmax] rollout steps done so far (rollouts advance in slices)
@@ -697,7 +697,8 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
             if (lane == 0) {
                 const unsigned long long s1 = gstep + 1;
                 p.t.arrive[root] = (s1 << 32) | (unsigned long long)(unsigned)w;
-                p.b.wl_node[0] = root; S->wl_count[(int)(s1 & 3ull)] = 1;
+                p.b.wl_node[(size_t)(s1 & 1ull) * p.wmax] = root; S->wl_count[(int)(s1 & 3ull)] = 1;
+                S->wl_count[(int)((s1 + 1) & 3ull)] = 0;             // the counter the first level step fills
             }
             warp_plan(p, root, (uint32_t)w, lane, A, 0);                 // known now: no extra phase
             if (lane == 0 && (uint32_t)w > SEQ_ALLOC_MAX) ++c_alloc;
@@ -715,6 +716,8 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
             ++gstep; ++lsteps;
             const int ring = (int)(gstep & 3ull), ring_next = (int)((gstep + 1) & 3ull);
             const unsigned long long stamp_next = (gstep + 1) << 32;
+            const int32_t *wl_cur = p.b.wl_node + (size_t)(gstep & 1ull) * p.wmax;
+            int32_t *wl_next = p.b.wl_node + (size_t)((gstep + 1) & 1ull) * p.wmax;
             // cnt arrivals at node Xn for the next level step: stamp the node and enter it in the worklist on its first
             // arrival (a plain L2 read first: a busy node is almost always stamped already), then one fire-and-forget add
             auto register_arrivals = [&](int Xn, uint32_t cnt) {
@@ -723,7 +726,7 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                     if (old < stamp_next) {
                         const int sl = atomicAdd(&S->wl_count[ring_next], 1);
                         DCHECK(S, sl < p.wmax, 25);
-                        p.b.wl_node[sl] = Xn;
+                        wl_next[sl] = Xn;
                     }
                 }
                 atomicAdd(&p.t.arrive[Xn], (unsigned long long)cnt);
@@ -732,7 +735,9 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
             if (gtid == 0 && lsteps <= 128) S->steplog[lsteps - 1][0] = (long long)(globaltimer_ns() - tmark);
             PHASE_MARK(1);
             const int nwl = *((volatile int32_t *)&S->wl_count[ring]);
-            if (gtid == 0) S->wl_count[ring_next] = 0;
+            // the counter of the level step after the next one is cleared a whole step ahead (blocks enter the expand
+            // phase, which fills ring_next, without another grid barrier); it was last read two steps ago
+            if (gtid == 0) S->wl_count[(int)((gstep + 2) & 3ull)] = 0;
             if (nwl == 0) break;
             // [allocate] one warp per worklist node computes the node's action plan for its arrivals: every warp
             // inspects 32 entries at once (strided by the warp count, so that the early, busy entries spread out)
@@ -740,7 +745,7 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
             for (int base = 0; base < nwl; base += nwarps * 32) {
                 const int e = base + lane * nwarps + vwarp;
                 int X = 0; uint32_t k = 0;
-                if (e < nwl) { X = p.b.wl_node[e]; k = (uint32_t)p.t.arrive[X]; }
+                if (e < nwl) { X = wl_cur[e]; k = (uint32_t)p.t.arrive[X]; }
                 unsigned todo = __ballot_sync(0xFFFFFFFFu, e < nwl);
                 while (todo) {
                     const int src = __ffs((int)todo) - 1;
@@ -957,8 +962,11 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                 // directly in the arena (a diverse warp gains nothing from hashing)
                 bool pending = act;
                 unsigned alone = 0u;                                     // lanes found to share their edge with nobody
+                // cheap test first: a warp whose neighbouring lanes rarely share an edge (a bushy tree) skips the rounds
+                const uint32_t nkey = __shfl_down_sync(0xFFFFFFFFu, key, 1);
+                const bool shared = __popc(__ballot_sync(0xFFFFFFFFu, act && key == nkey) & 0x7FFFFFFFu) >= 4;
 #pragma unroll
-                for (int round = 0; round < 3; ++round) {
+                for (int round = 0; round < 3 && shared; ++round) {
                     const unsigned todo = __ballot_sync(0xFFFFFFFFu, pending) & ~alone;
                     if (todo == 0u) break;
                     const int leader = __ffs((int)todo) - 1;
@@ -1452,7 +1460,7 @@ extern "C" int pomcp_create(const pomcp_config *cfg, int device, pomcp_handle **
     CK(cudaMalloc(&h->b.depth, wmax));
     CK(cudaMalloc(&h->b.path_node, wmax * dcap * sizeof(int32_t)));
     CK(cudaMalloc(&h->b.path_ar, wmax * dcap * sizeof(uint16_t)));
-    CK(cudaMalloc(&h->b.wl_node, wmax * sizeof(int32_t)));
+    CK(cudaMalloc(&h->b.wl_node, 2 * wmax * sizeof(int32_t)));
     CK(cudaMalloc(&h->b.wl_thr, wmax * 32 * sizeof(uint32_t)));
     CK(cudaMalloc(&h->b.ro_sum, wmax * sizeof(double)));
     CK(cudaMalloc(&h->b.ro_t, wmax));
