@@ -114,13 +114,14 @@ class POMCP(Solver):
         model = self.model
         # Generation schedule (simulations in flight): small budgets keep the waves narrow (quality first: at
         # n_sims = 500 widths up to 64 match the sequential planner's return, 128 starts to cost); large budgets use
-        # the throughput schedule of bench.py (first wave = 1/32 of a budget >= 2^19, 1/256 of a smaller one, x4 growth up to half of it; return at
-        # 1e6 simulations per move is insensitive to it, profiles/r01_schedule_sweep.txt).
+        # the throughput schedule of bench.py (first wave = 1/32 of the budget, x4 growth up to half of it: four
+        # generations; return at 1e5 and 1e6 simulations per move does not depend on the first width,
+        # profiles/r01_schedule_sweep.txt).
         if self.sims_per_rank <= 4096:
             auto = (max(1, min(1024, (self.sims_per_rank // 4 or 1) // 16)), 2, max(32, self.sims_per_rank // 4 or 1))
         else:
             wm = min(1 << 19, self.sims_per_rank // 2)
-            auto = (max(1, wm // (16 if self.sims_per_rank >= (1 << 19) else 128)), 4, wm)
+            auto = (max(1, wm // 16), 4, wm)
         w0 = int(getattr(model, "gen_w0", 0)) or auto[0]
         growth = int(getattr(model, "gen_growth", 0)) or auto[1]
         wmax = max(int(getattr(model, "gen_wmax", 0)) or auto[2], w0)
