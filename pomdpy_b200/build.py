@@ -6,7 +6,8 @@ HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpomcp_b200.so")
 SOURCES = ["pomcp_kernels.cu", "pomcp_refexact.cu", "vi_kernels.cu"]
-HEADERS = ["pomcp_device.cuh", os.path.join("..", "..", "include", "pomcp_b200.h"),
+HEADERS = ["pomcp_device.cuh", "pomcp_state.cuh", "pomcp_models.cuh", "pomcp_plan.cuh",
+           os.path.join("..", "..", "include", "pomcp_b200.h"),
            os.path.join("..", "..", "include", "vi_b200.h")]
 NVCC_FLAGS = ["-gencode", "arch=compute_100a,code=sm_100a", "-O3", "-lineinfo", "-fmad=false", "-std=c++17",
               "-shared", "-Xcompiler", "-fPIC"]

@@ -17,522 +17,9 @@
 #include "../../include/pomcp_b200.h"
 #include "pomcp_device.cuh"
 
-#define AS POMCP_AS
-
-// Bounds checks of the device code (compute-sanitizer is not available on the GPU pool): a -DPOMCP_CHECKS build
-// records the largest failing check code in DevState.check_failed; tests/test_gpu_debug_checks.py runs it.
-#ifdef POMCP_CHECKS
-#define DCHECK(S_, cond, code) do { if (!(cond)) atomicMax(&(S_)->check_failed, (code)); } while (0)
-#else
-#define DCHECK(S_, cond, code) do { } while (0)
-#endif
-// Section timers of the expand phase (-DPOMCP_TSEC diagnostic build only): per-thread clock64 deltas, summed over the
-// grid into steplog[127][0..7] at the end of the search.
-#ifdef POMCP_TSEC
-#define TSEC_DECL long long tsec_[8] = {0, 0, 0, 0, 0, 0, 0, 0}, tsec_prev_[8] = {0, 0, 0, 0, 0, 0, 0, 0}; long long tsec_t_ = 0, tsec_bk_ = 0
-#define TSEC_START() (tsec_t_ = clock64())
-#define TSEC(k) do { const long long n_ = clock64(); tsec_[k] += n_ - tsec_t_; tsec_t_ = n_; } while (0)
-#else
-#define TSEC_DECL
-#define TSEC_START() do { } while (0)
-#define TSEC(k) do { } while (0)
-#endif
-#define CHILD_LOCKED 0xFFFFFFFFu
-#define CHILD_VISITED 0x80000000u   // set on a child slot once a backup has passed through the child (N > 0)
-#define CHILD_ID(c) ((int)((c) & 0x7FFFFFFFu) - 1)
-#define SEARCH_THREADS 256
-#ifndef SEARCH_MIN_BLOCKS
-#define SEARCH_MIN_BLOCKS 4
-#endif
-#define ADV_THREADS 1024
-#define ADV_TRIES 4
-#define ROLL_SLICE 8            // rollout steps per slice while waiting at a barrier (even: Philox block pairs)
-#ifndef ARR_HT
-#define ARR_HT 1024            // per-block arrival table (shared memory): slots of {node id, arrivals in this level step}
-#endif
-#define ARR_PROBES 8
-#define PLAN_MASK 0            // kinds of a node's action plan (warp_plan)
-#define PLAN_PULLS 1
-#define PLAN_THRESHOLDS 2
-#define SEQ_ALLOC_MAX 16u      // arrivals <= this: exact virtual-pull allocation; more: water-filling
-#ifndef BISECT_ITERS
-#define BISECT_ITERS 14
-#endif
-
-// ---------------------------------------------------------------------------------------------------------
-// Device-resident state (one per handle).  Kernels read and write it without host round trips.
-// ---------------------------------------------------------------------------------------------------------
-struct DevState {
-    int32_t root;
-    int32_t node_count;
-    uint32_t actual, sampled;
-    int32_t n_bag, bag_sel;
-    int32_t wl_count[4];
-    int32_t stop;
-    uint32_t barrier;                  // arrival counter of grid_barrier (zeroed before each search)
-    int32_t check_failed, check_pad;
-    int32_t ro_cursor[2];              // work counters of the final rollout + backup phase (alternating per generation)
-    // root edge statistics as of the end of the last search / advance / plant (one copy serves pomcp_root_stats)
-    long long res_n[AS], res_q[AS];
-    uint32_t res_legal; int32_t res_valid;
-    // root edge statistics summed over the ranks of a root-parallel search (fused merge in the search kernel's tail)
-    long long mrg_n[AS], mrg_q[AS];
-    unsigned long long mrg_seq;        // sequence number of the merge that filled mrg_*; 0 = the exchange timed out
-    unsigned long long gstep;          // global level-step stamp, never reused
-    long long sims_done;               // simulations completed by the last search
-    long long counters[16];
-    long long phase_ns[8];            // device time per phase of the last search (thread 0's globaltimer)
-    // results of the last advance
-    int32_t adv_status, adv_accepted, adv_root_cell, adv_pad;
-    long long adv_tries;
-    // ---- profiling aid, not copied by the hot calls ----
-    long long steplog[128][8];        // last search, per level step: ns of [wait, allocate, wait, expand], worklist
-};
-#define DEVSTATE_HEAD (offsetof(DevState, steplog))
-
-struct Tree {                          // structure-of-arrays belief-tree arena
-    int32_t *n;                        // [cap][AS]   visit_count of edge (node, action)
-    long long *qfix;                   // [cap][AS]   sum of q in 2^-24 fixed point
-    uint32_t *child;                   // [cap][AS][ZS] child id + 1 keyed (action, observation), bit 31 = has statistics;
-                                       //              0 = none.  ZS = 2 for RockSample (obs_good)
-    uint32_t *legal;                   // [cap]       legal-action mask (fixed at creation)
-    int32_t *cell;                     // [cap]       tag of the node: robot cell (RockSample), 0 (tabular)
-    unsigned long long *arrive;        // [cap]       (stamp << 32) | arrivals in the current level step
-    uint4 *plan;                       // [cap][2]    action plan of the node for the current level step:
-                                       //             {kind << 16 | arrivals << 8 | last action, worklist slot, -, -},
-                                       //             {action mask (kind 0) | <= 16 pull bytes (kind 1)}; kind 2: thresholds in wl_thr[slot]
-    double *chance;                    // [cap][24]   --preferred_actions: chance_good per rock (null otherwise)
-    int16_t *good;                     // [cap][24]   --preferred_actions: goodness number per rock
-    const double *prob;                // [cells][n_rocks] sensor correctness probability
-};
-
-struct SimBuf {                        // per simulation-in-flight scratch, SoA over the generation
-    uint32_t *state;                   // packed state cell | rocks << 8
-    int32_t *node;                     // current node, or child-slot index when `pending`
-    uint8_t *flag;                     // status: 0 descending, 1 leaf (rollout pending / in progress), 2 done without rollout,
-                                       //         3 rollout finished
-    uint8_t *depth;                    // path entries recorded
-    int32_t *path_node;                // [dcap][wmax]
-    uint16_t *path_ar;                 // [dcap][wmax] action | obs_good << 5 | reward id << 8   (tabular: action | obs << 5)
-    double *path_rew;                  // [dcap][wmax] tabular models: the step reward (null for RockSample)
-    int32_t *wl_node;                  // [2][wmax] worklist of nodes with arrivals in this level step (set = step parity)
-    uint32_t *wl_thr;                  // [wmax][32] cumulative action thresholds of worklist nodes with a kind-2 plan
-    double *ro_sum;                    // [wmax] discounted reward sum of a rollout in progress
-    uint8_t *ro_t;                     // [wmax] rollout steps done so far (rollouts advance in slices)
-};
-
-struct SearchParams {
-    DevState *S;
-    const ModelHeader *model;
-    const uint64_t *thr53;
-    TabHeader tab;                     // tabular models (KIND 1); unused by RockSample
-    TabTables tt;
-    Tree t;
-    SimBuf b;
-    const uint32_t *bag[2];
-    long long n_sims;
-    uint32_t sim_offset, move, key0, key1;
-    uint32_t ks[20];                   // Philox key schedule: ks[2r], ks[2r+1] = (key0 + r*0x9E3779B9, key1 + r*0xBB67AE85)
-    int32_t w0, growth, wmax, max_depth, dcap, n_thr;
-    long long node_cap;
-    double ucb_c, discount;
-    unsigned long long timeout_ns;     // 0 = no wall-clock guard; measured from kernel start
-    // root-parallel merge over NVLink peer memory (world <= 8 GPUs of one box): every rank's exchange buffer, mapped
-    // into this process; layout MERGE_* below
-    unsigned long long peer_buf[POMCP_MAX_PEERS];
-    int32_t world, rank;
-    unsigned long long merge_seq;
-    int32_t pref_rollout, pad_pr;      // --preferred_actions with preferred rollouts (RockSample)
-};
-
-// Exchange buffer of one rank (int64 words): slots[2][POMCP_MAX_PEERS][64] then flags[2][POMCP_MAX_PEERS].  Set
-// `seq & 1` is used by merge number seq, so a peer that is already one search ahead writes the other set.
-#define MERGE_SLOT_WORDS (2 * POMCP_MAX_PEERS * 64)
-#define MERGE_WORDS (MERGE_SLOT_WORDS + 2 * POMCP_MAX_PEERS)
-
-// ---------------------------------------------------------------------------------------------------------
-// Model policies.  The planner kernels are templates over KIND: 0 = RockSample (tables staged in shared memory, the
-// reference's flagship and the benchmark), 1 = tabular POMDP (tables in global memory).  A policy provides the
-// generative step, the action set of a node tag and the rollout inner loop; everything else is model-agnostic.
-// ---------------------------------------------------------------------------------------------------------
-struct StepOut { uint32_t next, tag; int obs, rew, terminal; double reward; };
-
-template <int KIND> struct Mdl;
-
-template <> struct Mdl<0> {
-    struct Ctx { SmemModel M; uint32_t actual, sampled; };
-    static __device__ __forceinline__ size_t stage(unsigned char *smem, const ModelHeader *gm, const uint64_t *gthr,
-                                                   int n_thr, const TabHeader &, const TabTables &, Ctx &c)
-    {   // stage the model tables into shared memory; returns the first free byte offset (16-byte aligned)
-        static_assert(sizeof(ModelHeader) % 16 == 0, "ModelHeader is staged in 16-byte pieces");
-        const int nw = (int)(sizeof(ModelHeader) / 16);
-        uint4 *dst = reinterpret_cast<uint4 *>(smem);
-        const uint4 *src = reinterpret_cast<const uint4 *>(gm);
-        for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
-        size_t off = (sizeof(ModelHeader) + 15) & ~size_t(15);
-        uint64_t *thr = reinterpret_cast<uint64_t *>(smem + off);
-        for (int i = threadIdx.x; i < n_thr; i += blockDim.x) thr[i] = gthr[i];
-        off += ((size_t)n_thr * 8 + 15) & ~size_t(15);
-        c.M.hdr = reinterpret_cast<const ModelHeader *>(smem);
-        c.M.thr53 = thr;
-        return off;
-    }
-    static __device__ __forceinline__ int n_actions(const Ctx &c, const ModelHeader *gm) { return gm->n_actions; }
-    static __device__ __forceinline__ int zs(const Ctx &) { return 2; }
-    static __device__ __forceinline__ bool stage_d1(const Ctx &) { return true; }
-    static __device__ __forceinline__ uint32_t state_tag(uint32_t st) { return st & 0xFFu; }
-    static __device__ __forceinline__ uint32_t tag_legal(const Ctx &c, uint32_t tag) { return c.M.hdr->legal[tag]; }
-    static __device__ __forceinline__ bool tag_ok(const Ctx &c, uint32_t tag) { return tag < (uint32_t)c.M.hdr->n_cells; }
-    static __device__ __forceinline__ StepOut step(const Ctx &c, uint32_t st, int a, uint32_t wy, uint32_t wz)
-    {
-        const StepResult sr = rs_step(c.M, st & 0xFFu, st >> 8, a, u53_of(wy, wz), c.actual, c.sampled);
-        return StepOut{sr.cell | (sr.rocks << 8), sr.cell, sr.good, sr.rew, sr.terminal, 0.0};
-    }
-    static __device__ __forceinline__ uint16_t path_code(int a, const StepOut &o)
-    { return (uint16_t)(a | (o.obs << 5) | (o.rew << 8)); }
-    static __device__ __forceinline__ int path_obs(uint32_t ar) { return (int)((ar >> 5) & 1u); }
-    static __device__ __forceinline__ double path_reward(const Ctx &c, uint32_t ar, const double *) { return c.M.hdr->rew[ar >> 8]; }
-    // Rollout steps t .. t_end-1 from packed state st (uniform legal actions); true when the episode ended.
-    // One Philox block per two steps: (x, y) then (z, w); word 0 picks the action, word 1 is the top 32 bits of the
-    // 53-bit sensor uniform.
-    static __device__ __forceinline__ bool rollout(const Ctx &c, DevState *S, uint32_t sim, uint32_t move,
-                                                   const uint32_t *ks, int depth, const double *disc, uint32_t &st, int &t,
-                                                   int t_end, double &sum)
-    {
-        const ModelHeader *H = c.M.hdr;
-        uint32_t cell = st & 0xFFu, rocks = st >> 8;
-        const uint32_t actual = c.actual, sampled = c.sampled;
-        bool finished = false;
-        // one step with the draws (w0, w1); true when the episode ended
-        auto step = [&](uint32_t w0, uint32_t w1) -> bool {
-            const uint32_t mask = H->legal[cell];
-            const int a = nth_legal(H, mask, randbelow32(w0, (uint32_t)__popc(mask)));
-            DCHECK(S, a >= 0 && a < H->n_actions && cell < (uint32_t)H->n_cells, 41);
-            if (a < 4) {
-                cell = (uint32_t)((int)cell + H->delta[a]);
-                if (H->cell[cell] == POMCP_CELL_GOAL) { sum += H->rew[REW_EXIT] * disc[t]; return true; }
-            } else if (a == 4) {
-                const int code = H->cell[cell];
-                const int rew = (((actual & rocks) >> code) & 1u) ? REW_GOOD : REW_BAD;
-                rocks &= ~(1u << code);
-                sum += H->rew[rew] * disc[t];
-            } else {
-                const int k = a - 5;
-                if (!((sampled >> k) & 1u)) {
-                    const uint32_t truth = (actual >> k) & 1u;
-                    const uint32_t correct = ((uint64_t)w1 << 21) <= c.M.thr53[cell * H->n_rocks + k];
-                    const uint32_t good = correct ? truth : (truth ^ 1u);
-                    rocks = (rocks & ~(1u << k)) | (good << k);
-                }
-            }
-            return false;
-        };
-        // t is even on entry (slices are even, a finished rollout is never resumed): two steps per Philox block
-        while (t < t_end) {
-            const Philox4 r = philox4x32_10_ks((uint32_t)(depth + 1 + (t >> 1)), sim, move, DOM_SIM, ks);
-            if (step(r.x, r.y)) { ++t; finished = true; break; }
-            if (++t >= t_end) break;                                 // odd horizon
-            if (step(r.z, r.w)) { ++t; finished = true; break; }
-            ++t;
-        }
-        st = cell | (rocks << 8);
-        return finished;
-    }
-    // Preferred-action rollout: the rollout carries the rock statistics of its own history -- the
-    // leaf's, updated with every (action, observation) it generates (rock_position_history.py:96-137) -- and draws
-    // uniformly from generate_smart_actions (:170-234) instead of the legal set.  ch / gd: the statistics after the
-    // last tree step; mask: the smart-action set there.  Runs to the end (no slices).
-    struct PrefOut { uint32_t st; int t; double sum; int finished; };
-    static __device__ __noinline__ PrefOut rollout_preferred(SmemModel M, uint32_t actual, uint32_t sampled,
-                                                             const double *prob, const double *leaf_chance,
-                                                             const int16_t *leaf_good, int leaf_cell, int leaf_action,
-                                                             int leaf_obs, uint32_t sim, uint32_t move, uint32_t key0,
-                                                             uint32_t key1, int depth, const double *disc, uint32_t st,
-                                                             int t, int t_end, double sum)
-    {   // everything by value: a reference to the caller's locals (or to the kernel parameters) would push them into
-        // local memory on the hot path as well
-        const ModelHeader *H = M.hdr;
-        double ch[POMCP_RS]; int16_t gd[POMCP_RS];
-        uint32_t mask = child_smart_mask(H, prob, leaf_chance, leaf_good, ch, gd, leaf_cell, leaf_action, leaf_obs,
-                                         (int)(st & 0xFFu));
-        Philox4 r{0u, 0u, 0u, 0u};
-        for (; t < t_end; ++t) {
-            uint32_t w0, w1;
-            if ((t & 1) == 0) {
-                r = philox4x32_10((uint32_t)(depth + 1 + (t >> 1)), sim, move, DOM_SIM, key0, key1);
-                w0 = r.x; w1 = r.y;
-            } else { w0 = r.z; w1 = r.w; }
-            const int a = nth_bit(mask, randbelow32(w0, (uint32_t)__popc(mask)));
-            const StepResult sr = rs_step(M, st & 0xFFu, st >> 8, a, (uint64_t)w1 << 21, actual, sampled);
-            const double rew = H->rew[sr.rew];
-            if (rew != 0.0) sum += rew * disc[t];
-            mask = child_smart_mask(H, prob, ch, gd, ch, gd, (int)(st & 0xFFu), a, sr.good, (int)sr.cell);
-            st = sr.cell | (sr.rocks << 8);
-            if (sr.terminal) return PrefOut{st, t + 1, sum, 1};
-        }
-        return PrefOut{st, t, sum, 0};
-    }
-};
-
-template <> struct Mdl<1> {
-    struct Ctx { TabHeader h; TabTables t; };
-    static __device__ __forceinline__ size_t stage(unsigned char *, const ModelHeader *, const uint64_t *, int,
-                                                   const TabHeader &h, const TabTables &t, Ctx &c)
-    { c.h = h; c.t = t; return 0; }
-    static __device__ __forceinline__ int n_actions(const Ctx &c, const ModelHeader *) { return c.h.A; }
-    static __device__ __forceinline__ int zs(const Ctx &c) { return c.h.ZS; }
-    static __device__ __forceinline__ bool stage_d1(const Ctx &c) { return c.h.stage_d1 != 0; }
-    static __device__ __forceinline__ uint32_t state_tag(uint32_t) { return 0u; }
-    static __device__ __forceinline__ uint32_t tag_legal(const Ctx &c, uint32_t)
-    { return c.h.A >= 32 ? 0xFFFFFFFFu : ((1u << c.h.A) - 1u); }
-    static __device__ __forceinline__ bool tag_ok(const Ctx &, uint32_t tag) { return tag == 0u; }
-    static __device__ __forceinline__ StepOut step(const Ctx &c, uint32_t st, int a, uint32_t wy, uint32_t wz)
-    {
-        const size_t row = (size_t)a * c.h.S + st;
-        const int ns = tab_sample(c.t.Tc + row * c.h.S, c.h.S, wy);
-        const int ob = tab_sample(c.t.Oc + ((size_t)a * c.h.S + ns) * c.h.Z, c.h.Z, wz);
-        const int term = (int)((c.h.term_action_mask >> a) & 1u) | (int)__ldg(c.t.term_state + ns);
-        return StepOut{(uint32_t)ns, 0u, ob, 0, term, __ldg(c.t.R + row)};
-    }
-    static __device__ __forceinline__ uint16_t path_code(int a, const StepOut &o) { return (uint16_t)(a | (o.obs << 5)); }
-    static __device__ __forceinline__ int path_obs(uint32_t ar) { return (int)(ar >> 5); }
-    static __device__ __forceinline__ double path_reward(const Ctx &, uint32_t, const double *rew) { return *rew; }
-    // word 0 picks the action (all actions are legal), word 1 the next state; observations are not drawn
-    static __device__ __forceinline__ bool rollout(const Ctx &c, DevState *, uint32_t sim, uint32_t move,
-                                                   const uint32_t *ks, int depth, const double *disc, uint32_t &st, int &t,
-                                                   int t_end, double &sum)
-    {
-        Philox4 r{0u, 0u, 0u, 0u};
-        for (; t < t_end; ++t) {
-            uint32_t w0, w1;
-            if ((t & 1) == 0) {
-                r = philox4x32_10_ks((uint32_t)(depth + 1 + (t >> 1)), sim, move, DOM_SIM, ks);
-                w0 = r.x; w1 = r.y;
-            } else { w0 = r.z; w1 = r.w; }
-            const int a = (int)randbelow32(w0, (uint32_t)c.h.A);
-            const size_t row = (size_t)a * c.h.S + st;
-            const double rew = __ldg(c.t.R + row);
-            st = (uint32_t)tab_sample(c.t.Tc + row * c.h.S, c.h.S, w1);
-            if (rew != 0.0) sum += rew * disc[t];
-            if (((c.h.term_action_mask >> a) & 1u) | __ldg(c.t.term_state + st)) { ++t; return true; }
-        }
-        return false;
-    }
-};
-
-// Grid-wide barrier of the cooperative search kernel: one arrival counter that only grows (zeroed by the host before
-// each launch); block b has passed `epoch` barriers, so barrier e completes when the counter reaches (e+1)*blocks.
-// Waiting threads back off with nanosleep instead of hammering L2, which matters in the phases where a handful of
-// warps work and ~600 blocks wait.  The cooperative launch guarantees that all blocks are resident.
-__device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int nblocks, unsigned int &epoch)
-{
-    __syncthreads();
-    ++epoch;
-    if (threadIdx.x == 0) {
-        __threadfence();                                   // release this block's writes
-        atomicAdd(counter, 1u);
-        const unsigned int target = epoch * nblocks;
-        while (*((volatile unsigned int *)counter) < target) __nanosleep(32);
-        __threadfence();                                   // acquire (also invalidates this SM's L1)
-    }
-    __syncthreads();
-}
-
-__device__ __forceinline__ unsigned long long globaltimer_ns()
-{
-    unsigned long long t;
-    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
-    return t;
-}
-
-// mean return of an edge in single precision (the UCB arithmetic is fp32; sums stay exact integers)
-__device__ __forceinline__ float edge_mean(long long qfix, int n)
-{
-    return ((float)qfix * (1.0f / 16777216.0f)) / (float)n;
-}
-
-// Publish the root's edge statistics in the state block (threads 0..AS-1 of one block): pomcp_root_stats is then a
-// single device-to-host copy.
-__device__ __forceinline__ void publish_root(DevState *S, const Tree &t, int root, int tid)
-{
-    if (tid < AS) {
-        S->res_n[tid] = t.n[(size_t)root * AS + tid];
-        S->res_q[tid] = t.qfix[(size_t)root * AS + tid];
-    }
-    if (tid == 0) { S->res_legal = t.legal[root]; S->res_valid = 1; }
-}
-
-// ---------------------------------------------------------------------------------------------------------
-// Batch-UCB allocation for a node with k >= 2 simultaneous arrivals (warp-cooperative, lane = action).
-// Water-filling of k pulls over the UCB1 indices mean + c*sqrt(ln(N+1)/n); output: 32-bit cumulative thresholds.
-// ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_allocation(const SearchParams &p, int X, uint32_t k, int lane, int A,
-                                                uint32_t *thr_out, int slot)
-{
-    const unsigned full = 0xFFFFFFFFu;
-    const uint32_t mask = p.t.legal[X];
-    const bool legal = lane < A && ((mask >> lane) & 1u);
-    const int n = legal ? p.t.n[(size_t)X * AS + lane] : 0;
-    const long long qf = legal ? p.t.qfix[(size_t)X * AS + lane] : 0;
-    int N = n;
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) N += __shfl_xor_sync(full, N, off);
-    const int untried = __popc(__ballot_sync(full, legal && n == 0));
-    const int nlegal = __popc(__ballot_sync(full, legal));
-    const float cf = (float)p.ucb_c;
-    float v = 0.0f;
-    if (N == 0) v = legal ? 1.0f : 0.0f;
-    else if ((uint32_t)untried >= k) v = (legal && n == 0) ? 1.0f : 0.0f;
-    else {
-        const float L = det_logf_u32((uint32_t)N + 1u);
-        const float c2L = (cf * cf) * L;
-        const float qbar = legal ? (n == 0 ? 0.0f : edge_mean(qf, n)) : -INFINITY;
-        float qmax = qbar;
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) qmax = fmaxf(qmax, __shfl_xor_sync(full, qmax, off));
-        const unsigned best_lanes = __ballot_sync(full, legal && qbar == qmax);
-        const int nbest = __shfl_sync(full, n, __ffs((int)best_lanes) - 1);
-        if (!(c2L > 0.0f)) v = (legal && qbar == qmax) ? 1.0f : 0.0f;
-        else {
-            const float kd = (float)k;
-            float lo = qmax + 0.999f * sqrtf(c2L / (kd + (float)nbest));
-            float hi = qmax + 1.001f * sqrtf((c2L * (float)nlegal) / kd) + 1.0f;
-            for (int it = 0; it <= BISECT_ITERS; ++it) {
-                const float mid = it < BISECT_ITERS ? 0.5f * (lo + hi) : lo;
-                float t = 0.0f;
-                if (legal) {
-                    const float d = mid - qbar;
-                    const float mm = c2L / (d * d);
-                    if (n == 0) t = mm > 1.0f ? mm : 1.0f;
-                    else { const float e = mm - (float)n; t = e > 0.0f ? e : 0.0f; }
-                }
-                if (it == BISECT_ITERS) { v = t; break; }
-                float s = t;
-#pragma unroll
-                for (int off = 16; off >= 1; off >>= 1) s = s + __shfl_xor_sync(full, s, off);
-                if (s >= kd) lo = mid; else hi = mid;
-            }
-        }
-    }
-    float x = v;                                    // inclusive scan, Hillis-Steele order
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const float y = __shfl_up_sync(full, x, off);
-        if (lane >= off) x = x + y;
-    }
-    const float V = __shfl_sync(full, x, 31);
-    const float f = (x / V) * 4294967296.0f;
-    // running maximum over the actions with positive weight: non-decreasing thresholds, and an action without
-    // weight repeats its predecessor's (prefix sums of different lanes round differently), so it is never drawn
-    uint32_t th = v > 0.0f ? (f >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)f) : 0u;
-#pragma unroll
-    for (int off = 1; off < 32; off <<= 1) {
-        const uint32_t y = __shfl_up_sync(full, th, off);
-        if (lane >= off && y > th) th = y;
-    }
-    thr_out[lane] = th;
-    const unsigned pos = __ballot_sync(full, v > 0.0f);
-    // every G-th threshold goes into the node's plan record: a simulation finds its group of G actions there and
-    // needs one more (16-byte aligned row) access for the thresholds inside the group
-    const int G = (A + 5) / 6;
-    uint32_t cg[6];
-#pragma unroll
-    for (int g = 0; g < 6; ++g) { const int src = g * G + G - 1; cg[g] = __shfl_sync(full, th, src < 31 ? src : 31); }
-    if (lane == 0) {
-        p.t.plan[(size_t)X * 2] = make_uint4((uint32_t)((31 - __clz((int)pos)) | (PLAN_THRESHOLDS << 16)), (uint32_t)slot, cg[4], cg[5]);
-        p.t.plan[(size_t)X * 2 + 1] = make_uint4(cg[0], cg[1], cg[2], cg[3]);
-    }
-}
-
-// Action plan of a node with k <= SEQ_ALLOC_MAX arrivals (warp-cooperative, lane = action; statistics are read-only
-// within a generation, so the plan is computed once per node and level step instead of once per simulation).
-//   kind 0  uniform draw over an action mask:  at least k untried actions (n == 0 scores +inf, pomcp.py:64-65), or
-//           k == 1: the UCB1 arg-max set (action_selectors.py:6-37; the draw breaks ties), or c = 0: the best means
-//   kind 1  the k arrivals share the virtual-pull sequence "pull j takes the UCB1 arg-max (lowest id on ties) given
-//           the statistics plus the virtual visits of pulls 0..j-1"; a simulation takes pull j = floor(x0*k/2^32)
-__device__ __forceinline__ void warp_plan_few(const SearchParams &p, int X, uint32_t k, int lane, int A, int slot)
-{
-    const unsigned full = 0xFFFFFFFFu;
-    const uint32_t mask = p.t.legal[X];
-    const bool legal = lane < A && ((mask >> lane) & 1u);
-    const int n = legal ? p.t.n[(size_t)X * AS + lane] : 0;
-    const long long qf = legal ? p.t.qfix[(size_t)X * AS + lane] : 0;
-    int N = n;
-#pragma unroll
-    for (int off = 16; off >= 1; off >>= 1) N += __shfl_xor_sync(full, N, off);
-    const unsigned untried = __ballot_sync(full, legal && n == 0);
-    if ((uint32_t)__popc(untried) >= k) {
-        if (lane == 0) { p.t.plan[(size_t)X * 2] = make_uint4(PLAN_MASK << 16, (uint32_t)slot, 0u, 0u); p.t.plan[(size_t)X * 2 + 1].x = untried; }
-        return;
-    }
-    const float L = det_logf_u32((uint32_t)N + 1u);
-    const float cf = (float)p.ucb_c;
-    if (k == 1) {                                                    // no untried action here: every legal n > 0
-        const float sc = legal ? edge_mean(qf, n) + cf * sqrtf(L / (float)n) : -INFINITY;
-        float best = sc;
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) best = fmaxf(best, __shfl_xor_sync(full, best, off));
-        const unsigned ties = __ballot_sync(full, legal && sc == best);
-        if (lane == 0) { p.t.plan[(size_t)X * 2] = make_uint4(PLAN_MASK << 16, (uint32_t)slot, 0u, 0u); p.t.plan[(size_t)X * 2 + 1].x = ties; }
-        return;
-    }
-    const float c2L = (cf * cf) * L;
-    const float qb = n == 0 ? 0.0f : edge_mean(qf, n);
-    if (!(c2L > 0.0f)) {
-        float qmax = legal ? qb : -INFINITY;
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) qmax = fmaxf(qmax, __shfl_xor_sync(full, qmax, off));
-        const unsigned qties = __ballot_sync(full, legal && qb == qmax);
-        if (lane == 0) { p.t.plan[(size_t)X * 2] = make_uint4(PLAN_MASK << 16, (uint32_t)slot, 0u, 0u); p.t.plan[(size_t)X * 2 + 1].x = qties; }
-        return;
-    }
-    float sc = legal ? (n == 0 ? INFINITY : qb + cf * sqrtf(L / (float)n)) : -INFINITY;
-    int va = 0;
-    uint32_t seq[4] = {0u, 0u, 0u, 0u};
-    for (uint32_t pull = 0; pull < k; ++pull) {
-        float bs = sc;
-#pragma unroll
-        for (int off = 16; off >= 1; off >>= 1) bs = fmaxf(bs, __shfl_xor_sync(full, bs, off));
-        const int w = __ffs((int)__ballot_sync(full, sc == bs)) - 1;
-        seq[pull >> 2] |= (uint32_t)w << (8 * (pull & 3u));
-        if (lane == w) { va += 1; sc = qb + cf * sqrtf(L / (float)(n + va)); }
-    }
-    if (lane == 0) {
-        p.t.plan[(size_t)X * 2] = make_uint4((PLAN_PULLS << 16) | (k << 8), (uint32_t)slot, 0u, 0u);
-        p.t.plan[(size_t)X * 2 + 1] = make_uint4(seq[0], seq[1], seq[2], seq[3]);
-    }
-}
-
-// Plan of node X for its k arrivals of this level step (one warp).
-__device__ __forceinline__ void warp_plan(const SearchParams &p, int X, uint32_t k, int lane, int A, int slot)
-{
-    if (k > SEQ_ALLOC_MAX) warp_allocation(p, X, k, lane, A, p.b.wl_thr + (size_t)slot * 32, slot);
-    else warp_plan_few(p, X, k, lane, A, slot);
-}
-
-// The action of one simulation from its node's plan and its 32-bit draw x0.
-__device__ __forceinline__ int plan_action(const SearchParams &p, int X, uint32_t x0, int A)
-{
-    const uint4 head = p.t.plan[(size_t)X * 2], data = p.t.plan[(size_t)X * 2 + 1];
-    const int meta = (int)head.x, kind = meta >> 16;
-    if (kind == PLAN_THRESHOLDS) {                       // first action whose threshold exceeds x0
-        const int G = (A + 5) / 6;                       // thresholds are non-decreasing: find the group of G ...
-        const int g = x0 < data.x ? 0 : x0 < data.y ? 1 : x0 < data.z ? 2 : x0 < data.w ? 3 : x0 < head.z ? 4 :
-                      x0 < head.w ? 5 : 6;
-        if (g == 6) return meta & 255;
-        const uint32_t *thr = p.b.wl_thr + (size_t)head.y * 32 + g * G;
-        uint32_t tq[6];
-#pragma unroll
-        for (int q = 0; q < 6; ++q) tq[q] = (q < G && g * G + q < 32) ? thr[q] : 0xFFFFFFFFu;   // ... then the action
-#pragma unroll
-        for (int q = 0; q < 6; ++q) if (x0 < tq[q]) return g * G + q;
-        return meta & 255;
-    }
-    if (kind == PLAN_MASK) return nth_bit(data.x, randbelow32(x0, (uint32_t)__popc(data.x)));
-    const uint32_t j = randbelow32(x0, (uint32_t)(meta >> 8) & 255u);
-    const uint32_t word = (j >> 2) == 0 ? data.x : (j >> 2) == 1 ? data.y : (j >> 2) == 2 ? data.z : data.w;
-    return (int)((word >> (8 * (j & 3u))) & 255u);
-}
+#include "pomcp_state.cuh"
+#include "pomcp_models.cuh"
+#include "pomcp_plan.cuh"
 
 // ---------------------------------------------------------------------------------------------------------
 // K1: the search.  One persistent cooperative kernel per move; simulations advance in generations.  Within a

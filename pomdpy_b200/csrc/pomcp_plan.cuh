@@ -1,0 +1,218 @@
+// pomcp_plan.cuh -- grid barrier and small helpers, and the per-node action plans of a level step: batch-UCB
+// allocation (many arrivals), virtual-pull sequence (few), and the lookup a simulation makes.
+#pragma once
+#include "pomcp_state.cuh"
+
+// Grid-wide barrier of the cooperative search kernel: one arrival counter that only grows (zeroed by the host before
+// each launch); block b has passed `epoch` barriers, so barrier e completes when the counter reaches (e+1)*blocks.
+// Waiting threads back off with nanosleep instead of hammering L2, which matters in the phases where a handful of
+// warps work and ~600 blocks wait.  The cooperative launch guarantees that all blocks are resident.
+__device__ __forceinline__ void grid_barrier(unsigned int *counter, unsigned int nblocks, unsigned int &epoch)
+{
+    __syncthreads();
+    ++epoch;
+    if (threadIdx.x == 0) {
+        __threadfence();                                   // release this block's writes
+        atomicAdd(counter, 1u);
+        const unsigned int target = epoch * nblocks;
+        while (*((volatile unsigned int *)counter) < target) __nanosleep(32);
+        __threadfence();                                   // acquire (also invalidates this SM's L1)
+    }
+    __syncthreads();
+}
+
+__device__ __forceinline__ unsigned long long globaltimer_ns()
+{
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %globaltimer;" : "=l"(t));
+    return t;
+}
+
+// mean return of an edge in single precision (the UCB arithmetic is fp32; sums stay exact integers)
+__device__ __forceinline__ float edge_mean(long long qfix, int n)
+{
+    return ((float)qfix * (1.0f / 16777216.0f)) / (float)n;
+}
+
+// Publish the root's edge statistics in the state block (threads 0..AS-1 of one block): pomcp_root_stats is then a
+// single device-to-host copy.
+__device__ __forceinline__ void publish_root(DevState *S, const Tree &t, int root, int tid)
+{
+    if (tid < AS) {
+        S->res_n[tid] = t.n[(size_t)root * AS + tid];
+        S->res_q[tid] = t.qfix[(size_t)root * AS + tid];
+    }
+    if (tid == 0) { S->res_legal = t.legal[root]; S->res_valid = 1; }
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// Batch-UCB allocation for a node with k >= 2 simultaneous arrivals (warp-cooperative, lane = action).
+// Water-filling of k pulls over the UCB1 indices mean + c*sqrt(ln(N+1)/n); output: 32-bit cumulative thresholds.
+// ---------------------------------------------------------------------------------------------------------
+__device__ __forceinline__ void warp_allocation(const SearchParams &p, int X, uint32_t k, int lane, int A,
+                                                uint32_t *thr_out, int slot)
+{
+    const unsigned full = 0xFFFFFFFFu;
+    const uint32_t mask = p.t.legal[X];
+    const bool legal = lane < A && ((mask >> lane) & 1u);
+    const int n = legal ? p.t.n[(size_t)X * AS + lane] : 0;
+    const long long qf = legal ? p.t.qfix[(size_t)X * AS + lane] : 0;
+    int N = n;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) N += __shfl_xor_sync(full, N, off);
+    const int untried = __popc(__ballot_sync(full, legal && n == 0));
+    const int nlegal = __popc(__ballot_sync(full, legal));
+    const float cf = (float)p.ucb_c;
+    float v = 0.0f;
+    if (N == 0) v = legal ? 1.0f : 0.0f;
+    else if ((uint32_t)untried >= k) v = (legal && n == 0) ? 1.0f : 0.0f;
+    else {
+        const float L = det_logf_u32((uint32_t)N + 1u);
+        const float c2L = (cf * cf) * L;
+        const float qbar = legal ? (n == 0 ? 0.0f : edge_mean(qf, n)) : -INFINITY;
+        float qmax = qbar;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) qmax = fmaxf(qmax, __shfl_xor_sync(full, qmax, off));
+        const unsigned best_lanes = __ballot_sync(full, legal && qbar == qmax);
+        const int nbest = __shfl_sync(full, n, __ffs((int)best_lanes) - 1);
+        if (!(c2L > 0.0f)) v = (legal && qbar == qmax) ? 1.0f : 0.0f;
+        else {
+            const float kd = (float)k;
+            float lo = qmax + 0.999f * sqrtf(c2L / (kd + (float)nbest));
+            float hi = qmax + 1.001f * sqrtf((c2L * (float)nlegal) / kd) + 1.0f;
+            for (int it = 0; it <= BISECT_ITERS; ++it) {
+                const float mid = it < BISECT_ITERS ? 0.5f * (lo + hi) : lo;
+                float t = 0.0f;
+                if (legal) {
+                    const float d = mid - qbar;
+                    const float mm = c2L / (d * d);
+                    if (n == 0) t = mm > 1.0f ? mm : 1.0f;
+                    else { const float e = mm - (float)n; t = e > 0.0f ? e : 0.0f; }
+                }
+                if (it == BISECT_ITERS) { v = t; break; }
+                float s = t;
+#pragma unroll
+                for (int off = 16; off >= 1; off >>= 1) s = s + __shfl_xor_sync(full, s, off);
+                if (s >= kd) lo = mid; else hi = mid;
+            }
+        }
+    }
+    float x = v;                                    // inclusive scan, Hillis-Steele order
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const float y = __shfl_up_sync(full, x, off);
+        if (lane >= off) x = x + y;
+    }
+    const float V = __shfl_sync(full, x, 31);
+    const float f = (x / V) * 4294967296.0f;
+    // running maximum over the actions with positive weight: non-decreasing thresholds, and an action without
+    // weight repeats its predecessor's (prefix sums of different lanes round differently), so it is never drawn
+    uint32_t th = v > 0.0f ? (f >= 4294967296.0f ? 0xFFFFFFFFu : (uint32_t)f) : 0u;
+#pragma unroll
+    for (int off = 1; off < 32; off <<= 1) {
+        const uint32_t y = __shfl_up_sync(full, th, off);
+        if (lane >= off && y > th) th = y;
+    }
+    thr_out[lane] = th;
+    const unsigned pos = __ballot_sync(full, v > 0.0f);
+    // every G-th threshold goes into the node's plan record: a simulation finds its group of G actions there and
+    // needs one more (16-byte aligned row) access for the thresholds inside the group
+    const int G = (A + 5) / 6;
+    uint32_t cg[6];
+#pragma unroll
+    for (int g = 0; g < 6; ++g) { const int src = g * G + G - 1; cg[g] = __shfl_sync(full, th, src < 31 ? src : 31); }
+    if (lane == 0) {
+        p.t.plan[(size_t)X * 2] = make_uint4((uint32_t)((31 - __clz((int)pos)) | (PLAN_THRESHOLDS << 16)), (uint32_t)slot, cg[4], cg[5]);
+        p.t.plan[(size_t)X * 2 + 1] = make_uint4(cg[0], cg[1], cg[2], cg[3]);
+    }
+}
+
+// Action plan of a node with k <= SEQ_ALLOC_MAX arrivals (warp-cooperative, lane = action; statistics are read-only
+// within a generation, so the plan is computed once per node and level step instead of once per simulation).
+//   kind 0  uniform draw over an action mask:  at least k untried actions (n == 0 scores +inf, pomcp.py:64-65), or
+//           k == 1: the UCB1 arg-max set (action_selectors.py:6-37; the draw breaks ties), or c = 0: the best means
+//   kind 1  the k arrivals share the virtual-pull sequence "pull j takes the UCB1 arg-max (lowest id on ties) given
+//           the statistics plus the virtual visits of pulls 0..j-1"; a simulation takes pull j = floor(x0*k/2^32)
+__device__ __forceinline__ void warp_plan_few(const SearchParams &p, int X, uint32_t k, int lane, int A, int slot)
+{
+    const unsigned full = 0xFFFFFFFFu;
+    const uint32_t mask = p.t.legal[X];
+    const bool legal = lane < A && ((mask >> lane) & 1u);
+    const int n = legal ? p.t.n[(size_t)X * AS + lane] : 0;
+    const long long qf = legal ? p.t.qfix[(size_t)X * AS + lane] : 0;
+    int N = n;
+#pragma unroll
+    for (int off = 16; off >= 1; off >>= 1) N += __shfl_xor_sync(full, N, off);
+    const unsigned untried = __ballot_sync(full, legal && n == 0);
+    if ((uint32_t)__popc(untried) >= k) {
+        if (lane == 0) { p.t.plan[(size_t)X * 2] = make_uint4(PLAN_MASK << 16, (uint32_t)slot, 0u, 0u); p.t.plan[(size_t)X * 2 + 1].x = untried; }
+        return;
+    }
+    const float L = det_logf_u32((uint32_t)N + 1u);
+    const float cf = (float)p.ucb_c;
+    if (k == 1) {                                                    // no untried action here: every legal n > 0
+        const float sc = legal ? edge_mean(qf, n) + cf * sqrtf(L / (float)n) : -INFINITY;
+        float best = sc;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) best = fmaxf(best, __shfl_xor_sync(full, best, off));
+        const unsigned ties = __ballot_sync(full, legal && sc == best);
+        if (lane == 0) { p.t.plan[(size_t)X * 2] = make_uint4(PLAN_MASK << 16, (uint32_t)slot, 0u, 0u); p.t.plan[(size_t)X * 2 + 1].x = ties; }
+        return;
+    }
+    const float c2L = (cf * cf) * L;
+    const float qb = n == 0 ? 0.0f : edge_mean(qf, n);
+    if (!(c2L > 0.0f)) {
+        float qmax = legal ? qb : -INFINITY;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) qmax = fmaxf(qmax, __shfl_xor_sync(full, qmax, off));
+        const unsigned qties = __ballot_sync(full, legal && qb == qmax);
+        if (lane == 0) { p.t.plan[(size_t)X * 2] = make_uint4(PLAN_MASK << 16, (uint32_t)slot, 0u, 0u); p.t.plan[(size_t)X * 2 + 1].x = qties; }
+        return;
+    }
+    float sc = legal ? (n == 0 ? INFINITY : qb + cf * sqrtf(L / (float)n)) : -INFINITY;
+    int va = 0;
+    uint32_t seq[4] = {0u, 0u, 0u, 0u};
+    for (uint32_t pull = 0; pull < k; ++pull) {
+        float bs = sc;
+#pragma unroll
+        for (int off = 16; off >= 1; off >>= 1) bs = fmaxf(bs, __shfl_xor_sync(full, bs, off));
+        const int w = __ffs((int)__ballot_sync(full, sc == bs)) - 1;
+        seq[pull >> 2] |= (uint32_t)w << (8 * (pull & 3u));
+        if (lane == w) { va += 1; sc = qb + cf * sqrtf(L / (float)(n + va)); }
+    }
+    if (lane == 0) {
+        p.t.plan[(size_t)X * 2] = make_uint4((PLAN_PULLS << 16) | (k << 8), (uint32_t)slot, 0u, 0u);
+        p.t.plan[(size_t)X * 2 + 1] = make_uint4(seq[0], seq[1], seq[2], seq[3]);
+    }
+}
+
+// Plan of node X for its k arrivals of this level step (one warp).
+__device__ __forceinline__ void warp_plan(const SearchParams &p, int X, uint32_t k, int lane, int A, int slot)
+{
+    if (k > SEQ_ALLOC_MAX) warp_allocation(p, X, k, lane, A, p.b.wl_thr + (size_t)slot * 32, slot);
+    else warp_plan_few(p, X, k, lane, A, slot);
+}
+
+// The action of one simulation from its node's plan and its 32-bit draw x0.
+__device__ __forceinline__ int plan_action(const SearchParams &p, int X, uint32_t x0, int A)
+{
+    const uint4 head = p.t.plan[(size_t)X * 2], data = p.t.plan[(size_t)X * 2 + 1];
+    const int meta = (int)head.x, kind = meta >> 16;
+    if (kind == PLAN_THRESHOLDS) {                       // first action whose threshold exceeds x0
+        const int G = (A + 5) / 6;                       // thresholds are non-decreasing: find the group of G ...
+        const int g = x0 < data.x ? 0 : x0 < data.y ? 1 : x0 < data.z ? 2 : x0 < data.w ? 3 : x0 < head.z ? 4 :
+                      x0 < head.w ? 5 : 6;
+        if (g == 6) return meta & 255;
+        const uint32_t *thr = p.b.wl_thr + (size_t)head.y * 32 + g * G;
+        uint32_t tq[6];
+#pragma unroll
+        for (int q = 0; q < 6; ++q) tq[q] = (q < G && g * G + q < 32) ? thr[q] : 0xFFFFFFFFu;   // ... then the action
+#pragma unroll
+        for (int q = 0; q < 6; ++q) if (x0 < tq[q]) return g * G + q;
+        return meta & 255;
+    }
+    if (kind == PLAN_MASK) return nth_bit(data.x, randbelow32(x0, (uint32_t)__popc(data.x)));
+    const uint32_t j = randbelow32(x0, (uint32_t)(meta >> 8) & 255u);
+    const uint32_t word = (j >> 2) == 0 ? data.x : (j >> 2) == 1 ? data.y : (j >> 2) == 2 ? data.z : data.w;
+    return (int)((word >> (8 * (j & 3u))) & 255u);
+}
