@@ -59,7 +59,8 @@ int pomcp_set_model_rocksample(pomcp_handle *h, int rows, int cols, const int8_t
  * as 32-bit cumulative thresholds: Tc[a][s][s'] = min(floor(2^32 * sum_{j<=s'} T[a][s][j]), 2^32 - 1) and
  * Oc[a][s'][z] likewise (every row must end at 0xFFFFFFFF); R[a][s]; term_action_mask marks the actions that end an
  * episode (Tiger: opening a door), term_state[s'] the absorbing states (may be NULL).  A packed state is the state
- * index; observations are indices 0..n_obs-1 (the obs_good argument of pomcp_advance / pomcp_node_stats). */
+ * index; observations are indices 0..n_obs-1 (the obs_good argument of pomcp_advance / pomcp_node_stats).  Rows of
+ * 64 or more states get a guide table on the device (same draws, fewer loads). */
 int pomcp_set_model_tabular(pomcp_handle *h, int n_states, int n_actions, int n_obs, const uint32_t *Tc,
                             const uint32_t *Oc, const double *R, uint32_t term_action_mask,
                             const uint8_t *term_state);

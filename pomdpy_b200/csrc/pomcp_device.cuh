@@ -130,13 +130,15 @@ struct TabHeader {
     int32_t S, A, Z, ZS;        // ZS: observation stride of the child table (power of two >= max(Z, 2))
     uint32_t term_action_mask;  // actions that end the episode (Tiger: opening a door)
     int32_t stage_d1;           // depth-1 edges fit the per-block shared-memory staging
-    int32_t pad0, pad1;
+    int32_t guide_bits;         // log2 of the guide-table buckets per transition row (0: no guide table)
+    int32_t pad1;
 };
 struct TabTables {
     const uint32_t *Tc;         // [A][S][S]
     const uint32_t *Oc;         // [A][S][Z]  (row: action, next state)
     const double *R;            // [A][S]
     const uint8_t *term_state;  // [S]
+    const uint16_t *Tg;         // [A][S][2^guide_bits + 1] guide table: first index whose threshold exceeds the bucket start
 };
 
 // first index k with cdf[k] > min(w, 2^32 - 2): zero-probability entries are never drawn
@@ -144,6 +146,17 @@ __device__ __forceinline__ int tab_sample(const uint32_t *cdf, int n, uint32_t w
 {
     if (w == 0xFFFFFFFFu) w = 0xFFFFFFFEu;
     int lo = 0, hi = n - 1;
+    while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(cdf + mid) > w) hi = mid; else lo = mid + 1; }
+    return lo;
+}
+
+// The same draw with a guide table (an accelerator, not a different rule): bucket j = w >> (32 - bits) can only draw
+// an index in [guide[j], guide[j + 1]], so the bisection runs over a handful of entries instead of the whole row.
+__device__ __forceinline__ int tab_sample_guided(const uint32_t *cdf, const uint16_t *guide, int bits, uint32_t w)
+{
+    if (w == 0xFFFFFFFFu) w = 0xFFFFFFFEu;
+    const uint32_t j = w >> (32 - bits);
+    int lo = __ldg(guide + j), hi = __ldg(guide + j + 1);
     while (lo < hi) { const int mid = (lo + hi) >> 1; if (__ldg(cdf + mid) > w) hi = mid; else lo = mid + 1; }
     return lo;
 }

@@ -895,6 +895,7 @@ static void free_all(pomcp_handle *h)
     cudaFree(h->b.path_ar); cudaFree(h->b.wl_node); cudaFree(h->b.wl_thr);
     cudaFree(h->b.ro_sum); cudaFree(h->b.ro_t); cudaFree(h->b.path_rew);
     cudaFree((void *)h->tt.Tc); cudaFree((void *)h->tt.Oc); cudaFree((void *)h->tt.R); cudaFree((void *)h->tt.term_state);
+    cudaFree((void *)h->tt.Tg);
     cudaFree(h->bag[0]); cudaFree(h->bag[1]);
     if (h->stage) cudaFreeHost(h->stage);
 }
@@ -959,6 +960,7 @@ extern "C" int pomcp_create(const pomcp_config *cfg, int device, pomcp_handle **
 static int release_tabular(pomcp_handle *h)
 {
     cudaFree((void *)h->tt.Tc); cudaFree((void *)h->tt.Oc); cudaFree((void *)h->tt.R); cudaFree((void *)h->tt.term_state);
+    cudaFree((void *)h->tt.Tg);
     h->tt = TabTables{};
     return 0;
 }
@@ -1068,6 +1070,32 @@ extern "C" int pomcp_set_model_tabular(pomcp_handle *h, int n_states, int n_acti
     memset(&t, 0, sizeof(t));
     t.S = n_states; t.A = n_actions; t.Z = n_obs; t.ZS = zs; t.term_action_mask = term_action_mask;
     t.stage_d1 = ((size_t)(1 + zs * n_actions) * n_actions * 12 <= (size_t)(24 << 10)) ? 1 : 0;
+    // Guide table of the transition rows (|S| >= 64): 2^bits buckets per row, about four thresholds per bucket, at
+    // most 256 MB in total.  guide[j] = first index whose threshold exceeds j << (32 - bits); guide[2^bits] = S - 1.
+    int gbits = 0;
+    if (n_states >= 64) {
+        while ((1 << (gbits + 1)) <= n_states / 4) ++gbits;
+        while (gbits > 0 && A * S * ((size_t)(1u << gbits) + 1) * 2 > ((size_t)256 << 20)) --gbits;
+    }
+    if (gbits > 0) {
+        const size_t G = (size_t)1 << gbits;
+        std::vector<uint16_t> guide(A * S * (G + 1));
+        for (size_t r = 0; r < A * S; ++r) {
+            const uint32_t *cdf = Tc + r * S;
+            uint16_t *g = guide.data() + r * (G + 1);
+            size_t k = 0;
+            for (size_t j = 0; j < G; ++j) {
+                const uint32_t w0 = (uint32_t)(j << (32 - gbits));
+                while (k + 1 < S && !(cdf[k] > w0)) ++k;
+                g[j] = (uint16_t)k;
+            }
+            g[G] = (uint16_t)(S - 1);
+        }
+        uint16_t *dG;
+        CK(cudaMalloc(&dG, guide.size() * sizeof(uint16_t))); h->tt.Tg = dG;
+        CK(cudaMemcpy(dG, guide.data(), guide.size() * sizeof(uint16_t), cudaMemcpyHostToDevice));
+    }
+    t.guide_bits = gbits;
     h->kind = 1; h->n_actions = n_actions;
     memset(&h->hmodel, 0, sizeof(h->hmodel));
     h->hmodel.n_actions = n_actions; h->hmodel.n_cells = 1;

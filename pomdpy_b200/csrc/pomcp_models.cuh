@@ -139,10 +139,16 @@ template <> struct Mdl<1> {
     static __device__ __forceinline__ uint32_t tag_legal(const Ctx &c, uint32_t)
     { return c.h.A >= 32 ? 0xFFFFFFFFu : ((1u << c.h.A) - 1u); }
     static __device__ __forceinline__ bool tag_ok(const Ctx &, uint32_t tag) { return tag == 0u; }
+    static __device__ __forceinline__ int next_state(const Ctx &c, size_t row, uint32_t w)
+    {
+        if (c.h.guide_bits)
+            return tab_sample_guided(c.t.Tc + row * c.h.S, c.t.Tg + row * ((size_t)(1u << c.h.guide_bits) + 1), c.h.guide_bits, w);
+        return tab_sample(c.t.Tc + row * c.h.S, c.h.S, w);
+    }
     static __device__ __forceinline__ StepOut step(const Ctx &c, uint32_t st, int a, uint32_t wy, uint32_t wz)
     {
         const size_t row = (size_t)a * c.h.S + st;
-        const int ns = tab_sample(c.t.Tc + row * c.h.S, c.h.S, wy);
+        const int ns = next_state(c, row, wy);
         const int ob = tab_sample(c.t.Oc + ((size_t)a * c.h.S + ns) * c.h.Z, c.h.Z, wz);
         const int term = (int)((c.h.term_action_mask >> a) & 1u) | (int)__ldg(c.t.term_state + ns);
         return StepOut{(uint32_t)ns, 0u, ob, 0, term, __ldg(c.t.R + row)};
@@ -165,7 +171,7 @@ template <> struct Mdl<1> {
             const int a = (int)randbelow32(w0, (uint32_t)c.h.A);
             const size_t row = (size_t)a * c.h.S + st;
             const double rew = __ldg(c.t.R + row);
-            st = (uint32_t)tab_sample(c.t.Tc + row * c.h.S, c.h.S, w1);
+            st = (uint32_t)next_state(c, row, w1);
             if (rew != 0.0) sum += rew * disc[t];
             if (((c.h.term_action_mask >> a) & 1u) | __ldg(c.t.term_state + st)) { ++t; return true; }
         }
