@@ -191,3 +191,20 @@ def test_preferred_action_heuristic_golden():
             assert [r.goodness_number for r in data.all_rock_data] == s["good"] == [st.good[k] for k in range(K)]
             assert [r.chance_good for r in data.all_rock_data] == s["chance"] == [st.chance[k] for k in range(K)]
             assert sum(1 << x for x in data.generate_smart_actions()) == s["mask"] == oracle.smart_mask(om, st, cell)
+
+
+def test_gs_oracle_regression_pins():
+    """The generation-synchronous oracle is the specification of the CUDA kernels; tests/golden/gs_pins.json pins its
+    output on nine fixed searches (RockSample with and without preferred actions / rollouts, tabular models) so that
+    a change of the specification cannot slip in unnoticed (oracle/refharness/make_gs_pins.py regenerates them)."""
+    import importlib.util
+    spec = importlib.util.spec_from_file_location("make_gs_pins", os.path.join(ROOT, "oracle", "refharness", "make_gs_pins.py"))
+    mod = importlib.util.module_from_spec(spec)
+    spec.loader.exec_module(mod)
+    with open(os.path.join(GOLDEN, "gs_pins.json")) as f:
+        pins = json.load(f)["pins"]
+    assert len(pins) == len(mod.CASES)
+    for pin in pins:
+        case = dict(pin["case"])
+        case["sched"] = tuple(case["sched"])
+        assert mod.run_case(case) == pin["moves"], case
