@@ -253,3 +253,48 @@ def test_preferred_actions_episode_bit_exact(tag, seed, n_sims, sched, rollouts)
         assert g.update(a, o.obs_good, sampled, move=mv) == pl.advance(a, o.obs_good, sampled, move=mv)
         assert np.array_equal(pl.root_particles()[0], g.bag())
     pl.close()
+
+
+def test_cuda_planner_reproduces_committed_gs_pins():
+    """The CUDA planner against the COMMITTED fixtures of the specification (tests/golden/gs_pins.json): no oracle in
+    the loop -- root statistics, greedy actions, counters, belief updates of nine fixed searches."""
+    import json
+    import os
+    from helpers import GOLDEN
+    from pomdpy_b200 import native
+    from pomdpy_b200.solvers.pomcp import greedy_action
+    from pomdpy_b200.tabular import random_pomdp, tiger
+    with open(os.path.join(GOLDEN, "gs_pins.json")) as f:
+        pins = json.load(f)["pins"]
+    for pin in pins:
+        c = pin["case"]
+        w0, growth, wmax = c["sched"]
+        kw = dict(seed=c["seed"], gen_w0=w0, gen_growth=growth, gen_wmax=wmax, node_capacity=1 << 17,
+                  max_particle_count=500)
+        if c["kind"] == "rs":
+            t = golden_tables(c["tag"])
+            actual, bag, _ = random_world_and_bag(t, c["seed"])
+            pl = make_planner(t, **kw)
+            if c["pref"]:
+                pl.set_preferred_actions(True, t["prob"], rollouts=c["pref"] == 2)
+            pl.set_world(actual, 0)
+            pl.set_root_particles(bag, int(t["start_cell"]))
+        else:
+            m = tiger() if c["model"] == "tiger" else random_pomdp(*[int(x) for x in c["model"].split("-")[1:]], seed=c["seed"])
+            bag = m.sample_init_states_packed(1000, np.random.RandomState(c["seed"]))
+            pl = native.Planner(ucb_coefficient=c["ucb"], max_depth=40, **kw)
+            pl.set_model_tabular(m.Tc, m.Oc, m.R, m.term_action_mask, m.term_state)
+            pl.set_root_particles(bag)
+        for move, want in enumerate(pin["moves"]):
+            pl.search(c["n_sims"], move=move)
+            st = pl.root_stats()
+            assert st["n"].tolist() == want["n"] and st["qfix"].tolist() == want["qfix"] and st["legal"] == want["legal"], c
+            a = greedy_action(st["n"], st["qfix"], st["legal"], c["seed"], move)
+            cnt = pl.counters()
+            assert a == want["action"] and cnt["nodes"] == want["nodes"], c
+            u = pl.advance(a, move & 1, 0, move=move)
+            assert [u["status"], u["tries"], u["accepted"]] == want["update"], c
+            if u["status"] == 2:
+                break
+            assert int(pl.root_particles()[0].astype(np.uint64).sum()) == want["bag_sum"], c
+        pl.close()
