@@ -82,7 +82,8 @@ struct ModelHeader {            // lives in global memory; copied verbatim into 
 
 struct SmemModel {
     const ModelHeader *hdr;
-    const uint64_t *thr53;      // [n_cells][n_rocks]
+    const uint64_t *thr53;      // [n_cells][n_rocks] (global memory)
+    const uint32_t *thr32;      // thr53 >> 21, saturated: the rollouts' copy in shared memory
 };
 
 struct StepResult {

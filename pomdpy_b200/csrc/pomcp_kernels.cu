@@ -1022,7 +1022,7 @@ extern "C" int pomcp_set_model_rocksample(pomcp_handle *h, int rows, int cols, c
     if (set_child_stride(h, 2)) return -1;
     // launch geometry of the cooperative search kernel
     const int A = m.n_actions;
-    size_t smem = ((sizeof(ModelHeader) + 15) & ~size_t(15)) + (((size_t)h->n_thr * 8 + 15) & ~size_t(15)) +
+    size_t smem = ((sizeof(ModelHeader) + 15) & ~size_t(15)) + (((size_t)h->n_thr * 4 + 15) & ~size_t(15)) +
                   (((size_t)h->cfg.max_depth * 8 + 15) & ~size_t(15)) + (size_t)(1 + 2 * A) * A * 12 + (((size_t)2 * A * 4 + 15) & ~size_t(15)) + (size_t)ARR_HT * 16 + 32;
     h->search_smem = smem;
     CK(cudaFuncSetAttribute(pomcp_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

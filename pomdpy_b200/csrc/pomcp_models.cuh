@@ -22,12 +22,19 @@ template <> struct Mdl<0> {
         uint4 *dst = reinterpret_cast<uint4 *>(smem);
         const uint4 *src = reinterpret_cast<const uint4 *>(gm);
         for (int i = threadIdx.x; i < nw; i += blockDim.x) dst[i] = src[i];
+        // The rollouts draw only the top 32 bits of the sensor uniform ((w << 21) <= thr53  <=>  w <= thr53 >> 21;
+        // a certain sensor, thr53 = 2^53, saturates), so the shared-memory copy is the 32-bit table; tree levels and
+        // the belief update read the 53-bit thresholds from global memory (a few per simulation, L1-resident).
         size_t off = (sizeof(ModelHeader) + 15) & ~size_t(15);
-        uint64_t *thr = reinterpret_cast<uint64_t *>(smem + off);
-        for (int i = threadIdx.x; i < n_thr; i += blockDim.x) thr[i] = gthr[i];
-        off += ((size_t)n_thr * 8 + 15) & ~size_t(15);
+        uint32_t *thr32 = reinterpret_cast<uint32_t *>(smem + off);
+        for (int i = threadIdx.x; i < n_thr; i += blockDim.x) {
+            const uint64_t tq = gthr[i] >> 21;
+            thr32[i] = tq > 0xFFFFFFFFull ? 0xFFFFFFFFu : (uint32_t)tq;
+        }
+        off += ((size_t)n_thr * 4 + 15) & ~size_t(15);
         c.M.hdr = reinterpret_cast<const ModelHeader *>(smem);
-        c.M.thr53 = thr;
+        c.M.thr53 = gthr;
+        c.M.thr32 = thr32;
         return off;
     }
     static __device__ __forceinline__ int n_actions(const Ctx &c, const ModelHeader *gm) { return gm->n_actions; }
@@ -73,7 +80,7 @@ template <> struct Mdl<0> {
                 const int k = a - 5;
                 if (!((sampled >> k) & 1u)) {
                     const uint32_t truth = (actual >> k) & 1u;
-                    const uint32_t correct = ((uint64_t)w1 << 21) <= c.M.thr53[cell * H->n_rocks + k];
+                    const uint32_t correct = w1 <= c.M.thr32[cell * H->n_rocks + k];
                     const uint32_t good = correct ? truth : (truth ^ 1u);
                     rocks = (rocks & ~(1u << k)) | (good << k);
                 }
