@@ -761,10 +761,25 @@ static float butterfly_sum32(const float v[32])
     return x[0];
 }
 
-/* Batch-UCB allocation for k >= 2 simultaneous arrivals at a node: weights v[a] >= 0 from a
- * water-filling of k pulls over the UCB1 indices, turned into 32-bit cumulative thresholds.  An arrival with
- * 32-bit draw x takes the first action a with x < thr[a], or `*last` if there is none. */
-static void gs_allocation(const orc_gs *h, const gs_node *nd, int64_t k, uint32_t thr[32], int *last)
+/* ---------------------------------------------------------------------------------------------------------------
+ * Action plans.  Within a generation the statistics are read-only, so the action distribution of a node is a pure
+ * function of (its statistics, k) where k is the number of simulations of this generation EXPECTED at the node:
+ *     k(root) = generation width;   k(child of X under (a, o)) = k(X) * P_plan(a | X) * N(child) / n(X, a)
+ * (N(child) / n(X, a): the share of the edge's past visits that saw observation o).  A plan is one of
+ *     thresholds  k >= 16.5: batch-UCB allocation -- a water-filling of k pulls over the UCB1 indices
+ *     pulls       round(k) in 2..16: the virtual-pull sequence "pull j takes the UCB1 arg-max given the virtual
+ *                 visits of pulls 0..j-1"; a simulation takes pull floor(x0 * round(k) / 2^32)
+ *     mask        uniform draw over an action set: the untried actions (if at least round(k) of them), else for
+ *                 round(k) == 1 the UCB1 arg-max set (action_selectors.py:6-37), or for c = 0 the best means
+ * Nothing depends on how many simulations really meet at the node, so every simulation descends the tree on its own.
+ * --------------------------------------------------------------------------------------------------------------- */
+enum { GS_PLAN_MASK = 0, GS_PLAN_PULLS = 1, GS_PLAN_THRESHOLDS = 2 };
+typedef struct { int32_t kind, kq, last; uint32_t mask; uint8_t pulls[16]; uint32_t thr[32]; } gs_plan;
+
+/* Batch-UCB allocation: weights v[a] >= 0 from a water-filling of kd pulls over the UCB1 indices,
+ * turned into 32-bit cumulative thresholds.  A simulation with 32-bit draw x takes the first action a with
+ * x < thr[a], or `*last` if there is none. */
+static void gs_allocation(const orc_gs *h, const gs_node *nd, float kd, uint32_t thr[32], int *last)
 {
     int A = h->A;
     int64_t N = 0; int untried = 0, nlegal = 0;
@@ -772,7 +787,7 @@ static void gs_allocation(const orc_gs *h, const gs_node *nd, int64_t k, uint32_
     for (int a = 0; a < 32; ++a) v[a] = 0.0f;
     for (int a = 0; a < A; ++a) if ((nd->legal >> a) & 1u) { N += nd->n[a]; nlegal++; if (nd->n[a] == 0) untried++; }
     if (N == 0) { for (int a = 0; a < A; ++a) if ((nd->legal >> a) & 1u) v[a] = 1.0f; }
-    else if (untried >= k) { for (int a = 0; a < A; ++a) if (((nd->legal >> a) & 1u) && nd->n[a] == 0) v[a] = 1.0f; }
+    else if ((float)untried >= kd) { for (int a = 0; a < A; ++a) if (((nd->legal >> a) & 1u) && nd->n[a] == 0) v[a] = 1.0f; }
     else {
         float L = orc_det_logf_u32((uint32_t)N + 1u);
         float c2L = (cf * cf) * L;
@@ -784,7 +799,6 @@ static void gs_allocation(const orc_gs *h, const gs_node *nd, int64_t k, uint32_
         }
         if (!(c2L > 0.0f)) { for (int a = 0; a < A; ++a) if (((nd->legal >> a) & 1u) && qbar[a] == qmax) v[a] = 1.0f; }
         else {
-            float kd = (float)k;
             float lo = qmax + 0.999f * sqrtf(c2L / (kd + (float)nbest));
             float hi = qmax + 1.001f * sqrtf((c2L * (float)nlegal) / kd) + 1.0f;
             for (int it = 0; it <= ORC_BISECT_ITERS; ++it) {          /* bisection steps, then the weights at `lo` */
@@ -829,53 +843,81 @@ static int nth_set_bit(uint32_t mask, uint32_t j)
     return -1;
 }
 
-/* Action of one simulation at a node with k <= ORC_SEQ_ALLOC_MAX arrivals.
- *   k == 1: UCB1 arg-max (action_selectors.py:6-37 with mean = sum/n), uniform tie-break by the 32-bit draw x0.
- *   k >= 2: the arrivals share the virtual-pull sequence "pull j takes the UCB1 arg-max (lowest id on ties) given
- *           the statistics plus the virtual visits of pulls 0..j-1"; this simulation takes pull j = floor(x0*k/2^32).
- * Untried actions score +inf (solvers/pomcp.py:64-65): with at least k of them the draw is uniform over them. */
-static int gs_select(const orc_gs *h, const gs_node *nd, uint32_t x0, int64_t k)
+/* Plan of a node with statistics (N > 0) for kq = round(k) <= ORC_SEQ_ALLOC_MAX expected arrivals.
+ * Untried actions score +inf (solvers/pomcp.py:64-65): with at least kq of them the draw is uniform over them. */
+static void gs_plan_few(const orc_gs *h, const gs_node *nd, int kq, gs_plan *pl)
 {
     int A = h->A; const float cf = (float)h->ucb_c;
     int64_t N = 0; uint32_t untried = 0;
+    pl->kq = kq; pl->kind = GS_PLAN_MASK;
     for (int a = 0; a < A; ++a) if ((nd->legal >> a) & 1u) { N += nd->n[a]; if (nd->n[a] == 0) untried |= 1u << a; }
-    uint32_t nu = (uint32_t)__builtin_popcount(untried);
-    if ((int64_t)nu >= k) return nth_set_bit(untried, randbelow32(x0, nu));
+    if (__builtin_popcount(untried) >= kq) { pl->mask = untried; return; }
     float L = orc_det_logf_u32((uint32_t)N + 1u);
-    if (k == 1) {
+    if (kq == 1) {                             /* UCB1 arg-max set; the draw breaks ties */
         float best = -INFINITY; uint32_t ties = 0;
         for (int a = 0; a < A; ++a) {
             if (!((nd->legal >> a) & 1u)) continue;
             float s = gs_mean(nd, a) + cf * sqrtf(L / (float)nd->n[a]);
             if (s > best) { best = s; ties = 1u << a; } else if (s == best) ties |= 1u << a;
         }
-        return nth_set_bit(ties, randbelow32(x0, (uint32_t)__builtin_popcount(ties)));
+        pl->mask = ties; return;
     }
     float c2L = (cf * cf) * L;
     float sc[32]; int64_t va[32]; float qmax = -INFINITY; uint32_t qties = 0;
+    for (int a = 0; a < 32; ++a) { va[a] = 0; sc[a] = -INFINITY; }
     for (int a = 0; a < A; ++a) {
-        va[a] = 0; sc[a] = -INFINITY;
         if (!((nd->legal >> a) & 1u)) continue;
         float qb = gs_mean(nd, a);
         if (qb > qmax) { qmax = qb; qties = 1u << a; } else if (qb == qmax) qties |= 1u << a;
         sc[a] = nd->n[a] == 0 ? INFINITY : qb + cf * sqrtf(L / (float)nd->n[a]);
     }
-    if (!(c2L > 0.0f)) return nth_set_bit(qties, randbelow32(x0, (uint32_t)__builtin_popcount(qties)));
-    uint32_t j = randbelow32(x0, (uint32_t)k);
-    for (uint32_t pull = 0;; ++pull) {
+    if (!(c2L > 0.0f)) { pl->mask = qties; return; }
+    pl->kind = GS_PLAN_PULLS;
+    for (int pull = 0; pull < kq; ++pull) {
         int w = 0;
         for (int a = 1; a < A; ++a) if (sc[a] > sc[w]) w = a;
-        if (pull == j) return w;
+        pl->pulls[pull] = (uint8_t)w;
         va[w] += 1;
         sc[w] = gs_mean(nd, w) + cf * sqrtf(L / (float)(nd->n[w] + va[w]));
     }
 }
 
+static void gs_make_plan(const orc_gs *h, const gs_node *nd, float k, gs_plan *pl)
+{
+    if (k >= 16.5f) {
+        pl->kind = GS_PLAN_THRESHOLDS; pl->kq = 0;
+        gs_allocation(h, nd, k, pl->thr, &pl->last);
+    } else {
+        int kq = (int)(k + 0.5f);
+        gs_plan_few(h, nd, kq < 1 ? 1 : kq, pl);
+    }
+}
+
+/* The action a simulation with 32-bit draw x0 takes under a plan, and the plan's probability of that action. */
+static int gs_plan_action(const gs_plan *pl, uint32_t x0, float *prob)
+{
+    if (pl->kind == GS_PLAN_THRESHOLDS) {
+        int a = pl->last;
+        for (int b = 0; b < 32; ++b) if (x0 < pl->thr[b]) { a = b; break; }
+        *prob = (float)(pl->thr[a] - (a > 0 ? pl->thr[a - 1] : 0u)) * (1.0f / 4294967296.0f);
+        return a;
+    }
+    if (pl->kind == GS_PLAN_MASK) {
+        uint32_t m = (uint32_t)__builtin_popcount(pl->mask);
+        *prob = 1.0f / (float)m;
+        return nth_set_bit(pl->mask, randbelow32(x0, m));
+    }
+    int a = pl->pulls[randbelow32(x0, (uint32_t)pl->kq)], cnt = 0;
+    for (int j = 0; j < pl->kq; ++j) if (pl->pulls[j] == a) ++cnt;
+    *prob = (float)cnt / (float)pl->kq;
+    return a;
+}
+
 typedef struct {
     uint32_t sim;          /* global simulation index (stream id) */
     uint32_t st;           /* packed state */
-    int32_t node, depth;   /* current node / number of path entries */
-    int32_t status;        /* 0 descending, 1 leaf: rollout pending, 2 done (terminal or horizon) */
+    int32_t depth;         /* number of path entries */
+    int32_t status;        /* 1 leaf: rollout pending, 2 done (terminal or horizon) */
     int32_t *pnode; uint8_t *pact; double *prew;
     int32_t last_obs;      /* observation of the last tree step (start of the rollout's history) */
     double delayed;
@@ -914,8 +956,29 @@ static double gs_rollout(orc_gs *h, gs_sim *s, uint32_t move)
     return sum;
 }
 
+static int64_t gs_visits(const gs_node *nd) { int64_t N = 0; for (int b = 0; b < 32; ++b) N += nd->n[b]; return N; }
+
+/* A simulation standing at a node without statistics (N = 0): every legal action is untried, so UCB1 is a uniform
+ * draw (action_selectors.py:6-37 with +inf bonuses), the node cannot be expanded (solvers/pomcp.py:107) and the
+ * simulation ends in a rollout. */
+static void gs_virgin_step(orc_gs *h, gs_sim *s, int32_t Y, uint32_t move)
+{
+    int d = s->depth;
+    if (d >= h->max_depth) { s->status = 2; s->delayed = 0.0; return; }              /* solvers/pomcp.py:100 */
+    uint32_t x[4]; gs_block(h, (uint32_t)(d + 1), s->sim, move, DOM_SIM, x);
+    uint32_t mask = h->nodes[Y].legal;
+    int a = nth_set_bit(mask, randbelow32(x[0], (uint32_t)__builtin_popcount(mask)));
+    gs_step_out o; gs_step(h, s->st, a, x[1], x[2], 0, &o);
+    h->n_levels++;
+    s->pnode[d] = Y; s->pact[d] = (uint8_t)a; s->prew[d] = o.reward; s->depth = d + 1; s->last_obs = o.obs;
+    if (s->depth > h->max_tree_depth) h->max_tree_depth = s->depth;
+    s->st = o.next;
+    s->status = o.terminal ? 2 : 1; s->delayed = 0.0;
+}
+
 /* One search: n_sims simulations with global ids [sim_offset, sim_offset + n_sims), in generations of width
- * w0, w0*growth, ... capped at wmax. */
+ * w0, w0*growth, ... capped at wmax.  Statistics are read-only within a generation (the backups of a generation are
+ * applied after its last simulation), so the order of the simulations inside a generation does not matter. */
 int orc_gs_search(orc_gs *h, int64_t n_sims, uint32_t sim_offset, uint32_t move, int w0, int growth, int wmax)
 {
     if (w0 < 1) w0 = 1; if (growth < 1) growth = 1; if (wmax < w0) wmax = w0;
@@ -925,74 +988,60 @@ int orc_gs_search(orc_gs *h, int64_t n_sims, uint32_t sim_offset, uint32_t move,
     int32_t *pn = (int32_t *)malloc(sizeof(int32_t) * (size_t)wmax * (size_t)dcap);
     uint8_t *pa = (uint8_t *)malloc((size_t)wmax * (size_t)dcap);
     double *pr = (double *)malloc(sizeof(double) * (size_t)wmax * (size_t)dcap);
-    int64_t *arrivals = NULL; uint32_t *alloc_thr = NULL; int32_t *alloc_last = NULL; int32_t arr_cap = 0;
+    gs_plan *cache = NULL; int64_t *cache_stamp = NULL; int32_t cache_cap = 0;   /* plans of this generation, by node */
+    gs_plan fresh;
     while (done < n_sims) {
         int64_t w = W; if (w > n_sims - done) w = n_sims - done;
         h->n_generations++;
+        const int64_t stamp = h->n_generations;
+        const int32_t nn0 = h->n_nodes;            /* nodes created in this generation have no statistics: never planned */
+        if (cache_cap < nn0) {
+            cache_cap = nn0 * 2;
+            cache = (gs_plan *)realloc(cache, sizeof(gs_plan) * (size_t)cache_cap);
+            cache_stamp = (int64_t *)realloc(cache_stamp, sizeof(int64_t) * (size_t)cache_cap);
+            memset(cache_stamp, 0, sizeof(int64_t) * (size_t)cache_cap);
+        }
+        const int root_virgin = gs_visits(&h->nodes[h->root]) == 0;
         for (int64_t i = 0; i < w; ++i) {
             gs_sim *s = &S[i];
             s->sim = sim_offset + (uint32_t)(done + i);
             s->pnode = pn + i * dcap; s->pact = pa + i * dcap; s->prew = pr + i * dcap;
-            uint32_t x[4]; gs_block(h, 0, s->sim, move, DOM_SIM, x);
+            uint32_t x[4]; gs_block(h, 0, s->sim, move, DOM_SIM, x);           /* belief_node.py:47-48 */
             s->st = h->bag[randbelow32(x[0], (uint32_t)h->n_bag)];
-            s->node = h->root; s->depth = 0; s->status = 0; s->delayed = 0.0;
-        }
-        for (;;) {                                  /* level steps */
-            int64_t active = 0;
-            for (int64_t i = 0; i < w; ++i) if (S[i].status == 0) active++;
-            if (!active) break;
-            int32_t nn0 = h->n_nodes;               /* snapshot: nodes created in this step are not visited until the next */
-            if (arr_cap < h->n_nodes) {
-                arr_cap = h->n_nodes * 2;
-                arrivals = (int64_t *)realloc(arrivals, sizeof(int64_t) * (size_t)arr_cap);
-                alloc_thr = (uint32_t *)realloc(alloc_thr, sizeof(uint32_t) * 32 * (size_t)arr_cap);
-                alloc_last = (int32_t *)realloc(alloc_last, sizeof(int32_t) * (size_t)arr_cap);
-            }
-            /* phase 1: count arrivals per node */
-            for (int64_t i = 0; i < w; ++i) if (S[i].status == 0) arrivals[S[i].node] = 0;
-            for (int64_t i = 0; i < w; ++i) if (S[i].status == 0) arrivals[S[i].node]++;
-            /* phase 2: allocation for nodes with >= 2 arrivals (sign bit marks "computed") */
-            for (int64_t i = 0; i < w; ++i) {
-                if (S[i].status != 0) continue;
-                int32_t X = S[i].node;
-                int64_t Nx = 0; for (int b = 0; b < 32; ++b) Nx += h->nodes[X].n[b];
-                if (arrivals[X] > ORC_SEQ_ALLOC_MAX && Nx > 0) {   /* few arrivals / no statistics: gs_select */
-                    gs_allocation(h, &h->nodes[X], arrivals[X], alloc_thr + 32 * (size_t)X, &alloc_last[X]);
-                    arrivals[X] = -arrivals[X]; h->n_alloc_nodes++;
-                }
-            }
-            /* phase 3: choose, step, expand; statistics are read-only during the whole generation */
-            for (int64_t i = 0; i < w; ++i) {
-                gs_sim *s = &S[i];
-                if (s->status != 0) continue;
-                int32_t X = s->node; int d = s->depth;
-                if (d >= h->max_depth) { s->status = 2; s->delayed = 0.0; continue; }   /* solvers/pomcp.py:100 */
-                gs_node *nd = &h->nodes[X];
-                uint32_t x[4]; gs_block(h, (uint32_t)(d + 1), s->sim, move, DOM_SIM, x);
-                int a;
-                if (arrivals[X] > 0) a = gs_select(h, nd, x[0], arrivals[X]);
+            s->depth = 0; s->status = 0; s->delayed = 0.0;
+            if (root_virgin) { gs_virgin_step(h, s, h->root, move); continue; }
+            int32_t X = h->root; float k = (float)w;
+            for (;;) {                                                         /* solvers/pomcp.py:87-137 */
+                int d = s->depth;
+                if (d >= h->max_depth) { s->status = 2; break; }               /* :100 */
+                const gs_plan *pl;
+                if (k < 1.5f) { gs_make_plan(h, &h->nodes[X], k, &fresh); pl = &fresh; }
                 else {
-                    const uint32_t *thr = alloc_thr + 32 * (size_t)X;
-                    a = alloc_last[X];
-                    for (int b = 0; b < 32; ++b) if (x[0] < thr[b]) { a = b; break; }
+                    if (cache_stamp[X] != stamp) {
+                        gs_make_plan(h, &h->nodes[X], k, &cache[X]); cache_stamp[X] = stamp;
+                        if (cache[X].kind == GS_PLAN_THRESHOLDS) h->n_alloc_nodes++;
+                    }
+                    pl = &cache[X];
                 }
-                gs_step_out o; gs_step(h, s->st, a, x[1], x[2], 0, &o);
+                uint32_t x4[4]; gs_block(h, (uint32_t)(d + 1), s->sim, move, DOM_SIM, x4);
+                float pa_; const int a = gs_plan_action(pl, x4[0], &pa_);
+                gs_step_out o; gs_step(h, s->st, a, x4[1], x4[2], 0, &o);      /* :104 */
                 h->n_levels++;
                 s->pnode[d] = X; s->pact[d] = (uint8_t)a; s->prew[d] = o.reward; s->depth = d + 1; s->last_obs = o.obs;
                 if (s->depth > h->max_tree_depth) h->max_tree_depth = s->depth;
-                int og = o.obs;
-                int32_t child = *gs_child(h, X, a, og);
-                int64_t Nx = 0; for (int b = 0; b < 32; ++b) Nx += nd->n[b];
-                if (child < 0 && !o.terminal && Nx > 0 && d + 1 < dcap) {   /* solvers/pomcp.py:107 */
-                    child = gs_new_node(h, o.tag); nd = &h->nodes[X];
-                    gs_init_child(h, child, X, a, og);
-                    *gs_child(h, X, a, og) = child; h->n_created++;
-                }
                 s->st = o.next;
-                if (o.terminal) { s->status = 2; s->delayed = 0.0; }
-                else if (child >= 0) { s->node = child; }
-                else s->status = 1;
-                (void)nn0;
+                if (o.terminal) { s->status = 2; break; }
+                int32_t child = *gs_child(h, X, a, o.obs);                     /* :106 */
+                if (child < 0) {
+                    if (d + 1 >= dcap) { s->status = 1; break; }              /* depth cap of the tree: leaf (:119) */
+                    child = gs_new_node(h, o.tag);                             /* :107-108 (N(X) > 0 here) */
+                    gs_init_child(h, child, X, a, o.obs);
+                    *gs_child(h, X, a, o.obs) = child; h->n_created++;
+                }
+                const int64_t Nc = child < nn0 ? gs_visits(&h->nodes[child]) : 0;
+                if (Nc == 0) { gs_virgin_step(h, s, child, move); break; }
+                k = (k * pa_) * ((float)Nc / (float)h->nodes[X].n[a]);         /* expected arrivals at the child */
+                X = child;
             }
         }
         /* rollouts, then backup (commutative integer updates) */
@@ -1014,7 +1063,7 @@ int orc_gs_search(orc_gs *h, int64_t n_sims, uint32_t sim_offset, uint32_t move,
         done += w;
         if (W < wmax) { W *= growth; if (W > wmax) W = wmax; }
     }
-    free(S); free(pn); free(pa); free(pr); free(arrivals); free(alloc_thr); free(alloc_last);
+    free(S); free(pn); free(pa); free(pr); free(cache); free(cache_stamp);
     return 0;
 }
 

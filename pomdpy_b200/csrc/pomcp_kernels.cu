@@ -23,40 +23,38 @@
 
 // ---------------------------------------------------------------------------------------------------------
 // K1: the search.  One persistent cooperative kernel per move; simulations advance in generations.  Within a
-// generation the tree statistics are read-only; per tree level:
-//     [allocate]  nodes with many (> 16) arrivals get a batch-UCB allocation (warp per node, lane = action)
-//     [expand]    every simulation chooses, steps the model, looks up / creates the child and -- if the child has
-//                 statistics -- registers its arrival there for the next level; a child without statistics
-//                 ("virgin": N = 0, e.g. just created) is finished on the spot: uniform action, step, leaf
-// with one grid barrier after each; while a block waits at such a barrier it advances the rollouts of its own leaves
-// in slices.  Then [rollout + backup]: the remaining rollouts and the backups (commutative integer atomics) are
-// claimed 32 simulations at a time from a work counter.
+// generation the tree statistics are read-only, and the action plan of a node depends only on its statistics and on
+// the number of simulations EXPECTED there (pomcp_plan.cuh) -- so a generation is two phases and two grid barriers:
+//     [descend + rollout]  warps claim 32 simulations at a time; every simulation draws a root particle, walks down
+//                          the tree on its own (plan lookup: block cache in shared memory -> node record in L2 ->
+//                          computed by this warp), creates / finds the child and, at the first node without
+//                          statistics, takes a uniform action and rolls out
+//     [backup]             the recorded paths update the statistics (commutative integer atomics, folded per warp and
+//                          staged per block in shared memory)
 // ---------------------------------------------------------------------------------------------------------
-template <int KIND> struct SimCtx {
-    const SearchParams &p;
-    const typename Mdl<KIND>::Ctx &m;
-};
 
 // A simulation standing at a node without statistics (N = 0): every legal action is untried, so UCB1 is a uniform
 // draw (action_selectors.py:6-37 with +inf bonuses), the node cannot be expanded (solvers/pomcp.py:107) and the
 // simulation ends in a rollout.  `node_ref` is the node id, or -1 - child_slot while the id is being published.
 template <int KIND>
-__device__ __forceinline__ void virgin_step(const SimCtx<KIND> &c, int i, uint32_t sim, int node_ref, uint32_t mask,
-                                            uint32_t st, int d, long long &c_levels)
+__device__ __forceinline__ void virgin_step(const SearchParams &p, const typename Mdl<KIND>::Ctx &mc, int i, uint32_t sim,
+                                            int node_ref, uint32_t mask, uint32_t &st, int &d, int &status,
+                                            int &last_ref, uint32_t &last_ar, long long &c_levels)
 {
-    const SearchParams &p = c.p;
-    if (d >= p.max_depth) { p.b.flag[i] = 2; p.b.depth[i] = (uint8_t)d; return; }          // solvers/pomcp.py:100
-    DCHECK(p.S, mask != 0u && d < p.dcap && Mdl<KIND>::tag_ok(c.m, Mdl<KIND>::state_tag(st)), 11);
+    if (d >= p.max_depth) { status = 2; return; }                                          // solvers/pomcp.py:100
+    DCHECK(p.S, mask != 0u && d < p.dcap && Mdl<KIND>::tag_ok(mc, Mdl<KIND>::state_tag(st)), 11);
     const Philox4 r = philox4x32_10((uint32_t)(d + 1), sim, p.move, DOM_SIM, p.key0, p.key1);
     const int a = nth_bit(mask, randbelow32(r.x, (uint32_t)__popc(mask)));
-    const StepOut so = Mdl<KIND>::step(c.m, st, a, r.y, r.z);
+    const StepOut so = Mdl<KIND>::step(mc, st, a, r.y, r.z);
     ++c_levels;
+    const uint16_t code = Mdl<KIND>::path_code(a, so);
     p.b.path_node[(size_t)d * p.wmax + i] = node_ref;
-    p.b.path_ar[(size_t)d * p.wmax + i] = Mdl<KIND>::path_code(a, so);
+    p.b.path_ar[(size_t)d * p.wmax + i] = code;
     if (KIND == 1) p.b.path_rew[(size_t)d * p.wmax + i] = so.reward;
-    p.b.depth[i] = (uint8_t)(d + 1);
-    p.b.state[i] = so.next;
-    p.b.flag[i] = so.terminal ? 2 : 1;
+    last_ref = node_ref; last_ar = code;
+    d = d + 1;
+    st = so.next;
+    status = so.terminal ? 2 : 1;
 }
 
 __device__ __forceinline__ int row_sum(const int32_t *nrow)
@@ -71,6 +69,7 @@ template <int KIND>
 __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char *smem)
 {
     using MD = Mdl<KIND>;
+    const unsigned FULL = 0xFFFFFFFFu;
     unsigned int bar_epoch = 0;
 #define GRID_SYNC() grid_barrier(&p.S->barrier, gridDim.x, bar_epoch)
     typename MD::Ctx mc;
@@ -86,23 +85,20 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
     int *acc_n = reinterpret_cast<int *>(smem + off);
     off += (size_t)n_acc * 4;
     off = (off + 15) & ~size_t(15);                                  // the tables below hold 64-bit words
-    int *arr1 = reinterpret_cast<int *>(smem + off);               // arrivals at the root's children, per block
-    for (int i = threadIdx.x; i < ZS * A; i += blockDim.x) arr1[i] = 0;
-    off += ((size_t)ZS * A * 4 + 15) & ~size_t(15);
-    uint32_t *ht_key = reinterpret_cast<uint32_t *>(smem + off);    // arrivals at deeper nodes, per block (hash table)
+    uint32_t *ht_key = reinterpret_cast<uint32_t *>(smem + off);    // backup: visits and return sums of shared deeper edges
     int *ht_cnt = reinterpret_cast<int *>(smem + off + ARR_HT * 4);
-    long long *ht_q = reinterpret_cast<long long *>(smem + off + ARR_HT * 8);   // backup phase: return sums per edge
+    long long *ht_q = reinterpret_cast<long long *>(smem + off + ARR_HT * 8);
+    off += (size_t)ARR_HT * 16;
+    uint32_t *pc = reinterpret_cast<uint32_t *>(smem + off);        // plan cache of the hot nodes (PC_SLOTS x PC_WORDS)
     for (int i = threadIdx.x; i < ARR_HT; i += blockDim.x) { ht_key[i] = 0u; ht_cnt[i] = 0; ht_q[i] = 0; }
+    for (int i = threadIdx.x; i < PC_SLOTS; i += blockDim.x) { pc[i * PC_WORDS] = 0u; pc[i * PC_WORDS + 1] = 0u; }
     if (threadIdx.x == 0) { double d = 1.0; for (int t = 0; t < p.max_depth; ++t) { disc[t] = d; d *= p.discount; } }
     for (int i = threadIdx.x; i < n_acc; i += blockDim.x) { acc_q[i] = 0; acc_n[i] = 0; }
     __syncthreads();
 
     DevState *S = p.S;
-    const int T = gridDim.x * blockDim.x;
     const int gtid = blockIdx.x * blockDim.x + threadIdx.x;
     const int lane = threadIdx.x & 31;
-    const int gwarp = gtid >> 5, nwarps = T >> 5;
-    const int vwarp = (threadIdx.x >> 5) * gridDim.x + blockIdx.x;   // warp index that walks the blocks first
     const int root = S->root;
     if constexpr (KIND == 0) { mc.actual = S->actual; mc.sampled = S->sampled; }
     const uint32_t *bag = p.bag[S->bag_sel];
@@ -110,306 +106,258 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
     unsigned long long gstep = S->gstep;
     const unsigned long long t_start = globaltimer_ns();
     long long c_levels = 0, c_rollout = 0, c_created = 0, c_alloc = 0;
-    long long done = 0, gens = 0, lsteps = 0;
-    unsigned long long tp[6] = {0, 0, 0, 0, 0, 0}, tmark = t_start;   // phase clocks (gtid 0 only)
-#define PHASE_MARK(k) do { if (gtid == 0) { const unsigned long long now_ = globaltimer_ns(); tp[k] += now_ - tmark; tmark = now_; } } while (0)
-    const SimCtx<KIND> ctx{p, mc};
+    long long done = 0, gens = 0;
+    unsigned long long tp[4] = {0, 0, 0, 0}, tmark = t_start;       // phase clocks (gtid 0 only)
+#define PHASE_MARK(k) do { if (gtid == 0) { const unsigned long long now_ = globaltimer_ns(); tp[k] += now_ - tmark; \
+                                             if (gens <= 120) S->steplog[gens - 1][k] = (long long)(now_ - tmark); tmark = now_; } } while (0)
     TSEC_DECL;
+    const float pc_min_k = 4.0f * (float)gridDim.x;                  // expected arrivals that earn a node a slot in the block caches
     int W = p.w0;
-    long long gen_done = 0;                                          // simulations of earlier generations (stream ids)
-
-    // Advance the rollout of leaf simulation i by at most `budget` steps (an even number, or to the end): the state
-    // of a rollout in progress lives in p.b.state / ro_sum / ro_t, so any thread may resume it.
-    auto rollout_advance = [&](int i, int budget) {
-        const uint32_t sim = p.sim_offset + (uint32_t)(gen_done + i);
-        const int depth = p.b.depth[i];
-        uint32_t st = p.b.state[i];
-        double sum = p.b.ro_sum[i];
-        int t = p.b.ro_t[i];
-        const int t0 = t, t_end = (t + budget < p.max_depth) ? t + budget : p.max_depth;
-        bool finished;
-        if constexpr (KIND == 0) {
-            if (p.pref_rollout) {                                    // only called with the full budget (final phase)
-                int X = p.b.path_node[(size_t)(depth - 1) * p.wmax + i];
-                if (X < 0) X = CHILD_ID(p.t.child[(size_t)(-1 - X)]);
-                const uint32_t ar = p.b.path_ar[(size_t)(depth - 1) * p.wmax + i];
-                const typename Mdl<0>::PrefOut po =
-                    Mdl<0>::rollout_preferred(mc.M, mc.actual, mc.sampled, p.t.prob, p.t.chance + (size_t)X * POMCP_RS,
-                                              p.t.good + (size_t)X * POMCP_RS, p.t.cell[X], (int)(ar & 31u), MD::path_obs(ar),
-                                              sim, p.move, p.key0, p.key1, depth, disc, st, t, t_end, sum);
-                st = po.st; t = po.t; sum = po.sum; finished = po.finished != 0;
-            } else finished = MD::rollout(mc, S, sim, p.move, p.ks, depth, disc, st, t, t_end, sum);
-        } else finished = MD::rollout(mc, S, sim, p.move, p.ks, depth, disc, st, t, t_end, sum);
-        c_rollout += t - t0;
-        p.b.ro_sum[i] = sum;
-        if (finished || t >= p.max_depth) p.b.flag[i] = 3;
-        else { p.b.state[i] = st; p.b.ro_t[i] = (uint8_t)t; }
-    };
-
-    // Grid barrier that works while it waits: after arriving, the block keeps advancing the rollouts of its own leaf
-    // simulations in slices of ROLL_SLICE steps until every block has arrived.
-    int gen_w = 0;                                                   // width of the current generation
-    auto grid_sync_working = [&]() {
-        __syncthreads();
-        ++bar_epoch;
-        if (threadIdx.x == 0) { __threadfence(); atomicAdd(&S->barrier, 1u); }
-        const unsigned int target = bar_epoch * gridDim.x;
-        int next_j = 0;
-        for (;;) {
-            int released = 0;
-            if (threadIdx.x == 0) released = *((volatile unsigned int *)&S->barrier) >= target;
-            if (__syncthreads_or(released)) break;
-            int worked = 0;
-            for (; gtid + next_j * T < gen_w; ++next_j) {
-                const int i = gtid + next_j * T;
-                if ((p.b.flag[i] & 3) == 1 && !p.pref_rollout) { rollout_advance(i, ROLL_SLICE); worked = 1; break; }   // stay on i until done
-            }
-            if (!__syncthreads_or(worked)) __nanosleep(64);
-        }
-        if (threadIdx.x == 0) __threadfence();
-        __syncthreads();
-    };
 
     GRID_SYNC();                                                    // everyone has read S before anyone writes it
 
     while (done < p.n_sims) {
         const int w = (int)((p.n_sims - done) < (long long)W ? (p.n_sims - done) : (long long)W);
-        ++gens;
-        gen_w = w; gen_done = done;
-        // ---- start of a generation: every simulation draws a root particle (belief_node.py:47-48) ----
-        const bool root_virgin = row_sum(p.t.n + (size_t)root * AS) == 0;
+        ++gens; ++gstep;
+        const uint32_t stamp = (uint32_t)gstep;                      // of the plans computed in this generation
+        const int Nroot = row_sum(p.t.n + (size_t)root * AS);
         const uint32_t root_mask = p.t.legal[root];
-        if (gtid == 0) S->ro_cursor[(gens + 1) & 1] = 0;            // the next generation's work counter
-        if (!root_virgin && gwarp == 0) {                            // all w simulations arrive at the root
-            if (lane == 0) {
-                const unsigned long long s1 = gstep + 1;
-                p.t.arrive[root] = (s1 << 32) | (unsigned long long)(unsigned)w;
-                p.b.wl_node[(size_t)(s1 & 1ull) * p.wmax] = root; S->wl_count[(int)(s1 & 3ull)] = 1;
-                S->wl_count[(int)((s1 + 1) & 3ull)] = 0;             // the counter the first level step fills
-            }
-            warp_plan(p, root, (uint32_t)w, lane, A, 0);                 // known now: no extra phase
-            if (lane == 0 && (uint32_t)w > SEQ_ALLOC_MAX) ++c_alloc;
-        }
-        for (int i = gtid; i < w; i += T) {
-            const uint32_t sim = p.sim_offset + (uint32_t)(done + i);
-            const Philox4 r = philox4x32_10(0u, sim, p.move, DOM_SIM, p.key0, p.key1);
-            const uint32_t st = bag[randbelow32(r.x, (uint32_t)n_bag)];
-            p.b.ro_t[i] = 0; p.b.ro_sum[i] = 0.0;
-            if (root_virgin) virgin_step<KIND>(ctx, i, sim, root, root_mask, st, 0, c_levels);
-            else { p.b.state[i] = st; p.b.node[i] = root; p.b.flag[i] = 0; p.b.depth[i] = 0; }
-        }
+        if (gtid == 0) { S->cursor[2 * ((gens + 1) & 1)] = 0; S->cursor[2 * ((gens + 1) & 1) + 1] = 0; }   // the next generation's
         PHASE_MARK(0);
-        if (!root_virgin) for (int level = 0;; ++level) {            // ---- level steps ----
-            ++gstep; ++lsteps;
-            const int ring = (int)(gstep & 3ull), ring_next = (int)((gstep + 1) & 3ull);
-            const unsigned long long stamp_next = (gstep + 1) << 32;
-            const int32_t *wl_cur = p.b.wl_node + (size_t)(gstep & 1ull) * p.wmax;
-            int32_t *wl_next = p.b.wl_node + (size_t)((gstep + 1) & 1ull) * p.wmax;
-            // cnt arrivals at node Xn for the next level step: stamp the node and enter it in the worklist on its first
-            // arrival (a plain L2 read first: a busy node is almost always stamped already), then one fire-and-forget add
-            auto register_arrivals = [&](int Xn, uint32_t cnt) {
-                if (*((volatile unsigned long long *)&p.t.arrive[Xn]) < stamp_next) {
-                    const unsigned long long old = atomicMax(&p.t.arrive[Xn], stamp_next);
-                    if (old < stamp_next) {
-                        const int sl = atomicAdd(&S->wl_count[ring_next], 1);
-                        DCHECK(S, sl < p.wmax, 25);
-                        wl_next[sl] = Xn;
-                    }
-                }
-                atomicAdd(&p.t.arrive[Xn], (unsigned long long)cnt);
-            };
-            grid_sync_working();                                     // arrivals of this level are complete
-            if (gtid == 0 && lsteps <= 128) S->steplog[lsteps - 1][0] = (long long)(globaltimer_ns() - tmark);
-            PHASE_MARK(1);
-            const int nwl = *((volatile int32_t *)&S->wl_count[ring]);
-            // the counter of the level step after the next one is cleared a whole step ahead (blocks enter the expand
-            // phase, which fills ring_next, without another grid barrier); it was last read two steps ago
-            if (gtid == 0) S->wl_count[(int)((gstep + 2) & 3ull)] = 0;
-            if (nwl == 0) break;
-            // [allocate] one warp per worklist node computes the node's action plan for its arrivals: every warp
-            // inspects 32 entries at once (strided by the warp count, so that the early, busy entries spread out)
-            if (level > 0) {
-            for (int base = 0; base < nwl; base += nwarps * 32) {
-                const int e = base + lane * nwarps + vwarp;
-                int X = 0; uint32_t k = 0;
-                if (e < nwl) { X = wl_cur[e]; k = (uint32_t)p.t.arrive[X]; }
-                unsigned todo = __ballot_sync(0xFFFFFFFFu, e < nwl);
-                while (todo) {
-                    const int src = __ffs((int)todo) - 1;
-                    todo &= todo - 1;
-                    const int es = base + src * nwarps + vwarp;
-                    const uint32_t ks = __shfl_sync(0xFFFFFFFFu, k, src);
-                    warp_plan(p, __shfl_sync(0xFFFFFFFFu, X, src), ks, lane, A, es);
-                    if (lane == 0 && ks > SEQ_ALLOC_MAX) ++c_alloc;
-                }
-            }
-            if (gtid == 0 && lsteps <= 128) S->steplog[lsteps - 1][1] = (long long)(globaltimer_ns() - tmark);
-            grid_sync_working();
-            }
-            if (gtid == 0 && lsteps <= 128) { S->steplog[lsteps - 1][2] = (long long)(globaltimer_ns() - tmark) - S->steplog[lsteps - 1][1]; S->steplog[lsteps - 1][4] = nwl; }
-            PHASE_MARK(2);
-            // [expand] choose an action, step the model, look up / create the child (solvers/pomcp.py:97-117)
-            for (int base = gtid - lane; base < w; base += T) {
-                const int i = base + lane;
-                int arrive_at = -1, arrive_slot = 0;                 // non-virgin child this simulation descends to
-                TSEC_START();
-                if (i < w && (p.b.flag[i] & 3) == 0) {
-                    const int X = p.b.node[i];
-                    const int d = p.b.depth[i];
-                    const uint32_t sim = p.sim_offset + (uint32_t)(done + i);
-                    DCHECK(S, X >= 0 && X < S->node_count && d < p.dcap, 21);
-                    if (d >= p.max_depth) p.b.flag[i] = 2;                                  // :100
-                    else {
-                        const Philox4 r = philox4x32_10((uint32_t)(d + 1), sim, p.move, DOM_SIM, p.key0, p.key1);
-                        TSEC(0);                                     // load sim (+ Philox)
-                        const int a = plan_action(p, X, r.x, A);
-                        DCHECK(S, a >= 0 && a < A && ((p.t.legal[X] >> a) & 1u), 22);
-                        TSEC(1);                                     // choice
-                        const uint32_t st = p.b.state[i];
-                        DCHECK(S, MD::state_tag(st) == (uint32_t)p.t.cell[X], 23);
-                        const StepOut so = MD::step(mc, st, a, r.y, r.z);                   // :104
-                        ++c_levels;
-                        p.b.path_node[(size_t)d * p.wmax + i] = X;
-                        p.b.path_ar[(size_t)d * p.wmax + i] = MD::path_code(a, so);
-                        if (KIND == 1) p.b.path_rew[(size_t)d * p.wmax + i] = so.reward;
-                        p.b.depth[i] = (uint8_t)(d + 1);
-                        p.b.state[i] = so.next;
-                        TSEC(2);                                     // step + path stores
-                        if (so.terminal) p.b.flag[i] = 2;
-                        else {
-                            const size_t cslot = ((size_t)X * AS + a) * ZS + so.obs;
-                            uint32_t cmask = MD::tag_legal(mc, so.tag); bool have_mask = false;   // the child's action set
-                            uint32_t c = p.t.child[cslot];                                  // :106
-                            if (c == 0 && d + 1 < p.dcap) {                                 // :107-108 (N(X) > 0 here)
-                                // one CAS per distinct child slot among the lanes that got here together
-                                const unsigned cm = __activemask();
-                                const unsigned same = __match_any_sync(cm, (unsigned long long)cslot);
-                                if (lane == __ffs((int)same) - 1) c = atomicCAS(&p.t.child[cslot], 0u, CHILD_LOCKED);
-                                c = __shfl_sync(same, c, __ffs((int)same) - 1);
-                                if (lane != __ffs((int)same) - 1 && c == 0) c = CHILD_LOCKED;   // the group leader creates it
-                                if (c == 0) {                                               // this thread creates it
-                                    const unsigned am = __activemask();                     // one arena bump per warp
-                                    const int rk = __popc(am & ((1u << lane) - 1u));
-                                    int id0 = 0;
-                                    if (rk == 0) id0 = atomicAdd(&S->node_count, __popc(am));
-                                    const int id = __shfl_sync(am, id0, __ffs((int)am) - 1) + rk;
-                                    DCHECK(S, id > 0 && (long long)id < p.node_cap, 24);
-                                    p.t.cell[id] = (int32_t)so.tag;
-                                    if constexpr (KIND == 0) if (p.t.chance)                // create_child + smart action set
-                                        cmask = child_smart_mask(mc.M.hdr, p.t.prob, p.t.chance + (size_t)X * POMCP_RS,
-                                                                 p.t.good + (size_t)X * POMCP_RS,
-                                                                 p.t.chance + (size_t)id * POMCP_RS,
-                                                                 p.t.good + (size_t)id * POMCP_RS, (int)(st & 0xFFu), a,
-                                                                 so.obs, (int)so.tag);
-                                    p.t.legal[id] = cmask;
-                                    // The id may be picked up by another SM in this very phase.  Without preferred
-                                    // actions such a reader derives the action set from its own state and touches no
-                                    // field of the node before the next grid barrier; with them it reads legal[id]:
-                                    // node fields before the id
-                                    if (KIND == 0 && p.t.chance) __threadfence();
-                                    __stcg(&p.t.child[cslot], (uint32_t)id + 1u);
-                                    ++c_created;
-                                    c = CHILD_LOCKED; have_mask = true;
-                                }
-                            }
-                            TSEC(3);                                                        // child lookup / creation
-                            if (c == 0) p.b.flag[i] = 1;                                    // depth cap: leaf (:119)
-                            else if (c == CHILD_LOCKED) {                                   // created in this step
-                                if constexpr (KIND == 0) if (p.t.chance && !have_mask)      // id not published yet: derive the set
-                                    cmask = child_smart_mask(mc.M.hdr, p.t.prob, p.t.chance + (size_t)X * POMCP_RS,
-                                                             p.t.good + (size_t)X * POMCP_RS, nullptr, nullptr,
-                                                             (int)(st & 0xFFu), a, so.obs, (int)so.tag);
-                                virgin_step<KIND>(ctx, i, sim, -1 - (int)cslot, cmask, so.next, d + 1, c_levels);
-                            } else {
-                                const int id = CHILD_ID(c);
-                                if (!(c & CHILD_VISITED)) {                                 // no statistics yet (N = 0)
-                                    // the node may have been published in this very phase by another SM: with
-                                    // preferred actions its action set is read from L2 (ld.cg), never from a possibly
-                                    // stale L1 line; otherwise it follows from the simulation's own state
-                                    if (KIND == 0 && p.t.chance) cmask = __ldcg(&p.t.legal[id]);
-                                    virgin_step<KIND>(ctx, i, sim, id, cmask, so.next, d + 1, c_levels);
-                                }
-                                else { p.b.node[i] = id; arrive_at = id; arrive_slot = a * ZS + so.obs; }   // descend
-                            }
-                        }
-                    }
-                }
-                TSEC(4);                                             // leaf (virgin step) or descend
-                __syncwarp();
-                TSEC(5);
-                // arrivals for the next level are counted per block in shared memory -- from the root in a table
-                // indexed by child slot (<= ZS|A| children), deeper in a small hash table keyed by node id -- and
-                // published once per block and node after the loop: a busy node sees one atomic per block, not one per
-                // warp, and no simulation waits for the round trip
-                if (arrive_at >= 0) {
-                    if (level == 0) atomicAdd(&arr1[arrive_slot], 1);
-                    else {
-                        uint32_t hq = (((uint32_t)arrive_at * 2654435761u) >> 16) & (ARR_HT - 1);
-                        int probe = 0;
-                        for (; probe < ARR_PROBES; ++probe, hq = (hq + 1u) & (ARR_HT - 1)) {
-                            const uint32_t prev = atomicCAS(&ht_key[hq], 0u, (uint32_t)arrive_at);
-                            if (prev == 0u || prev == (uint32_t)arrive_at) { atomicAdd(&ht_cnt[hq], 1); break; }
-                        }
-                        if (probe == ARR_PROBES) register_arrivals(arrive_at, 1u);      // table crowded: publish directly
-                    }
-                }
-                TSEC(6);                                             // arrival registration
-            }
-            __syncthreads();                                         // publish this block's arrivals
-            if (level == 0) {
-                for (int t = threadIdx.x; t < ZS * A; t += blockDim.x) {
-                    const int cnt = arr1[t];
-                    if (cnt == 0) continue;
-                    arr1[t] = 0;
-                    register_arrivals(CHILD_ID(p.t.child[(size_t)root * AS * ZS + t]), (uint32_t)cnt);
-                }
-            } else {
-                for (int t = threadIdx.x; t < ARR_HT; t += blockDim.x) {
-                    const uint32_t key = ht_key[t];
-                    if (key == 0u) continue;
-                    const int cnt = ht_cnt[t];
-                    ht_key[t] = 0u; ht_cnt[t] = 0;
-                    register_arrivals((int)key, (uint32_t)cnt);
-                }
-            }
-            if (gtid == 0 && lsteps <= 128) S->steplog[lsteps - 1][3] = (long long)(globaltimer_ns() - tmark);
-#ifdef POMCP_TSEC
-            if (lsteps <= 63) {                                      // per level step: rows 64.. of the step log
-                for (int k = 0; k < 8; ++k) {
-                    long long v = tsec_[k] - tsec_prev_[k];
-                    tsec_prev_[k] = tsec_[k];
-                    for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-                    if (lane == 0 && v) atomicAdd(reinterpret_cast<unsigned long long *>(&S->steplog[63 + lsteps][k]), (unsigned long long)v);
-                }
-            }
-#endif
-            PHASE_MARK(3);
-        }
-        // ---- rollout (belief_tree_solver.py:123-152, from the post-action state) + backup (:126-137) ----
-        GRID_SYNC();              // every slice in flight has been stored: leaves are claimed by other threads below
-        // Simulations are claimed 32 at a time from a work counter: rollouts that already advanced while their
-        // owner waited at a barrier are resumed (or skipped) by whoever claims them, which balances the tail.
+        // ---- descent (solvers/pomcp.py:87-137) + rollout (belief_tree_solver.py:123-152, from the post-action state) ----
         for (;;) {
             int base = 0;
-            if (lane == 0) base = atomicAdd(&S->ro_cursor[gens & 1], 32);
-            base = __shfl_sync(0xFFFFFFFFu, base, 0);
+            if (lane == 0) base = atomicAdd(&S->cursor[2 * (gens & 1)], 32);
+            base = __shfl_sync(FULL, base, 0);
+            if (base >= w) break;
+            const int i = base + lane;
+            const uint32_t sim = p.sim_offset + (uint32_t)(done + i);
+            int status = i < w ? 0 : 4;                              // 0 descending, 1 leaf: rollout pending, 2 ended in the tree, 4 no simulation
+            uint32_t st = 0u; int X = root, d = 0, na = Nroot;
+            float kpre = (float)w;                                   // expected arrivals at X = kpre * N(X) / na
+            int last_ref = root; uint32_t last_ar = 0u;              // the last tree step (preferred-action rollouts)
+            TSEC_START();
+            if (status == 0) {                                       // root particle (belief_node.py:47-48)
+                const Philox4 r = philox4x32_10(0u, sim, p.move, DOM_SIM, p.key0, p.key1);
+                st = bag[randbelow32(r.x, (uint32_t)n_bag)];
+                if (Nroot == 0) virgin_step<KIND>(p, mc, i, sim, root, root_mask, st, d, status, last_ref, last_ar, c_levels);
+            }
+            float kx = -1.0f;                                        // expected arrivals at X (< 0: not computed yet)
+            bool filler = false;                                     // this lane fetches X's plan for the whole block
+            while (__any_sync(FULL, status == 0)) {                  // one tree level per iteration, for the lanes whose
+                bool act = status == 0;                              // plan is at hand; the others retry (nobody blocks)
+                if (act && d >= p.max_depth) { status = 2; act = false; }                  // :100
+                // -- the plan of node X: block cache (shared memory), node record (L2), or computed here
+                uint32_t *pce = pc + (((uint32_t)X * 2654435761u) >> (32 - PC_BITS)) * PC_WORDS;
+                bool have = false, cand = false, progressed = false;
+                uint4 head = make_uint4(0u, 0u, 0u, 0u), data = head;
+                const uint32_t *sthr = nullptr;
+                if (act && !filler && *((volatile uint32_t *)pce) == (uint32_t)X + 1u) {
+                    if (*((volatile uint32_t *)(pce + 1)) != 0u) {   // cached by this block (else: being fetched, retry)
+                        __threadfence_block();
+                        kx = __uint_as_float(pce[2]);
+                        head = *reinterpret_cast<const uint4 *>(pce + 4); data = *reinterpret_cast<const uint4 *>(pce + 8);
+                        sthr = pce + 12;
+                        have = true;
+                    }
+                } else if (act) {
+                    bool retry = false;
+                    if (kx < 0.0f) {
+                        const int N = row_sum(p.t.n + (size_t)X * AS);
+                        if (N == 0) {                                // a node without statistics: uniform action, leaf
+                            uint32_t vm = MD::tag_legal(mc, MD::state_tag(st));
+                            // published in this very phase, maybe by another SM: with preferred actions its action set
+                            // is read from L2, never from a possibly stale L1 line
+                            if (KIND == 0 && p.t.chance) vm = __ldcg(&p.t.legal[X]);
+                            virgin_step<KIND>(p, mc, i, sim, X, vm, st, d, status, last_ref, last_ar, c_levels);
+                            retry = true; progressed = true;
+                        } else {
+                            kx = kpre * ((float)N / (float)na);
+                            if (kx >= pc_min_k) {                    // hot: one lane of the block fetches it for all
+                                const uint32_t prev = atomicCAS(pce, 0u, (uint32_t)X + 1u);
+                                filler = prev == 0u;
+                                retry = prev == (uint32_t)X + 1u;    // another warp is at it: pick it up from the cache
+                            }
+                        }
+                    }
+                    if (!retry) {
+                        if (kx >= 1.5f) {
+                            head = __ldcg(&p.t.plan[(size_t)X * 2]); data = __ldcg(&p.t.plan[(size_t)X * 2 + 1]);
+                            have = head.y == stamp;
+                        }
+                        if (!have && kx < 16.5f) {                   // few expected arrivals: this thread computes the plan
+                            const int kq = (int)(kx + 0.5f);         // (also if another thread is at it: no waiting)
+                            const bool won = kx >= 1.5f && head.y != PLAN_LOCKED &&
+                                atomicCAS(reinterpret_cast<uint32_t *>(&p.t.plan[(size_t)X * 2]) + 1, head.y, PLAN_LOCKED) == head.y;
+                            const PlanRec r = thread_plan_few(p, X, (uint32_t)(kq < 1 ? 1 : kq), A, stamp);
+                            head = r.head; data = r.data; have = true;
+                            if (won) {                               // publish: data, then the head with the stamp
+                                __stcg(&p.t.plan[(size_t)X * 2 + 1], data);
+                                __threadfence();
+                                __stcg(&p.t.plan[(size_t)X * 2], head);
+                            }
+                        } else if (!have) cand = head.y != PLAN_LOCKED;   // a batch-UCB allocation nobody has claimed
+                    }
+                }
+                // one allocation per warp and iteration (lane = action): the warp takes the first unclaimed one it can
+                // get; the others are left to the warps that arrive meanwhile, or to the next iteration
+                unsigned cm = __ballot_sync(FULL, cand);
+                while (cm) {
+                    const int src = __ffs((int)cm) - 1;
+                    cm &= cm - 1;
+                    int won = 0;
+                    if (lane == src)
+                        won = atomicCAS(reinterpret_cast<uint32_t *>(&p.t.plan[(size_t)X * 2]) + 1, head.y, PLAN_LOCKED) == head.y;
+                    if (__shfl_sync(FULL, won, src)) {
+                        const PlanRec r = warp_plan(p, __shfl_sync(FULL, X, src), __shfl_sync(FULL, kx, src), lane, A, stamp,
+                                                    true, c_alloc);
+                        if (lane == src) { head = r.head; data = r.data; have = true; }
+                        break;
+                    }
+                }
+                unsigned fill = __ballot_sync(FULL, filler && have);
+                while (fill) {                                       // copy hot plans into the block cache
+                    const int src = __ffs((int)fill) - 1;
+                    fill &= fill - 1;
+                    const int Xs = __shfl_sync(FULL, X, src);
+                    uint32_t *e = pc + (((uint32_t)Xs * 2654435761u) >> (32 - PC_BITS)) * PC_WORDS;
+                    e[12 + lane] = __ldcg(&p.t.thr[(size_t)Xs * 32 + lane]);
+                    if (lane == src) {
+                        e[2] = __float_as_uint(kx);
+                        *reinterpret_cast<uint4 *>(e + 4) = head; *reinterpret_cast<uint4 *>(e + 8) = data;
+                    }
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == src) { *((volatile uint32_t *)(e + 1)) = 1u; filler = false; }
+                }
+                act = act && have;
+                TSEC(0);                                             // plan acquisition
+                // -- choose, step the model, look up / create the child (solvers/pomcp.py:97-117)
+                if (act) {
+                    DCHECK(S, X >= 0 && X < S->node_count && d < p.dcap, 21);
+                    const Philox4 r = philox4x32_10((uint32_t)(d + 1), sim, p.move, DOM_SIM, p.key0, p.key1);
+                    float pa;
+                    const int a = plan_action(head, data, sthr, p.t.thr + (size_t)X * 32, r.x, A, pa);
+                    DCHECK(S, a >= 0 && a < A && ((p.t.legal[X] >> a) & 1u), 22);
+                    DCHECK(S, MD::state_tag(st) == (uint32_t)p.t.cell[X], 23);
+                    const StepOut so = MD::step(mc, st, a, r.y, r.z);                       // :104
+                    ++c_levels;
+                    const uint16_t code = MD::path_code(a, so);
+                    p.b.path_node[(size_t)d * p.wmax + i] = X;
+                    p.b.path_ar[(size_t)d * p.wmax + i] = code;
+                    if (KIND == 1) p.b.path_rew[(size_t)d * p.wmax + i] = so.reward;
+                    last_ref = X; last_ar = code;
+                    const uint32_t pcell = st & 0xFFu;
+                    progressed = true;
+                    d = d + 1;
+                    st = so.next;
+                    TSEC(1);                                         // choice + step + path stores
+                    if (so.terminal) status = 2;
+                    else {
+                        const size_t cslot = ((size_t)X * AS + a) * ZS + so.obs;
+                        uint32_t cmask = MD::tag_legal(mc, so.tag); bool have_mask = false;   // the child's action set
+                        uint32_t c = p.t.child[cslot];                                      // :106
+                        if (c == 0 && d < p.dcap) {                                         // :107-108 (N(X) > 0 here)
+                            // one CAS per distinct child slot among the lanes that got here together
+                            const unsigned cm = __activemask();
+                            const unsigned same = __match_any_sync(cm, (unsigned long long)cslot);
+                            if (lane == __ffs((int)same) - 1) c = atomicCAS(&p.t.child[cslot], 0u, CHILD_LOCKED);
+                            c = __shfl_sync(same, c, __ffs((int)same) - 1);
+                            if (lane != __ffs((int)same) - 1 && c == 0) c = CHILD_LOCKED;   // the group leader creates it
+                            if (c == 0) {                                                   // this thread creates it
+                                const unsigned am = __activemask();                         // one arena bump per warp
+                                const int rk = __popc(am & ((1u << lane) - 1u));
+                                int id0 = 0;
+                                if (rk == 0) id0 = atomicAdd(&S->node_count, __popc(am));
+                                const int id = __shfl_sync(am, id0, __ffs((int)am) - 1) + rk;
+                                DCHECK(S, id > 0 && (long long)id < p.node_cap, 24);
+                                p.t.cell[id] = (int32_t)so.tag;
+                                if constexpr (KIND == 0) if (p.t.chance)                    // create_child + smart action set
+                                    cmask = child_smart_mask(mc.M.hdr, p.t.prob, p.t.chance + (size_t)X * POMCP_RS,
+                                                             p.t.good + (size_t)X * POMCP_RS,
+                                                             p.t.chance + (size_t)id * POMCP_RS,
+                                                             p.t.good + (size_t)id * POMCP_RS, (int)pcell, a,
+                                                             so.obs, (int)so.tag);
+                                p.t.legal[id] = cmask;
+                                // The id may be picked up by another SM in this very phase.  Without preferred actions
+                                // such a reader derives the action set from its own state and reads only the (zero)
+                                // statistics of the node; with them it reads legal[id] and the rock statistics: node
+                                // fields before the id
+                                if (KIND == 0 && p.t.chance) __threadfence();
+                                __stcg(&p.t.child[cslot], (uint32_t)id + 1u);
+                                ++c_created;
+                                c = CHILD_LOCKED; have_mask = true;
+                            }
+                        }
+                        if (c == 0) status = 1;                                             // depth cap: leaf (:119)
+                        else if (c == CHILD_LOCKED) {                                       // created in this generation
+                            if constexpr (KIND == 0) if (p.t.chance && !have_mask)          // id not published yet: derive the set
+                                cmask = child_smart_mask(mc.M.hdr, p.t.prob, p.t.chance + (size_t)X * POMCP_RS,
+                                                         p.t.good + (size_t)X * POMCP_RS, nullptr, nullptr,
+                                                         (int)pcell, a, so.obs, (int)so.tag);
+                            virgin_step<KIND>(p, mc, i, sim, -1 - (int)cslot, cmask, st, d, status, last_ref, last_ar, c_levels);
+                        } else {                                                            // descend
+                            na = p.t.n[(size_t)X * AS + a];
+                            kpre = kx * pa;
+                            X = CHILD_ID(c);
+                            kx = -1.0f;
+                        }
+                    }
+                }
+                TSEC(2);                                             // child lookup / creation / leaf
+                if (!__any_sync(FULL, progressed)) __nanosleep(100); // every lane waits for a plan another warp computes
+            }
+            // -- rollout
+            double sum = 0.0;
+            if (status == 1) {
+                int t = 0;
+                if constexpr (KIND == 0) {
+                    if (p.pref_rollout) {
+                        int Xl = last_ref;
+                        if (Xl < 0) {                                // the leaf's id is being published by its creator
+                            uint32_t c;
+                            while ((c = __ldcg(&p.t.child[(size_t)(-1 - Xl)])) == CHILD_LOCKED) __nanosleep(64);
+                            Xl = CHILD_ID(c);
+                        }
+                        const typename Mdl<0>::PrefOut po =
+                            Mdl<0>::rollout_preferred(mc.M, mc.actual, mc.sampled, p.t.prob, p.t.chance + (size_t)Xl * POMCP_RS,
+                                                      p.t.good + (size_t)Xl * POMCP_RS, __ldcg(&p.t.cell[Xl]), (int)(last_ar & 31u),
+                                                      MD::path_obs(last_ar), sim, p.move, p.key0, p.key1, d, disc, st, 0,
+                                                      p.max_depth, 0.0);
+                        t = po.t; sum = po.sum;
+                    } else MD::rollout(mc, S, sim, p.move, p.ks, d, disc, st, t, p.max_depth, sum);
+                } else MD::rollout(mc, S, sim, p.move, p.ks, d, disc, st, t, p.max_depth, sum);
+                c_rollout += t;
+            }
+            if (status != 4) {
+                p.b.flag[i] = status == 1 ? 3 : 2;
+                p.b.depth[i] = (uint8_t)d;
+                p.b.ro_sum[i] = sum;
+            }
+            TSEC(3);                                                 // rollout
+        }
+        GRID_SYNC();              // the statistics were read-only up to here; every path and return is stored
+        PHASE_MARK(1);
+        // ---- backup (solvers/pomcp.py:126-137) ----
+        for (;;) {
+            int base = 0;
+            if (lane == 0) base = atomicAdd(&S->cursor[2 * (gens & 1) + 1], 32);
+            base = __shfl_sync(FULL, base, 0);
             if (base >= w) break;
             const int i = base + lane;
             const bool have = i < w;
             TSEC_START();
-            if (have && (p.b.flag[i] & 3) == 1) rollout_advance(i, p.max_depth);
-            TSEC(7);                                                 // final phase: rollouts
-            // Backup (solvers/pomcp.py:126-137), level by level from the deepest path entry of the warp: at level d the
-            // active lanes usually update the SAME edge (inside an episode the re-rooted tree is a long chain), so the
-            // warp first checks for a common edge and then issues one update for all of them.  Updates go to the
-            // per-block tables in shared memory -- root and depth-1 edges by index, deeper edges into the hash table
-            // keyed by edge -- which are flushed once per block after the loop: a hot edge sees one global atomic per
-            // block instead of one per simulation.  Integer sums: any order gives the same result.
+            // Level by level from the deepest path entry of the warp: at level d the active lanes usually update the
+            // SAME edge (inside an episode the re-rooted tree is a long chain), so the warp first checks for a common
+            // edge and then issues one update for all of them.  Updates go to the per-block tables in shared memory
+            // -- root and depth-1 edges by index, deeper edges into the hash table keyed by edge -- which are flushed
+            // once per block after the loop: a hot edge sees one global atomic per block instead of one per
+            // simulation.  Integer sums: any order gives the same result.
             const int depth = have ? (int)p.b.depth[i] : 0;
-            double delayed = (have && (p.b.flag[i] & 3) == 3) ? p.b.ro_sum[i] : 0.0;
+            double delayed = (have && p.b.flag[i] == 3) ? p.b.ro_sum[i] : 0.0;
             int dmax = depth;
 #pragma unroll
-            for (int off = 16; off >= 1; off >>= 1) dmax = max(dmax, __shfl_xor_sync(0xFFFFFFFFu, dmax, off));
+            for (int o = 16; o >= 1; o >>= 1) dmax = max(dmax, __shfl_xor_sync(FULL, dmax, o));
             for (int d = dmax - 1; d >= 0; --d) {
                 const bool act = d < depth;
                 uint32_t key = 0u;                                   // 1 + staged index, or 0x80000000 | edge index
@@ -421,27 +369,15 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                                      p.discount * delayed;
                     qi = __double2ll_rn(q * POMCP_QFIX_SCALE);
                     delayed = q;
-                    if (d == 0) {
-                        key = 1u + (uint32_t)a;
-                        if (!stage_d1 && depth > 1) {                        // the depth-1 child has statistics from now on
-                            uint32_t *cs = &p.t.child[((size_t)root * AS + a) * ZS + MD::path_obs(ar)];
-                            if (!(*((volatile uint32_t *)cs) & CHILD_VISITED)) atomicOr(cs, CHILD_VISITED);
-                        }
+                    if (d == 0) key = 1u + (uint32_t)a;
+                    else if (d == 1 && stage_d1) {
+                        const uint32_t ar0 = p.b.path_ar[i];
+                        key = 1u + (uint32_t)((1 + (int)(ar0 & 31) * ZS + MD::path_obs(ar0)) * A + a);
                     } else {
                         int X = p.b.path_node[(size_t)d * p.wmax + i];
-                        if (d == 1 && stage_d1) {
-                            const uint32_t ar0 = p.b.path_ar[i];
-                            key = 1u + (uint32_t)((1 + (int)(ar0 & 31) * ZS + MD::path_obs(ar0)) * A + a);
-                        } else {
-                            if (X < 0) X = CHILD_ID(p.t.child[(size_t)(-1 - X)]);   // id published after this sim passed
-                            DCHECK(S, X > 0 && X < S->node_count && a < A, 31);
-                            key = 0x80000000u | (uint32_t)(X * AS + a);
-                        }
-                        if (d + 1 < depth) {                                 // the child below this edge now has statistics
-                            if (X < 0) X = CHILD_ID(p.t.child[(size_t)(-1 - X)]);
-                            uint32_t *cs = &p.t.child[((size_t)X * AS + a) * ZS + MD::path_obs(ar)];
-                            if (!(*((volatile uint32_t *)cs) & CHILD_VISITED)) atomicOr(cs, CHILD_VISITED);
-                        }
+                        if (X < 0) X = CHILD_ID(p.t.child[(size_t)(-1 - X)]);   // id published after this simulation passed
+                        DCHECK(S, X > 0 && X < S->node_count && a < A, 31);
+                        key = 0x80000000u | (uint32_t)(X * AS + a);
                     }
                 }
                 // up to three rounds of "the first pending lane's edge, for every lane that shares it" (a chain level has
@@ -450,20 +386,20 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                 bool pending = act;
                 unsigned alone = 0u;                                     // lanes found to share their edge with nobody
                 // cheap test first: a warp whose neighbouring lanes rarely share an edge (a bushy tree) skips the rounds
-                const uint32_t nkey = __shfl_down_sync(0xFFFFFFFFu, key, 1);
-                const bool shared = __popc(__ballot_sync(0xFFFFFFFFu, act && key == nkey) & 0x7FFFFFFFu) >= 4;
+                const uint32_t nkey = __shfl_down_sync(FULL, key, 1);
+                const bool shared = __popc(__ballot_sync(FULL, act && key == nkey) & 0x7FFFFFFFu) >= 4;
 #pragma unroll
                 for (int round = 0; round < 3 && shared; ++round) {
-                    const unsigned todo = __ballot_sync(0xFFFFFFFFu, pending) & ~alone;
+                    const unsigned todo = __ballot_sync(FULL, pending) & ~alone;
                     if (todo == 0u) break;
                     const int leader = __ffs((int)todo) - 1;
-                    const uint32_t lkey = __shfl_sync(0xFFFFFFFFu, key, leader);
+                    const uint32_t lkey = __shfl_sync(FULL, key, leader);
                     const bool in_grp = pending && key == lkey;
-                    const unsigned grp = __ballot_sync(0xFFFFFFFFu, in_grp);
+                    const unsigned grp = __ballot_sync(FULL, in_grp);
                     if (__popc(grp) < 2) { alone |= grp; continue; }         // nothing to share: leave it to the tail
                     long long sum = in_grp ? qi : 0;
 #pragma unroll
-                    for (int off = 16; off >= 1; off >>= 1) sum += __shfl_xor_sync(0xFFFFFFFFu, sum, off);
+                    for (int o = 16; o >= 1; o >>= 1) sum += __shfl_xor_sync(FULL, sum, o);
                     if (lane == leader) {
                         const int cnt = __popc(grp);
                         if (!(lkey & 0x80000000u)) {
@@ -500,22 +436,16 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                     }
                 }
             }
-#ifdef POMCP_TSEC
-            { const long long n_ = clock64(); tsec_bk_ += n_ - tsec_t_; }   // final phase: backup
-#endif
+            TSEC(4);                                                 // backup
         }
+        PHASE_MARK(2);
         __syncthreads();
         for (int e = threadIdx.x; e < n_acc; e += blockDim.x) {      // flush the staged root / depth-1 edges
             const int dn = acc_n[e];
             if (dn == 0) continue;
             const int slot = e / A, a = e - slot * A;
             int X = root;
-            if (slot > 0) {                                          // a depth-1 node: it has statistics from now on
-                uint32_t *cs = &p.t.child[(size_t)root * AS * ZS + (slot - 1)];
-                const uint32_t cv = *((volatile uint32_t *)cs);
-                X = CHILD_ID(cv);
-                if (!(cv & CHILD_VISITED)) atomicOr(cs, CHILD_VISITED);
-            }
+            if (slot > 0) X = CHILD_ID(p.t.child[(size_t)root * AS * ZS + (slot - 1)]);   // a depth-1 node
             atomicAdd(&p.t.n[(size_t)X * AS + a], dn);
             atomicAdd(reinterpret_cast<unsigned long long *>(&p.t.qfix[(size_t)X * AS + a]), (unsigned long long)acc_q[e]);
             acc_n[e] = 0; acc_q[e] = 0;
@@ -528,11 +458,12 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
             atomicAdd(reinterpret_cast<unsigned long long *>(&p.t.qfix[e]), (unsigned long long)ht_q[t]);
             ht_key[t] = 0u; ht_cnt[t] = 0; ht_q[t] = 0;
         }
+        for (int t = threadIdx.x; t < PC_SLOTS; t += blockDim.x) { pc[t * PC_WORDS] = 0u; pc[t * PC_WORDS + 1] = 0u; }   // next generation: new plans
         done += w;
         if (W < p.wmax) { long long nw = (long long)W * p.growth; W = nw > p.wmax ? p.wmax : (int)nw; }
         if (p.timeout_ns && gtid == 0 && globaltimer_ns() - t_start > p.timeout_ns) S->stop = 1;
         GRID_SYNC();
-        PHASE_MARK(4);
+        PHASE_MARK(3);
         if (p.timeout_ns && *((volatile int32_t *)&S->stop)) break;   // action_selection_timeout
     }
 
@@ -562,7 +493,7 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
             const unsigned long long t0 = globaltimer_ns();
             while (*own < p.merge_seq) {                             // peer threadIdx.x has delivered merge `seq`
                 __nanosleep(200);
-                if (globaltimer_ns() - t0 > 2000000000ull) { ok = 0; break; }   // a peer never searched: give up
+                if (globaltimer_ns() - t0 > p.merge_timeout_ns) { ok = 0; break; }   // a peer never searched: give up
             }
         }
         ok = __syncthreads_and(ok);
@@ -578,10 +509,10 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
     // counters (warp-reduced) and persistent state
 #pragma unroll
     for (int o = 16; o >= 1; o >>= 1) {
-        c_levels += __shfl_xor_sync(0xFFFFFFFFu, c_levels, o);
-        c_rollout += __shfl_xor_sync(0xFFFFFFFFu, c_rollout, o);
-        c_created += __shfl_xor_sync(0xFFFFFFFFu, c_created, o);
-        c_alloc += __shfl_xor_sync(0xFFFFFFFFu, c_alloc, o);
+        c_levels += __shfl_xor_sync(FULL, c_levels, o);
+        c_rollout += __shfl_xor_sync(FULL, c_rollout, o);
+        c_created += __shfl_xor_sync(FULL, c_created, o);
+        c_alloc += __shfl_xor_sync(FULL, c_alloc, o);
     }
     if (lane == 0) {
         atomicAdd(reinterpret_cast<unsigned long long *>(&S->counters[0]), (unsigned long long)c_levels);
@@ -590,14 +521,9 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
         atomicAdd(reinterpret_cast<unsigned long long *>(&S->counters[4]), (unsigned long long)c_alloc);
     }
 #ifdef POMCP_TSEC
-    {
-        long long v = tsec_bk_;
-        for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
-        if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long *>(&S->steplog[125][0]), (unsigned long long)v);
-    }
     for (int k = 0; k < 8; ++k) {
         long long v = tsec_[k];
-        for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(0xFFFFFFFFu, v, o);
+        for (int o = 16; o >= 1; o >>= 1) v += __shfl_xor_sync(FULL, v, o);
         if (lane == 0) atomicAdd(reinterpret_cast<unsigned long long *>(&S->steplog[127][k]), (unsigned long long)v);
     }
 #endif
@@ -606,11 +532,10 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
         S->sims_done = done;
         S->stop = 0;
         S->counters[5] += gens;
-        S->counters[6] += lsteps;
         S->counters[7] = (long long)(globaltimer_ns() - t_start);
         S->counters[8] = done;
-        for (int k = 0; k < 6; ++k) S->phase_ns[k] = (long long)tp[k];
-        for (int k = 0; k < 6; ++k) S->steplog[126][k] = (long long)tp[k];   // profiling aid: phase totals of this search
+        for (int k = 0; k < 4; ++k) S->phase_ns[k] = (long long)tp[k];
+        for (int k = 0; k < 4; ++k) S->steplog[126][k] = (long long)tp[k];   // profiling aid: phase totals of this search
     }
 }
 
@@ -869,6 +794,7 @@ struct pomcp_handle {
     int world = 1, rank = 0;        // fused root merge (pomcp_set_peer_merge)
     unsigned long long peer_buf[POMCP_MAX_PEERS] = {0, 0, 0, 0, 0, 0, 0, 0};
     unsigned long long merge_seq = 0;
+    unsigned long long merge_timeout_ns = 2000000000ull;   // how long the fused merge waits for a peer (POMCP_MERGE_TIMEOUT_S)
     void *stage = nullptr;          // pinned host staging
     cudaStream_t last_stream = nullptr;
 };
@@ -890,10 +816,9 @@ static void free_all(pomcp_handle *h)
 {
     cudaFree(h->dS); cudaFree(h->dmodel); cudaFree(h->dthr);
     cudaFree(h->t.n); cudaFree(h->t.qfix); cudaFree(h->t.child); cudaFree(h->t.legal); cudaFree(h->t.cell);
-    cudaFree(h->t.arrive); cudaFree(h->t.plan); cudaFree(h->t.chance); cudaFree(h->t.good); cudaFree((void *)h->t.prob);
-    cudaFree(h->b.state); cudaFree(h->b.node); cudaFree(h->b.flag); cudaFree(h->b.depth); cudaFree(h->b.path_node);
-    cudaFree(h->b.path_ar); cudaFree(h->b.wl_node); cudaFree(h->b.wl_thr);
-    cudaFree(h->b.ro_sum); cudaFree(h->b.ro_t); cudaFree(h->b.path_rew);
+    cudaFree(h->t.thr); cudaFree(h->t.plan); cudaFree(h->t.chance); cudaFree(h->t.good); cudaFree((void *)h->t.prob);
+    cudaFree(h->b.flag); cudaFree(h->b.depth); cudaFree(h->b.path_node);
+    cudaFree(h->b.path_ar); cudaFree(h->b.ro_sum); cudaFree(h->b.path_rew);
     cudaFree((void *)h->tt.Tc); cudaFree((void *)h->tt.Oc); cudaFree((void *)h->tt.R); cudaFree((void *)h->tt.term_state);
     cudaFree((void *)h->tt.Tg);
     cudaFree(h->bag[0]); cudaFree(h->bag[1]);
@@ -927,6 +852,10 @@ extern "C" int pomcp_create(const pomcp_config *cfg, int device, pomcp_handle **
     CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
     if (!coop) return fail(h, "device lacks cooperative launch");
     h->cap = cfg->node_capacity;
+    if (const char *mt = getenv("POMCP_MERGE_TIMEOUT_S")) {
+        const double v = atof(mt);
+        if (v > 0) h->merge_timeout_ns = (unsigned long long)(v * 1e9);
+    }
     const size_t cap = (size_t)h->cap, wmax = (size_t)cfg->gen_wmax, dcap = (size_t)cfg->tree_depth_cap;
     CK(cudaMalloc(&h->dS, sizeof(DevState)));
     CK(cudaMemset(h->dS, 0, sizeof(DevState)));
@@ -936,22 +865,17 @@ extern "C" int pomcp_create(const pomcp_config *cfg, int device, pomcp_handle **
     CK(cudaMalloc(&h->t.child, cap * AS * 2 * sizeof(uint32_t)));
     CK(cudaMalloc(&h->t.legal, cap * sizeof(uint32_t)));
     CK(cudaMalloc(&h->t.cell, cap * sizeof(int32_t)));
-    CK(cudaMalloc(&h->t.arrive, cap * sizeof(unsigned long long)));
+    CK(cudaMalloc(&h->t.thr, cap * 32 * sizeof(uint32_t)));
     CK(cudaMalloc(&h->t.plan, cap * 2 * sizeof(uint4)));
+    CK(cudaMemset(h->t.plan, 0, cap * 2 * sizeof(uint4)));           // stamp 0: no plan yet (stamps only grow)
     CK(cudaMemset(h->t.n, 0, cap * AS * sizeof(int32_t)));
     CK(cudaMemset(h->t.qfix, 0, cap * AS * sizeof(long long)));
     CK(cudaMemset(h->t.child, 0, cap * AS * 2 * sizeof(uint32_t)));
-    CK(cudaMemset(h->t.arrive, 0, cap * sizeof(unsigned long long)));
-    CK(cudaMalloc(&h->b.state, wmax * sizeof(uint32_t)));
-    CK(cudaMalloc(&h->b.node, wmax * sizeof(int32_t)));
     CK(cudaMalloc(&h->b.flag, wmax));
     CK(cudaMalloc(&h->b.depth, wmax));
     CK(cudaMalloc(&h->b.path_node, wmax * dcap * sizeof(int32_t)));
     CK(cudaMalloc(&h->b.path_ar, wmax * dcap * sizeof(uint16_t)));
-    CK(cudaMalloc(&h->b.wl_node, 2 * wmax * sizeof(int32_t)));
-    CK(cudaMalloc(&h->b.wl_thr, wmax * 32 * sizeof(uint32_t)));
     CK(cudaMalloc(&h->b.ro_sum, wmax * sizeof(double)));
-    CK(cudaMalloc(&h->b.ro_t, wmax));
     CK(cudaMallocHost(&h->stage, 1 << 16));
     return 0;
 }
@@ -968,6 +892,9 @@ static int release_tabular(pomcp_handle *h)
 // (Re)allocate the child table for an observation stride of `zs` slots per (node, action).
 static int set_child_stride(pomcp_handle *h, int zs)
 {
+    // a child slot that is still being created is referred to as -1 - slot index in a 32-bit path entry
+    if ((unsigned long long)h->cap * AS * (unsigned long long)zs > (1ull << 31))
+        return fail(h, "node_capacity * 32 * observation stride exceeds 2^31 child slots: lower node_capacity");
     if (zs != h->zs) {
         CK(cudaDeviceSynchronize());
         cudaFree(h->t.child); h->t.child = nullptr;
@@ -1023,7 +950,7 @@ extern "C" int pomcp_set_model_rocksample(pomcp_handle *h, int rows, int cols, c
     // launch geometry of the cooperative search kernel
     const int A = m.n_actions;
     size_t smem = ((sizeof(ModelHeader) + 15) & ~size_t(15)) + (((size_t)h->n_thr * 4 + 15) & ~size_t(15)) +
-                  (((size_t)h->cfg.max_depth * 8 + 15) & ~size_t(15)) + (size_t)(1 + 2 * A) * A * 12 + (((size_t)2 * A * 4 + 15) & ~size_t(15)) + (size_t)ARR_HT * 16 + 32;
+                  (((size_t)h->cfg.max_depth * 8 + 15) & ~size_t(15)) + (size_t)(1 + 2 * A) * A * 12 + (size_t)ARR_HT * 16 + (size_t)PC_SLOTS * PC_WORDS * 4 + 48;
     h->search_smem = smem;
     CK(cudaFuncSetAttribute(pomcp_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(pomcp_search_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1105,7 +1032,7 @@ extern "C" int pomcp_set_model_tabular(pomcp_handle *h, int n_states, int n_acti
     if (!h->b.path_rew)
         CK(cudaMalloc(&h->b.path_rew, (size_t)h->cfg.gen_wmax * (size_t)h->cfg.tree_depth_cap * sizeof(double)));
     const size_t n_acc = t.stage_d1 ? (size_t)(1 + zs * n_actions) * n_actions : (size_t)n_actions;
-    size_t smem = (((size_t)h->cfg.max_depth * 8 + 15) & ~size_t(15)) + n_acc * 12 + (((size_t)zs * n_actions * 4 + 15) & ~size_t(15)) + (size_t)ARR_HT * 16 + 32;
+    size_t smem = (((size_t)h->cfg.max_depth * 8 + 15) & ~size_t(15)) + n_acc * 12 + (size_t)ARR_HT * 16 + (size_t)PC_SLOTS * PC_WORDS * 4 + 48;
     if (smem < 512) smem = 512;                              // the belief update keeps 34 ints there
     h->search_smem = smem;
     CK(cudaFuncSetAttribute(pomcp_search_tab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
@@ -1264,6 +1191,7 @@ extern "C" int pomcp_search(pomcp_handle *h, int64_t n_sims, uint32_t sim_offset
     p.max_depth = h->cfg.max_depth; p.dcap = h->cfg.tree_depth_cap; p.n_thr = h->n_thr; p.node_cap = h->cap;
     p.ucb_c = h->cfg.ucb_coefficient; p.discount = h->cfg.discount;
     p.timeout_ns = timeout_s > 0 ? (unsigned long long)(timeout_s * 1e9) : 0ull;   // checked between generations
+    p.merge_timeout_ns = h->merge_timeout_ns;
     p.pref_rollout = h->pref_rollout;
     p.world = h->world; p.rank = h->rank;
     if (h->world > 1) {
@@ -1274,8 +1202,7 @@ extern "C" int pomcp_search(pomcp_handle *h, int64_t n_sims, uint32_t sim_offset
     int blocks = (int)((widest + SEARCH_THREADS - 1) / SEARCH_THREADS);
     if (blocks < 1) blocks = 1;
     if (blocks > h->coop_blocks) blocks = h->coop_blocks;
-    CK(cudaMemsetAsync(&h->dS->barrier, 0, sizeof(uint32_t), s));
-    CK(cudaMemsetAsync(h->dS->ro_cursor, 0, 2 * sizeof(int32_t), s));
+    CK(cudaMemsetAsync(h->dS->cursor, 0, 6 * sizeof(int32_t), s));   // cursor[4], stop, barrier
     void *args[] = {&p};
     CK(cudaLaunchCooperativeKernel(h->kind == 0 ? (void *)pomcp_search_kernel : (void *)pomcp_search_tab_kernel,
                                    dim3(blocks), dim3(SEARCH_THREADS), args, h->search_smem, s));

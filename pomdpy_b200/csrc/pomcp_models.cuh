@@ -112,9 +112,11 @@ template <> struct Mdl<0> {
     {   // everything by value: a reference to the caller's locals (or to the kernel parameters) would push them into
         // local memory on the hot path as well
         const ModelHeader *H = M.hdr;
+        // The leaf may have been created in this very phase by another SM: its rows are read from L2 (its neighbours'
+        // rows share cache lines with it, and an earlier read of those may have left a stale copy in this SM's L1)
         double ch[POMCP_RS]; int16_t gd[POMCP_RS];
-        uint32_t mask = child_smart_mask(H, prob, leaf_chance, leaf_good, ch, gd, leaf_cell, leaf_action, leaf_obs,
-                                         (int)(st & 0xFFu));
+        for (int k = 0; k < H->n_rocks; ++k) { ch[k] = __ldcg(leaf_chance + k); gd[k] = __ldcg(leaf_good + k); }
+        uint32_t mask = child_smart_mask(H, prob, ch, gd, ch, gd, leaf_cell, leaf_action, leaf_obs, (int)(st & 0xFFu));
         Philox4 r{0u, 0u, 0u, 0u};
         for (; t < t_end; ++t) {
             uint32_t w0, w1;

@@ -1,5 +1,5 @@
-// pomcp_plan.cuh -- grid barrier and small helpers, and the per-node action plans of a level step: batch-UCB
-// allocation (many arrivals), virtual-pull sequence (few), and the lookup a simulation makes.
+// pomcp_plan.cuh -- grid barrier and small helpers, and the per-node action plans of a generation: batch-UCB
+// allocation (many expected arrivals), virtual-pull sequence (few), and the lookup a simulation makes.
 #pragma once
 #include "pomcp_state.cuh"
 
@@ -46,11 +46,17 @@ __device__ __forceinline__ void publish_root(DevState *S, const Tree &t, int roo
 }
 
 // ---------------------------------------------------------------------------------------------------------
-// Batch-UCB allocation for a node with k >= 2 simultaneous arrivals (warp-cooperative, lane = action).
-// Water-filling of k pulls over the UCB1 indices mean + c*sqrt(ln(N+1)/n); output: 32-bit cumulative thresholds.
+// Action plans.  Within a generation the statistics are read-only, so the action distribution of a
+// node is a pure function of (its statistics, k), k = the number of simulations of the generation EXPECTED there:
+//     k(root) = generation width;   k(child of X under (a, o)) = k(X) * P_plan(a | X) * N(child) / n(X, a).
+// Nothing depends on how many simulations really meet at a node, so every simulation descends the tree on its own --
+// no level barriers -- and whichever warp reaches a node first computes its plan (lane = action) and publishes it.
 // ---------------------------------------------------------------------------------------------------------
-__device__ __forceinline__ void warp_allocation(const SearchParams &p, int X, uint32_t k, int lane, int A,
-                                                uint32_t *thr_out, int slot)
+struct PlanRec { uint4 head, data; };
+
+// Batch-UCB allocation, k >= 16.5: water-filling of k pulls over the UCB1 indices mean + c*sqrt(ln(N+1)/n); output:
+// 32-bit cumulative thresholds in t.thr[X], every G-th of them in the plan record.
+__device__ __forceinline__ PlanRec warp_allocation(const SearchParams &p, int X, float kd, int lane, int A, uint32_t stamp)
 {
     const unsigned full = 0xFFFFFFFFu;
     const uint32_t mask = p.t.legal[X];
@@ -65,7 +71,7 @@ __device__ __forceinline__ void warp_allocation(const SearchParams &p, int X, ui
     const float cf = (float)p.ucb_c;
     float v = 0.0f;
     if (N == 0) v = legal ? 1.0f : 0.0f;
-    else if ((uint32_t)untried >= k) v = (legal && n == 0) ? 1.0f : 0.0f;
+    else if ((float)untried >= kd) v = (legal && n == 0) ? 1.0f : 0.0f;
     else {
         const float L = det_logf_u32((uint32_t)N + 1u);
         const float c2L = (cf * cf) * L;
@@ -77,7 +83,6 @@ __device__ __forceinline__ void warp_allocation(const SearchParams &p, int X, ui
         const int nbest = __shfl_sync(full, n, __ffs((int)best_lanes) - 1);
         if (!(c2L > 0.0f)) v = (legal && qbar == qmax) ? 1.0f : 0.0f;
         else {
-            const float kd = (float)k;
             float lo = qmax + 0.999f * sqrtf(c2L / (kd + (float)nbest));
             float hi = qmax + 1.001f * sqrtf((c2L * (float)nlegal) / kd) + 1.0f;
             for (int it = 0; it <= BISECT_ITERS; ++it) {
@@ -113,27 +118,26 @@ __device__ __forceinline__ void warp_allocation(const SearchParams &p, int X, ui
         const uint32_t y = __shfl_up_sync(full, th, off);
         if (lane >= off && y > th) th = y;
     }
-    thr_out[lane] = th;
+    __stcg(&p.t.thr[(size_t)X * 32 + lane], th);
     const unsigned pos = __ballot_sync(full, v > 0.0f);
     // every G-th threshold goes into the node's plan record: a simulation finds its group of G actions there and
-    // needs one more (16-byte aligned row) access for the thresholds inside the group
+    // needs one more access for the thresholds inside the group
     const int G = (A + 5) / 6;
     uint32_t cg[6];
 #pragma unroll
     for (int g = 0; g < 6; ++g) { const int src = g * G + G - 1; cg[g] = __shfl_sync(full, th, src < 31 ? src : 31); }
-    if (lane == 0) {
-        p.t.plan[(size_t)X * 2] = make_uint4((uint32_t)((31 - __clz((int)pos)) | (PLAN_THRESHOLDS << 16)), (uint32_t)slot, cg[4], cg[5]);
-        p.t.plan[(size_t)X * 2 + 1] = make_uint4(cg[0], cg[1], cg[2], cg[3]);
-    }
+    PlanRec r;
+    r.head = make_uint4((uint32_t)((31 - __clz((int)pos)) | (PLAN_THRESHOLDS << 16)), stamp, cg[4], cg[5]);
+    r.data = make_uint4(cg[0], cg[1], cg[2], cg[3]);
+    return r;
 }
 
-// Action plan of a node with k <= SEQ_ALLOC_MAX arrivals (warp-cooperative, lane = action; statistics are read-only
-// within a generation, so the plan is computed once per node and level step instead of once per simulation).
+// Plan of a node for k = round(expected arrivals) <= SEQ_ALLOC_MAX (warp-cooperative, lane = action).
 //   kind 0  uniform draw over an action mask:  at least k untried actions (n == 0 scores +inf, pomcp.py:64-65), or
 //           k == 1: the UCB1 arg-max set (action_selectors.py:6-37; the draw breaks ties), or c = 0: the best means
-//   kind 1  the k arrivals share the virtual-pull sequence "pull j takes the UCB1 arg-max (lowest id on ties) given
-//           the statistics plus the virtual visits of pulls 0..j-1"; a simulation takes pull j = floor(x0*k/2^32)
-__device__ __forceinline__ void warp_plan_few(const SearchParams &p, int X, uint32_t k, int lane, int A, int slot)
+//   kind 1  the virtual-pull sequence "pull j takes the UCB1 arg-max (lowest id on ties) given the statistics plus
+//           the virtual visits of pulls 0..j-1"; a simulation takes pull j = floor(x0*k/2^32)
+__device__ __forceinline__ PlanRec warp_plan_few(const SearchParams &p, int X, uint32_t k, int lane, int A, uint32_t stamp)
 {
     const unsigned full = 0xFFFFFFFFu;
     const uint32_t mask = p.t.legal[X];
@@ -143,11 +147,11 @@ __device__ __forceinline__ void warp_plan_few(const SearchParams &p, int X, uint
     int N = n;
 #pragma unroll
     for (int off = 16; off >= 1; off >>= 1) N += __shfl_xor_sync(full, N, off);
+    PlanRec r;
+    r.head = make_uint4(PLAN_MASK << 16, stamp, 0u, 0u);
+    r.data = make_uint4(0u, 0u, 0u, 0u);
     const unsigned untried = __ballot_sync(full, legal && n == 0);
-    if ((uint32_t)__popc(untried) >= k) {
-        if (lane == 0) { p.t.plan[(size_t)X * 2] = make_uint4(PLAN_MASK << 16, (uint32_t)slot, 0u, 0u); p.t.plan[(size_t)X * 2 + 1].x = untried; }
-        return;
-    }
+    if ((uint32_t)__popc(untried) >= k) { r.data.x = untried; return r; }
     const float L = det_logf_u32((uint32_t)N + 1u);
     const float cf = (float)p.ucb_c;
     if (k == 1) {                                                    // no untried action here: every legal n > 0
@@ -155,9 +159,8 @@ __device__ __forceinline__ void warp_plan_few(const SearchParams &p, int X, uint
         float best = sc;
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) best = fmaxf(best, __shfl_xor_sync(full, best, off));
-        const unsigned ties = __ballot_sync(full, legal && sc == best);
-        if (lane == 0) { p.t.plan[(size_t)X * 2] = make_uint4(PLAN_MASK << 16, (uint32_t)slot, 0u, 0u); p.t.plan[(size_t)X * 2 + 1].x = ties; }
-        return;
+        r.data.x = __ballot_sync(full, legal && sc == best);
+        return r;
     }
     const float c2L = (cf * cf) * L;
     const float qb = n == 0 ? 0.0f : edge_mean(qf, n);
@@ -165,9 +168,8 @@ __device__ __forceinline__ void warp_plan_few(const SearchParams &p, int X, uint
         float qmax = legal ? qb : -INFINITY;
 #pragma unroll
         for (int off = 16; off >= 1; off >>= 1) qmax = fmaxf(qmax, __shfl_xor_sync(full, qmax, off));
-        const unsigned qties = __ballot_sync(full, legal && qb == qmax);
-        if (lane == 0) { p.t.plan[(size_t)X * 2] = make_uint4(PLAN_MASK << 16, (uint32_t)slot, 0u, 0u); p.t.plan[(size_t)X * 2 + 1].x = qties; }
-        return;
+        r.data.x = __ballot_sync(full, legal && qb == qmax);
+        return r;
     }
     float sc = legal ? (n == 0 ? INFINITY : qb + cf * sqrtf(L / (float)n)) : -INFINITY;
     int va = 0;
@@ -180,39 +182,148 @@ __device__ __forceinline__ void warp_plan_few(const SearchParams &p, int X, uint
         seq[pull >> 2] |= (uint32_t)w << (8 * (pull & 3u));
         if (lane == w) { va += 1; sc = qb + cf * sqrtf(L / (float)(n + va)); }
     }
-    if (lane == 0) {
-        p.t.plan[(size_t)X * 2] = make_uint4((PLAN_PULLS << 16) | (k << 8), (uint32_t)slot, 0u, 0u);
-        p.t.plan[(size_t)X * 2 + 1] = make_uint4(seq[0], seq[1], seq[2], seq[3]);
+    r.head.x = (PLAN_PULLS << 16) | (k << 8);
+    r.data = make_uint4(seq[0], seq[1], seq[2], seq[3]);
+    return r;
+}
+
+// The same plan computed by ONE thread (the fringe of the tree: most nodes there expect one or two arrivals, and the
+// 32 simulations of a warp stand at 32 different nodes -- lane = simulation beats lane = action).  Identical
+// arithmetic, hence identical plans: sums and maxima do not depend on the order, ties go to the lowest action.
+__device__ __forceinline__ PlanRec thread_plan_few(const SearchParams &p, int X, uint32_t k, int A, uint32_t stamp)
+{
+    const uint32_t mask = p.t.legal[X];
+    const int32_t *nrow = p.t.n + (size_t)X * AS;
+    const long long *qrow = p.t.qfix + (size_t)X * AS;
+    int N = 0; uint32_t untried = 0u;
+    for (int a = 0; a < A; ++a) {
+        if (!((mask >> a) & 1u)) continue;
+        const int n = nrow[a];
+        N += n;
+        if (n == 0) untried |= 1u << a;
     }
+    PlanRec r;
+    r.head = make_uint4(PLAN_MASK << 16, stamp, 0u, 0u);
+    r.data = make_uint4(0u, 0u, 0u, 0u);
+    if ((uint32_t)__popc(untried) >= k) { r.data.x = untried; return r; }
+    const float L = det_logf_u32((uint32_t)N + 1u);
+    const float cf = (float)p.ucb_c;
+    if (k == 1) {                                                    // UCB1 arg-max set
+        float best = -INFINITY; uint32_t ties = 0u;
+        for (int a = 0; a < A; ++a) {
+            if (!((mask >> a) & 1u)) continue;
+            const int n = nrow[a];
+            const float sc = edge_mean(qrow[a], n) + cf * sqrtf(L / (float)n);
+            if (sc > best) { best = sc; ties = 1u << a; } else if (sc == best) ties |= 1u << a;
+        }
+        r.data.x = ties;
+        return r;
+    }
+    const float c2L = (cf * cf) * L;
+    float sc[AS];
+    float qmax = -INFINITY; uint32_t qties = 0u;
+    for (int a = 0; a < A; ++a) {
+        sc[a] = -INFINITY;
+        if (!((mask >> a) & 1u)) continue;
+        const int n = nrow[a];
+        const float qb = n == 0 ? 0.0f : edge_mean(qrow[a], n);
+        if (qb > qmax) { qmax = qb; qties = 1u << a; } else if (qb == qmax) qties |= 1u << a;
+        sc[a] = n == 0 ? INFINITY : qb + cf * sqrtf(L / (float)n);
+    }
+    if (!(c2L > 0.0f)) { r.data.x = qties; return r; }
+    uint32_t seq[4] = {0u, 0u, 0u, 0u};
+    for (uint32_t pull = 0; pull < k; ++pull) {
+        int w = 0; float bs = sc[0];
+        for (int a = 1; a < A; ++a) if (sc[a] > bs) { bs = sc[a]; w = a; }
+        seq[pull >> 2] |= (uint32_t)w << (8 * (pull & 3u));
+        int va = 0;                                                  // pulls of w so far, this one included
+        for (uint32_t j = 0; j <= pull; ++j) va += (int)((seq[j >> 2] >> (8 * (j & 3u))) & 255u) == w ? 1 : 0;
+        const int n = nrow[w];
+        const float qb = n == 0 ? 0.0f : edge_mean(qrow[w], n);
+        sc[w] = qb + cf * sqrtf(L / (float)(n + va));
+    }
+    r.head.x = (PLAN_PULLS << 16) | (k << 8);
+    r.data = make_uint4(seq[0], seq[1], seq[2], seq[3]);
+    return r;
 }
 
-// Plan of node X for its k arrivals of this level step (one warp).
-__device__ __forceinline__ void warp_plan(const SearchParams &p, int X, uint32_t k, int lane, int A, int slot)
+// Plan of node X (which has statistics) for kx expected arrivals, computed by one warp; every lane returns it.
+// publish: store it in the node's record for the other simulations of this generation -- thresholds and data first,
+// then the head with the generation stamp (a reader that sees the stamp sees the rest).
+__device__ __forceinline__ PlanRec warp_plan(const SearchParams &p, int X, float kx, int lane, int A, uint32_t stamp,
+                                             bool publish, long long &c_alloc)
 {
-    if (k > SEQ_ALLOC_MAX) warp_allocation(p, X, k, lane, A, p.b.wl_thr + (size_t)slot * 32, slot);
-    else warp_plan_few(p, X, k, lane, A, slot);
+    PlanRec r;
+    if (kx >= 16.5f) {
+        r = warp_allocation(p, X, kx, lane, A, stamp);
+        if (lane == 0) ++c_alloc;
+    } else {
+        const int kq = (int)(kx + 0.5f);
+        r = warp_plan_few(p, X, (uint32_t)(kq < 1 ? 1 : kq), lane, A, stamp);
+    }
+    if (publish) {
+        __threadfence();                                             // every lane's threshold store
+        __syncwarp();
+        if (lane == 0) {
+            __stcg(&p.t.plan[(size_t)X * 2 + 1], r.data);
+            __threadfence();
+            __stcg(&p.t.plan[(size_t)X * 2], r.head);
+        }
+    }
+    return r;
 }
 
-// The action of one simulation from its node's plan and its 32-bit draw x0.
-__device__ __forceinline__ int plan_action(const SearchParams &p, int X, uint32_t x0, int A)
+// The action of one simulation from its node's plan and its 32-bit draw x0, and the plan's probability of that
+// action.  Thresholds come from the block's shared-memory copy (sthr) if the node is cached there, else from L2.
+__device__ __forceinline__ int plan_action(const uint4 head, const uint4 data, const uint32_t *sthr, const uint32_t *gthr,
+                                           uint32_t x0, int A, float &prob)
 {
-    const uint4 head = p.t.plan[(size_t)X * 2], data = p.t.plan[(size_t)X * 2 + 1];
     const int meta = (int)head.x, kind = meta >> 16;
     if (kind == PLAN_THRESHOLDS) {                       // first action whose threshold exceeds x0
         const int G = (A + 5) / 6;                       // thresholds are non-decreasing: find the group of G ...
         const int g = x0 < data.x ? 0 : x0 < data.y ? 1 : x0 < data.z ? 2 : x0 < data.w ? 3 : x0 < head.z ? 4 :
                       x0 < head.w ? 5 : 6;
-        if (g == 6) return meta & 255;
-        const uint32_t *thr = p.b.wl_thr + (size_t)head.y * 32 + g * G;
-        uint32_t tq[6];
+        int a = meta & 255;                              // the last action with weight, if no threshold exceeds x0
+        uint32_t hi_t, lo_t;
+        if (g < 6) {
+            uint32_t tq[6];
 #pragma unroll
-        for (int q = 0; q < 6; ++q) tq[q] = (q < G && g * G + q < 32) ? thr[q] : 0xFFFFFFFFu;   // ... then the action
+            for (int q = 0; q < 6; ++q) {
+                const int idx = g * G + q;
+                tq[q] = (q < G && idx < 32) ? (sthr ? sthr[idx] : __ldcg(gthr + idx)) : 0xFFFFFFFFu;   // ... then the action
+            }
+            const uint32_t below = g == 0 ? 0u : g == 1 ? data.x : g == 2 ? data.y : g == 3 ? data.z : g == 4 ? data.w : head.z;
+            int q = 0;
 #pragma unroll
-        for (int q = 0; q < 6; ++q) if (x0 < tq[q]) return g * G + q;
-        return meta & 255;
+            for (int t = 5; t >= 0; --t) if (x0 < tq[t]) q = t;
+            if (x0 < tq[q]) {
+                a = g * G + q;
+                hi_t = tq[q];
+                lo_t = q == 0 ? below : tq[q - 1 < 0 ? 0 : q - 1];
+                prob = (float)(hi_t - lo_t) * (1.0f / 4294967296.0f);
+                return a;
+            }
+        }
+        hi_t = sthr ? sthr[a] : __ldcg(gthr + a);
+        lo_t = a == 0 ? 0u : (sthr ? sthr[a - 1] : __ldcg(gthr + a - 1));
+        prob = (float)(hi_t - lo_t) * (1.0f / 4294967296.0f);
+        return a;
     }
-    if (kind == PLAN_MASK) return nth_bit(data.x, randbelow32(x0, (uint32_t)__popc(data.x)));
-    const uint32_t j = randbelow32(x0, (uint32_t)(meta >> 8) & 255u);
+    if (kind == PLAN_MASK) {
+        const uint32_t m = (uint32_t)__popc(data.x);
+        prob = 1.0f / (float)m;
+        return nth_bit(data.x, randbelow32(x0, m));
+    }
+    const uint32_t k = (uint32_t)(meta >> 8) & 255u;
+    const uint32_t j = randbelow32(x0, k);
     const uint32_t word = (j >> 2) == 0 ? data.x : (j >> 2) == 1 ? data.y : (j >> 2) == 2 ? data.z : data.w;
-    return (int)((word >> (8 * (j & 3u))) & 255u);
+    const uint32_t a = (word >> (8 * (j & 3u))) & 255u;
+    int cnt = 0;
+#pragma unroll
+    for (int t = 0; t < 16; ++t) {
+        const uint32_t wd = (t >> 2) == 0 ? data.x : (t >> 2) == 1 ? data.y : (t >> 2) == 2 ? data.z : data.w;
+        cnt += ((uint32_t)t < k && ((wd >> (8 * (t & 3))) & 255u) == a) ? 1 : 0;
+    }
+    prob = (float)cnt / (float)k;
+    return (int)a;
 }

@@ -28,7 +28,6 @@
 #define TSEC(k) do { } while (0)
 #endif
 #define CHILD_LOCKED 0xFFFFFFFFu
-#define CHILD_VISITED 0x80000000u   // set on a child slot once a backup has passed through the child (N > 0)
 #define CHILD_ID(c) ((int)((c) & 0x7FFFFFFFu) - 1)
 #define SEARCH_THREADS 256
 #ifndef SEARCH_MIN_BLOCKS
@@ -36,15 +35,24 @@
 #endif
 #define ADV_THREADS 1024
 #define ADV_TRIES 4
-#define ROLL_SLICE 8            // rollout steps per slice while waiting at a barrier (even: Philox block pairs)
 #ifndef ARR_HT
-#define ARR_HT 1024            // per-block arrival table (shared memory): slots of {node id, arrivals in this level step}
+#define ARR_HT 1024            // per-block backup table (shared memory): slots of {edge, visits, return sum} of shared edges
 #endif
 #define ARR_PROBES 8
 #define PLAN_MASK 0            // kinds of a node's action plan (warp_plan)
 #define PLAN_PULLS 1
 #define PLAN_THRESHOLDS 2
-#define SEQ_ALLOC_MAX 16u      // arrivals <= this: exact virtual-pull allocation; more: water-filling
+#define PLAN_LOCKED 0xFFFFFFFFu // stamp of a plan record while one warp computes it
+#define SEQ_ALLOC_MAX 16u      // expected arrivals < 16.5: virtual-pull sequence / arg-max set; more: water-filling
+// Per-block cache of the hot plans (the upper tree levels, where thousands of simulations of a generation pass) in
+// shared memory: PC_SLOTS direct-mapped entries of PC_WORDS 32-bit words
+//   [0] key = node id + 1 (0: free)  [1] ready  [2] expected arrivals (float bits)  [4..7] head  [8..11] data
+//   [12..43] the 32 cumulative thresholds
+#ifndef PC_BITS
+#define PC_BITS 6
+#endif
+#define PC_SLOTS (1 << PC_BITS)
+#define PC_WORDS 44
 #ifndef BISECT_ITERS
 #define BISECT_ITERS 14
 #endif
@@ -57,18 +65,18 @@ struct DevState {
     int32_t node_count;
     uint32_t actual, sampled;
     int32_t n_bag, bag_sel;
-    int32_t wl_count[4];
+    int32_t cursor[4];                 // work counters of a generation: [2 * parity] descent + rollout, [2 * parity + 1] backup
     int32_t stop;
     uint32_t barrier;                  // arrival counter of grid_barrier (zeroed before each search)
     int32_t check_failed, check_pad;
-    int32_t ro_cursor[2];              // work counters of the final rollout + backup phase (alternating per generation)
+    int32_t pad_c[2];
     // root edge statistics as of the end of the last search / advance / plant (one copy serves pomcp_root_stats)
     long long res_n[AS], res_q[AS];
     uint32_t res_legal; int32_t res_valid;
     // root edge statistics summed over the ranks of a root-parallel search (fused merge in the search kernel's tail)
     long long mrg_n[AS], mrg_q[AS];
     unsigned long long mrg_seq;        // sequence number of the merge that filled mrg_*; 0 = the exchange timed out
-    unsigned long long gstep;          // global level-step stamp, never reused
+    unsigned long long gstep;          // generation stamp of the plan records, never reused
     long long sims_done;               // simulations completed by the last search
     long long counters[16];
     long long phase_ns[8];            // device time per phase of the last search (thread 0's globaltimer)
@@ -76,39 +84,33 @@ struct DevState {
     int32_t adv_status, adv_accepted, adv_root_cell, adv_pad;
     long long adv_tries;
     // ---- profiling aid, not copied by the hot calls ----
-    long long steplog[128][8];        // last search, per level step: ns of [wait, allocate, wait, expand], worklist
+    long long steplog[128][8];        // last search: row g < 120 = ns of generation g's [start, descent + rollout, backup, flush]; row 126 = totals
 };
 #define DEVSTATE_HEAD (offsetof(DevState, steplog))
 
 struct Tree {                          // structure-of-arrays belief-tree arena
     int32_t *n;                        // [cap][AS]   visit_count of edge (node, action)
     long long *qfix;                   // [cap][AS]   sum of q in 2^-24 fixed point
-    uint32_t *child;                   // [cap][AS][ZS] child id + 1 keyed (action, observation), bit 31 = has statistics;
-                                       //              0 = none.  ZS = 2 for RockSample (obs_good)
+    uint32_t *child;                   // [cap][AS][ZS] child id + 1 keyed (action, observation); 0 = none, ~0 = being
+                                       //              created.  ZS = 2 for RockSample (obs_good)
     uint32_t *legal;                   // [cap]       legal-action mask (fixed at creation)
     int32_t *cell;                     // [cap]       tag of the node: robot cell (RockSample), 0 (tabular)
-    unsigned long long *arrive;        // [cap]       (stamp << 32) | arrivals in the current level step
-    uint4 *plan;                       // [cap][2]    action plan of the node for the current level step:
-                                       //             {kind << 16 | arrivals << 8 | last action, worklist slot, -, -},
-                                       //             {action mask (kind 0) | <= 16 pull bytes (kind 1)}; kind 2: thresholds in wl_thr[slot]
+    uint4 *plan;                       // [cap][2]    action plan of the node for the generation `stamp`:
+                                       //             {kind << 16 | pulls << 8 | last action, stamp, coarse thresholds 4, 5},
+                                       //             {action mask (kind 0) | <= 16 pull bytes (kind 1) | coarse thresholds 0..3 (kind 2)}
+    uint32_t *thr;                     // [cap][32]   kind 2: the 32 cumulative action thresholds
     double *chance;                    // [cap][24]   --preferred_actions: chance_good per rock (null otherwise)
     int16_t *good;                     // [cap][24]   --preferred_actions: goodness number per rock
     const double *prob;                // [cells][n_rocks] sensor correctness probability
 };
 
-struct SimBuf {                        // per simulation-in-flight scratch, SoA over the generation
-    uint32_t *state;                   // packed state cell | rocks << 8
-    int32_t *node;                     // current node, or child-slot index when `pending`
-    uint8_t *flag;                     // status: 0 descending, 1 leaf (rollout pending / in progress), 2 done without rollout,
-                                       //         3 rollout finished
+struct SimBuf {                        // what a simulation hands from the descent to the backup, SoA over the generation
+    uint8_t *flag;                     // 2 ended in the tree (terminal / horizon), 3 ended with a rollout
     uint8_t *depth;                    // path entries recorded
     int32_t *path_node;                // [dcap][wmax]
     uint16_t *path_ar;                 // [dcap][wmax] action | obs_good << 5 | reward id << 8   (tabular: action | obs << 5)
     double *path_rew;                  // [dcap][wmax] tabular models: the step reward (null for RockSample)
-    int32_t *wl_node;                  // [2][wmax] worklist of nodes with arrivals in this level step (set = step parity)
-    uint32_t *wl_thr;                  // [wmax][32] cumulative action thresholds of worklist nodes with a kind-2 plan
-    double *ro_sum;                    // [wmax] discounted reward sum of a rollout in progress
-    uint8_t *ro_t;                     // [wmax] rollout steps done so far (rollouts advance in slices)
+    double *ro_sum;                    // [wmax] discounted reward sum of the rollout
 };
 
 struct SearchParams {
@@ -132,6 +134,7 @@ struct SearchParams {
     unsigned long long peer_buf[POMCP_MAX_PEERS];
     int32_t world, rank;
     unsigned long long merge_seq;
+    unsigned long long merge_timeout_ns;
     int32_t pref_rollout, pad_pr;      // --preferred_actions with preferred rollouts (RockSample)
 };
 

@@ -221,7 +221,7 @@ def test_preferred_actions_episode_bit_exact(tag, seed, n_sims, sched, rollouts)
     w0, growth, wmax = sched
     if rollouts and n_sims == 6000:
         n_sims = 600                                        # strictly sequential case: keep the oracle quick
-    kw = dict(seed=seed, gen_w0=w0, gen_growth=growth, gen_wmax=wmax, node_capacity=1 << 17)
+    kw = dict(seed=seed, gen_w0=w0, gen_growth=growth, gen_wmax=wmax, node_capacity=1 << 19)
     t = golden_tables(tag)
     actual, bag, rng = random_world_and_bag(t, seed)
     om = oracle_model(t)
@@ -234,7 +234,7 @@ def test_preferred_actions_episode_bit_exact(tag, seed, n_sims, sched, rollouts)
     cell, rocks, sampled = int(t["start_cell"]), int(bag[0] >> 8), 0
     for mv in range(10):
         g.search(n_sims, move=mv, w0=w0, growth=growth, wmax=wmax)
-        pl.search(n_sims, move=mv)
+        assert pl.search(n_sims, move=mv) == 0                     # 1 would mean: arena full, subtree dropped
         st = _assert_same_root(g, pl)
         assert bin(st["legal"]).count("1") < om.n_actions          # the in-tree set is restricted
         for a in range(om.n_actions):
