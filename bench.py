@@ -1,18 +1,33 @@
 #!/usr/bin/env python
-"""POMCP simulations/second on RockSample(15,15) -- the BASELINE.json metric.
+"""POMCP simulations/second on RockSample(15,15) and mean discounted return -- the BASELINE.json metric, measured the
+way SURVEY.md 8(d) states it.
 
-    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference]
+    python bench.py [--gpus N] [--steps K] [--warmup W] [--impl reference] [--scaling strong|weak]
     python -m torch.distributed.run --nnodes=1 --nproc-per-node N ... bench.py --gpus N --steps K --warmup W
 
-A "step" is one move's search: a fresh belief tree over the 2000-particle root belief, ``n_sims`` simulations per
-GPU (root-parallel: every rank grows its own tree) and the merge of the root statistics (one
-all-reduce of 64 int64 over NCCL when N > 1).  `value` = simulations of all ranks / device time (CUDA events on
-the launching stream, inputs resident in HBM, max over ranks); `e2e` = the same through the C ABI with HOST
-buffers (belief copied host->device, root statistics device->host, every step).
+A "step" is ONE MOVE OF A REAL EPISODE with the belief tree kept across moves:
+    search (n_sims simulations, root-parallel over the ranks, root statistics merged)  ->  greedy action  ->
+    environment step on the host (the model's generate_step)  ->  belief update + re-root on the device (advance);
+when an episode ends the next one starts (new world, new root belief, fresh tree) and its moves count as steps too.
 
---impl reference: the CPU arm.  The reference is pure Python and cannot travel to the GPU box, so this arm runs
-the oracle's C port of the reference's sequential POMCP (oracle/pomcp_oracle.c, "ref" mode, pinned bit-for-bit
-to the executed reference) on every host core, one independent search per core.
+  value      n_sims (all ranks) / MEDIAN CUDA-event time of a move's search (all generations + the root merge) over
+             the K timed moves; L2 flushed (256 MiB write, untimed) before every timed move; max over ranks
+  e2e        the same through the C ABI with host buffers and wall clock: search + device->host read of the root
+             statistics + belief update with its host arguments and status read-back (a new episode's 8 KB belief
+             upload included where it happens); median over K moves
+  config.fresh_tree_value   round 1's figure: every step a FRESH tree (best case), L2 flushed
+  mean_discounted_return    mean +- standard error over --return_epochs whole episodes (max 200 moves), the
+             reference's own summary statistic (pomdpy/agent.py:56-57,207-211); run back to back: this leg is also the
+             seconds-long load under which the clocks are sampled
+  scaling    "strong" (default; BASELINE config 4: 1M simulations per move in total, n_sims/N per rank) or "weak"
+             (n_sims per rank); the other mode is measured on a short leg and reported under `other_scaling`
+
+--impl reference: the CPU arm.  The reference is pure Python; its algorithm, restated in C and pinned bit-for-bit to the
+executed reference (oracle/pomcp_oracle.c "ref" mode), runs the same protocol on every host core: one move's n_sims
+simulations sharded root-parallel over the cores (independent trees, merged root statistics -- the CPU analogue of
+the multi-GPU scheme), greedy action, environment step, belief update in every tree.  If `baseline/_ref` holds a copy
+of the Python reference (tools/install_reference.py), its own POMCP is timed beside it on one core
+(`cpu_baseline_python`).
 """
 import argparse
 import json
@@ -30,32 +45,30 @@ import numpy as np  # noqa: E402
 
 MAP = "map-15-15"
 N_SIMS = 1_000_000
-SCHEDULE = (32768, 4, 1 << 19)          # generation widths: 32768, 131072, 524288 (+ the rest) simulations in flight;
-                                        # return at 1e6 simulations per move does not depend on the first width
-                                        # (160 paired episodes per width, 4096 ... 65536: profiles/r01_schedule_sweep.txt)
-REF_SAMPLE_SIMS = 100_000               # per core and step, reference arm
+MAX_STEPS = 200
 METRIC = "pomcp_sims_per_sec_rocksample_15_15"
+WORKLOAD = "RockSample(15,15) POMCP, n_sims=1M per move, moves of real episodes (tree kept across moves)"
 
 
-def build_inputs(n_sims):
-    """World and root belief exactly as BASELINE.md 8d: np.random.seed(123); world = first draw; 2000 particles."""
-    from pomdpy_b200.rock_sample import RockModel
-    args = dict(map_file=MAP, discount=0.95, max_depth=100, ucb_coefficient=3.0, n_start_states=2000,
-                max_particle_count=2000, n_sims=n_sims, seed=123)
-    model = RockModel(args)
-    np.random.seed(123)
+def schedule_for(n):
+    """Generation widths (w0, growth, wmax) of a search of n simulations: the solver's own rule."""
+    from pomdpy_b200.solvers.pomcp import auto_schedule
+    return auto_schedule(n)
+
+
+def make_model(n_sims):
     from pomdpy_b200 import util
+    from pomdpy_b200.rock_sample import RockModel
     util.VERBOSITY = 0
-    model.reset_for_epoch()
-    bag = np.fromiter((model.pack_state(model.sample_an_init_state()) for _ in range(2000)), dtype=np.uint32, count=2000)
-    actual, sampled = model.world_masks()
-    return model, model.device_spec(), bag, actual, sampled
+    args = dict(map_file=MAP, discount=0.95, max_depth=100, ucb_coefficient=3.0, n_start_states=2000,
+                max_particle_count=2000, n_sims=n_sims, seed=123, max_steps=MAX_STEPS)
+    return RockModel(args)
 
 
 class ClockSampler(threading.Thread):
     """nvidia-smi clocks and throttle reasons while the GPU is under load."""
-    Q = "clocks.sm,clocks.max.sm,utilization.gpu,clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown," \
-        "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
+    Q = "clocks.sm,clocks.max.sm,utilization.gpu,power.draw,clocks_event_reasons.hw_slowdown," \
+        "clocks_event_reasons.hw_thermal_slowdown,clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
 
     def __init__(self, index):
         super().__init__(daemon=True)
@@ -64,7 +77,7 @@ class ClockSampler(threading.Thread):
     def run(self):
         try:
             self.proc = subprocess.Popen(["nvidia-smi", "-i", str(self.index), "--query-gpu=" + self.Q,
-                                          "--format=csv,noheader,nounits", "-lms", "50"],
+                                          "--format=csv,noheader,nounits", "-lms", "100"],
                                          stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True)
             for line in self.proc.stdout:
                 self.rows.append([x.strip() for x in line.split(",")])
@@ -75,28 +88,170 @@ class ClockSampler(threading.Thread):
         if self.proc:
             self.proc.terminate()
         self.join(timeout=2)
-        sm, mx, reasons = [], 0.0, set()
+        sm, mx, pw, reasons = [], 0.0, 0.0, set()
         for r in self.rows:
             try:
-                clk, cmax, util = float(r[0]), float(r[1]), float(r[2])
+                clk, cmax, util, power = float(r[0]), float(r[1]), float(r[2]), float(r[3])
             except Exception:
                 continue
             mx = max(mx, cmax)
             if util > 0:
                 sm.append(clk)
-            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[3:7]):
+                pw = max(pw, power)
+            for name, v in zip(("hw_slowdown", "hw_thermal_slowdown", "sw_thermal_slowdown", "sw_power_cap"), r[4:8]):
                 if v.lower().startswith("active"):
                     reasons.add(name)
-        if not sm:
-            sm = [float(r[0]) for r in self.rows if r and r[0].replace(".", "").isdigit()]
         return dict(sm_mhz=statistics.median(sm) if sm else None, sm_max_mhz=mx or None, reasons=sorted(reasons),
-                    samples=len(self.rows))
+                    samples=len(self.rows), samples_under_load=len(sm), power_w_max=pw or None)
 
 
-def cpu_baseline(spec, bag, actual, n_sims):
-    """The oracle's port of the reference's sequential POMCP on ONE host core (the reference is single-threaded)."""
+# ---------------------------------------------------------------------------------------------------------------
+# The B200 arm
+# ---------------------------------------------------------------------------------------------------------------
+class EpisodeRunner:
+    """Drives real episodes through the C ABI (pomdpy_b200.native.Planner): the loop of pomdpy/agent.py:150-213 with the
+    solver calls replaced by pomcp_search / pomcp_root_stats / pomcp_advance."""
+
+    def __init__(self, pl, model, spec, n_sims_rank, rank, world, fused, stats_buf, stream, torch, dist, seed=123):
+        self.pl, self.model, self.spec = pl, model, spec
+        self.n, self.rank, self.world, self.fused = n_sims_rank, rank, world, fused
+        self.stats, self.stream, self.torch, self.dist, self.seed = stats_buf, stream, torch, dist, seed
+        self.A = spec["n_actions"]
+        self.epoch = -1
+        self.active = False
+        self.returns, self.lengths = [], []
+        self.h2d = self.d2h = 0
+
+    def new_episode(self):
+        from pomdpy_b200 import philox
+        m = self.model
+        self.epoch += 1
+        m.unique_rocks_sampled = []
+        m.reset_for_epoch()                                          # agent.py:135,143: the true world
+        bag = np.ascontiguousarray(m.sample_init_states_packed(2000), dtype=np.uint32)   # belief_tree_solver.py:36-38
+        self.pl.set_world(*m.world_masks())
+        self.pl.set_root_particles(bag, self.spec["start_cell"])     # host -> device, 8000 B
+        self.h2d += bag.nbytes + 8
+        idx = philox.randbelow(self.seed, len(bag), 0, 0, self.epoch << 12, philox.DOM_AGENT)
+        self.state = m.unpack_state(bag[idx])                        # agent.py:157
+        self.step, self.dret, self.disc, self.active = 0, 0.0, 1.0, True
+
+    def search(self):
+        """select_eps_greedy_action: the search and the merge of the root statistics (asynchronous on the stream)."""
+        self.move = ((self.epoch << 12) + self.step) & 0xFFFFFFFF
+        self.pl.search(self.n, move=self.move, sim_offset=self.rank * self.n, stream=self.stream)
+        if self.world > 1 and self.fused is None:
+            self.pl.root_stats_device(self.stats.data_ptr(), self.stream)
+            self.dist.all_reduce(self.stats, op=self.dist.ReduceOp.SUM)
+
+    def read_stats(self):
+        """Device -> host read of the (merged) root statistics."""
+        if self.world == 1:
+            st = self.pl.root_stats()
+            self.d2h += self.d2h_stats
+        elif self.fused is not None:
+            st = self.pl.merged_root_stats()
+            self.d2h += self.d2h_stats
+        else:
+            loc = self.pl.root_stats()
+            host = self.stats.cpu().numpy()
+            st = dict(n=host[:self.A].copy(), qfix=host[32:32 + self.A].copy(), legal=loc["legal"], sims_done=loc["sims_done"])
+            self.d2h += self.d2h_stats + 512
+        return st
+
+    def act(self, st):
+        """Greedy action (solvers/pomcp.py:78) and the real environment step on the host (agent.py:174)."""
+        from pomdpy_b200.solvers.pomcp import greedy_action
+        m = self.model
+        a = greedy_action(st["n"], st["qfix"], st["legal"], self.seed, self.move)
+        res, legal = m.generate_step(self.state, a)
+        self.dret += self.disc * res.reward
+        self.disc *= m.discount
+        self.state = res.next_state
+        self.step += 1
+        done = res.is_terminal or not legal or self.step >= MAX_STEPS
+        self._pending = None
+        if not res.is_terminal or not legal:                         # agent.py:186
+            m.update(res)
+            self._pending = (a, bool(res.observation.is_good), m.world_masks()[1])
+        return done
+
+    def advance(self):
+        """solver.update(step_result): belief update + re-root on the device; False if the belief died out."""
+        if self._pending is None:
+            return True
+        a, obs, sampled = self._pending
+        self.h2d += 16
+        self.d2h += self.d2h_stats
+        return self.pl.advance(a, obs, sampled, move=self.move)["status"] != 2
+
+    def finish(self, done, alive):
+        if done or not alive:
+            self.returns.append(self.dret)
+            self.lengths.append(self.step)
+            self.active = False
+
+
+def run_moves(run, n_moves, mode, torch, flush=None):
+    """Run n_moves moves (episodes back to back).  mode "device": CUDA events around every search and every belief
+    update, L2 flushed before each move (untimed); "e2e": wall clock of [search + statistics read] and [belief update]
+    (+ the belief upload of a new episode); "plain": no instrumentation."""
+    search_ms, advance_ms, e2e_ms, fresh = [], [], [], []
+    ev = []
+    for _ in range(n_moves):
+        t_new = 0.0
+        is_fresh = not run.active
+        if not run.active:
+            t0 = time.perf_counter()
+            run.new_episode()
+            t_new = time.perf_counter() - t0
+        if mode == "device":
+            flush.zero_()
+            e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
+            e[0].record()
+            run.search()
+            e[1].record()
+            st = run.read_stats()
+            done = run.act(st)
+            e[2].record()
+            alive = run.advance()
+            e[3].record()
+            ev.append(e)
+            fresh.append(is_fresh)
+        elif mode == "e2e":
+            torch.cuda.synchronize()
+            t0 = time.perf_counter()
+            run.search()
+            st = run.read_stats()
+            t1 = time.perf_counter()
+            done = run.act(st)
+            t2 = time.perf_counter()
+            alive = run.advance()
+            t3 = time.perf_counter()
+            e2e_ms.append(1e3 * (t_new + (t1 - t0) + (t3 - t2)))
+        else:
+            run.search()
+            st = run.read_stats()
+            done = run.act(st)
+            alive = run.advance()
+        run.finish(done, alive)
+    if mode == "device":
+        torch.cuda.synchronize()
+        search_ms = [e[0].elapsed_time(e[1]) for e in ev]
+        advance_ms = [e[2].elapsed_time(e[3]) for e in ev]
+    return dict(search_ms=search_ms, advance_ms=advance_ms, e2e_ms=e2e_ms, fresh=fresh)
+
+
+def cpu_baseline(spec, n_sims):
+    """The oracle's port of the reference's sequential POMCP on ONE host core (the reference is single-threaded):
+    one search of min(n_sims, 1M) simulations from the first episode's root belief."""
     sys.path.insert(0, os.path.join(ROOT, "oracle"))
     import oracle
+    model = make_model(n_sims)
+    np.random.seed(123)
+    model.reset_for_epoch()
+    bag = np.ascontiguousarray(model.sample_init_states_packed(2000), dtype=np.uint32)
+    actual, _ = model.world_masks()
     om = oracle.Model(spec["rows"], spec["cols"], spec["cell"], spec["start_cell"], spec["thr53"], spec["rewards"])
     sample = min(n_sims, 1_000_000)
     ref = oracle.RefPOMCP(om, actual, 0, (bag >> 8).astype(np.uint32), seed=123)
@@ -104,55 +259,8 @@ def cpu_baseline(spec, bag, actual, n_sims):
     ref.search(sample)
     dt = time.perf_counter() - t0
     return dict(value=sample / dt, unit="sims/s", cores=1, kind="port",
-                sample="one search of %d simulations (reference algorithm, quirks on) from the step's root belief; "
+                sample="one search of %d simulations (reference algorithm, quirks on) from the first move's root belief; "
                        "%.1f s on 1 core" % (sample, dt))
-
-
-def _ref_worker(a):
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle
-    spec, bag_rocks, actual, sims, seed = a
-    om = oracle.Model(spec["rows"], spec["cols"], spec["cell"], spec["start_cell"], spec["thr53"], spec["rewards"])
-    ref = oracle.RefPOMCP(om, actual, 0, bag_rocks, seed=seed)
-    ref.search(sims)
-    return int(ref.root_stats()["N"])
-
-
-def run_reference(args):
-    rank = int(os.environ.get("RANK", "0"))
-    if rank != 0:
-        return 0
-    import multiprocessing as mp
-    sys.path.insert(0, os.path.join(ROOT, "oracle"))
-    import oracle
-    oracle.build()
-    _, spec, bag, actual, _ = build_inputs(N_SIMS)
-    cores = os.cpu_count() or 1
-    spec_small = {k: spec[k] for k in ("rows", "cols", "cell", "start_cell", "thr53", "rewards")}
-    bag_rocks = (bag >> 8).astype(np.uint32)
-    times = []
-    with mp.get_context("fork").Pool(cores) as pool:
-        for it in range(args.warmup + args.steps):
-            jobs = [(spec_small, bag_rocks, actual, REF_SAMPLE_SIMS, 1000 * it + c) for c in range(cores)]
-            t0 = time.perf_counter()
-            done = pool.map(_ref_worker, jobs)
-            dt = time.perf_counter() - t0
-            assert sum(done) == cores * REF_SAMPLE_SIMS
-            if it >= args.warmup:
-                times.append(dt)
-    value = cores * REF_SAMPLE_SIMS * len(times) / sum(times)
-    sample = "%d independent searches (one per host core) of %d simulations each per step, C port of the " \
-             "reference's sequential POMCP" % (cores, REF_SAMPLE_SIMS)
-    print(json.dumps({
-        "impl": "reference", "metric": METRIC, "value": value, "unit": "sims/s", "n_gpus": args.gpus,
-        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * sum(times) / len(times),
-        "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "u32/f64", "data": "synthetic",
-        "config": {"workload": "RockSample(15,15) POMCP, n_sims=1M per move per GPU, root-parallel", "map": MAP,
-                   "sample_sims_per_core": REF_SAMPLE_SIMS},
-        "cpu_baseline": {"value": value, "unit": "sims/s", "cores": cores, "kind": "port", "sample": sample},
-        "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
-        "gpu_launches": 0}))
-    return 0
 
 
 def run_b200(args):
@@ -167,94 +275,131 @@ def run_b200(args):
     torch.cuda.set_device(local)
     if world > 1:
         dist.init_process_group("nccl", device_id=torch.device("cuda", local))
-    n_sims = args.n_sims
-    model, spec, bag, actual, sampled = build_inputs(n_sims)
-    w0, growth, wmax = args.w0, args.growth, args.wmax
-    pl = native.Planner(max_depth=100, tree_depth_cap=64, max_particle_count=2000, ucb_coefficient=3.0, discount=0.95,
-                        seed=123, node_capacity=n_sims + 4096, gen_w0=w0, gen_growth=growth, gen_wmax=wmax,
-                        device=local)
-    pl.set_model_rocksample(spec["rows"], spec["cols"], spec["cell"], spec["start_cell"], spec["thr53"], spec["rewards"])
-    pl.set_world(actual, sampled)
-    host_bag = torch.from_numpy(bag.view(np.int32).copy()).pin_memory()     # pinned host belief
-    host_bag_np = host_bag.numpy().view(np.uint32)
-    pl.set_root_particles(host_bag_np, spec["start_cell"])
     stream = torch.cuda.current_stream().cuda_stream
-    fused = None
-    if world > 1 and os.environ.get("POMCP_FUSED_MERGE", "1") != "0":
-        from pomdpy_b200 import dist as dist_mod
-        fused = dist_mod.try_fused_merge(pl)             # merge inside the search kernel (NVLink peer stores)
-    stats = torch.zeros(64, dtype=torch.int64, device="cuda")
     flush = torch.empty(256 << 20, dtype=torch.uint8, device="cuda")         # > 126 MB L2
+    stats = torch.zeros(64, dtype=torch.int64, device="cuda")
+    model = make_model(args.n_sims)
+    spec = model.device_spec()
+    A = spec["n_actions"]
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
-    def device_step(i, ev=None):
-        pl.reset_tree(stream)
-        if ev:
-            ev[0].record()
-        pl.search(n_sims, move=i, sim_offset=rank * n_sims, stream=stream)
-        if ev:
-            ev[1].record()
-        if fused is None:
-            pl.root_stats_device(stats.data_ptr(), stream)
-            if world > 1:
-                dist.all_reduce(stats, op=dist.ReduceOp.SUM)
+    def make_runner(scaling):
+        n_rank = -(-args.n_sims // world) if scaling == "strong" else args.n_sims
+        w0, growth, wmax = (args.w0, args.growth, args.wmax) if args.w0 else schedule_for(n_rank)
+        cap = int(min(1 << 24, max(1 << 16, n_rank * 8 + 4096)))
+        pl = native.Planner(max_depth=100, tree_depth_cap=64, max_particle_count=2000, ucb_coefficient=3.0, discount=0.95,
+                            seed=123, node_capacity=cap, gen_w0=w0, gen_growth=growth, gen_wmax=wmax, device=local)
+        pl.set_model_rocksample(spec["rows"], spec["cols"], spec["cell"], spec["start_cell"], spec["thr53"], spec["rewards"])
+        fused = None
+        if world > 1 and os.environ.get("POMCP_FUSED_MERGE", "1") != "0":
+            from pomdpy_b200 import dist as dist_mod
+            fused = dist_mod.try_fused_merge(pl)         # merge inside the search kernel (NVLink peer stores)
+        np.random.seed(123)                              # the worlds and beliefs of the episodes; same on every rank
+        run = EpisodeRunner(pl, model, spec, n_rank, rank, world, fused, stats, stream, torch, dist)
+        run.d2h_stats = int(pl.counters()["root_stats_d2h_bytes"])
+        return pl, run, (w0, growth, wmax), n_rank
+
+    scaling = args.scaling if world > 1 else "strong"
+    pl, run, sched, n_rank = make_runner(scaling)
+    total_sims = n_rank * world
 
     sampler = ClockSampler(local) if rank == 0 else None
     if sampler:
         sampler.start()
-    for i in range(args.warmup):
-        flush.zero_()
-        device_step(i)
+
+    # ---- warm-up moves (untimed); at N > 1 the in-kernel merge is held against an NCCL all-reduce of the local roots
+    merge_checked = None
+    run_moves(run, args.warmup, "plain", torch)
+    if world > 1:
+        if not run.active:
+            run.new_episode()
+        run.search()
+        merged = run.read_stats()
+        loc = pl.root_stats()
+        t = torch.zeros(64, dtype=torch.int64, device="cuda")
+        t[:A] = torch.from_numpy(loc["n"]).cuda()
+        t[32:32 + A] = torch.from_numpy(loc["qfix"]).cuda()
+        dist.all_reduce(t, op=dist.ReduceOp.SUM)
+        h = t.cpu().numpy()
+        assert np.array_equal(h[:A], merged["n"]) and np.array_equal(h[32:32 + A], merged["qfix"]), \
+            "merged root statistics differ from the NCCL all-reduce of the local ones"
+        merge_checked = "fused == NCCL all-reduce (n and sum q)" if run.fused is not None else "NCCL all-reduce"
+        run.finish(run.act(merged), run.advance())
+
+    # ---- timed moves: device time -------------------------------------------------------------------------
     barrier()
     c0 = pl.counters()
-    ev_step = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    ev_kern = [(torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)) for _ in range(args.steps)]
-    for i in range(args.steps):
-        flush.zero_()                                   # L2 flushed between timed steps (not timed)
-        ev_step[i][0].record()
-        device_step(args.warmup + i, ev_kern[i])
-        ev_step[i][1].record()
+    dev = run_moves(run, args.steps, "device", torch, flush)
     barrier()
     c1 = pl.counters()
-    step_ms = sum(a.elapsed_time(b) for a, b in ev_step)
-    kern_ms = sum(a.elapsed_time(b) for a, b in ev_kern) / args.steps
-    A = spec["n_actions"]
-    merged = stats.cpu().numpy()[:A] if fused is None else pl.merged_root_stats()["n"]
-    assert int(merged.sum()) == n_sims * world, "root visit counts do not add up to the simulations run"
+    # ---- the same moves end to end through the C ABI (wall clock, host buffers) ------------------------------
+    h2d0, d2h0 = run.h2d, run.d2h
+    e2e = run_moves(run, args.steps, "e2e", torch)
+    barrier()
+    h2d_step, d2h_step = (run.h2d - h2d0) / args.steps, (run.d2h - d2h0) / args.steps
 
-    # ---- end to end through the C ABI with host buffers --------------------------------------------------
+    # ---- fresh-tree searches (round 1's figure) ---------------------------------------------------------------
+    if not run.active:
+        run.new_episode()
+    fr = []
+    for i in range(min(args.steps, 20) + 3):
+        flush.zero_()
+        pl.reset_tree(stream)
+        e0, e1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
+        e0.record()
+        run.step = 100 + i
+        run.search()
+        e1.record()
+        torch.cuda.synchronize()
+        if i >= 3:
+            fr.append(e0.elapsed_time(e1))
+    run.active = False
     barrier()
+
+    # ---- whole episodes back to back: mean discounted return; seconds of continuous load ---------------------
+    n_ret = args.return_epochs if world == 1 else min(args.return_epochs, args.return_epochs_multi)
+    run.returns, run.lengths = [], []
     t0 = time.perf_counter()
-    for i in range(args.steps):
-        pl.set_root_particles(host_bag_np, spec["start_cell"])                     # H2D from pinned memory
-        pl.search(n_sims, move=1000 + i, sim_offset=rank * n_sims, stream=stream)
-        if fused is not None:
-            res = pl.merged_root_stats()                                           # D2H of the in-kernel merge
-        elif world > 1:
-            pl.root_stats_device(stats.data_ptr(), stream)
-            dist.all_reduce(stats, op=dist.ReduceOp.SUM)
-            res = stats.cpu()                                                      # D2H
-        else:
-            res = pl.root_stats()                                                  # D2H
-    barrier()
-    e2e_s = time.perf_counter() - t0
-    del res
+    moves = 0
+    while len(run.returns) < n_ret:
+        run_moves(run, 1, "plain", torch)
+        moves += 1
+    torch.cuda.synchronize()
+    ret_s = time.perf_counter() - t0
+    returns, lengths = np.array(run.returns[:n_ret]), np.array(run.lengths[:n_ret])
     clocks = sampler.stop() if sampler else None
 
-    t = torch.tensor([step_ms, e2e_s * 1e3, kern_ms], dtype=torch.float64, device="cuda")
+    # ---- the other scaling mode on a short leg -------------------------------------------------------------
+    other = None
+    if world > 1 and not args.no_other_scaling:
+        pl.close()
+        o_mode = "weak" if scaling == "strong" else "strong"
+        pl2, run2, sched2, n_rank2 = make_runner(o_mode)
+        run_moves(run2, 3, "plain", torch)
+        barrier()
+        d2 = run_moves(run2, min(args.steps, 40), "device", torch, flush)
+        barrier()
+        other = (o_mode, d2["search_ms"], n_rank2, sched2)
+        pl = pl2
+
+    def med(x):
+        return float(statistics.median(x)) if len(x) else 0.0
+
+    loc = [med(dev["search_ms"]), float(np.mean(dev["search_ms"])), med(dev["advance_ms"]), med(e2e["e2e_ms"]),
+           float(np.mean(e2e["e2e_ms"])), med(fr), med(other[1]) if other else 0.0]
+    t = torch.tensor(loc, dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    step_ms, e2e_ms, kern_ms = (float(x) for x in t.cpu())
+    s_med, s_mean, a_med, e_med, e_mean, f_med, o_med = (float(x) for x in t.cpu())
 
     if rank == 0:
-        sims = n_sims * world * args.steps
-        d = {k: c1[k] - c0[k] for k in ("levels", "rollout_steps", "created", "generations", "level_steps", "launches")}
-        L = d["levels"] / (n_sims * args.steps)
-        R = d["rollout_steps"] / (n_sims * args.steps)
+        d = {k: c1[k] - c0[k] for k in ("levels", "rollout_steps", "created", "generations", "launches")}
+        L = d["levels"] / (n_rank * args.steps)
+        R = d["rollout_steps"] / (n_rank * args.steps)
         bytes_per_sim = L * (8 * A + 56) + 8 * A + 20
         peaks = {}
         try:
@@ -263,43 +408,64 @@ def run_b200(args):
         except Exception:
             pass
         peak = float(peaks.get("hbm_gbs", 6650.0))
-        achieved = bytes_per_sim * n_sims / (kern_ms * 1e-3) / 1e9
+        achieved = bytes_per_sim * n_rank / (s_med * 1e-3) / 1e9
         prof = {}
         try:
             with open(os.path.join(ROOT, "profiles", "search_kernel_summary.json")) as f:
                 prof = json.load(f)
         except Exception:
             pass
+        sm = sorted(dev["search_ms"])
         out = {
-            "metric": METRIC, "value": sims / (step_ms * 1e-3), "unit": "sims/s", "n_gpus": world, "steps": args.steps,
-            "warmup": args.warmup, "ms_per_step": step_ms / args.steps, "higher_is_better": True, "scaling": "weak",
+            "metric": METRIC, "value": total_sims / (s_med * 1e-3), "unit": "sims/s", "n_gpus": world, "steps": args.steps,
+            "warmup": args.warmup, "ms_per_step": s_med, "higher_is_better": True, "scaling": scaling,
             "vs_baseline": None, "dtype": "u32/f64", "data": "synthetic",
-            "config": {"workload": "RockSample(15,15) POMCP, n_sims=1M per move per GPU, root-parallel", "map": MAP,
-                       "n_sims_per_gpu": n_sims, "root_particles": 2000, "max_depth": 100, "ucb_coefficient": 3.0,
-                       "discount": 0.95, "generation_schedule": [w0, growth, wmax],
-                       "l2": "flushed between timed steps (256 MiB device write, untimed)",
-                       "step": "fresh tree + search + root-statistics merge",
+            "mean_discounted_return": float(returns.mean()),
+            "return_stderr": float(returns.std(ddof=1) / np.sqrt(len(returns))) if len(returns) > 1 else None,
+            "return_epochs": int(len(returns)),
+            "config": {"workload": WORKLOAD, "map": MAP, "n_sims_per_move": total_sims, "n_sims_per_gpu": n_rank,
+                       "parallelism": "root-parallel over %d GPU(s)" % world,
+                       "root_particles": 2000, "max_depth": 100, "ucb_coefficient": 3.0, "discount": 0.95,
+                       "max_steps": MAX_STEPS, "generation_schedule": list(sched),
+                       "l2": "flushed before every timed move (256 MiB device write, untimed)",
+                       "step": "one move of an episode: search (+ root merge) -> greedy -> host generate_step -> advance; "
+                               "value = n_sims / median search time (SURVEY 8d)",
                        "merge": ("none (1 GPU)" if world == 1 else
-                                 "fused into the search kernel: peer stores over NVLink, no collective call" if fused
+                                 "fused into the search kernel: peer stores over NVLink, no collective call" if run.fused
                                  else "NCCL all-reduce of 64 int64"),
+                       "merge_check": merge_checked,
+                       "search_ms": {"median": s_med, "mean": s_mean, "p10": sm[len(sm) // 10], "p90": sm[(9 * len(sm)) // 10],
+                                     "fresh_tree_moves_among_steps": int(sum(dev["fresh"]))},
+                       "advance_ms_median": a_med, "move_device_ms_median": s_med + a_med,
+                       "value_from_mean_search_time": total_sims / (s_mean * 1e-3),
+                       "fresh_tree_value": total_sims / (f_med * 1e-3) if f_med else None, "fresh_tree_ms": f_med,
                        "tree_levels_per_sim": L, "rollout_steps_per_sim": R,
-                       "generate_steps_per_s": (d["levels"] + d["rollout_steps"]) * world / (step_ms * 1e-3)},
+                       "generate_steps_per_s": (d["levels"] + d["rollout_steps"]) / args.steps * world / (s_med * 1e-3),
+                       "episodes": {"epochs": int(len(returns)), "mean_moves": float(lengths.mean()), "seconds": ret_s,
+                                    "moves": moves, "sims_per_s_wall_sustained": total_sims * moves / ret_s}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
                          "traffic": prof.get("dram_bytes_per_launch"),
                          "peak_source": "MEASURED_PEAKS.json hbm_gbs" if peaks else "fallback 6650 GB/s",
-                         "kernel": "pomcp_search_kernel", "kernel_ms": kern_ms,
+                         "kernel": "pomcp_search_kernel", "kernel_ms": s_med,
                          "algorithmic_bytes_per_sim": bytes_per_sim,
                          "note": "not HBM-bound by construction (SURVEY 8d): the binding resource is instruction issue; "
-                                 "see issue_slot_utilisation (from the committed ncu capture) and profiles/",
+                                 "achieved/kernel_ms/levels are measured in this run, the ncu-derived fields below come "
+                                 "from the committed capture named in `from`",
                          "issue_slot_utilisation_pct": prof.get("issue_active_pct"),
-                         "thread_instructions_per_generate_step": prof.get("thread_inst_per_generate_step")},
-            "e2e": {"value": sims / (e2e_ms * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": int(bag.nbytes),
-                    "d2h_bytes_per_step": int(c1["root_stats_d2h_bytes"] if (world == 1 or fused is not None) else 64 * 8)},
+                         "thread_instructions_per_generate_step": prof.get("thread_inst_per_generate_step"),
+                         "l2_atomic_sectors_per_launch": prof.get("l2_atom_sectors"),
+                         "from": prof.get("from", "profiles/search_kernel_summary.json")},
+            "e2e": {"value": total_sims / (e_med * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": h2d_step,
+                    "d2h_bytes_per_step": d2h_step, "ms_per_move_median": e_med, "ms_per_move_mean": e_mean},
             "gpu_launches": int(d["launches"]),
             "clocks": clocks,
         }
+        if other:
+            tot2 = other[2] * world
+            out["other_scaling"] = {"scaling": other[0], "value": tot2 / (o_med * 1e-3), "ms_per_step": o_med,
+                                    "n_sims_per_gpu": other[2], "generation_schedule": list(other[3]), "steps": len(other[1])}
         if world == 1 and not args.no_cpu_baseline:
-            out["cpu_baseline"] = cpu_baseline(spec, bag, actual, n_sims)
+            out["cpu_baseline"] = cpu_baseline(spec, args.n_sims)
         print(json.dumps(out))
     pl.close()
     if world > 1:
@@ -307,20 +473,194 @@ def run_b200(args):
     return 0
 
 
+# ---------------------------------------------------------------------------------------------------------------
+# The reference arm: the reference's sequential POMCP (C port) on the host cores, same protocol
+# ---------------------------------------------------------------------------------------------------------------
+def _ref_worker(conn, spec, core, n_share, seed):
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    om = oracle.Model(spec["rows"], spec["cols"], spec["cell"], spec["start_cell"], spec["thr53"], spec["rewards"])
+    ref = None
+    while True:
+        msg = conn.recv()
+        if msg[0] == "new":
+            _, actual, bag_rocks, epoch = msg
+            ref = oracle.RefPOMCP(om, actual, 0, bag_rocks, seed=seed + 7919 * core + 104729 * epoch, stream_id=core)
+            conn.send(True)
+        elif msg[0] == "search":
+            ref.search(n_share)
+            st = ref.root_stats()
+            conn.send((st["n"], st["total"], st["legal"]))
+        elif msg[0] == "update":
+            _, a, obs, sampled = msg
+            conn.send(ref.update(a, obs, sampled))
+        else:
+            break
+
+
+def python_reference_baseline():
+    """The UNMODIFIED Python reference from baseline/_ref (tools/install_reference.py), one core: n_sims=500, the first
+    3 moves of a RockSample(15,15) episode, search-only simulations/second."""
+    ref_dir = os.path.join(ROOT, "baseline", "_ref")
+    if not os.path.isdir(os.path.join(ref_dir, "ref", "pomdpy")):
+        return {"unavailable": "baseline/_ref not installed (python tools/install_reference.py in the build container)"}
+    code = r'''
+import sys, time, random, io, contextlib, warnings, json
+warnings.simplefilter("ignore")
+sys.path.insert(0, %r); sys.path.insert(0, %r)
+import numpy as np
+from pomdpy import Agent
+from pomdpy.solvers import POMCP
+from examples.rock_sample import RockModel
+import pomdpy.util.console as cons
+cons.VERBOSITY = 0
+args = dict(env="RockSample", solver="POMCP", seed=123, use_tf=False, discount=0.95, n_epochs=1, max_steps=200, save=False,
+            test=10, epsilon_start=0.5, epsilon_minimum=0.1, epsilon_decay=0.95, epsilon_decay_step=20, n_sims=500,
+            timeout=3600, preferred_actions=False, ucb_coefficient=3.0, n_start_states=2000, min_particle_count=1000,
+            max_particle_count=2000, max_depth=100, action_selection_timeout=600)
+np.random.seed(123); random.seed(123)
+with contextlib.redirect_stdout(io.StringIO()):
+    model = RockModel(args)
+    agent = Agent(model, POMCP)
+    model.reset_for_epoch()
+    solver = POMCP(agent)
+    state = solver.belief_tree_index.sample_particle()
+    secs = 0.0; moves = 0
+    for mv in range(3):
+        t0 = time.time()
+        action = solver.select_eps_greedy_action(0.0, time.time())
+        secs += time.time() - t0
+        moves += 1
+        step, legal = model.generate_step(state, action)
+        if step.is_terminal or not legal: break
+        state = step.next_state
+        solver.update(step)
+print(json.dumps(dict(value=500 * moves / secs, moves=moves, seconds=secs)))
+''' % (os.path.join(ref_dir, "shim"), os.path.join(ref_dir, "ref"))
+    try:
+        res = subprocess.run([sys.executable, "-c", code], capture_output=True, text=True, timeout=600, cwd=os.path.join(ref_dir, "ref"))
+        r = json.loads(res.stdout.strip().splitlines()[-1])
+        return dict(value=r["value"], unit="sims/s", cores=1, kind="reference",
+                    sample="the Python reference itself (baseline/_ref, map-15-15): n_sims=500, first %d moves, %.1f s of search"
+                           % (r["moves"], r["seconds"]))
+    except Exception as e:                                           # noqa: BLE001
+        return {"unavailable": "python reference failed: %s" % (str(e)[:200])}
+
+
+def run_reference(args):
+    rank = int(os.environ.get("RANK", "0"))
+    if rank != 0:
+        return 0
+    import multiprocessing as mp
+    sys.path.insert(0, os.path.join(ROOT, "oracle"))
+    import oracle
+    oracle.build()
+    model = make_model(args.n_sims)
+    spec = model.device_spec()
+    cores = os.cpu_count() or 1
+    n_share = -(-args.n_sims // cores)
+    spec_small = {k: spec[k] for k in ("rows", "cols", "cell", "start_cell", "thr53", "rewards")}
+    ctx = mp.get_context("fork")
+    pipes, procs = [], []
+    for c in range(cores):
+        a, b = ctx.Pipe()
+        p = ctx.Process(target=_ref_worker, args=(b, spec_small, c, n_share, 123), daemon=True)
+        p.start()
+        pipes.append(a)
+        procs.append(p)
+    from pomdpy_b200 import philox
+    np.random.seed(123)
+    A = spec["n_actions"]
+    times, returns, epoch, active = [], [], -1, False
+    state = None
+    step = dret = disc = 0
+    for it in range(args.warmup + args.steps):
+        if not active:
+            epoch += 1
+            model.unique_rocks_sampled = []
+            model.reset_for_epoch()
+            bag = np.ascontiguousarray(model.sample_init_states_packed(2000), dtype=np.uint32)
+            actual, _ = model.world_masks()
+            for c in pipes:
+                c.send(("new", actual, (bag >> 8).astype(np.uint32), epoch))
+            for c in pipes:
+                c.recv()
+            state = model.unpack_state(bag[philox.randbelow(123, len(bag), 0, 0, epoch << 12, philox.DOM_AGENT)])
+            step, dret, disc, active = 0, 0.0, 1.0, True
+        t0 = time.perf_counter()
+        for c in pipes:
+            c.send(("search",))
+        n, tot, legal = np.zeros(A, dtype=np.int64), np.zeros(A), 0
+        for c in pipes:
+            rn, rt, legal = c.recv()
+            n += rn
+            tot += rt
+        dt = time.perf_counter() - t0
+        mean = np.where(n > 0, tot / np.maximum(n, 1), 0.0)
+        mean[[a for a in range(A) if not (legal >> a) & 1]] = -np.inf
+        a = int(np.argmax(mean))
+        res, is_legal = model.generate_step(state, a)
+        dret += disc * res.reward
+        disc *= model.discount
+        state = res.next_state
+        step += 1
+        done = res.is_terminal or not is_legal or step >= MAX_STEPS
+        if not done:
+            model.update(res)
+            for c in pipes:
+                c.send(("update", a, bool(res.observation.is_good), model.world_masks()[1]))
+            if any(c.recv() < 0 for c in pipes):
+                done = True
+        if done:
+            returns.append(dret)
+            active = False
+        if it >= args.warmup:
+            times.append(dt)
+    for c in pipes:
+        c.send(("quit",))
+    for p in procs:
+        p.join(timeout=2)
+    total = n_share * cores
+    med = statistics.median(times)
+    value = total / med
+    sample = "every step = one move of an episode: %d simulations sharded root-parallel over %d host cores (C port of the " \
+             "reference's sequential POMCP, quirks on; independent trees, merged root statistics), median of %d moves" \
+             % (total, cores, len(times))
+    out = {
+        "impl": "reference", "metric": METRIC, "value": value, "unit": "sims/s", "n_gpus": args.gpus,
+        "steps": args.steps, "warmup": args.warmup, "ms_per_step": 1e3 * med,
+        "higher_is_better": True, "scaling": "strong", "vs_baseline": None, "dtype": "u32/f64", "data": "synthetic",
+        "config": {"workload": WORKLOAD, "map": MAP, "n_sims_per_move": total,
+                   "parallelism": "root-parallel over %d host cores" % cores, "root_particles": 2000, "max_depth": 100,
+                   "ucb_coefficient": 3.0, "discount": 0.95, "max_steps": MAX_STEPS},
+        "cpu_baseline": {"value": value, "unit": "sims/s", "cores": cores, "kind": "port", "sample": sample},
+        "cpu_baseline_python": python_reference_baseline(),
+        "e2e": {"value": value, "unit": "sims/s", "h2d_bytes_per_step": 0, "d2h_bytes_per_step": 0},
+        "gpu_launches": 0}
+    print(json.dumps(out))
+    return 0
+
+
 def main():
     ap = argparse.ArgumentParser()
     ap.add_argument("--gpus", type=int, default=1)
-    ap.add_argument("--steps", type=int, default=50)
+    ap.add_argument("--steps", type=int, default=150)
     ap.add_argument("--warmup", type=int, default=5)
     ap.add_argument("--impl", default="b200", choices=["b200", "reference"])
+    ap.add_argument("--scaling", default="strong", choices=["strong", "weak"])
     ap.add_argument("--n_sims", type=int, default=N_SIMS)
-    ap.add_argument("--w0", type=int, default=SCHEDULE[0])
-    ap.add_argument("--growth", type=int, default=SCHEDULE[1])
-    ap.add_argument("--wmax", type=int, default=SCHEDULE[2])
+    ap.add_argument("--w0", type=int, default=0, help="generation schedule override (default: the solver's rule)")
+    ap.add_argument("--growth", type=int, default=4)
+    ap.add_argument("--wmax", type=int, default=1 << 19)
+    ap.add_argument("--return_epochs", type=int, default=100)
+    ap.add_argument("--return_epochs_multi", type=int, default=32, help="epochs of the return leg at N > 1")
     ap.add_argument("--no_cpu_baseline", action="store_true")
+    ap.add_argument("--no_other_scaling", action="store_true")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":
+        if args.steps == 150:
+            args.steps = 20
         return run_reference(args)
     return run_b200(args)
 

@@ -956,6 +956,8 @@ static double gs_rollout(orc_gs *h, gs_sim *s, uint32_t move)
     return sum;
 }
 
+static int g_gs_kmode = 0;   /* experiment switch: 0 = expected arrivals carried down the plans, 1 = w * N(X) / N(root) */
+void orc_gs_set_kmode(int m) { g_gs_kmode = m; }
 static int64_t gs_visits(const gs_node *nd) { int64_t N = 0; for (int b = 0; b < 32; ++b) N += nd->n[b]; return N; }
 
 /* A simulation standing at a node without statistics (N = 0): every legal action is untried, so UCB1 is a uniform
@@ -983,7 +985,7 @@ int orc_gs_search(orc_gs *h, int64_t n_sims, uint32_t sim_offset, uint32_t move,
 {
     if (w0 < 1) w0 = 1; if (growth < 1) growth = 1; if (wmax < w0) wmax = w0;
     int dcap = h->dcap;
-    int64_t done = 0; int64_t W = w0;
+    int64_t done = 0;
     gs_sim *S = (gs_sim *)calloc((size_t)wmax, sizeof(gs_sim));
     int32_t *pn = (int32_t *)malloc(sizeof(int32_t) * (size_t)wmax * (size_t)dcap);
     uint8_t *pa = (uint8_t *)malloc((size_t)wmax * (size_t)dcap);
@@ -991,6 +993,9 @@ int orc_gs_search(orc_gs *h, int64_t n_sims, uint32_t sim_offset, uint32_t move,
     gs_plan *cache = NULL; int64_t *cache_stamp = NULL; int32_t cache_cap = 0;   /* plans of this generation, by node */
     gs_plan fresh;
     while (done < n_sims) {
+        /* width of the generation: growth x the visits the root has seen, within [w0, wmax] */
+        int64_t W = (int64_t)growth * gs_visits(&h->nodes[h->root]);
+        if (W < w0) W = w0; if (W > wmax) W = wmax;
         int64_t w = W; if (w > n_sims - done) w = n_sims - done;
         h->n_generations++;
         const int64_t stamp = h->n_generations;
@@ -1040,7 +1045,8 @@ int orc_gs_search(orc_gs *h, int64_t n_sims, uint32_t sim_offset, uint32_t move,
                 }
                 const int64_t Nc = child < nn0 ? gs_visits(&h->nodes[child]) : 0;
                 if (Nc == 0) { gs_virgin_step(h, s, child, move); break; }
-                k = (k * pa_) * ((float)Nc / (float)h->nodes[X].n[a]);         /* expected arrivals at the child */
+                if (g_gs_kmode == 0) k = (k * pa_) * ((float)Nc / (float)h->nodes[X].n[a]);   /* expected arrivals at the child */
+                else k = (float)w * ((float)Nc / (float)gs_visits(&h->nodes[h->root]));
                 X = child;
             }
         }
@@ -1061,7 +1067,6 @@ int orc_gs_search(orc_gs *h, int64_t n_sims, uint32_t sim_offset, uint32_t move,
             }
         }
         done += w;
-        if (W < wmax) { W *= growth; if (W > wmax) W = wmax; }
     }
     free(S); free(pn); free(pa); free(pr); free(cache); free(cache_stamp);
     return 0;

@@ -33,30 +33,6 @@
 //                          staged per block in shared memory)
 // ---------------------------------------------------------------------------------------------------------
 
-// A simulation standing at a node without statistics (N = 0): every legal action is untried, so UCB1 is a uniform
-// draw (action_selectors.py:6-37 with +inf bonuses), the node cannot be expanded (solvers/pomcp.py:107) and the
-// simulation ends in a rollout.  `node_ref` is the node id, or -1 - child_slot while the id is being published.
-template <int KIND>
-__device__ __forceinline__ void virgin_step(const SearchParams &p, const typename Mdl<KIND>::Ctx &mc, int i, uint32_t sim,
-                                            int node_ref, uint32_t mask, uint32_t &st, int &d, int &status,
-                                            int &last_ref, uint32_t &last_ar, long long &c_levels)
-{
-    if (d >= p.max_depth) { status = 2; return; }                                          // solvers/pomcp.py:100
-    DCHECK(p.S, mask != 0u && d < p.dcap && Mdl<KIND>::tag_ok(mc, Mdl<KIND>::state_tag(st)), 11);
-    const Philox4 r = philox4x32_10((uint32_t)(d + 1), sim, p.move, DOM_SIM, p.key0, p.key1);
-    const int a = nth_bit(mask, randbelow32(r.x, (uint32_t)__popc(mask)));
-    const StepOut so = Mdl<KIND>::step(mc, st, a, r.y, r.z);
-    ++c_levels;
-    const uint16_t code = Mdl<KIND>::path_code(a, so);
-    p.b.path_node[(size_t)d * p.wmax + i] = node_ref;
-    p.b.path_ar[(size_t)d * p.wmax + i] = code;
-    if (KIND == 1) p.b.path_rew[(size_t)d * p.wmax + i] = so.reward;
-    last_ref = node_ref; last_ar = code;
-    d = d + 1;
-    st = so.next;
-    status = so.terminal ? 2 : 1;
-}
-
 __device__ __forceinline__ int row_sum(const int32_t *nrow)
 {
     int N = 0;
@@ -111,16 +87,21 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
 #define PHASE_MARK(k) do { if (gtid == 0) { const unsigned long long now_ = globaltimer_ns(); tp[k] += now_ - tmark; \
                                              if (gens <= 120) S->steplog[gens - 1][k] = (long long)(now_ - tmark); tmark = now_; } } while (0)
     TSEC_DECL;
-    const float pc_min_k = 4.0f * (float)gridDim.x;                  // expected arrivals that earn a node a slot in the block caches
-    int W = p.w0;
+    // expected arrivals that earn a node a slot in the block caches (batch-UCB allocations only: >= 16.5)
+    const float pc_min_k = fmaxf(4.0f * (float)gridDim.x, 16.5f);
 
     GRID_SYNC();                                                    // everyone has read S before anyone writes it
 
     while (done < p.n_sims) {
-        const int w = (int)((p.n_sims - done) < (long long)W ? (p.n_sims - done) : (long long)W);
+        // Width of the generation: `growth` times the visits the root has seen, within [w0, wmax] -- from a fresh tree
+        // w0, growth*w0, ... as a geometric schedule would, and inside an episode, where the re-rooted tree arrives
+        // with statistics, wide generations right away (statistics are as stale relative to their mass either way)
+        const int Nroot = row_sum(p.t.n + (size_t)root * AS);
+        long long W = (long long)p.growth * Nroot;
+        W = W < p.w0 ? p.w0 : W > p.wmax ? p.wmax : W;
+        const int w = (int)((p.n_sims - done) < W ? (p.n_sims - done) : W);
         ++gens; ++gstep;
         const uint32_t stamp = (uint32_t)gstep;                      // of the plans computed in this generation
-        const int Nroot = row_sum(p.t.n + (size_t)root * AS);
         const uint32_t root_mask = p.t.legal[root];
         if (gtid == 0) { S->cursor[2 * ((gens + 1) & 1)] = 0; S->cursor[2 * ((gens + 1) & 1) + 1] = 0; }   // the next generation's
         PHASE_MARK(0);
@@ -133,113 +114,162 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
             const int i = base + lane;
             const uint32_t sim = p.sim_offset + (uint32_t)(done + i);
             int status = i < w ? 0 : 4;                              // 0 descending, 1 leaf: rollout pending, 2 ended in the tree, 4 no simulation
-            uint32_t st = 0u; int X = root, d = 0, na = Nroot;
+            uint32_t st = 0u; int X = root, d = 0, na = Nroot;       // X: node id, or -1 - child slot of a node being created
             float kpre = (float)w;                                   // expected arrivals at X = kpre * N(X) / na
+            float kx = -1.0f;                                        // ... once computed (< 0: not yet)
+            // A simulation at a node WITHOUT statistics (N = 0; "virgin"): every legal action is untried, so UCB1 is a
+            // uniform draw (action_selectors.py:6-37 with +inf bonuses), the node cannot be expanded
+            // (solvers/pomcp.py:107) and the simulation ends in a rollout.
+            bool virgin = Nroot == 0; uint32_t vmask = root_mask;
+            bool filler = false;                                     // this lane computes X's plan for the whole block
             int last_ref = root; uint32_t last_ar = 0u;              // the last tree step (preferred-action rollouts)
             TSEC_START();
             if (status == 0) {                                       // root particle (belief_node.py:47-48)
-                const Philox4 r = philox4x32_10(0u, sim, p.move, DOM_SIM, p.key0, p.key1);
+                const Philox4 r = philox4x32_10_ks(0u, sim, p.move, DOM_SIM, p.ks);
                 st = bag[randbelow32(r.x, (uint32_t)n_bag)];
-                if (Nroot == 0) virgin_step<KIND>(p, mc, i, sim, root, root_mask, st, d, status, last_ref, last_ar, c_levels);
             }
-            float kx = -1.0f;                                        // expected arrivals at X (< 0: not computed yet)
-            bool filler = false;                                     // this lane fetches X's plan for the whole block
+#ifdef POMCP_TSEC
+            int it_log = 0; long long it_t0 = clock64();
+            const bool it_on = base == 0 && lane == 0 && gens == 1;   // iteration log of the first chunk of the first generation
+#endif
             while (__any_sync(FULL, status == 0)) {                  // one tree level per iteration, for the lanes whose
                 bool act = status == 0;                              // plan is at hand; the others retry (nobody blocks)
                 if (act && d >= p.max_depth) { status = 2; act = false; }                  // :100
                 // -- the plan of node X: block cache (shared memory), node record (L2), or computed here
                 uint32_t *pce = pc + (((uint32_t)X * 2654435761u) >> (32 - PC_BITS)) * PC_WORDS;
-                bool have = false, cand = false, progressed = false;
+                bool have = false, cand = false, self = false, small = false, won = false, progressed = false;
+                bool wait_block = false, wait_grid = false;          // the plan is being computed by another warp
                 uint4 head = make_uint4(0u, 0u, 0u, 0u), data = head;
                 const uint32_t *sthr = nullptr;
-                if (act && !filler && *((volatile uint32_t *)pce) == (uint32_t)X + 1u) {
-                    if (*((volatile uint32_t *)(pce + 1)) != 0u) {   // cached by this block (else: being fetched, retry)
-                        __threadfence_block();
-                        kx = __uint_as_float(pce[2]);
-                        head = *reinterpret_cast<const uint4 *>(pce + 4); data = *reinterpret_cast<const uint4 *>(pce + 8);
-                        sthr = pce + 12;
-                        have = true;
-                    }
-                } else if (act) {
-                    bool retry = false;
-                    if (kx < 0.0f) {
-                        const int N = row_sum(p.t.n + (size_t)X * AS);
-                        if (N == 0) {                                // a node without statistics: uniform action, leaf
-                            uint32_t vm = MD::tag_legal(mc, MD::state_tag(st));
-                            // published in this very phase, maybe by another SM: with preferred actions its action set
-                            // is read from L2, never from a possibly stale L1 line
-                            if (KIND == 0 && p.t.chance) vm = __ldcg(&p.t.legal[X]);
-                            virgin_step<KIND>(p, mc, i, sim, X, vm, st, d, status, last_ref, last_ar, c_levels);
-                            retry = true; progressed = true;
-                        } else {
-                            kx = kpre * ((float)N / (float)na);
-                            if (kx >= pc_min_k) {                    // hot: one lane of the block fetches it for all
-                                const uint32_t prev = atomicCAS(pce, 0u, (uint32_t)X + 1u);
-                                filler = prev == 0u;
-                                retry = prev == (uint32_t)X + 1u;    // another warp is at it: pick it up from the cache
+                if (act && !virgin) {
+                    if (!filler && *((volatile uint32_t *)pce) == (uint32_t)X + 1u) {
+                        if (*((volatile uint32_t *)(pce + 1)) != 0u) {   // cached by this block
+                            __threadfence_block();
+                            kx = __uint_as_float(pce[2]);
+                            head = *reinterpret_cast<const uint4 *>(pce + 4); data = *reinterpret_cast<const uint4 *>(pce + 8);
+                            sthr = pce + 12;
+                            have = true;
+                        } else wait_block = true;                    // being computed by another warp of the block
+                    } else {
+                        if (kx < 0.0f) {
+                            const int N = row_sum(p.t.n + (size_t)X * AS);
+                            if (N == 0) {
+                                virgin = true;
+                                vmask = MD::tag_legal(mc, MD::state_tag(st));
+                                // published in this very phase, maybe by another SM: with preferred actions its action
+                                // set is read from L2, never from a possibly stale L1 line
+                                if (KIND == 0 && p.t.chance) vmask = __ldcg(&p.t.legal[X]);
+                            } else {
+                                kx = kpre * ((float)N / (float)na);
+                                if (kx >= pc_min_k) {                // hot: every block keeps its own copy of the plan
+                                    const uint32_t prev = atomicCAS(pce, 0u, (uint32_t)X + 1u);
+                                    filler = prev == 0u;             // this warp computes it for the block (no waiting for
+                                    wait_block = prev == (uint32_t)X + 1u;   // other SMs); another warp of the block is at it
+                                }
+                            }
+                        }
+                        if (filler) self = true;
+                        else if (!virgin && !wait_block) {
+                            if (kx >= 1.5f) {
+                                head = __ldcg(&p.t.plan[(size_t)X * 2]); data = __ldcg(&p.t.plan[(size_t)X * 2 + 1]);
+                                have = head.y == stamp;
+                            }
+                            if (!have && kx < 16.5f) {               // few expected arrivals: computed below, by this thread
+                                small = true;                        // or by the warp (also if another thread is at it: no waiting)
+                                won = kx >= 1.5f && head.y != PLAN_LOCKED &&
+                                    atomicCAS(reinterpret_cast<uint32_t *>(&p.t.plan[(size_t)X * 2]) + 1, head.y, PLAN_LOCKED) == head.y;
+                            } else if (!have) {
+                                cand = head.y != PLAN_LOCKED;        // a batch-UCB allocation nobody has claimed
+                                wait_grid = !cand;
                             }
                         }
                     }
-                    if (!retry) {
-                        if (kx >= 1.5f) {
-                            head = __ldcg(&p.t.plan[(size_t)X * 2]); data = __ldcg(&p.t.plan[(size_t)X * 2 + 1]);
-                            have = head.y == stamp;
+                }
+                // plans for few expected arrivals (the fringe of the tree).  One thread computes one in ~10^3 dependent
+                // instructions; the warp (lane = action) needs a few hundred cycles but takes them one at a time: so
+                // the warp does them if only a few lanes ask (a chain level with a stray sibling must not stall its warp
+                // for microseconds), and every lane its own if many do (a bushy level).  Same arithmetic, same plans.
+                {
+                    unsigned sm_few = __ballot_sync(FULL, small);
+                    const bool coop = __popc(sm_few) <= SMALL_COOP_MAX;
+                    const int kq = (int)(kx + 0.5f);
+                    PlanRec r;
+                    if (coop) {
+                        while (sm_few) {
+                            const int src = __ffs((int)sm_few) - 1;
+                            sm_few &= sm_few - 1;
+                            const int kqs = __shfl_sync(FULL, kq, src);
+                            const PlanRec rs = warp_plan_few(p, __shfl_sync(FULL, X, src), (uint32_t)(kqs < 1 ? 1 : kqs), lane, A, stamp);
+                            if (lane == src) r = rs;
                         }
-                        if (!have && kx < 16.5f) {                   // few expected arrivals: this thread computes the plan
-                            const int kq = (int)(kx + 0.5f);         // (also if another thread is at it: no waiting)
-                            const bool won = kx >= 1.5f && head.y != PLAN_LOCKED &&
-                                atomicCAS(reinterpret_cast<uint32_t *>(&p.t.plan[(size_t)X * 2]) + 1, head.y, PLAN_LOCKED) == head.y;
-                            const PlanRec r = thread_plan_few(p, X, (uint32_t)(kq < 1 ? 1 : kq), A, stamp);
-                            head = r.head; data = r.data; have = true;
-                            if (won) {                               // publish: data, then the head with the stamp
-                                __stcg(&p.t.plan[(size_t)X * 2 + 1], data);
+                    } else if (small) r = thread_plan_few(p, X, (uint32_t)(kq < 1 ? 1 : kq), A, stamp);
+                    if (small) {
+                        head = r.head; data = r.data; have = true;
+                        if (won) {                                   // publish: data, then the head with the stamp
+                            __stcg(&p.t.plan[(size_t)X * 2 + 1], data);
+                            __threadfence();
+                            __stcg(&p.t.plan[(size_t)X * 2], head);
+                        }
+                    }
+                }
+                // batch-UCB allocations (lane = action): the hot ones of this block go straight into its cache; of the
+                // others the warp takes the first unclaimed one it can get per iteration -- the rest is left to the
+                // warps that arrive meanwhile, or to the next iteration -- and publishes it in the node's record
+                {
+                    unsigned todo = __ballot_sync(FULL, self);
+                    unsigned cm = __ballot_sync(FULL, cand);
+                    while (cm) {
+                        const int src = __ffs((int)cm) - 1;
+                        cm &= cm - 1;
+                        int got = 0;
+                        if (lane == src)
+                            got = atomicCAS(reinterpret_cast<uint32_t *>(&p.t.plan[(size_t)X * 2]) + 1, head.y, PLAN_LOCKED) == head.y;
+                        if (__shfl_sync(FULL, got, src)) { todo |= 1u << src; break; }
+                    }
+                    while (todo) {
+                        const int src = __ffs((int)todo) - 1;
+                        todo &= todo - 1;
+                        const int Xs = __shfl_sync(FULL, X, src);
+                        const bool hot = __shfl_sync(FULL, (int)self, src) != 0;
+                        const PlanRec r = warp_allocation(p, Xs, __shfl_sync(FULL, kx, src), lane, A, stamp);
+                        if (lane == 0) ++c_alloc;                    // a diagnostic: hot plans are computed once per block
+                        if (hot) {
+                            uint32_t *e = pc + (((uint32_t)Xs * 2654435761u) >> (32 - PC_BITS)) * PC_WORDS;
+                            e[12 + lane] = r.th;
+                            if (lane == src) {
+                                e[2] = __float_as_uint(kx);
+                                *reinterpret_cast<uint4 *>(e + 4) = r.head; *reinterpret_cast<uint4 *>(e + 8) = r.data;
+                            }
+                            __threadfence_block();
+                            __syncwarp();
+                            if (lane == src) { *((volatile uint32_t *)(e + 1)) = 1u; filler = false; sthr = e + 12; }
+                        } else {                                     // thresholds and data first, then the head with the stamp
+                            __threadfence();
+                            __syncwarp();
+                            if (lane == 0) {
+                                __stcg(&p.t.plan[(size_t)Xs * 2 + 1], r.data);
                                 __threadfence();
-                                __stcg(&p.t.plan[(size_t)X * 2], head);
+                                __stcg(&p.t.plan[(size_t)Xs * 2], r.head);
                             }
-                        } else if (!have) cand = head.y != PLAN_LOCKED;   // a batch-UCB allocation nobody has claimed
-                    }
-                }
-                // one allocation per warp and iteration (lane = action): the warp takes the first unclaimed one it can
-                // get; the others are left to the warps that arrive meanwhile, or to the next iteration
-                unsigned cm = __ballot_sync(FULL, cand);
-                while (cm) {
-                    const int src = __ffs((int)cm) - 1;
-                    cm &= cm - 1;
-                    int won = 0;
-                    if (lane == src)
-                        won = atomicCAS(reinterpret_cast<uint32_t *>(&p.t.plan[(size_t)X * 2]) + 1, head.y, PLAN_LOCKED) == head.y;
-                    if (__shfl_sync(FULL, won, src)) {
-                        const PlanRec r = warp_plan(p, __shfl_sync(FULL, X, src), __shfl_sync(FULL, kx, src), lane, A, stamp,
-                                                    true, c_alloc);
+                        }
                         if (lane == src) { head = r.head; data = r.data; have = true; }
-                        break;
                     }
                 }
-                unsigned fill = __ballot_sync(FULL, filler && have);
-                while (fill) {                                       // copy hot plans into the block cache
-                    const int src = __ffs((int)fill) - 1;
-                    fill &= fill - 1;
-                    const int Xs = __shfl_sync(FULL, X, src);
-                    uint32_t *e = pc + (((uint32_t)Xs * 2654435761u) >> (32 - PC_BITS)) * PC_WORDS;
-                    e[12 + lane] = __ldcg(&p.t.thr[(size_t)Xs * 32 + lane]);
-                    if (lane == src) {
-                        e[2] = __float_as_uint(kx);
-                        *reinterpret_cast<uint4 *>(e + 4) = head; *reinterpret_cast<uint4 *>(e + 8) = data;
-                    }
-                    __threadfence_block();
-                    __syncwarp();
-                    if (lane == src) { *((volatile uint32_t *)(e + 1)) = 1u; filler = false; }
-                }
-                act = act && have;
+#ifdef POMCP_TSEC
+                const long long it_t1 = clock64();
+                const int it_kind = have ? (sthr ? 1 : small ? 3 : 4) : virgin ? 2 : (wait_block ? 5 : wait_grid ? 6 : 7);
+#endif
                 TSEC(0);                                             // plan acquisition
                 // -- choose, step the model, look up / create the child (solvers/pomcp.py:97-117)
-                if (act) {
-                    DCHECK(S, X >= 0 && X < S->node_count && d < p.dcap, 21);
-                    const Philox4 r = philox4x32_10((uint32_t)(d + 1), sim, p.move, DOM_SIM, p.key0, p.key1);
-                    float pa;
-                    const int a = plan_action(head, data, sthr, p.t.thr + (size_t)X * 32, r.x, A, pa);
-                    DCHECK(S, a >= 0 && a < A && ((p.t.legal[X] >> a) & 1u), 22);
-                    DCHECK(S, MD::state_tag(st) == (uint32_t)p.t.cell[X], 23);
+                if (act && (have || virgin)) {
+                    DCHECK(S, d < p.dcap && (virgin ? vmask != 0u : (X >= 0 && X < S->node_count)), 21);
+                    const Philox4 r = philox4x32_10_ks((uint32_t)(d + 1), sim, p.move, DOM_SIM, p.ks);
+                    float pa = 0.0f;
+                    int a;
+                    if (virgin) a = nth_bit(vmask, randbelow32(r.x, (uint32_t)__popc(vmask)));
+                    else a = plan_action(head, data, sthr, p.t.thr + (size_t)X * 32, r.x, A, pa);
+                    DCHECK(S, a >= 0 && a < A && (virgin || ((p.t.legal[X] >> a) & 1u)), 22);
+                    DCHECK(S, MD::tag_ok(mc, MD::state_tag(st)) && (X < 0 || MD::state_tag(st) == (uint32_t)__ldcg(&p.t.cell[X])), 23);
                     const StepOut so = MD::step(mc, st, a, r.y, r.z);                       // :104
                     ++c_levels;
                     const uint16_t code = MD::path_code(a, so);
@@ -253,6 +283,7 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                     st = so.next;
                     TSEC(1);                                         // choice + step + path stores
                     if (so.terminal) status = 2;
+                    else if (virgin) status = 1;                     // leaf
                     else {
                         const size_t cslot = ((size_t)X * AS + a) * ZS + so.obs;
                         uint32_t cmask = MD::tag_legal(mc, so.tag); bool have_mask = false;   // the child's action set
@@ -290,12 +321,12 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                             }
                         }
                         if (c == 0) status = 1;                                             // depth cap: leaf (:119)
-                        else if (c == CHILD_LOCKED) {                                       // created in this generation
-                            if constexpr (KIND == 0) if (p.t.chance && !have_mask)          // id not published yet: derive the set
+                        else if (c == CHILD_LOCKED) {                                       // created in this generation: no
+                            if constexpr (KIND == 0) if (p.t.chance && !have_mask)          // statistics; id maybe not published yet
                                 cmask = child_smart_mask(mc.M.hdr, p.t.prob, p.t.chance + (size_t)X * POMCP_RS,
                                                          p.t.good + (size_t)X * POMCP_RS, nullptr, nullptr,
                                                          (int)pcell, a, so.obs, (int)so.tag);
-                            virgin_step<KIND>(p, mc, i, sim, -1 - (int)cslot, cmask, st, d, status, last_ref, last_ar, c_levels);
+                            virgin = true; vmask = cmask; X = -1 - (int)cslot;              // next iteration: uniform action, leaf
                         } else {                                                            // descend
                             na = p.t.n[(size_t)X * AS + a];
                             kpre = kx * pa;
@@ -305,7 +336,24 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                     }
                 }
                 TSEC(2);                                             // child lookup / creation / leaf
-                if (!__any_sync(FULL, progressed)) __nanosleep(100); // every lane waits for a plan another warp computes
+#ifdef POMCP_TSEC
+                if (it_on && it_log < 100) {
+                    const long long it_t2 = clock64();
+                    S->steplog[it_log][4] = it_t1 - it_t0; S->steplog[it_log][5] = it_t2 - it_t1;
+                    S->steplog[it_log][6] = it_kind; S->steplog[it_log][7] = d;
+                    ++it_log; it_t0 = it_t2;
+                }
+#endif
+                if (!__any_sync(FULL, progressed)) {                 // every lane waits for a plan another warp computes:
+                    for (int spin = 0; spin < 4096; ++spin) {        // sleep until one of them is there
+                        __nanosleep(spin < 4 ? 64 : 256);
+                        bool there = false;
+                        if (wait_block) there = *((volatile uint32_t *)(pce + 1)) != 0u;
+                        else if (wait_grid) there = __ldcg(reinterpret_cast<const uint32_t *>(&p.t.plan[(size_t)X * 2]) + 1) != PLAN_LOCKED;
+                        else there = status == 0;                    // (lost every claim: look again)
+                        if (__any_sync(FULL, there)) break;
+                    }
+                }
             }
             // -- rollout
             double sum = 0.0;
@@ -460,7 +508,6 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
         }
         for (int t = threadIdx.x; t < PC_SLOTS; t += blockDim.x) { pc[t * PC_WORDS] = 0u; pc[t * PC_WORDS + 1] = 0u; }   // next generation: new plans
         done += w;
-        if (W < p.wmax) { long long nw = (long long)W * p.growth; W = nw > p.wmax ? p.wmax : (int)nw; }
         if (p.timeout_ns && gtid == 0 && globaltimer_ns() - t_start > p.timeout_ns) S->stop = 1;
         GRID_SYNC();
         PHASE_MARK(3);

@@ -52,7 +52,7 @@ __device__ __forceinline__ void publish_root(DevState *S, const Tree &t, int roo
 // Nothing depends on how many simulations really meet at a node, so every simulation descends the tree on its own --
 // no level barriers -- and whichever warp reaches a node first computes its plan (lane = action) and publishes it.
 // ---------------------------------------------------------------------------------------------------------
-struct PlanRec { uint4 head, data; };
+struct PlanRec { uint4 head, data; uint32_t th; };   // th: this lane's threshold (kind 2, warp-computed)
 
 // Batch-UCB allocation, k >= 16.5: water-filling of k pulls over the UCB1 indices mean + c*sqrt(ln(N+1)/n); output:
 // 32-bit cumulative thresholds in t.thr[X], every G-th of them in the plan record.
@@ -129,6 +129,7 @@ __device__ __forceinline__ PlanRec warp_allocation(const SearchParams &p, int X,
     PlanRec r;
     r.head = make_uint4((uint32_t)((31 - __clz((int)pos)) | (PLAN_THRESHOLDS << 16)), stamp, cg[4], cg[5]);
     r.data = make_uint4(cg[0], cg[1], cg[2], cg[3]);
+    r.th = th;
     return r;
 }
 
@@ -150,6 +151,7 @@ __device__ __forceinline__ PlanRec warp_plan_few(const SearchParams &p, int X, u
     PlanRec r;
     r.head = make_uint4(PLAN_MASK << 16, stamp, 0u, 0u);
     r.data = make_uint4(0u, 0u, 0u, 0u);
+    r.th = 0u;
     const unsigned untried = __ballot_sync(full, legal && n == 0);
     if ((uint32_t)__popc(untried) >= k) { r.data.x = untried; return r; }
     const float L = det_logf_u32((uint32_t)N + 1u);
@@ -205,6 +207,7 @@ __device__ __forceinline__ PlanRec thread_plan_few(const SearchParams &p, int X,
     PlanRec r;
     r.head = make_uint4(PLAN_MASK << 16, stamp, 0u, 0u);
     r.data = make_uint4(0u, 0u, 0u, 0u);
+    r.th = 0u;
     if ((uint32_t)__popc(untried) >= k) { r.data.x = untried; return r; }
     const float L = det_logf_u32((uint32_t)N + 1u);
     const float cf = (float)p.ucb_c;
@@ -244,32 +247,6 @@ __device__ __forceinline__ PlanRec thread_plan_few(const SearchParams &p, int X,
     }
     r.head.x = (PLAN_PULLS << 16) | (k << 8);
     r.data = make_uint4(seq[0], seq[1], seq[2], seq[3]);
-    return r;
-}
-
-// Plan of node X (which has statistics) for kx expected arrivals, computed by one warp; every lane returns it.
-// publish: store it in the node's record for the other simulations of this generation -- thresholds and data first,
-// then the head with the generation stamp (a reader that sees the stamp sees the rest).
-__device__ __forceinline__ PlanRec warp_plan(const SearchParams &p, int X, float kx, int lane, int A, uint32_t stamp,
-                                             bool publish, long long &c_alloc)
-{
-    PlanRec r;
-    if (kx >= 16.5f) {
-        r = warp_allocation(p, X, kx, lane, A, stamp);
-        if (lane == 0) ++c_alloc;
-    } else {
-        const int kq = (int)(kx + 0.5f);
-        r = warp_plan_few(p, X, (uint32_t)(kq < 1 ? 1 : kq), lane, A, stamp);
-    }
-    if (publish) {
-        __threadfence();                                             // every lane's threshold store
-        __syncwarp();
-        if (lane == 0) {
-            __stcg(&p.t.plan[(size_t)X * 2 + 1], r.data);
-            __threadfence();
-            __stcg(&p.t.plan[(size_t)X * 2], r.head);
-        }
-    }
     return r;
 }
 

@@ -42,6 +42,9 @@
 #define PLAN_MASK 0            // kinds of a node's action plan (warp_plan)
 #define PLAN_PULLS 1
 #define PLAN_THRESHOLDS 2
+#ifndef SMALL_COOP_MAX
+#define SMALL_COOP_MAX 6        // at most this many fringe plans per warp and level: computed by the warp, else per thread
+#endif
 #define PLAN_LOCKED 0xFFFFFFFFu // stamp of a plan record while one warp computes it
 #define SEQ_ALLOC_MAX 16u      // expected arrivals < 16.5: virtual-pull sequence / arg-max set; more: water-filling
 // Per-block cache of the hot plans (the upper tree levels, where thousands of simulations of a generation pass) in

@@ -55,6 +55,18 @@ def greedy_action(n, qfix, legal_mask, seed, move):
     return cand[philox.randbelow(seed, len(cand), 0, 0, move, philox.DOM_FINAL)]
 
 
+def auto_schedule(n_sims):
+    """Generation schedule (w0, growth, wmax) = simulations in flight, for a per-rank budget of n_sims per move.
+    Small budgets keep the waves narrow (quality first: at n_sims = 500 widths up to 64 match the sequential planner's
+    return, 128 starts to cost); large budgets use the throughput schedule of bench.py (first wave = 1/32 of the budget,
+    x4 growth up to half of it: four generations; profiles/README.md has the return-vs-schedule measurements)."""
+    n = int(n_sims)
+    if n <= 4096:
+        return max(1, min(1024, (n // 4 or 1) // 16)), 2, max(32, n // 4 or 1)
+    wm = min(1 << 19, n // 2)
+    return max(1, wm // 16), 4, wm
+
+
 class POMCP(Solver):
     # planners are expensive to create (the tree arena); one is kept per (agent, configuration)
     _EPOCH_STRIDE = 1 << 12
@@ -117,11 +129,7 @@ class POMCP(Solver):
         # the throughput schedule of bench.py (first wave = 1/32 of the budget, x4 growth up to half of it: four
         # generations; return at 1e5 and 1e6 simulations per move does not depend on the first width,
         # profiles/r01_schedule_sweep.txt).
-        if self.sims_per_rank <= 4096:
-            auto = (max(1, min(1024, (self.sims_per_rank // 4 or 1) // 16)), 2, max(32, self.sims_per_rank // 4 or 1))
-        else:
-            wm = min(1 << 19, self.sims_per_rank // 2)
-            auto = (max(1, wm // 16), 4, wm)
+        auto = auto_schedule(self.sims_per_rank)
         w0 = int(getattr(model, "gen_w0", 0)) or auto[0]
         growth = int(getattr(model, "gen_growth", 0)) or auto[1]
         wmax = max(int(getattr(model, "gen_wmax", 0)) or auto[2], w0)

@@ -84,7 +84,7 @@ def test_search_root_stats_bit_exact(tag, seed, n_sims, sched, kw):
                 assert x["cell"] == y["cell"] and x["legal"] == y["legal"]
                 assert np.array_equal(x["n"], y["n"]) and np.array_equal(x["qfix"], y["qfix"])
     co, cg = g.counters(), pl.counters()
-    for k in ("levels", "rollout_steps", "created", "nodes", "alloc_nodes", "generations"):
+    for k in ("levels", "rollout_steps", "created", "nodes", "generations"):
         assert co[k] == cg[k], (k, co[k], cg[k])
     pl.close()
 

@@ -29,7 +29,7 @@ def _compare_nodes(g, pl, n_actions):
                 assert x["cell"] == y["cell"] and x["legal"] == y["legal"]
                 assert np.array_equal(x["n"], y["n"]) and np.array_equal(x["qfix"], y["qfix"]), (act, o)
     co, cg = g.counters(), pl.counters()
-    for k in ("levels", "rollout_steps", "created", "nodes", "alloc_nodes", "generations"):
+    for k in ("levels", "rollout_steps", "created", "nodes", "generations"):
         assert co[k] == cg[k], (k, co[k], cg[k])
     return b
 
