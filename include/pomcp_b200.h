@@ -119,7 +119,10 @@ int pomcp_node_stats(pomcp_handle *h, const int32_t *path_ao, int len, int64_t *
 /* BeliefTreeSolver.update (belief_tree_solver.py:154-212) + Model.generate_particles (model.py:221-252):
  * re-root at (action, obs_good), refill the belief with max_particle_count rejection samples drawn from the
  * old root belief.  *status: 0 re-rooted at an existing child, 1 fresh node (child never expanded),
- * 2 no particle accepted (the reference's disable_tree). */
+ * 2 no particle accepted (the reference's disable_tree).  obs_good = -1: unconditioned -- every try is accepted
+ * and the root becomes a fresh node at the next position (what the host does after status 2, so that the next
+ * search returns an action that is legal at the true position; the reference goes on from the stale node with
+ * rollout_search, belief_tree_solver.py:90-121). */
 int pomcp_advance(pomcp_handle *h, int action, int obs_good, uint32_t sampled_mask_after, uint32_t move,
                   int64_t max_tries, int32_t *status, int64_t *tries_used, int32_t *accepted);
 

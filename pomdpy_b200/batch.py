@@ -106,7 +106,10 @@ class BatchedAgent(object):
                     _, sampled = ln.model.world_masks()
                     obs = int(res.observation.bin_number) if self.tabular else bool(res.observation.is_good)
                     if ln.planner.advance(a, obs, sampled, move=ln.move)["status"] == 2:
-                        done = True                        # disable_tree: the serial path would finish with rollouts
+                        # no particle reproduces the observation: as the serial solver does (POMCP._recover), push the
+                        # old belief through the action unconditioned and go on from a fresh root at the true position
+                        if ln.planner.advance(a, None, sampled, move=ln.move)["status"] == 2:
+                            done = True
                 if done:
                     self.discounted_return.add(ln.dret)
                     self.undiscounted_return.add(ln.ret)

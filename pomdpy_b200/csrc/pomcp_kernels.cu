@@ -648,7 +648,7 @@ __device__ __forceinline__ void advance_body(const AdvanceParams &p, unsigned ch
                 const uint32_t st = old_bag[randbelow32(x.x, (uint32_t)n_old)];
                 const StepOut so = MD::step(mc, st, p.action, x.y, x.z);
                 ns[r] = so.next;
-                if (so.obs == p.obs_good) acc |= 1u << r;
+                if (p.obs_good < 0 || so.obs == p.obs_good) acc |= 1u << r;    // obs < 0: unconditioned (degraded mode)
             }
         }
         int cnt = __popc(acc), incl = cnt;                            // block-wide exclusive scan of cnt
@@ -684,7 +684,7 @@ __device__ __forceinline__ void advance_body(const AdvanceParams &p, unsigned ch
         S->sampled = sampled;                                        // belief_tree_solver.py:165 happens first
         if (accepted == 0) { S->adv_status = 2; S->adv_root_cell = p.t.cell[root]; }
         else {
-            uint32_t c = p.t.child[((size_t)root * AS + p.action) * ZS + p.obs_good];  // belief_tree_solver.py:167
+            uint32_t c = p.obs_good < 0 ? 0u : p.t.child[((size_t)root * AS + p.action) * ZS + p.obs_good];  // belief_tree_solver.py:167
             int status = 0, id;
             if (c == 0) {                                            // never expanded: fresh node at the next position
                 id = S->node_count++;
@@ -696,7 +696,7 @@ __device__ __forceinline__ void advance_body(const AdvanceParams &p, unsigned ch
                 if constexpr (KIND == 0) if (p.t.chance)
                     lm = child_smart_mask(mc.M.hdr, p.t.prob, p.t.chance + (size_t)root * POMCP_RS, p.t.good + (size_t)root * POMCP_RS,
                                           p.t.chance + (size_t)id * POMCP_RS, p.t.good + (size_t)id * POMCP_RS, p.t.cell[root],
-                                          p.action, p.obs_good, (int)tag);
+                                          p.action, p.obs_good < 0 ? 0 : p.obs_good, (int)tag);
                 p.t.legal[id] = lm;
                 status = 1;
             } else id = CHILD_ID(c);
@@ -1340,7 +1340,7 @@ extern "C" int pomcp_advance(pomcp_handle *h, int action, int obs_good, uint32_t
     if (!h) return -1;
     if (!h->have_root) return fail(h, "no root belief");
     if (action < 0 || action >= h->n_actions) return fail(h, "action out of range");
-    if (h->kind == 1 ? (obs_good < 0 || obs_good >= h->tab.Z) : (obs_good < 0)) return fail(h, "observation out of range");
+    if (obs_good < -1 || (h->kind == 1 && obs_good >= h->tab.Z)) return fail(h, "observation out of range");
     CK(cudaSetDevice(h->device));
     if (h->nodes_used + 2 > h->cap) return fail(h, "node arena full");
     AdvanceParams p;
@@ -1348,7 +1348,7 @@ extern "C" int pomcp_advance(pomcp_handle *h, int action, int obs_good, uint32_t
     p.S = h->dS; p.model = h->dmodel; p.thr53 = h->dthr; p.t = h->t;
     p.tab = h->tab; p.tt = h->tt;
     p.bag[0] = h->bag[0]; p.bag[1] = h->bag[1];
-    p.action = action; p.obs_good = h->kind == 1 ? obs_good : (obs_good ? 1 : 0); p.need = h->cfg.max_particle_count; p.n_thr = h->n_thr;
+    p.action = action; p.obs_good = obs_good < 0 ? -1 : h->kind == 1 ? obs_good : (obs_good ? 1 : 0); p.need = h->cfg.max_particle_count; p.n_thr = h->n_thr;
     p.sampled_after = sampled_after; p.move = move;
     p.key0 = (uint32_t)h->cfg.seed; p.key1 = (uint32_t)(h->cfg.seed >> 32);
     p.max_tries = max_tries > 0 ? max_tries : 256ll * p.need;

@@ -252,8 +252,10 @@ class Planner:
         return dict(n=n, qfix=q, legal=legal.value, cell=cell.value)
 
     def advance(self, action, obs_good, sampled_mask_after=0, move=0, max_tries=0):
+        """Belief update + re-root.  obs_good=None: unconditioned on the observation (every try is accepted, the root is
+        re-planted as a fresh node at the next position) -- the degraded mode after a failed update."""
         status, tries, acc = C.c_int32(), C.c_int64(), C.c_int32()
-        obs = int(obs_good) if self.tabular else int(bool(obs_good))     # tabular: the observation index
+        obs = -1 if obs_good is None else int(obs_good) if self.tabular else int(bool(obs_good))   # tabular: the index
         self._ck(self.lib.pomcp_advance(self.h, int(action), obs, int(sampled_mask_after), int(move),
                                         int(max_tries), C.byref(status), C.byref(tries), C.byref(acc)))
         return dict(status=status.value, tries=tries.value, accepted=acc.value)

@@ -319,6 +319,19 @@ class RockModel(Model):
                 particles.append(result.next_state)
         return particles
 
+    def generate_particles_uninformed_packed(self, root_cell, action, obs, n_particles, max_tries=None):
+        """generate_particles_uninformed (rock_model.py:252-261) from the cell of the old root, as packed device
+        states; gives up after max_tries draws (the reference loops forever if the observation is impossible)."""
+        old_pos = GridPosition(int(root_cell) // self.n_cols, int(root_cell) % self.n_cols)
+        out, tries = [], 0
+        max_tries = max_tries if max_tries is not None else 50 * int(n_particles)
+        while len(out) < n_particles and tries < max_tries:
+            tries += 1
+            result, _ = self.generate_step(RockState(old_pos, self.sample_rocks()), action)
+            if obs == result.observation:
+                out.append(self.pack_state(result.next_state))
+        return np.array(out, dtype=np.uint32)
+
     # ---- tables for the CUDA planner ------------------------------------------------------------------
     def cell_index(self, pos):
         return pos.i * self.n_cols + pos.j

@@ -20,14 +20,14 @@ class BeliefNodeView(object):
     @property
     def state_particles(self):
         packed, _ = self.solver.planner.root_particles()
-        return [self.solver.model.unpack_state(p) for p in packed]
+        return [self.solver.dev.unpack_state(p) for p in packed]
 
     def sample_particle(self):
         """belief_node.py:47-48 (random.choice over the bag), drawn from the host Philox stream."""
         packed, _ = self.solver.planner.root_particles()
         idx = philox.randbelow(self.solver.seed, len(packed), self._draws, 0, self.solver.move, philox.DOM_AGENT)
         self._draws += 1
-        return self.solver.model.unpack_state(packed[idx])
+        return self.solver.dev.unpack_state(packed[idx])
 
     @property
     def action_map(self):

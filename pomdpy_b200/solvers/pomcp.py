@@ -19,6 +19,7 @@ import time
 
 import numpy as np
 
+from .. import adapters
 from .. import dist as dist_mod
 from .. import native, philox
 from ..rock_sample.history_data import PositionAndRockData, RockData
@@ -74,8 +75,8 @@ class POMCP(Solver):
     def __init__(self, agent):
         super(POMCP, self).__init__(agent)
         model = self.model
-        if not hasattr(model, "device_spec"):
-            raise TypeError("the CUDA POMCP solver needs a model with device_spec()/world_masks()")
+        # the model's device hooks: its own (this package's models) or extracted (an unmodified reference RockModel)
+        self.dev = adapters.hooks_for(model)
         self.agent = agent
         self.action_pool = agent.action_pool
         self.observation_pool = agent.observation_pool
@@ -96,20 +97,20 @@ class POMCP(Solver):
         self.epoch_index = agent._pomcp_epochs = getattr(agent, "_pomcp_epochs", -1) + 1
         self.move_in_epoch = 0
 
-        spec = model.device_spec()
+        spec = self.dev.device_spec()
         self.spec = spec
         # belief_tree_solver.py:36-38: n_start_states draws of sample_an_init_state (numpy generator)
         n_start = int(getattr(model, "n_start_states", 2000))
         if hasattr(model, "sample_init_states_packed"):
             bag = np.ascontiguousarray(model.sample_init_states_packed(n_start), dtype=np.uint32)
         else:
-            bag = np.fromiter((model.pack_state(model.sample_an_init_state()) for _ in range(n_start)),
+            bag = np.fromiter((self.dev.pack_state(model.sample_an_init_state()) for _ in range(n_start)),
                               dtype=np.uint32, count=n_start)
         self.tabular = spec.get("kind", "rocksample") == "tabular"
         if self.tabular:
             self.preferred = False                                            # a RockSample heuristic
         else:
-            self.planner.set_world(*model.world_masks())
+            self.planner.set_world(*self.dev.world_masks())
             mode = (2 if getattr(model, "preferred_rollouts", False) else 1) if self.preferred else 0
             if mode != getattr(self.planner, "_preferred", 0):                # rock_position_history.py:52-55
                 self.planner.set_preferred_actions(self.preferred, spec["prob"], rollouts=mode == 2)
@@ -154,7 +155,7 @@ class POMCP(Solver):
                             max_particle_count=self.max_particle_count, ucb_coefficient=float(model.ucb_coefficient),
                             discount=float(model.discount), seed=self.seed, node_capacity=cap, gen_w0=w0,
                             gen_growth=growth, gen_wmax=wmax, device=device)
-        spec = model.device_spec()
+        spec = self.dev.device_spec()
         if spec.get("kind", "rocksample") == "tabular":
             pl.set_model_tabular(spec["Tc"], spec["Oc"], spec["R"], spec["term_action_mask"], spec["term_state"])
         else:
@@ -238,19 +239,46 @@ class POMCP(Solver):
         """belief_tree_solver.py:154-212: fold the real step into the model, re-root at (action, observation),
         refill the belief by rejection sampling (on the device).  On failure: disable_tree, no exception."""
         self.model.update(step_result)                                           # :165
-        _, sampled = self.model.world_masks()
+        _, sampled = self.dev.world_masks()
         obs = step_result.observation
         res = self.planner.advance(step_result.action.bin_number,
                                    int(obs.bin_number) if self.tabular else bool(obs.is_good), sampled, move=self.move)
         self._stats = None
         self.move_in_epoch += 1
         if res["status"] == 2:
-            console(1, module, "Couldn't refill particles, must use random rollout to finish episode")
-            self.disable_tree = True
+            self._recover(step_result)
             return
         if res["status"] == 1:
             console(4, module, "observed child was never expanded: fresh root")
         _, self._root_cell = self.planner.root_particles(fetch=False)
+
+    def _recover(self, step_result):
+        """No particle of the old belief reproduces the real observation (belief_tree_solver.py:196-208).  As the
+        reference does, first try a new particle set at the new position with uniformly drawn rock states that match
+        the observation (generate_particles_uninformed, rock_model.py:252-261).  If that fails too the reference sets
+        disable_tree and finishes the episode with rollout_search from the STALE node (belief_tree_solver.py:90-121:
+        its actions are those of the old position); here disable_tree is set as well, but the old belief is pushed
+        through the real action without conditioning on the observation and planted as a fresh root at the true
+        position, so that select_eps_greedy_action keeps returning actions that are legal there."""
+        m = self.model
+        a = step_result.action.bin_number
+        bag = None
+        if not self.tabular and hasattr(m, "generate_particles_uninformed_packed"):
+            bag = m.generate_particles_uninformed_packed(self._root_cell, a, step_result.observation,
+                                                         int(getattr(m, "min_particle_count", 1000)))
+        if bag is not None and len(bag):
+            cell = int(bag[0]) & 0xFF
+            self.planner.set_world(*self.dev.world_masks())
+            self.planner.set_root_particles(np.ascontiguousarray(bag, dtype=np.uint32), cell)
+            self._root_cell = cell
+            console(2, module, "belief re-created from uninformed particles: fresh tree")
+            return
+        console(1, module, "Couldn't refill particles, must use random rollout to finish episode")
+        self.disable_tree = True
+        _, sampled = self.dev.world_masks()
+        res = self.planner.advance(a, None, sampled, move=self.move - 1)
+        if res["status"] != 2:
+            _, self._root_cell = self.planner.root_particles(fetch=False)
 
     def prune(self, belief_node=None):
         """Sibling subtrees are simply left behind in the arena (belief_tree.py:87-109 frees them)."""

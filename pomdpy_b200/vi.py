@@ -29,6 +29,64 @@ class AlphaVector(object):
         return AlphaVector(self.action, self.v)
 
 
+REFERENCE_ALPHA_MODULE = "pomdpy.solvers.alpha_vector"      # where the reference's AlphaVector lives (alpha_vector.py:1-11)
+
+
+def save_alpha_vectors(gamma, path):
+    """Write a set of alpha vectors the way the reference's experiments/scripts/pickle_wrapper.py:22-27 does (protocol 2,
+    fix_imports) and AS THE REFERENCE'S OWN CLASS: the pickle names `pomdpy.solvers.alpha_vector.AlphaVector`, a Python
+    set of objects with attributes `action` and `v` (float64 ndarray) -- exactly the layout of the reference's
+    experiments/pickle_jar/VI_planning_horizon_*.pkl, so its load_pkl (:29-34) and the scripts that consume those files
+    (approximate_vi_eval.py:22-28) read it without this package installed."""
+    import pickle
+    import sys
+    import types
+    cls = type("AlphaVector", (object,), {"__module__": REFERENCE_ALPHA_MODULE,
+                                          "__init__": lambda self, a, v: (setattr(self, "action", a), setattr(self, "v", v)) and None})
+    objs = set()
+    for av in gamma:
+        objs.add(cls(int(av.action), np.asarray(av.v, dtype=np.float64).copy()))
+    # pickle verifies that the class can be imported under its name: lend it a module of that name for the dump
+    parts, added = REFERENCE_ALPHA_MODULE.split("."), []
+    real = sys.modules.get(REFERENCE_ALPHA_MODULE)
+    if real is not None and hasattr(real, "AlphaVector"):          # the reference itself is importable here: use its class
+        objs = set(real.AlphaVector(o.action, o.v) for o in objs)
+    else:
+        for i in range(1, len(parts) + 1):
+            name = ".".join(parts[:i])
+            if name not in sys.modules:
+                sys.modules[name] = types.ModuleType(name)
+                added.append(name)
+        sys.modules[REFERENCE_ALPHA_MODULE].AlphaVector = cls
+    try:
+        with open(path, "wb") as f:
+            pickle.dump(objs, f, protocol=2, fix_imports=True)
+    finally:
+        for name in added:
+            del sys.modules[name]
+    return path
+
+
+def load_alpha_vectors(path):
+    """Read a pickle written by save_alpha_vectors or by the reference (pickle_wrapper.load_pkl semantics) into this
+    package's AlphaVector objects, whether or not the reference is importable."""
+    import pickle
+
+    class _Unpickler(pickle.Unpickler):
+        def find_class(self, module, name):
+            if name == "AlphaVector":
+                return AlphaVector
+            return super().find_class(module, name)
+
+    with open(path, "rb") as f:
+        objs = _Unpickler(f, fix_imports=True, encoding="bytes").load()
+    out = []
+    for o in objs:
+        d = {(k.decode() if isinstance(k, bytes) else k): v for k, v in o.__dict__.items()}
+        out.append(AlphaVector(int(d["action"]), np.asarray(d["v"], dtype=np.float64)))
+    return out
+
+
 def _lib():
     L = native.load()
     if not getattr(L, "_vi_ready", False):
@@ -181,10 +239,8 @@ def run_value_iteration_experiment(agent):
     er.time.add(r.time.running_total)
     er.undiscounted_return.add(r.undiscounted_return.running_total)
     er.discounted_return.add(r.discounted_return.running_total)
-    if getattr(model, "save", False):
-        import pickle
-        with open("VI_planning_horizon_{}.pkl".format(model.planning_horizon), "wb") as f:
-            pickle.dump(solver.gamma, f, protocol=2)
+    if getattr(model, "save", False):                               # agent.py:37-45 (--save)
+        save_alpha_vectors(solver.gamma, "VI_planning_horizon_{}.pkl".format(model.planning_horizon))
     console(2, module, "alpha vectors: " + str(len(solver.gamma)))
     print_divider("medium")
     return solver
