@@ -173,8 +173,7 @@ __device__ __forceinline__ int nth_legal(const ModelHeader *H, uint32_t mask, ui
 // j-th set bit of an arbitrary 32-bit mask
 __device__ __forceinline__ int nth_bit(uint32_t mask, uint32_t j)
 {
-    for (uint32_t i = 0; i < j; ++i) mask &= mask - 1;
-    return __ffs((int)mask) - 1;
+    return (int)__fns(mask, 0u, (int)j + 1);
 }
 
 // ---------------------------------------------------------------------------------------------------------

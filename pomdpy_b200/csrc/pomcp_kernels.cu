@@ -406,28 +406,40 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
             int dmax = depth;
 #pragma unroll
             for (int o = 16; o >= 1; o >>= 1) dmax = max(dmax, __shfl_xor_sync(FULL, dmax, o));
+            // the path entries are read two levels ahead of their use (and the id of a node that was still being
+            // published when the simulation passed one level ahead): the loads overlap the updates of the levels above
+            const auto load_entry = [&](int d, uint32_t &ar, int &X, double &rw) {
+                const bool on = d >= 0 && d < depth;
+                ar = on ? (uint32_t)p.b.path_ar[(size_t)d * p.wmax + i] : 0u;
+                X = (on && d > 0 && !(d == 1 && stage_d1)) ? p.b.path_node[(size_t)d * p.wmax + i] : 0;
+                if (KIND == 1) rw = on ? p.b.path_rew[(size_t)d * p.wmax + i] : 0.0;
+            };
+            uint32_t ar0 = 0u, ar1 = 0u, ar2 = 0u; int x0 = 0, x1 = 0, x2 = 0; double rw0 = 0.0, rw1 = 0.0, rw2 = 0.0;
+            load_entry(dmax - 1, ar0, x0, rw0);
+            load_entry(dmax - 2, ar1, x1, rw1);
+            if (x0 < 0) x0 = CHILD_ID(p.t.child[(size_t)(-1 - x0)]);
+            const uint32_t ar_root = (have && depth > 1 && stage_d1) ? (uint32_t)p.b.path_ar[i] : 0u;   // keys of depth-1 edges
             for (int d = dmax - 1; d >= 0; --d) {
+                load_entry(d - 2, ar2, x2, rw2);
+                if (x1 < 0) x1 = CHILD_ID(p.t.child[(size_t)(-1 - x1)]);   // id published after this simulation passed
                 const bool act = d < depth;
                 uint32_t key = 0u;                                   // 1 + staged index, or 0x80000000 | edge index
                 long long qi = 0;
                 if (act) {
-                    const uint32_t ar = p.b.path_ar[(size_t)d * p.wmax + i];
+                    const uint32_t ar = ar0;
                     const int a = ar & 31;
-                    const double q = MD::path_reward(mc, ar, KIND == 1 ? p.b.path_rew + (size_t)d * p.wmax + i : nullptr) +
-                                     p.discount * delayed;
+                    const double q = MD::path_reward(mc, ar, KIND == 1 ? &rw0 : nullptr) + p.discount * delayed;
                     qi = __double2ll_rn(q * POMCP_QFIX_SCALE);
                     delayed = q;
                     if (d == 0) key = 1u + (uint32_t)a;
-                    else if (d == 1 && stage_d1) {
-                        const uint32_t ar0 = p.b.path_ar[i];
-                        key = 1u + (uint32_t)((1 + (int)(ar0 & 31) * ZS + MD::path_obs(ar0)) * A + a);
-                    } else {
-                        int X = p.b.path_node[(size_t)d * p.wmax + i];
-                        if (X < 0) X = CHILD_ID(p.t.child[(size_t)(-1 - X)]);   // id published after this simulation passed
-                        DCHECK(S, X > 0 && X < S->node_count && a < A, 31);
-                        key = 0x80000000u | (uint32_t)(X * AS + a);
+                    else if (d == 1 && stage_d1)
+                        key = 1u + (uint32_t)((1 + (int)(ar_root & 31) * ZS + MD::path_obs(ar_root)) * A + a);
+                    else {
+                        DCHECK(S, x0 > 0 && x0 < S->node_count && a < A, 31);
+                        key = 0x80000000u | (uint32_t)(x0 * AS + a);
                     }
                 }
+                ar0 = ar1; x0 = x1; rw0 = rw1; ar1 = ar2; x1 = x2; rw1 = rw2;
                 // up to three rounds of "the first pending lane's edge, for every lane that shares it" (a chain level has
                 // one or two nodes), aggregated into the block tables; what is left updates on its own, deeper edges
                 // directly in the arena (a diverse warp gains nothing from hashing)

@@ -198,6 +198,7 @@ __device__ __forceinline__ PlanRec thread_plan_few(const SearchParams &p, int X,
     const int32_t *nrow = p.t.n + (size_t)X * AS;
     const long long *qrow = p.t.qfix + (size_t)X * AS;
     int N = 0; uint32_t untried = 0u;
+#pragma unroll 1
     for (int a = 0; a < A; ++a) {
         if (!((mask >> a) & 1u)) continue;
         const int n = nrow[a];
@@ -213,7 +214,8 @@ __device__ __forceinline__ PlanRec thread_plan_few(const SearchParams &p, int X,
     const float cf = (float)p.ucb_c;
     if (k == 1) {                                                    // UCB1 arg-max set
         float best = -INFINITY; uint32_t ties = 0u;
-        for (int a = 0; a < A; ++a) {
+    #pragma unroll 1
+    for (int a = 0; a < A; ++a) {
             if (!((mask >> a) & 1u)) continue;
             const int n = nrow[a];
             const float sc = edge_mean(qrow[a], n) + cf * sqrtf(L / (float)n);
@@ -225,6 +227,7 @@ __device__ __forceinline__ PlanRec thread_plan_few(const SearchParams &p, int X,
     const float c2L = (cf * cf) * L;
     float sc[AS];
     float qmax = -INFINITY; uint32_t qties = 0u;
+#pragma unroll 1
     for (int a = 0; a < A; ++a) {
         sc[a] = -INFINITY;
         if (!((mask >> a) & 1u)) continue;
@@ -235,11 +238,14 @@ __device__ __forceinline__ PlanRec thread_plan_few(const SearchParams &p, int X,
     }
     if (!(c2L > 0.0f)) { r.data.x = qties; return r; }
     uint32_t seq[4] = {0u, 0u, 0u, 0u};
+#pragma unroll 1
     for (uint32_t pull = 0; pull < k; ++pull) {
         int w = 0; float bs = sc[0];
+#pragma unroll 1
         for (int a = 1; a < A; ++a) if (sc[a] > bs) { bs = sc[a]; w = a; }
         seq[pull >> 2] |= (uint32_t)w << (8 * (pull & 3u));
         int va = 0;                                                  // pulls of w so far, this one included
+#pragma unroll 1
         for (uint32_t j = 0; j <= pull; ++j) va += (int)((seq[j >> 2] >> (8 * (j & 3u))) & 255u) == w ? 1 : 0;
         const int n = nrow[w];
         const float qb = n == 0 ? 0.0f : edge_mean(qrow[w], n);
