@@ -336,7 +336,12 @@ def run_b200(args):
     dev = run_moves(run, args.steps, "device", torch, flush)
     barrier()
     c1 = pl.counters()
-    # ---- the same moves end to end through the C ABI (wall clock, host buffers) ------------------------------
+    # ---- the SAME moves (same worlds, same random streams: the episodes are replayed from the start) end to end
+    # through the C ABI: wall clock, host buffers -----------------------------------------------------------------
+    np.random.seed(123)
+    run.epoch, run.active = -1, False
+    run_moves(run, args.warmup + (1 if world > 1 else 0), "plain", torch)
+    barrier()
     h2d0, d2h0 = run.h2d, run.d2h
     e2e = run_moves(run, args.steps, "e2e", torch)
     barrier()

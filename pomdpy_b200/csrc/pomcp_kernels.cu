@@ -136,13 +136,19 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                 bool act = status == 0;                              // plan is at hand; the others retry (nobody blocks)
                 if (act && d >= p.max_depth) { status = 2; act = false; }                  // :100
                 // -- the plan of node X: block cache (shared memory), node record (L2), or computed here
-                uint32_t *pce = pc + (((uint32_t)X * 2654435761u) >> (32 - PC_BITS)) * PC_WORDS;
+                // the block cache is 2-way set associative: entry = way 0 or 1 of the set the node id hashes to
+                uint32_t *pset = pc + (((uint32_t)X * 2654435761u) >> (33 - PC_BITS)) * (2 * PC_WORDS);
+                uint32_t *pce = nullptr;
+                if (status == 0 && !virgin) {
+                    if (*((volatile uint32_t *)pset) == (uint32_t)X + 1u) pce = pset;
+                    else if (*((volatile uint32_t *)(pset + PC_WORDS)) == (uint32_t)X + 1u) pce = pset + PC_WORDS;
+                }
                 bool have = false, cand = false, self = false, small = false, won = false, progressed = false;
                 bool wait_block = false, wait_grid = false;          // the plan is being computed by another warp
                 uint4 head = make_uint4(0u, 0u, 0u, 0u), data = head;
                 const uint32_t *sthr = nullptr;
                 if (act && !virgin) {
-                    if (!filler && *((volatile uint32_t *)pce) == (uint32_t)X + 1u) {
+                    if (!filler && pce != nullptr) {
                         if (*((volatile uint32_t *)(pce + 1)) != 0u) {   // cached by this block
                             __threadfence_block();
                             kx = __uint_as_float(pce[2]);
@@ -162,9 +168,15 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                             } else {
                                 kx = kpre * ((float)N / (float)na);
                                 if (kx >= pc_min_k) {                // hot: every block keeps its own copy of the plan
-                                    const uint32_t prev = atomicCAS(pce, 0u, (uint32_t)X + 1u);
+                                    pce = pset;
+                                    uint32_t prev = atomicCAS(pce, 0u, (uint32_t)X + 1u);
+                                    if (prev != 0u && prev != (uint32_t)X + 1u) {        // way 0 holds another node
+                                        pce = pset + PC_WORDS;
+                                        prev = atomicCAS(pce, 0u, (uint32_t)X + 1u);
+                                    }
                                     filler = prev == 0u;             // this warp computes it for the block (no waiting for
                                     wait_block = prev == (uint32_t)X + 1u;   // other SMs); another warp of the block is at it
+                                    if (!filler && !wait_block) pce = nullptr;          // set full: use the node's record
                                 }
                             }
                         }
@@ -231,10 +243,11 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                         todo &= todo - 1;
                         const int Xs = __shfl_sync(FULL, X, src);
                         const bool hot = __shfl_sync(FULL, (int)self, src) != 0;
+                        const int eoff = __shfl_sync(FULL, pce ? (int)(pce - pc) : 0, src);
                         const PlanRec r = warp_allocation(p, Xs, __shfl_sync(FULL, kx, src), lane, A, stamp);
                         if (lane == 0) ++c_alloc;                    // a diagnostic: hot plans are computed once per block
                         if (hot) {
-                            uint32_t *e = pc + (((uint32_t)Xs * 2654435761u) >> (32 - PC_BITS)) * PC_WORDS;
+                            uint32_t *e = pc + eoff;
                             e[12 + lane] = r.th;
                             if (lane == src) {
                                 e[2] = __float_as_uint(kx);

@@ -237,22 +237,23 @@ __device__ __forceinline__ PlanRec thread_plan_few(const SearchParams &p, int X,
         sc[a] = n == 0 ? INFINITY : qb + cf * sqrtf(L / (float)n);
     }
     if (!(c2L > 0.0f)) { r.data.x = qties; return r; }
-    uint32_t seq[4] = {0u, 0u, 0u, 0u};
+    unsigned long long seq_lo = 0ull, seq_hi = 0ull;                 // the pull bytes (no indexed local array)
 #pragma unroll 1
     for (uint32_t pull = 0; pull < k; ++pull) {
         int w = 0; float bs = sc[0];
 #pragma unroll 1
         for (int a = 1; a < A; ++a) if (sc[a] > bs) { bs = sc[a]; w = a; }
-        seq[pull >> 2] |= (uint32_t)w << (8 * (pull & 3u));
+        if (pull < 8u) seq_lo |= (unsigned long long)w << (8 * pull); else seq_hi |= (unsigned long long)w << (8 * (pull - 8u));
         int va = 0;                                                  // pulls of w so far, this one included
 #pragma unroll 1
-        for (uint32_t j = 0; j <= pull; ++j) va += (int)((seq[j >> 2] >> (8 * (j & 3u))) & 255u) == w ? 1 : 0;
+        for (uint32_t j = 0; j <= pull; ++j)
+            va += (int)(((j < 8u ? seq_lo >> (8 * j) : seq_hi >> (8 * (j - 8u))) & 255ull) == (unsigned long long)w);
         const int n = nrow[w];
         const float qb = n == 0 ? 0.0f : edge_mean(qrow[w], n);
         sc[w] = qb + cf * sqrtf(L / (float)(n + va));
     }
     r.head.x = (PLAN_PULLS << 16) | (k << 8);
-    r.data = make_uint4(seq[0], seq[1], seq[2], seq[3]);
+    r.data = make_uint4((uint32_t)seq_lo, (uint32_t)(seq_lo >> 32), (uint32_t)seq_hi, (uint32_t)(seq_hi >> 32));
     return r;
 }
 
@@ -269,22 +270,18 @@ __device__ __forceinline__ int plan_action(const uint4 head, const uint4 data, c
         int a = meta & 255;                              // the last action with weight, if no threshold exceeds x0
         uint32_t hi_t, lo_t;
         if (g < 6) {
-            uint32_t tq[6];
-#pragma unroll
-            for (int q = 0; q < 6; ++q) {
-                const int idx = g * G + q;
-                tq[q] = (q < G && idx < 32) ? (sthr ? sthr[idx] : __ldcg(gthr + idx)) : 0xFFFFFFFFu;   // ... then the action
-            }
+            // ... then the action: the (at most 6) thresholds of the group, as scalars (no indexed local array)
+            const int b0 = g * G;
+#define PLAN_TQ(q) (((q) < G && b0 + (q) < 32) ? (sthr ? sthr[b0 + (q)] : __ldcg(gthr + b0 + (q))) : 0xFFFFFFFFu)
+            const uint32_t t0 = PLAN_TQ(0), t1 = PLAN_TQ(1), t2 = PLAN_TQ(2), t3 = PLAN_TQ(3), t4 = PLAN_TQ(4), t5 = PLAN_TQ(5);
+#undef PLAN_TQ
             const uint32_t below = g == 0 ? 0u : g == 1 ? data.x : g == 2 ? data.y : g == 3 ? data.z : g == 4 ? data.w : head.z;
-            int q = 0;
-#pragma unroll
-            for (int t = 5; t >= 0; --t) if (x0 < tq[t]) q = t;
-            if (x0 < tq[q]) {
-                a = g * G + q;
-                hi_t = tq[q];
-                lo_t = q == 0 ? below : tq[q - 1 < 0 ? 0 : q - 1];
+            const int q = x0 < t0 ? 0 : x0 < t1 ? 1 : x0 < t2 ? 2 : x0 < t3 ? 3 : x0 < t4 ? 4 : x0 < t5 ? 5 : 6;
+            if (q < 6) {
+                hi_t = q == 0 ? t0 : q == 1 ? t1 : q == 2 ? t2 : q == 3 ? t3 : q == 4 ? t4 : t5;
+                lo_t = q == 0 ? below : q == 1 ? t0 : q == 2 ? t1 : q == 3 ? t2 : q == 4 ? t3 : t4;
                 prob = (float)(hi_t - lo_t) * (1.0f / 4294967296.0f);
-                return a;
+                return b0 + q;
             }
         }
         hi_t = sthr ? sthr[a] : __ldcg(gthr + a);

@@ -116,6 +116,10 @@ class POMCP(Solver):
                 self.planner.set_preferred_actions(self.preferred, spec["prob"], rollouts=mode == 2)
                 self.planner._preferred = mode
         self.planner.set_root_particles(bag, spec.get("start_cell", 0))
+        if self.world > 1 and getattr(self.planner, "_fused_merge", None) is not None:
+            # the in-kernel merge waits a bounded time (POMCP_MERGE_TIMEOUT_S, default 2 s) for the peers' root
+            # statistics: line the ranks up once per epoch so that per-epoch setup skew cannot eat into it
+            d.barrier()
         self._root_cell = spec.get("start_cell", 0)
         self._stats = None
         self.belief_tree_index = BeliefNodeView(self)
