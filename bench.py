@@ -196,7 +196,7 @@ def run_moves(run, n_moves, mode, torch, flush=None):
     """Run n_moves moves (episodes back to back).  mode "device": CUDA events around every search and every belief
     update, L2 flushed before each move (untimed); "e2e": wall clock of [search + statistics read] and [belief update]
     (+ the belief upload of a new episode); "plain": no instrumentation."""
-    search_ms, advance_ms, e2e_ms, fresh = [], [], [], []
+    search_ms, advance_ms, e2e_ms, fresh, wait_ms, kern_ms = [], [], [], [], [], []
     ev = []
     for _ in range(n_moves):
         t_new = 0.0
@@ -212,6 +212,10 @@ def run_moves(run, n_moves, mode, torch, flush=None):
             run.search()
             e[1].record()
             st = run.read_stats()
+            if run.world > 1:                                        # in-kernel timers: the search, and its wait for the peers
+                c = run.pl.counters()
+                wait_ms.append(c["merge_wait_ns"] * 1e-6)
+                kern_ms.append((c["last_search_ns"] - c["merge_wait_ns"]) * 1e-6)
             done = run.act(st)
             e[2].record()
             alive = run.advance()
@@ -239,7 +243,7 @@ def run_moves(run, n_moves, mode, torch, flush=None):
         torch.cuda.synchronize()
         search_ms = [e[0].elapsed_time(e[1]) for e in ev]
         advance_ms = [e[2].elapsed_time(e[3]) for e in ev]
-    return dict(search_ms=search_ms, advance_ms=advance_ms, e2e_ms=e2e_ms, fresh=fresh)
+    return dict(search_ms=search_ms, advance_ms=advance_ms, e2e_ms=e2e_ms, fresh=fresh, wait_ms=wait_ms, kern_ms=kern_ms)
 
 
 def cpu_baseline(spec, n_sims):
@@ -395,11 +399,11 @@ def run_b200(args):
         return float(statistics.median(x)) if len(x) else 0.0
 
     loc = [med(dev["search_ms"]), float(np.mean(dev["search_ms"])), med(dev["advance_ms"]), med(e2e["e2e_ms"]),
-           float(np.mean(e2e["e2e_ms"])), med(fr), med(other[1]) if other else 0.0]
+           float(np.mean(e2e["e2e_ms"])), med(fr), med(other[1]) if other else 0.0, med(dev["kern_ms"]), med(dev["wait_ms"])]
     t = torch.tensor(loc, dtype=torch.float64, device="cuda")
     if world > 1:
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
-    s_med, s_mean, a_med, e_med, e_mean, f_med, o_med = (float(x) for x in t.cpu())
+    s_med, s_mean, a_med, e_med, e_mean, f_med, o_med, k_med, w_med = (float(x) for x in t.cpu())
 
     if rank == 0:
         d = {k: c1[k] - c0[k] for k in ("levels", "rollout_steps", "created", "generations", "launches")}
@@ -442,6 +446,8 @@ def run_b200(args):
                        "search_ms": {"median": s_med, "mean": s_mean, "p10": sm[len(sm) // 10], "p90": sm[(9 * len(sm)) // 10],
                                      "fresh_tree_moves_among_steps": int(sum(dev["fresh"]))},
                        "advance_ms_median": a_med, "move_device_ms_median": s_med + a_med,
+                       "search_kernel_ms_before_merge_median": k_med if world > 1 else None,
+                       "merge_wait_for_slowest_peer_ms_median": w_med if world > 1 else None,
                        "value_from_mean_search_time": total_sims / (s_mean * 1e-3),
                        "fresh_tree_value": total_sims / (f_med * 1e-3) if f_med else None, "fresh_tree_ms": f_med,
                        "tree_levels_per_sim": L, "rollout_steps_per_sim": R,

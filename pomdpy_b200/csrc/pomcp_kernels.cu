@@ -90,6 +90,7 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
     // expected arrivals that earn a node a slot in the block caches (batch-UCB allocations only: >= 16.5)
     const float pc_min_k = fmaxf(4.0f * (float)gridDim.x, 16.5f);
 
+    if (gtid == 0) S->phase_ns[4] = 0;
     GRID_SYNC();                                                    // everyone has read S before anyone writes it
 
     while (done < p.n_sims) {
@@ -567,6 +568,7 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                 __nanosleep(200);
                 if (globaltimer_ns() - t0 > p.merge_timeout_ns) { ok = 0; break; }   // a peer never searched: give up
             }
+            atomicMax(reinterpret_cast<unsigned long long *>(&S->phase_ns[4]), globaltimer_ns() - t0);   // wait for the slowest peer
         }
         ok = __syncthreads_and(ok);
         __threadfence_system();
@@ -607,6 +609,7 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
         S->counters[7] = (long long)(globaltimer_ns() - t_start);
         S->counters[8] = done;
         for (int k = 0; k < 4; ++k) S->phase_ns[k] = (long long)tp[k];
+        if (p.world <= 1) S->phase_ns[4] = 0;
         for (int k = 0; k < 4; ++k) S->steplog[126][k] = (long long)tp[k];   // profiling aid: phase totals of this search
     }
 }
@@ -1500,7 +1503,8 @@ extern "C" int pomcp_counters(pomcp_handle *h, int64_t out[16])
     out[9] = h->launches;
     out[10] = h->coop_blocks;
     out[11] = SEARCH_THREADS;
-    for (int i = 0; i < 2; ++i) out[13 + i] = st.phase_ns[1 + i];   // barrier wait / allocate
+    out[13] = st.phase_ns[1];                                       // descent + rollout phases of the last search
+    out[14] = st.phase_ns[4];                                       // fused merge: wait for the slowest peer (last search)
     out[15] = st.check_failed;                                      // POMCP_CHECKS builds
     out[12] = (int64_t)DEVSTATE_HEAD;                               // D2H bytes of pomcp_root_stats
     return 0;

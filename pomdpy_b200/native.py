@@ -300,7 +300,7 @@ class Planner:
         self._ck(self.lib.pomcp_counters(self.h, _p(c, C.c_int64)))
         names = ("levels", "rollout_steps", "created", "nodes", "alloc_nodes", "generations", "level_steps",
                  "last_search_ns", "last_search_sims", "launches", "coop_blocks", "threads_per_block",
-                 "root_stats_d2h_bytes", "phase_wait_ns", "phase_alloc_ns", "check_failed")
+                 "root_stats_d2h_bytes", "phase_descend_ns", "merge_wait_ns", "check_failed")
         return dict(zip(names, c.tolist()))
 
 

@@ -15,6 +15,15 @@ import ref_env  # noqa: E402
 pytestmark = pytest.mark.skipif(not ref_env.reference_available(), reason="reference tree not present on this box")
 
 
+@pytest.fixture(autouse=True)
+def _keep_sys_path():
+    """ref_env puts the reference copy first on sys.path (its root holds a pomcp.py / vi.py of its own): undo that after
+    every test so that later tests import this repository's CLI modules."""
+    saved = list(sys.path)
+    yield
+    sys.path[:] = saved
+
+
 @pytest.mark.parametrize("tag", MAPS)
 def test_spec_extracted_from_the_reference_model_equals_the_golden_tables(tag):
     from pomdpy_b200 import adapters

@@ -17,5 +17,5 @@ for (w0, g, wmax) in [(1024, 2, 1 << 17), (1024, 2, 1 << 18), (4096, 4, 1 << 19)
         ts.append((t1 - t0, c["last_search_ns"] * 1e-9))
     print(json.dumps(dict(sched=(w0, g, wmax), wall_ms=[round(x[0] * 1e3, 3) for x in ts], dev_ms=[round(x[1] * 1e3, 3) for x in ts],
                           sims_per_s=n_sims / min(x[1] for x in ts), levels=c["levels"], rollout=c["rollout_steps"], gens=c["generations"],
-                          lsteps=c["level_steps"], ph=[round(c[k]*1e-6,3) for k in ("phase_wait_ns","phase_alloc_ns")], blocks=c["coop_blocks"], nodes=c["nodes"])), flush=True)
+                          descend_ms=round(c["phase_descend_ns"]*1e-6,3), blocks=c["coop_blocks"], nodes=c["nodes"])), flush=True)
     pl.close()
