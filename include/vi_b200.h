@@ -46,6 +46,24 @@ int vi_point_based_backup_dev(int device, int S, int A, int Z, int G, int P, con
                               int32_t *pruned_action_dev, int32_t *keep_dev, int32_t *n_out_dev, void *stream,
                               char *err, int errlen);
 
+/* Policy execution -- Agent.run_value_iteration (pomdpy/agent.py:215-264): per step the arg-max alpha vector gives the
+ * action (value_iteration.py:161-181), the environment steps, the belief is updated (tiger_model.py:109-131 generalised
+ * to any tabular model), until a terminal action or max_steps.  One block per epoch, the whole episode in one launch:
+ * no host round trip per step; `n_epochs` episodes at once.  The environment is the tabular model itself (hidden state
+ * s ~ b0, s' ~ T[a][s], z ~ O[a][s'], r = R[a][s]); actions in term_action_mask end the episode (opening a door in Tiger).
+ * Random draws: Philox4x32-10, key = seed, counter = (step, epoch, 0, 5).  out_dev [n_epochs][4] =
+ * {discounted return, undiscounted return, steps, last action}.  All pointers on the device. */
+int vi_policy_rollout_dev(int device, int S, int A, int Z, int G, const double *alpha_dev, const int32_t *action_dev,
+                          const double *T_dev, const double *O_dev, const double *R_dev, const double *b0_dev,
+                          uint32_t term_action_mask, double discount, int max_steps, int n_epochs, uint64_t seed,
+                          double *out_dev, void *stream, char *err, int errlen);
+
+/* Belief-point expansion of point-based value iteration (stochastic simulation with a random action): for p < P,
+ * beliefs[P + p] = update(beliefs[p], a, z) with a uniform, z ~ P(z | b_p, a) (counter = (round, p, 0, 6)).
+ * beliefs_dev holds 2 * P rows of S doubles. */
+int vi_expand_beliefs_dev(int device, int S, int A, int Z, int P, const double *T_dev, const double *O_dev,
+                          double *beliefs_dev, uint32_t round, uint64_t seed, void *stream, char *err, int errlen);
+
 #ifdef __cplusplus
 }
 #endif

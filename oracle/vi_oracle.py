@@ -112,3 +112,119 @@ def point_based_backup(T, O, R, gamma, beliefs, discount):
         a = action[p]
         alpha[p] = R[a] + discount * proj[a, np.arange(Z), best[a, p], :].sum(axis=0)
     return alpha, action, best, value, score
+
+
+# ---------------------------------------------------------------------------------------------------------------
+# Policy execution and belief expansion (checkers of vi_policy_rollout_dev / vi_expand_beliefs_dev): the same
+# arithmetic in the same order -- sequential sums where the kernel sums sequentially, lane-strided partial sums and a
+# butterfly / pairwise-halving reduction where a warp / the block reduces -- so that the comparison is exact.
+# ---------------------------------------------------------------------------------------------------------------
+VI_RT = 256
+
+
+def _u53(a, b):
+    return float(((int(a) >> 5) << 26) | (int(b) >> 6)) * (1.0 / 9007199254740992.0)
+
+
+def _sample_index(p, u):
+    acc = 0.0
+    for j in range(len(p)):
+        acc = acc + float(p[j])
+        if u < acc:
+            return j
+    return len(p) - 1
+
+
+def _block_sum(parts):
+    red = np.array(parts, dtype=np.float64)
+    off = VI_RT // 2
+    while off >= 1:
+        red[:off] = red[:off] + red[off:2 * off]
+        off //= 2
+    return float(red[0])
+
+
+def _strided_parts(vals):
+    """per-thread partial sums: thread t adds the elements t, t + 256, ... in that order"""
+    parts = np.zeros(VI_RT)
+    for j0 in range(0, len(vals), VI_RT):
+        chunk = vals[j0:j0 + VI_RT]
+        parts[:len(chunk)] = parts[:len(chunk)] + chunk
+    return parts
+
+
+def _pred(Ta, b):
+    """pred[j] = sum_i T[a][i][j] b[i], i in index order"""
+    acc = np.zeros(Ta.shape[1])
+    for i in range(Ta.shape[0]):
+        acc = acc + Ta[i, :] * b[i]
+    return acc
+
+
+def _warp_dot(v, b):
+    lanes = np.zeros(32)
+    for j0 in range(0, len(v), 32):
+        c = v[j0:j0 + 32] * b[j0:j0 + 32]
+        lanes[:len(c)] = lanes[:len(c)] + c
+    x = lanes
+    for off in (16, 8, 4, 2, 1):
+        x = x + x[np.arange(32) ^ off]
+    return float(x[0])
+
+
+def belief_update(b, Ta, Oa, z):
+    nb = _pred(Ta, b) * Oa[:, z]
+    tot = _block_sum(_strided_parts(nb))
+    return (nb / tot if tot > 0.0 else b), tot
+
+
+def policy_rollout(alpha, act, T, O, R, b0, discount, max_steps, n_epochs, seed=0, term_action_mask=0):
+    """agent.py:215-264 on a tabular model; returns [n_epochs][4] = discounted, undiscounted, steps, last action."""
+    import oracle
+    key = [seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF]
+    S = T.shape[1]
+    out = np.zeros((n_epochs, 4))
+    for e in range(n_epochs):
+        b = np.array(b0, dtype=np.float64)
+        r = oracle.philox([0xFFFFFFFF, e, 0, 5], key)
+        s = _sample_index(b, _u53(r[0], r[1]))
+        ret = dret = 0.0
+        disc, steps, last = 1.0, 0, -1
+        for t in range(max_steps):
+            vals = [_warp_dot(alpha[g], b) for g in range(alpha.shape[0])]
+            g = int(np.argmax(vals))                                  # first maximum = lowest g on ties
+            a = int(act[g])
+            r = oracle.philox([t, e, 0, 5], key)
+            s2 = _sample_index(T[a, s], _u53(r[0], r[1]))
+            z = _sample_index(O[a, s2], _u53(r[2], r[3]))
+            rew = float(R[a, s])
+            ret = ret + rew
+            dret = dret + disc * rew
+            disc = disc * discount
+            s, steps, last = s2, steps + 1, a
+            if (term_action_mask >> a) & 1:
+                break
+            b, _ = belief_update(b, T[a], O[a], z)
+        out[e] = (dret, ret, steps, last)
+    return out
+
+
+def expand_beliefs(B, P, T, O, round_index, seed=0):
+    """rows P..2P-1 = one successor of each of the first P points (random action, sampled observation)."""
+    import oracle
+    key = [seed & 0xFFFFFFFF, (seed >> 32) & 0xFFFFFFFF]
+    A, Z = T.shape[0], O.shape[2]
+    B = np.array(B, dtype=np.float64)
+    for p in range(P):
+        r = oracle.philox([round_index, p, 0, 6], key)
+        a = (int(r[0]) * A) >> 32
+        pred = _pred(T[a], B[p])
+        pz = [_block_sum(_strided_parts(pred * O[a][:, z])) for z in range(Z)]
+        tot = 0.0
+        for v in pz:
+            tot = tot + v
+        z = _sample_index(pz, _u53(r[1], r[2]) * tot)
+        nb = pred * O[a][:, z]
+        t2 = _block_sum(_strided_parts(nb))
+        B[P + p] = nb / t2 if t2 > 0.0 else B[p]
+    return B

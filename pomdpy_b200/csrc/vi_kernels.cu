@@ -11,6 +11,7 @@
 #include <string>
 
 #include "../../include/vi_b200.h"
+#include "pomcp_device.cuh"     // Philox4x32-10
 
 #define VCK(call)                                                                    \
     do {                                                                             \
@@ -365,6 +366,193 @@ extern "C" int vi_point_based_backup_dev(int device, int S, int A, int Z, int G,
         vi_prune_kernel<<<(P + 127) / 128, 128, 0, st>>>(S, P, alpha_dev, 1e-10, keep_dev);
         vi_compact_kernel<<<1, 1024, 0, st>>>(S, P, alpha_dev, action_dev, keep_dev, pruned_dev, pruned_action_dev, n_out_dev);
     }
+    VCK(cudaGetLastError());
+    return 0;
+}
+
+// ---------------------------------------------------------------------------------------------------------
+// (f).4: policy execution and the point-based value-iteration LOOP on the device.
+// ---------------------------------------------------------------------------------------------------------
+#define VI_RT 256                 // threads per block of the rollout / expansion kernels
+#define VI_DOM_POLICY 5u          // Philox domains of these kernels (pomcp_device.cuh uses 0..3)
+#define VI_DOM_EXPAND 6u
+
+__device__ __forceinline__ double vi_u53(uint32_t a, uint32_t b)
+{ return (double)(((uint64_t)(a >> 5) << 26) | (uint64_t)(b >> 6)) * (1.0 / 9007199254740992.0); }
+
+// sum of one value per thread over the block, in a fixed order (pairwise halving): every thread gets the result
+__device__ __forceinline__ double vi_block_sum(double v, double *red)
+{
+    red[threadIdx.x] = v;
+    __syncthreads();
+    for (int off = VI_RT / 2; off >= 1; off >>= 1) {
+        if ((int)threadIdx.x < off) red[threadIdx.x] = red[threadIdx.x] + red[threadIdx.x + off];
+        __syncthreads();
+    }
+    const double s = red[0];
+    __syncthreads();
+    return s;
+}
+
+// first index j with u < p[0] + ... + p[j] (sequential, index order; the last index if rounding leaves u above the sum)
+__device__ __forceinline__ int vi_sample_index(const double *p, int n, int stride, double u)
+{
+    double acc = 0.0;
+    for (int j = 0; j < n; ++j) { acc = acc + p[(size_t)j * stride]; if (u < acc) return j; }
+    return n - 1;
+}
+
+// nb[j] = O[a][j][z] * sum_i T[a][i][j] * b[i], then normalised (Model.belief_update / tiger_model.py:109-131 for any
+// tabular model): thread j sums over i in index order, the normaliser is a fixed-order block sum.  Returns the
+// normaliser = P(z | b, a) on every thread; if it is 0 (impossible observation) the belief is left unchanged.
+__device__ __forceinline__ double vi_belief_update(int S, int Z, const double *Ta, const double *Oa, int z, double *b, double *nb,
+                                                   double *red)
+{
+    double part = 0.0;
+    for (int j = threadIdx.x; j < S; j += VI_RT) {
+        double acc = 0.0;
+        for (int i = 0; i < S; ++i) acc = acc + Ta[(size_t)i * S + j] * b[i];
+        acc = acc * Oa[(size_t)j * Z + z];
+        nb[j] = acc;
+        part = part + acc;
+    }
+    const double tot = vi_block_sum(part, red);
+    if (tot > 0.0) for (int j = threadIdx.x; j < S; j += VI_RT) b[j] = nb[j] / tot;
+    __syncthreads();
+    return tot;
+}
+
+// Policy execution (agent.py:215-264 run_value_iteration: arg-max alpha vector -> action -> environment step -> belief
+// update, until a terminal step or max_steps), one block per epoch, the whole episode in one launch: no host round trip
+// per step.  The environment is the tabular model itself (hidden state s ~ b0, s' ~ T[a][s], z ~ O[a][s'], r = R[a][s];
+// actions in term_action_mask end the episode, as opening a door does in the reference's Tiger).
+// out[epoch] = {discounted return, undiscounted return, steps, last action}.
+__global__ void __launch_bounds__(VI_RT) vi_policy_rollout_kernel(int S, int A, int Z, int G, const double *__restrict__ alpha,
+                                                                  const int32_t *__restrict__ act, const double *__restrict__ T,
+                                                                  const double *__restrict__ O, const double *__restrict__ R,
+                                                                  const double *__restrict__ b0, uint32_t term_action_mask,
+                                                                  double discount, int max_steps, uint32_t key0, uint32_t key1,
+                                                                  double *__restrict__ out)
+{
+    extern __shared__ __align__(16) unsigned char vsm[];
+    double *b = reinterpret_cast<double *>(vsm), *nb = b + S, *red = nb + S;
+    double *wbest = red + VI_RT; int *wbest_g = reinterpret_cast<int *>(wbest + VI_RT / 32);
+    __shared__ int sh_i[4];
+    const int epoch = blockIdx.x, lane = threadIdx.x & 31, wid = threadIdx.x >> 5;
+    for (int j = threadIdx.x; j < S; j += VI_RT) b[j] = b0[j];
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const Philox4 r = philox4x32_10(0xFFFFFFFFu, (uint32_t)epoch, 0u, VI_DOM_POLICY, key0, key1);
+        sh_i[0] = vi_sample_index(b, S, 1, vi_u53(r.x, r.y));                 // the hidden true state
+    }
+    __syncthreads();
+    int s = sh_i[0];
+    double ret = 0.0, dret = 0.0, disc = 1.0;
+    int steps = 0, last_a = -1;
+    for (int t = 0; t < max_steps; ++t) {
+        // arg-max_g alpha_g . b (value_iteration.py:161-181; lowest g on ties): a warp per vector, lane-strided sums
+        double best = -INFINITY; int best_g = -1;
+        for (int g = wid; g < G; g += VI_RT / 32) {
+            double acc = 0.0;
+            for (int j = lane; j < S; j += 32) acc = acc + alpha[(size_t)g * S + j] * b[j];
+#pragma unroll
+            for (int off = 16; off >= 1; off >>= 1) acc = acc + __shfl_xor_sync(0xFFFFFFFFu, acc, off);
+            if (acc > best) { best = acc; best_g = g; }
+        }
+        if (lane == 0) { wbest[wid] = best; wbest_g[wid] = best_g; }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            double bv = -INFINITY; int bg = -1;
+            for (int w = 0; w < VI_RT / 32; ++w)
+                if (wbest_g[w] >= 0 && (wbest[w] > bv || (wbest[w] == bv && wbest_g[w] < bg))) { bv = wbest[w]; bg = wbest_g[w]; }
+            const int a = act[bg];
+            const Philox4 r = philox4x32_10((uint32_t)t, (uint32_t)epoch, 0u, VI_DOM_POLICY, key0, key1);
+            const int s2 = vi_sample_index(T + ((size_t)a * S + s) * S, S, 1, vi_u53(r.x, r.y));
+            const int z = vi_sample_index(O + ((size_t)a * S + s2) * Z, Z, 1, vi_u53(r.z, r.w));
+            sh_i[0] = a; sh_i[1] = s2; sh_i[2] = z;
+        }
+        __syncthreads();
+        const int a = sh_i[0], s2 = sh_i[1], z = sh_i[2];
+        const double rew = R[(size_t)a * S + s];
+        ret = ret + rew; dret = dret + disc * rew; disc = disc * discount;
+        s = s2; ++steps; last_a = a;
+        if ((term_action_mask >> a) & 1u) break;                                // agent.py:244-246
+        vi_belief_update(S, Z, T + (size_t)a * S * S, O + (size_t)a * S * Z, z, b, nb, red);   // :233-234
+    }
+    if (threadIdx.x == 0) {
+        out[(size_t)epoch * 4 + 0] = dret; out[(size_t)epoch * 4 + 1] = ret;
+        out[(size_t)epoch * 4 + 2] = (double)steps; out[(size_t)epoch * 4 + 3] = (double)last_a;
+    }
+}
+
+extern "C" int vi_policy_rollout_dev(int device, int S, int A, int Z, int G, const double *alpha_dev, const int32_t *action_dev,
+                                     const double *T_dev, const double *O_dev, const double *R_dev, const double *b0_dev,
+                                     uint32_t term_action_mask, double discount, int max_steps, int n_epochs, uint64_t seed,
+                                     double *out_dev, void *stream, char *err, int errlen)
+{
+    VCK(cudaSetDevice(device));
+    if (S < 1 || G < 1 || n_epochs < 1 || A < 1 || A > 32) { snprintf(err, errlen, "bad sizes"); return -1; }
+    const size_t smem = (size_t)(2 * S + VI_RT + VI_RT / 32) * sizeof(double) + (VI_RT / 32) * sizeof(int) + 16;
+    if (smem > 200 * 1024) { snprintf(err, errlen, "|S| too large for the belief in shared memory"); return -1; }
+    VCK(cudaFuncSetAttribute(vi_policy_rollout_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vi_policy_rollout_kernel<<<n_epochs, VI_RT, smem, (cudaStream_t)stream>>>(S, A, Z, G, alpha_dev, action_dev, T_dev, O_dev, R_dev,
+                                                                                b0_dev, term_action_mask, discount, max_steps,
+                                                                                (uint32_t)seed, (uint32_t)(seed >> 32), out_dev);
+    VCK(cudaGetLastError());
+    return 0;
+}
+
+// Belief-point expansion of point-based value iteration (stochastic simulation with a random action): belief p gets
+// the successor b' = update(b_p, a, z), a uniform in [0, A), z ~ P(z | b_p, a); it is stored as point P + p.
+__global__ void __launch_bounds__(VI_RT) vi_expand_beliefs_kernel(int S, int A, int Z, int P, const double *__restrict__ T,
+                                                                  const double *__restrict__ O, double *__restrict__ beliefs,
+                                                                  uint32_t round, uint32_t key0, uint32_t key1)
+{
+    extern __shared__ __align__(16) unsigned char vsm[];
+    double *b = reinterpret_cast<double *>(vsm), *nb = b + S, *red = nb + S, *pz = red + VI_RT;
+    __shared__ int sh_z;
+    const int p = blockIdx.x;
+    for (int j = threadIdx.x; j < S; j += VI_RT) b[j] = beliefs[(size_t)p * S + j];
+    __syncthreads();
+    const Philox4 r = philox4x32_10(round, (uint32_t)p, 0u, VI_DOM_EXPAND, key0, key1);
+    const int a = (int)__umulhi(r.x, (uint32_t)A);
+    const double *Ta = T + (size_t)a * S * S, *Oa = O + (size_t)a * S * Z;
+    // pred[j] = sum_i T[a][i][j] b[i] (kept in nb), then P(z) = sum_j pred[j] O[a][j][z]
+    for (int j = threadIdx.x; j < S; j += VI_RT) {
+        double acc = 0.0;
+        for (int i = 0; i < S; ++i) acc = acc + Ta[(size_t)i * S + j] * b[i];
+        nb[j] = acc;
+    }
+    __syncthreads();
+    for (int z = 0; z < Z; ++z) {
+        double part = 0.0;
+        for (int j = threadIdx.x; j < S; j += VI_RT) part = part + nb[j] * Oa[(size_t)j * Z + z];
+        const double tot = vi_block_sum(part, red);
+        if (threadIdx.x == 0) pz[z] = tot;
+    }
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        double tot = 0.0;
+        for (int z = 0; z < Z; ++z) tot = tot + pz[z];
+        sh_z = vi_sample_index(pz, Z, 1, vi_u53(r.y, r.z) * tot);
+    }
+    __syncthreads();
+    const int z = sh_z;
+    double part = 0.0;
+    for (int j = threadIdx.x; j < S; j += VI_RT) { const double v = nb[j] * Oa[(size_t)j * Z + z]; nb[j] = v; part = part + v; }
+    const double tot = vi_block_sum(part, red);
+    for (int j = threadIdx.x; j < S; j += VI_RT) beliefs[(size_t)(P + p) * S + j] = tot > 0.0 ? nb[j] / tot : b[j];
+}
+
+extern "C" int vi_expand_beliefs_dev(int device, int S, int A, int Z, int P, const double *T_dev, const double *O_dev,
+                                     double *beliefs_dev, uint32_t round, uint64_t seed, void *stream, char *err, int errlen)
+{
+    VCK(cudaSetDevice(device));
+    const size_t smem = (size_t)(2 * S + VI_RT + Z) * sizeof(double) + 16;
+    if (smem > 200 * 1024) { snprintf(err, errlen, "|S| too large for the belief in shared memory"); return -1; }
+    VCK(cudaFuncSetAttribute(vi_expand_beliefs_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
+    vi_expand_beliefs_kernel<<<P, VI_RT, smem, (cudaStream_t)stream>>>(S, A, Z, P, T_dev, O_dev, beliefs_dev, round,
+                                                                        (uint32_t)seed, (uint32_t)(seed >> 32));
     VCK(cudaGetLastError());
     return 0;
 }

@@ -57,13 +57,21 @@ def greedy_action(n, qfix, legal_mask, seed, move):
 
 
 def auto_schedule(n_sims):
-    """Generation schedule (w0, growth, wmax) = simulations in flight, for a per-rank budget of n_sims per move.
-    Small budgets keep the waves narrow (quality first: at n_sims = 500 widths up to 64 match the sequential planner's
-    return, 128 starts to cost); large budgets use the throughput schedule of bench.py (first wave = 1/32 of the budget,
-    x4 growth up to half of it: four generations; profiles/README.md has the return-vs-schedule measurements)."""
+    """Generation schedule (w0, growth, wmax) for a per-rank budget of n_sims per move.  A generation is
+    clamp(growth * visits(root), w0, wmax) simulations wide (pomcp_kernels.cu), so w0 is the width against an empty root
+    and wmax the width once the root has statistics.  Measured (profiles/r02_quality.md):
+      n <= 4096    narrow waves, w0 = n/64, x2, <= n/4: at n_sims = 500 widths up to 64 match the sequential planner's
+                   return, 128 starts to cost
+      n <  50000   w0 = n/256, x2, <= n/8 (about a dozen generations): at 1e4 simulations this agrees with the
+                   sequential planner's decisive choices in 97 % of the searches; four wide generations only in 82 %
+      n >= 50000   the throughput schedule, w0 = n/32, x4, <= n/2 (four generations from a fresh tree, two inside an
+                   episode): 99 % agreement at 1e5, and the return at 1e5 / 1e6 does not depend on the schedule
+                   (2 ... 64 generations per move)"""
     n = int(n_sims)
     if n <= 4096:
         return max(1, min(1024, (n // 4 or 1) // 16)), 2, max(32, n // 4 or 1)
+    if n < 50000:
+        return max(1, n // 256), 2, max(64, n // 8)
     wm = min(1 << 19, n // 2)
     return max(1, wm // 16), 4, wm
 

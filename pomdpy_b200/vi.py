@@ -98,6 +98,9 @@ def _lib():
         vp = C.c_void_p
         L.vi_point_based_backup_dev.argtypes = [C.c_int] * 6 + [vp] * 5 + [dbl] + [vp] * 7 + [C.c_int] + [vp] * 5 + \
                                                [C.c_char_p, C.c_int]
+        u32, u64 = C.c_uint32, C.c_uint64
+        L.vi_policy_rollout_dev.argtypes = [C.c_int] * 5 + [vp] * 6 + [u32, dbl, C.c_int, C.c_int, u64, vp, vp, C.c_char_p, C.c_int]
+        L.vi_expand_beliefs_dev.argtypes = [C.c_int] * 5 + [vp] * 3 + [u32, u64, vp, C.c_char_p, C.c_int]
         L._vi_ready = True
     return L
 
@@ -173,6 +176,81 @@ def point_based_backup(T, O, R, gamma, beliefs, discount, prune=True, device=0, 
     return out + (w,) if keep_work else out
 
 
+def policy_rollout(alpha, action, T, O, R, b0, discount, max_steps, n_epochs, seed=0, term_action_mask=0, device=0):
+    """Agent.run_value_iteration's policy execution (agent.py:215-264) for n_epochs episodes in ONE kernel launch (a
+    block per epoch; belief, arg-max over the alpha vectors, environment step and belief update all on the device).
+    Torch CUDA float64 tensors (action: int32) in; returns a [n_epochs][4] CPU array
+    {discounted return, undiscounted return, steps, last action}."""
+    import torch
+    A, S, _ = T.shape
+    Z, G = O.shape[2], alpha.shape[0]
+    for t in (alpha, T, O, R, b0):
+        assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
+    assert action.is_cuda and action.dtype == torch.int32 and action.is_contiguous()
+    out = torch.zeros((n_epochs, 4), dtype=torch.float64, device=T.device)
+    err = C.create_string_buffer(256)
+    rc = _lib().vi_policy_rollout_dev(int(device), S, A, Z, G, alpha.data_ptr(), action.data_ptr(), T.data_ptr(), O.data_ptr(),
+                                      R.data_ptr(), b0.data_ptr(), int(term_action_mask), float(discount), int(max_steps),
+                                      int(n_epochs), int(seed) & 0xFFFFFFFFFFFFFFFF, out.data_ptr(),
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream), err, 256)
+    if rc != 0:
+        raise native.PomcpError(err.value.decode() or "vi_policy_rollout_dev failed")
+    return out.cpu().numpy()
+
+
+def expand_beliefs(beliefs, P, T, O, round_index, seed=0, device=0):
+    """Belief-point expansion (stochastic simulation, random action): rows P..2P-1 of `beliefs` [>= 2P][S] are filled
+    with one successor of each of the first P points."""
+    import torch
+    A, S, _ = T.shape
+    assert beliefs.is_cuda and beliefs.dtype == torch.float64 and beliefs.is_contiguous() and beliefs.shape[0] >= 2 * P
+    err = C.create_string_buffer(256)
+    rc = _lib().vi_expand_beliefs_dev(int(device), S, A, O.shape[2], int(P), T.data_ptr(), O.data_ptr(), beliefs.data_ptr(),
+                                      int(round_index), int(seed) & 0xFFFFFFFFFFFFFFFF,
+                                      C.c_void_p(torch.cuda.current_stream().cuda_stream), err, 256)
+    if rc != 0:
+        raise native.PomcpError(err.value.decode() or "vi_expand_beliefs_dev failed")
+    return beliefs
+
+
+def pad_vector_set(gamma, Z):
+    """The projection GEMM wants |O| * |Gamma| to be a multiple of 64: repeat the first vector (duplicates change
+    neither the arg-max values nor, with lowest-index ties, the choices)."""
+    import torch
+    G = gamma.shape[0]
+    need = 64 // np.gcd(64, Z)
+    pad = (-G) % need
+    return gamma if pad == 0 else torch.cat([gamma, gamma[:1].expand(pad, -1)], dim=0).contiguous()
+
+
+def pbvi(T, O, R, beliefs0, discount, iterations, max_points=1024, expand_every=1, gamma0=None, seed=0, device=0,
+         log=None):
+    """Point-based value iteration, everything on the device: `iterations` point-based backups (vi_point_based_backup_dev:
+    projection and belief scores on the fp64 tensor cores, one vector per belief point, dominance prune); the belief set
+    starts as `beliefs0` [P0][S] (P0 a multiple of 128) and doubles by stochastic-simulation expansion
+    (vi_expand_beliefs_dev) every `expand_every` backups until max_points.  The host only sequences the launches and
+    reads the size of the pruned set (4 bytes) after each backup.  Returns (alpha [n][S], action [n], beliefs [P][S])."""
+    import torch
+    A, S, _ = T.shape
+    Z = O.shape[2]
+    P = beliefs0.shape[0]
+    B = torch.zeros((max(max_points, P), S), dtype=torch.float64, device=T.device)
+    B[:P] = beliefs0
+    if gamma0 is None:                       # the usual lower bound: min_a,s R / (1 - discount) for every state
+        gamma0 = torch.full((1, S), float(R.min().item()) / (1.0 - discount), dtype=torch.float64, device=T.device)
+    gamma, act = gamma0.contiguous(), torch.zeros(gamma0.shape[0], dtype=torch.int32, device=T.device)
+    for it in range(iterations):
+        alpha, act = point_based_backup(T, O, R, pad_vector_set(gamma, Z), B[:P].contiguous(), discount)
+        gamma = alpha.contiguous().clone()
+        act = act.contiguous().clone()
+        if log is not None:
+            log.append(dict(iteration=it, points=P, vectors=int(gamma.shape[0])))
+        if (it + 1) % expand_every == 0 and 2 * P <= max_points:
+            expand_beliefs(B, P, T, O, it, seed=seed, device=device)
+            P *= 2
+    return gamma, act, B[:P]
+
+
 class ValueIteration(Solver):
     def __init__(self, agent):
         super(ValueIteration, self).__init__(agent)
@@ -211,34 +289,31 @@ class ValueIteration(Solver):
 
 
 def run_value_iteration_experiment(agent):
-    """Agent.discounted_return, ValueIteration branch (agent.py:37-45, 215-264)."""
+    """Agent.discounted_return, ValueIteration branch (agent.py:37-45, 215-264): solve once, then n_epochs episodes of
+    policy execution.  The episodes run on the device, all at once (vi_policy_rollout_dev): the belief, the arg-max over
+    the alpha vectors, the environment step and the belief update never leave the GPU."""
+    import torch
     model = agent.model
     solver = agent.solver_factory(agent)
     t0 = time.time()
-    solver.value_iteration(model.get_transition_matrix(), model.get_observation_matrix(), model.get_reward_matrix(),
-                           model.planning_horizon)
-    vectors = sorted(solver.gamma, key=lambda av: (av.action, tuple(av.v)))     # deterministic scan order
-    b = model.get_initial_belief_state()
-    reward, discounted_reward, discount = 0, 0, 1.0
-    model.reset_for_epoch()
-    for i in range(model.max_steps):
-        action, _ = solver.select_action(b, vectors)
-        step_result = model.generate_step(action)
-        if not step_result.is_terminal:
-            b = model.belief_update(b, action, step_result.observation)
-        reward += step_result.reward
-        discounted_reward += discount * step_result.reward
-        discount *= model.discount
-        agent.display_step_result(i, step_result)
-        if step_result.is_terminal:
-            console(3, module, "Terminated after episode step " + str(i + 1))
-            break
-    agent.results.time.add(time.time() - t0)
-    agent.results.update_reward_results(reward, discounted_reward)
-    er, r = agent.experiment_results, agent.results
-    er.time.add(r.time.running_total)
-    er.undiscounted_return.add(r.undiscounted_return.running_total)
-    er.discounted_return.add(r.discounted_return.running_total)
+    T, O, R = model.get_transition_matrix(), model.get_observation_matrix(), model.get_reward_matrix()
+    solver.value_iteration(T, O, R, model.planning_horizon)
+    n_epochs = max(1, int(getattr(model, "n_epochs", 1)))
+    dev = torch.device("cuda", torch.cuda.current_device())
+    as_dev = lambda x: torch.from_numpy(np.ascontiguousarray(x, dtype=np.float64)).to(dev)
+    term_mask = int(getattr(model, "terminal_action_mask", 0b110 if type(model).__name__ == "TigerModel" else 0))
+    res = policy_rollout(as_dev(solver.alpha), torch.from_numpy(np.ascontiguousarray(solver.actions, dtype=np.int32)).to(dev),
+                         as_dev(T), as_dev(O), as_dev(R), as_dev(model.get_initial_belief_state()), model.discount,
+                         int(model.max_steps), n_epochs, seed=int(getattr(model, "seed", 0)), term_action_mask=term_mask)
+    elapsed = time.time() - t0
+    er = agent.experiment_results
+    for e in range(n_epochs):
+        agent.results.update_reward_results(float(res[e, 1]), float(res[e, 0]))
+        er.undiscounted_return.add(float(res[e, 1]))
+        er.discounted_return.add(float(res[e, 0]))
+        er.time.add(elapsed / n_epochs)
+        console(3, module, "epoch %d: %d steps, discounted return %.3f" % (e + 1, int(res[e, 2]), res[e, 0]))
+    agent.results.time.add(elapsed)
     if getattr(model, "save", False):                               # agent.py:37-45 (--save)
         save_alpha_vectors(solver.gamma, "VI_planning_horizon_{}.pkl".format(model.planning_horizon))
     console(2, module, "alpha vectors: " + str(len(solver.gamma)))

@@ -173,3 +173,66 @@ def test_oracle_point_based_backup_is_the_one_step_lookahead():
         assert np.allclose(look, value[:, p], rtol=1e-12, atol=1e-12)
         assert act[p] == int(np.argmax(look))
         assert np.isclose(alpha[p] @ B[p], look.max(), rtol=1e-12)
+
+
+@pytest.mark.gpu
+def test_policy_execution_on_the_device_equals_the_restatement():
+    """vi_policy_rollout_dev (agent.py:215-264 for n_epochs episodes in one launch) against the numpy restatement with
+    the same draws: Tiger with the horizon-4 vectors (episodes end on opening a door) and a random 96-state POMDP."""
+    import torch
+    from pomdpy_b200 import vi
+    from pomdpy_b200.tiger.tiger_model import TigerModel as TM
+    T, O, R = (np.asarray(x, dtype=np.float64) for x in (TM.get_transition_matrix(), TM.get_observation_matrix(), TM.get_reward_matrix()))
+    alpha, act = vi.solve_reference(T, O, R, 0.95, 4)
+    dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    b0 = np.array([0.5, 0.5])
+    got = vi.policy_rollout(dev(alpha), dev(act.astype(np.int32)), dev(T), dev(O), dev(R), dev(b0), 0.95, 12, 40, seed=9,
+                            term_action_mask=0b110)
+    want = vi_oracle.policy_rollout(alpha, act, T, O, R, b0, 0.95, 12, 40, seed=9, term_action_mask=0b110)
+    assert np.array_equal(got, want)
+    assert set(got[:, 3].astype(int)) <= {0, 1, 2} and got[:, 2].min() >= 1
+    rng = np.random.default_rng(4)
+    S, A, Z, G = 96, 4, 5, 7
+    T = rng.dirichlet(np.ones(S) * 0.3, size=(A, S))
+    O = rng.dirichlet(np.ones(Z), size=(A, S))
+    R = rng.uniform(-1, 1, size=(A, S))
+    alpha = rng.uniform(-2, 2, size=(G, S))
+    act = rng.integers(0, A, size=G).astype(np.int32)
+    b0 = rng.dirichlet(np.ones(S))
+    got = vi.policy_rollout(dev(alpha), dev(act), dev(T), dev(O), dev(R), dev(b0), 0.9, 15, 6, seed=3)
+    want = vi_oracle.policy_rollout(alpha, act, T, O, R, b0, 0.9, 15, 6, seed=3)
+    assert np.array_equal(got[:, 2:], want[:, 2:]) and np.allclose(got[:, :2], want[:, :2], rtol=1e-12, atol=1e-12)
+
+
+@pytest.mark.gpu
+def test_belief_expansion_and_the_pbvi_loop():
+    """vi_expand_beliefs_dev against the restatement (same draws), and the device PBVI loop: the value at the belief
+    points never decreases from one backup to the next (the initial vector is a lower bound), the belief set doubles
+    up to max_points, every vector is a valid lower bound of the next iterate."""
+    import torch
+    from pomdpy_b200 import vi
+    rng = np.random.default_rng(8)
+    S, A, Z = 128, 4, 64
+    T = rng.dirichlet(np.ones(S) * 0.2, size=(A, S))
+    O = rng.dirichlet(np.ones(Z) * 0.5, size=(A, S))
+    R = rng.uniform(-1, 1, size=(A, S))
+    B0 = rng.dirichlet(np.ones(S) * 0.1, size=128)
+    dev = lambda x: torch.from_numpy(np.ascontiguousarray(x)).cuda()
+    Bd = torch.zeros((256, S), dtype=torch.float64, device="cuda")
+    Bd[:128] = dev(B0)
+    vi.expand_beliefs(Bd, 128, dev(T), dev(O), 3, seed=11)
+    want = vi_oracle.expand_beliefs(np.vstack([B0, np.zeros((128, S))]), 128, T, O, 3, seed=11)
+    got = Bd.cpu().numpy()
+    assert np.array_equal(got[:128], B0) and np.allclose(got[128:], want[128:], rtol=1e-13, atol=1e-15)
+    assert np.allclose(got[128:].sum(axis=1), 1.0)
+    log = []
+    gamma, act, B = vi.pbvi(dev(T), dev(O), dev(R), dev(B0), 0.9, iterations=5, max_points=512, log=log, seed=11)
+    assert [e["points"] for e in log] == [128, 256, 512, 512, 512] and B.shape[0] == 512
+    assert 1 <= gamma.shape[0] <= 512 and set(act.cpu().numpy().tolist()) <= set(range(A))
+    # monotone improvement at the first 128 points: rerun with fewer iterations and compare the envelopes
+    g3, _, _ = vi.pbvi(dev(T), dev(O), dev(R), dev(B0), 0.9, iterations=3, max_points=512, seed=11)
+    env5 = (dev(B0) @ gamma.T).max(dim=1).values.cpu().numpy()
+    env3 = (dev(B0) @ g3.T).max(dim=1).values.cpu().numpy()
+    assert np.all(env5 >= env3 - 1e-9)
+    lower = R.min() / (1 - 0.9)
+    assert np.all(env3 >= lower - 1e-9)
