@@ -267,6 +267,20 @@ def cpu_baseline(spec, n_sims):
                        "%.1f s on 1 core" % (sample, dt))
 
 
+def secondary_value_iteration():
+    """BASELINE configs 2 and 5 (the secondary kernel, bench_vi.py): Tiger value iteration at horizon 8 end to end, the
+    |S| = 4096 projection GEMMs and one point-based backup.  Secondary figures; failures are reported, not raised."""
+    import contextlib
+    import io
+    try:
+        import bench_vi
+        with contextlib.redirect_stdout(io.StringIO()):
+            return {"config2_tiger_vi_horizon8": bench_vi.tiger(), "config5_projection": bench_vi.synthetic(),
+                    "config5_point_based_backup": bench_vi.synthetic_backup()}
+    except Exception as e:                                           # noqa: BLE001
+        return {"unavailable": str(e)[:300]}
+
+
 def run_b200(args):
     import torch
     import torch.distributed as dist
@@ -477,6 +491,9 @@ def run_b200(args):
                                     "n_sims_per_gpu": other[2], "generation_schedule": list(other[3]), "steps": len(other[1])}
         if world == 1 and not args.no_cpu_baseline:
             out["cpu_baseline"] = cpu_baseline(spec, args.n_sims)
+            out["cpu_baseline_python"] = python_reference_baseline()
+        if world == 1 and not args.no_secondary:
+            out["secondary"] = secondary_value_iteration()
         print(json.dumps(out))
     pl.close()
     if world > 1:
@@ -667,6 +684,7 @@ def main():
     ap.add_argument("--return_epochs_multi", type=int, default=32, help="epochs of the return leg at N > 1")
     ap.add_argument("--no_cpu_baseline", action="store_true")
     ap.add_argument("--no_other_scaling", action="store_true")
+    ap.add_argument("--no_secondary", action="store_true", help="skip the value-iteration figures (configs 2 and 5)")
     args = ap.parse_args()
     args.warmup = max(args.warmup, 3)
     if args.impl == "reference":

@@ -34,11 +34,13 @@ def tiger():
     t0 = time.perf_counter()
     ov, oa = vi_oracle.value_iteration(T, O, R, 0.95, 8)
     t_cpu = time.perf_counter() - t0
-    print(json.dumps({"metric": "tiger_vi_horizon8_seconds", "value": min(ts), "unit": "s", "higher_is_better": False,
-                      "alpha_vectors": int(len(alpha)), "identical_to_oracle": bool(np.array_equal(alpha, ov)),
-                      "cpu_baseline": {"value": t_cpu, "unit": "s", "cores": 1, "kind": "port",
-                                       "sample": "numpy oracle, same 8 backups"},
-                      "reference_published_s": 1493.2}))
+    out = {"metric": "tiger_vi_horizon8_seconds", "value": min(ts), "unit": "s", "higher_is_better": False,
+           "alpha_vectors": int(len(alpha)), "identical_to_oracle": bool(np.array_equal(alpha, ov)),
+           "cpu_baseline": {"value": t_cpu, "unit": "s", "cores": 1, "kind": "port",
+                            "sample": "numpy oracle, same 8 backups"},
+           "reference_published_s": 1493.2}
+    print(json.dumps(out))
+    return out
 
 
 def synthetic(S=4096, A=16, Z=64, G=64):
@@ -73,12 +75,14 @@ def synthetic(S=4096, A=16, Z=64, G=64):
     got = proj[:, rows, :].cpu().numpy()
     want = np.einsum("art,ato,gt->arog", T[:, rows, :], O, gamma).reshape(A, len(rows), Z * G)
     err = float(np.abs(got - want).max() / np.abs(want).max())
-    print(json.dumps({"metric": "vi_textbook_projection_tflops_fp64", "value": flop / (ms * 1e-3) / 1e12, "unit": "TFLOP/s",
+    out = ({"metric": "vi_textbook_projection_tflops_fp64", "value": flop / (ms * 1e-3) / 1e12, "unit": "TFLOP/s",
                       "ms": ms, "higher_is_better": True, "config": {"S": S, "A": A, "O": Z, "Gamma": G},
                       "max_rel_err_vs_float64_numpy": err, "cublas_dgemm_tflops": flop / (ms_lib * 1e-3) / 1e12,
                       "roofline": {"bound": "tensor", "achieved": flop / (ms * 1e-3) / 1e12, "peak": 40.0,
                                    "unit": "TFLOP/s", "frac": flop / (ms * 1e-3) / 1e12 / 40.0,
-                                   "peak_source": "nominal fp64 tensor (DMMA) rate of B200; no measured fp64 peak in MEASURED_PEAKS.json"}}))
+                                   "peak_source": "nominal fp64 tensor (DMMA) rate of B200; no measured fp64 peak in MEASURED_PEAKS.json"}})
+    print(json.dumps(out))
+    return out
 
 
 def synthetic_backup(S=4096, A=16, Z=64, G=64, P=1024):
@@ -115,10 +119,12 @@ def synthetic_backup(S=4096, A=16, Z=64, G=64, P=1024):
         cols = np.arange(Z) * G + gbest[a, p]
         want = R[a] + 0.95 * proj[a][:, torch.from_numpy(cols).cuda()].sum(dim=1).cpu().numpy()
         err_alpha = max(err_alpha, float(np.abs(galpha[p] - want).max() / np.abs(want).max()))
-    print(json.dumps({"metric": "vi_point_based_backup_ms", "value": ms, "unit": "ms", "higher_is_better": False,
-                      "config": {"S": S, "A": A, "O": Z, "Gamma": G, "belief_points": P},
-                      "tflops_fp64_gemm_part": flop / (ms * 1e-3) / 1e12, "vectors_after_prune": int(len(alpha)),
-                      "max_rel_err_scores_vs_float64_numpy": err_score, "max_rel_err_alpha_vs_float64_numpy": err_alpha}))
+    out = {"metric": "vi_point_based_backup_ms", "value": ms, "unit": "ms", "higher_is_better": False,
+           "config": {"S": S, "A": A, "O": Z, "Gamma": G, "belief_points": P},
+           "tflops_fp64_gemm_part": flop / (ms * 1e-3) / 1e12, "vectors_after_prune": int(len(alpha)),
+           "max_rel_err_scores_vs_float64_numpy": err_score, "max_rel_err_alpha_vs_float64_numpy": err_alpha}
+    print(json.dumps(out))
+    return out
 
 
 if __name__ == "__main__":
