@@ -33,6 +33,18 @@
 //                          staged per block in shared memory)
 // ---------------------------------------------------------------------------------------------------------
 
+// 64-bit add to a shared-memory word as two native 32-bit atomic adds (low word, then high word plus the carry): a
+// 64-bit atomicAdd on shared memory is a compare-and-swap loop, which spins when the warps of a block update the same
+// hot edge.  The sums are only read after a block barrier, when every add has landed.
+__device__ __forceinline__ void smem_add64(long long *dst, long long v)
+{
+
+    uint32_t *w = reinterpret_cast<uint32_t *>(dst);
+    const uint32_t lo = (uint32_t)(unsigned long long)v, hi = (uint32_t)((unsigned long long)v >> 32);
+    const uint32_t old = atomicAdd(&w[0], lo);
+    atomicAdd(&w[1], hi + (uint32_t)(old + lo < old));
+}
+
 __device__ __forceinline__ int row_sum(const int32_t *nrow)
 {
     int N = 0;
@@ -66,6 +78,10 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
     long long *ht_q = reinterpret_cast<long long *>(smem + off + ARR_HT * 8);
     off += (size_t)ARR_HT * 16;
     uint32_t *pc = reinterpret_cast<uint32_t *>(smem + off);        // plan cache of the hot nodes (PC_SLOTS x PC_WORDS)
+    off += (size_t)PC_SLOTS * PC_WORDS * 4;
+    int *sq = reinterpret_cast<int *>(smem + off);                   // hot-node queue: head, tail, pending, pad, nodes[], k[]
+    int *sq_node = sq + 4;
+    float *sq_k = reinterpret_cast<float *>(sq + 4 + SQ_CAP);
     for (int i = threadIdx.x; i < ARR_HT; i += blockDim.x) { ht_key[i] = 0u; ht_cnt[i] = 0; ht_q[i] = 0; }
     for (int i = threadIdx.x; i < PC_SLOTS; i += blockDim.x) { pc[i * PC_WORDS] = 0u; pc[i * PC_WORDS + 1] = 0u; }
     if (threadIdx.x == 0) { double d = 1.0; for (int t = 0; t < p.max_depth; ++t) { disc[t] = d; d *= p.discount; } }
@@ -105,6 +121,103 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
         const uint32_t stamp = (uint32_t)gstep;                      // of the plans computed in this generation
         const uint32_t root_mask = p.t.legal[root];
         if (gtid == 0) { S->cursor[2 * ((gens + 1) & 1)] = 0; S->cursor[2 * ((gens + 1) & 1) + 1] = 0; }   // the next generation's
+        // ---- the hot plans, ahead of the simulations.  The expected arrivals of a child follow from its parent's plan
+        // alone (k * P_plan(a) * N(child) / n(X, a)): no simulation has to get there first.  So every block walks the
+        // hot part of the tree (k >= pc_min_k: the upper levels, and the whole chain a re-rooted tree starts with) top
+        // down, its warps taking nodes from a queue, and fills its plan cache; the plan of a level then costs one
+        // allocation, not an allocation plus the step, child lookup and polling of the warps that wait for it.  What
+        // does not fit (queue, cache set) is left to the simulations (computed on arrival, as every cooler node is).
+        if (threadIdx.x == 0) {
+            sq[0] = 0; sq[1] = Nroot > 0 ? 1 : 0; sq[2] = sq[1]; sq[3] = sq[1];     // head, tail, pending, reserved
+            sq_node[0] = root; sq_k[0] = (float)w;
+        }
+        __syncthreads();
+        if ((float)w >= pc_min_k) for (;;) {
+            int idx = -1;
+            if (lane == 0) {
+                for (;;) {
+                    const int hd = *((volatile int *)&sq[0]);
+                    if (hd >= *((volatile int *)&sq[1])) { idx = *((volatile int *)&sq[2]) == 0 ? -2 : -1; break; }
+                    if (atomicCAS(&sq[0], hd, hd + 1) == hd) { idx = hd; break; }
+                }
+            }
+            idx = __shfl_sync(FULL, idx, 0);
+            if (idx == -2) break;
+            if (idx < 0) { __nanosleep(64); continue; }
+            const int X = *((volatile int *)&sq_node[idx]);
+            const float kx = *((volatile float *)&sq_k[idx]);
+#ifdef POMCP_TSEC
+            const long long sc_t0 = clock64();
+#endif
+            // a slot of the block cache (2-way set): nobody else is filling X, every node is queued once
+            uint32_t *e = nullptr;
+            if (lane == 0) {
+                uint32_t *pset = pc + (((uint32_t)X * 2654435761u) >> (33 - PC_BITS)) * (2 * PC_WORDS);
+                if (atomicCAS(pset, 0u, (uint32_t)X + 1u) == 0u) e = pset;
+                else if (atomicCAS(pset + PC_WORDS, 0u, (uint32_t)X + 1u) == 0u) e = pset + PC_WORDS;
+            }
+            const int eoff = __shfl_sync(FULL, e ? (int)(e - pc) : -1, 0);
+            const PlanRec r = warp_allocation(p, X, kx, lane, A, stamp);
+#ifdef POMCP_TSEC
+            const long long sc_t1 = clock64();
+#endif
+            if (lane == 0) ++c_alloc;
+            if (eoff >= 0) {
+                e = pc + eoff;
+                e[12 + lane] = r.th;
+                if (lane == 0) {
+                    e[2] = __float_as_uint(kx);
+                    *reinterpret_cast<uint4 *>(e + 4) = r.head; *reinterpret_cast<uint4 *>(e + 8) = r.data;
+                }
+                __threadfence_block();
+                __syncwarp();
+                if (lane == 0) *((volatile uint32_t *)(e + 1)) = 1u;
+            }
+            // the hot children: lane = action, same arithmetic as a simulation that descends (kpre = k * p, then * N / n)
+            const uint32_t th_prev = __shfl_up_sync(FULL, r.th, 1);
+            const float pa = (float)(r.th - (lane == 0 ? 0u : th_prev)) * (1.0f / 4294967296.0f);
+            const float kpre = kx * pa;
+            const int na = lane < A ? p.t.n[(size_t)X * AS + lane] : 0;
+            for (int o = 0; o < ZS; ++o) {
+                int child = -1; float kc = 0.0f;
+                if (lane < A && na > 0 && kpre >= pc_min_k) {
+                    const uint32_t c = p.t.child[((size_t)X * AS + lane) * ZS + o];
+                    if (c != 0u && c != CHILD_LOCKED) {
+                        const int id = CHILD_ID(c);
+                        const int N = row_sum(p.t.n + (size_t)id * AS);
+                        kc = kpre * ((float)N / (float)na);
+                        if (N > 0 && kc >= pc_min_k) child = id;
+                    }
+                }
+                const unsigned hot = __ballot_sync(FULL, child >= 0);
+                if (hot) {                                           // queue them: reserve, write, publish in reservation order
+                    const int m = __popc(hot);
+                    int base_slot = 0;
+                    if (lane == 0) { atomicAdd(&sq[2], m); base_slot = atomicAdd(&sq[3], m); }
+                    base_slot = __shfl_sync(FULL, base_slot, 0);
+                    const int slot = base_slot + __popc(hot & ((1u << lane) - 1u));
+                    if (child >= 0 && slot < SQ_CAP) { sq_node[slot] = child; sq_k[slot] = kc; }
+                    __threadfence_block();
+                    __syncwarp();
+                    if (lane == 0) {
+                        const int n_ok = max(0, min(m, SQ_CAP - base_slot));      // the rest does not fit: left to the simulations
+                        if (n_ok < m) atomicSub(&sq[2], m - n_ok);
+                        if (n_ok > 0) {
+                            while (*((volatile int *)&sq[1]) != base_slot) { }     // earlier reservations publish first
+                            *((volatile int *)&sq[1]) = base_slot + n_ok;
+                        }
+                    }
+                }
+            }
+            __threadfence_block();
+            if (lane == 0) atomicSub(&sq[2], 1);
+#ifdef POMCP_TSEC
+            if (blockIdx.x == 0 && lane == 0 && gens == 1 && idx < 100) {   // scout log of block 0, first generation
+                S->steplog[idx][4] = sc_t1 - sc_t0; S->steplog[idx][5] = clock64() - sc_t1;
+                S->steplog[idx][6] = 100 + (threadIdx.x >> 5); S->steplog[idx][7] = (long long)kx;
+            }
+#endif
+        }
         PHASE_MARK(0);
         // ---- descent (solvers/pomcp.py:87-137) + rollout (belief_tree_solver.py:123-152, from the post-action state) ----
         for (;;) {
@@ -131,7 +244,7 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
             }
 #ifdef POMCP_TSEC
             int it_log = 0; long long it_t0 = clock64();
-            const bool it_on = base == 0 && lane == 0 && gens == 1;   // iteration log of the first chunk of the first generation
+            const bool it_on = false;                               // (iteration log of a chunk: off, the scout log uses the columns)
 #endif
             while (__any_sync(FULL, status == 0)) {                  // one tree level per iteration, for the lanes whose
                 bool act = status == 0;                              // plan is at hand; the others retry (nobody blocks)
@@ -401,11 +514,9 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
         GRID_SYNC();              // the statistics were read-only up to here; every path and return is stored
         PHASE_MARK(1);
         // ---- backup (solvers/pomcp.py:126-137) ----
-        for (;;) {
-            int base = 0;
-            if (lane == 0) base = atomicAdd(&S->cursor[2 * (gens & 1) + 1], 32);
-            base = __shfl_sync(FULL, base, 0);
-            if (base >= w) break;
+        // (chunks of 32 simulations are dealt out statically here: the work per chunk is uniform, and a claim counter
+        // that ~5000 warps hit at the same moment serialises in L2)
+        for (int base = ((threadIdx.x >> 5) * (int)gridDim.x + (int)blockIdx.x) * 32; base < w; base += (int)gridDim.x * (SEARCH_THREADS / 32) * 32) {
             const int i = base + lane;
             const bool have = i < w;
             TSEC_START();
@@ -428,6 +539,13 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                 X = (on && d > 0 && !(d == 1 && stage_d1)) ? p.b.path_node[(size_t)d * p.wmax + i] : 0;
                 if (KIND == 1) rw = on ? p.b.path_rew[(size_t)d * p.wmax + i] : 0.0;
             };
+            // ... and before that the whole path is prefetched into L1 (one L2 round trip for all levels instead of one
+            // per level: a warp has only a few chunks, nothing else hides the latency of these loads)
+            for (int d = 0; d < depth; ++d) {
+                asm volatile("prefetch.global.L1 [%0];" :: "l"(p.b.path_ar + (size_t)d * p.wmax + i));
+                if (d > 0 && !(d == 1 && stage_d1)) asm volatile("prefetch.global.L1 [%0];" :: "l"(p.b.path_node + (size_t)d * p.wmax + i));
+                if (KIND == 1) asm volatile("prefetch.global.L1 [%0];" :: "l"(p.b.path_rew + (size_t)d * p.wmax + i));
+            }
             uint32_t ar0 = 0u, ar1 = 0u, ar2 = 0u; int x0 = 0, x1 = 0, x2 = 0; double rw0 = 0.0, rw1 = 0.0, rw2 = 0.0;
             load_entry(dmax - 1, ar0, x0, rw0);
             load_entry(dmax - 2, ar1, x1, rw1);
@@ -453,7 +571,6 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                         key = 0x80000000u | (uint32_t)(x0 * AS + a);
                     }
                 }
-                ar0 = ar1; x0 = x1; rw0 = rw1; ar1 = ar2; x1 = x2; rw1 = rw2;
                 // up to three rounds of "the first pending lane's edge, for every lane that shares it" (a chain level has
                 // one or two nodes), aggregated into the block tables; what is left updates on its own, deeper edges
                 // directly in the arena (a diverse warp gains nothing from hashing)
@@ -478,7 +595,7 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                         const int cnt = __popc(grp);
                         if (!(lkey & 0x80000000u)) {
                             atomicAdd(&acc_n[lkey - 1u], cnt);
-                            atomicAdd(reinterpret_cast<unsigned long long *>(&acc_q[lkey - 1u]), (unsigned long long)sum);
+                            smem_add64(&acc_q[lkey - 1u], sum);
                         } else {
                             uint32_t hq = ((lkey * 2654435761u) >> 16) & (ARR_HT - 1);
                             int probe = 0;
@@ -486,7 +603,7 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                                 const uint32_t prev = atomicCAS(&ht_key[hq], 0u, lkey);
                                 if (prev == 0u || prev == lkey) {
                                     atomicAdd(&ht_cnt[hq], cnt);
-                                    atomicAdd(reinterpret_cast<unsigned long long *>(&ht_q[hq]), (unsigned long long)sum);
+                                    smem_add64(&ht_q[hq], sum);
                                     break;
                                 }
                             }
@@ -502,13 +619,16 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                 if (pending) {
                     if (!(key & 0x80000000u)) {
                         atomicAdd(&acc_n[key - 1u], 1);
-                        atomicAdd(reinterpret_cast<unsigned long long *>(&acc_q[key - 1u]), (unsigned long long)qi);
+                        smem_add64(&acc_q[key - 1u], qi);
                     } else {
                         const size_t e = key & 0x7FFFFFFFu;
                         atomicAdd(&p.t.n[e], 1);
                         atomicAdd(reinterpret_cast<unsigned long long *>(&p.t.qfix[e]), (unsigned long long)qi);
                     }
                 }
+                // rotate the read-ahead registers only now: the loads issued at the top of the iteration had the whole
+                // iteration to complete
+                ar0 = ar1; x0 = x1; rw0 = rw1; ar1 = ar2; x1 = x2; rw1 = rw2;
             }
             TSEC(4);                                                 // backup
         }
@@ -1025,7 +1145,7 @@ extern "C" int pomcp_set_model_rocksample(pomcp_handle *h, int rows, int cols, c
     // launch geometry of the cooperative search kernel
     const int A = m.n_actions;
     size_t smem = ((sizeof(ModelHeader) + 15) & ~size_t(15)) + (((size_t)h->n_thr * 4 + 15) & ~size_t(15)) +
-                  (((size_t)h->cfg.max_depth * 8 + 15) & ~size_t(15)) + (size_t)(1 + 2 * A) * A * 12 + (size_t)ARR_HT * 16 + (size_t)PC_SLOTS * PC_WORDS * 4 + 48;
+                  (((size_t)h->cfg.max_depth * 8 + 15) & ~size_t(15)) + (size_t)(1 + 2 * A) * A * 12 + (size_t)ARR_HT * 16 + (size_t)PC_SLOTS * PC_WORDS * 4 + (size_t)(4 + 2 * SQ_CAP) * 4 + 48;
     h->search_smem = smem;
     CK(cudaFuncSetAttribute(pomcp_search_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));
     CK(cudaFuncSetAttribute(pomcp_search_kernel, cudaFuncAttributePreferredSharedMemoryCarveout, cudaSharedmemCarveoutMaxShared));
@@ -1107,7 +1227,7 @@ extern "C" int pomcp_set_model_tabular(pomcp_handle *h, int n_states, int n_acti
     if (!h->b.path_rew)
         CK(cudaMalloc(&h->b.path_rew, (size_t)h->cfg.gen_wmax * (size_t)h->cfg.tree_depth_cap * sizeof(double)));
     const size_t n_acc = t.stage_d1 ? (size_t)(1 + zs * n_actions) * n_actions : (size_t)n_actions;
-    size_t smem = (((size_t)h->cfg.max_depth * 8 + 15) & ~size_t(15)) + n_acc * 12 + (size_t)ARR_HT * 16 + (size_t)PC_SLOTS * PC_WORDS * 4 + 48;
+    size_t smem = (((size_t)h->cfg.max_depth * 8 + 15) & ~size_t(15)) + n_acc * 12 + (size_t)ARR_HT * 16 + (size_t)PC_SLOTS * PC_WORDS * 4 + (size_t)(4 + 2 * SQ_CAP) * 4 + 48;
     if (smem < 512) smem = 512;                              // the belief update keeps 34 ints there
     h->search_smem = smem;
     CK(cudaFuncSetAttribute(pomcp_search_tab_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem));

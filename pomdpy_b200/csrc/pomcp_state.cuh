@@ -56,6 +56,7 @@
 #endif
 #define PC_SLOTS (1 << PC_BITS)
 #define PC_WORDS 44
+#define SQ_CAP 192                // per-block queue of the hot nodes whose plans are computed ahead of the simulations
 #ifndef BISECT_ITERS
 #define BISECT_ITERS 14
 #endif

@@ -38,6 +38,6 @@ print("phase totals us [start, descend+rollout, backup, flush+barrier]:", [round
 if L[127].any():
     tot = float(L[127, :5].sum())
     print("section shares (clock64 over all threads): plan %.3f  choose+step %.3f  child %.3f  rollout %.3f  backup %.3f" % tuple(L[127, k] / tot for k in range(5)))
-    print("iteration log of block 0 / warp 0 / lane 0, first chunk of generation 0 (cycles): [plan, rest, kind 1 cache 2 self 3 few 4 record 5 wait-block 6 wait-grid 7 none, depth]")
+    print("scout log of block 0, generation 0, per queued hot node (cycles): [allocation, cache fill + children + queue, 100 + warp, k]")
     for i in range(100):
         if L[i, 4] or L[i, 5]: print(i, L[i, 4:8].tolist())

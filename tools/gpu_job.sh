@@ -1,4 +1,5 @@
 cd /root/repo
-timeout 900 python -m pytest tests/test_vi.py tests/test_cli_surface.py -q > gpurun_out/r2_vitests.log 2>&1; echo "vi tests rc $?"
-tail -15 gpurun_out/r2_vitests.log
-timeout 300 python vi.py --env Tiger --solver ValueIteration --planning_horizon 6 --n_epochs 50 --max_steps 20 --seed 123 2>&1 | tail -12
+timeout 300 python tools/episode_steplog.py 14 > gpurun_out/r2_episode.log 2>&1; echo "episode rc $?"
+tail -19 gpurun_out/r2_episode.log
+timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_parity_full.py -q -x > gpurun_out/r2_gputests.log 2>&1; echo "gpu tests rc $?"
+tail -4 gpurun_out/r2_gputests.log
