@@ -11,7 +11,9 @@ A "step" is ONE MOVE OF A REAL EPISODE with the belief tree kept across moves:
 when an episode ends the next one starts (new world, new root belief, fresh tree) and its moves count as steps too.
 
   value      n_sims (all ranks) / MEDIAN CUDA-event time of a move's search (all generations + the root merge) over
-             the K timed moves; L2 flushed (256 MiB write, untimed) before every timed move; max over ranks
+             the K timed moves -- every stride-th move of the episodes, stride chosen so that the K moves span at
+             least one whole episode (early moves search a chain-like tree, later ones a bushy one: 0.85 vs 1.3 ms);
+             L2 flushed (256 MiB write, untimed) before every timed move; max over ranks
   e2e        the same through the C ABI with host buffers and wall clock: search + device->host read of the root
              statistics + belief update with its host arguments and status read-back (a new episode's 8 KB belief
              upload included where it happens); median over K moves
@@ -46,6 +48,7 @@ import numpy as np  # noqa: E402
 MAP = "map-15-15"
 N_SIMS = 1_000_000
 MAX_STEPS = 200
+EPISODE_MOVES = 140                     # an episode on this map lasts ~130 moves: the timed moves span at least that many
 METRIC = "pomcp_sims_per_sec_rocksample_15_15"
 WORKLOAD = "RockSample(15,15) POMCP, n_sims=1M per move, moves of real episodes (tree kept across moves)"
 
@@ -192,13 +195,16 @@ class EpisodeRunner:
             self.active = False
 
 
-def run_moves(run, n_moves, mode, torch, flush=None):
+def run_moves(run, n_moves, mode, torch, flush=None, stride=1):
     """Run n_moves moves (episodes back to back).  mode "device": CUDA events around every search and every belief
     update, L2 flushed before each move (untimed); "e2e": wall clock of [search + statistics read] and [belief update]
-    (+ the belief upload of a new episode); "plain": no instrumentation."""
+    (+ the belief upload of a new episode); "plain": no instrumentation.  stride > 1: only every stride-th move is
+    instrumented (the others run plain in between), so that few timed moves still span whole episodes."""
     search_ms, advance_ms, e2e_ms, fresh, wait_ms, kern_ms = [], [], [], [], [], []
     ev = []
     for _ in range(n_moves):
+        if stride > 1 and mode != "plain":
+            run_moves(run, stride - 1, "plain", torch)
         t_new = 0.0
         is_fresh = not run.active
         if not run.active:
@@ -351,7 +357,9 @@ def run_b200(args):
     # ---- timed moves: device time -------------------------------------------------------------------------
     barrier()
     c0 = pl.counters()
-    dev = run_moves(run, args.steps, "device", torch, flush)
+    # the K timed moves are spread over at least one whole episode (~130 moves on this map): every stride-th move
+    stride = max(1, -(-EPISODE_MOVES // args.steps))
+    dev = run_moves(run, args.steps, "device", torch, flush, stride=stride)
     barrier()
     c1 = pl.counters()
     # ---- the SAME moves (same worlds, same random streams: the episodes are replayed from the start) end to end
@@ -361,9 +369,9 @@ def run_b200(args):
     run_moves(run, args.warmup + (1 if world > 1 else 0), "plain", torch)
     barrier()
     h2d0, d2h0 = run.h2d, run.d2h
-    e2e = run_moves(run, args.steps, "e2e", torch)
+    e2e = run_moves(run, args.steps, "e2e", torch, stride=stride)
     barrier()
-    h2d_step, d2h_step = (run.h2d - h2d0) / args.steps, (run.d2h - d2h0) / args.steps
+    h2d_step, d2h_step = (run.h2d - h2d0) / (args.steps * stride), (run.d2h - d2h0) / (args.steps * stride)
 
     # ---- fresh-tree searches (round 1's figure) ---------------------------------------------------------------
     if not run.active:
@@ -404,7 +412,7 @@ def run_b200(args):
         pl2, run2, sched2, n_rank2 = make_runner(o_mode)
         run_moves(run2, 3, "plain", torch)
         barrier()
-        d2 = run_moves(run2, min(args.steps, 40), "device", torch, flush)
+        d2 = run_moves(run2, min(args.steps, 40), "device", torch, flush, stride=max(1, -(-EPISODE_MOVES // min(args.steps, 40))))
         barrier()
         other = (o_mode, d2["search_ms"], n_rank2, sched2)
         pl = pl2
@@ -421,8 +429,8 @@ def run_b200(args):
 
     if rank == 0:
         d = {k: c1[k] - c0[k] for k in ("levels", "rollout_steps", "created", "generations", "launches")}
-        L = d["levels"] / (n_rank * args.steps)
-        R = d["rollout_steps"] / (n_rank * args.steps)
+        L = d["levels"] / (n_rank * args.steps * stride)
+        R = d["rollout_steps"] / (n_rank * args.steps * stride)
         bytes_per_sim = L * (8 * A + 56) + 8 * A + 20
         peaks = {}
         try:
@@ -465,7 +473,8 @@ def run_b200(args):
                        "value_from_mean_search_time": total_sims / (s_mean * 1e-3),
                        "fresh_tree_value": total_sims / (f_med * 1e-3) if f_med else None, "fresh_tree_ms": f_med,
                        "tree_levels_per_sim": L, "rollout_steps_per_sim": R,
-                       "generate_steps_per_s": (d["levels"] + d["rollout_steps"]) / args.steps * world / (s_med * 1e-3),
+                       "generate_steps_per_s": (d["levels"] + d["rollout_steps"]) / (args.steps * stride) * world / (s_med * 1e-3),
+                       "timed_moves": "every %d-th move of the episodes (the %d timed moves span %d moves)" % (stride, args.steps, stride * args.steps),
                        "episodes": {"epochs": int(len(returns)), "mean_moves": float(lengths.mean()), "seconds": ret_s,
                                     "moves": moves, "sims_per_s_wall_sustained": total_sims * moves / ret_s}},
             "roofline": {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak,
@@ -482,7 +491,7 @@ def run_b200(args):
                          "from": prof.get("from", "profiles/search_kernel_summary.json")},
             "e2e": {"value": total_sims / (e_med * 1e-3), "unit": "sims/s", "h2d_bytes_per_step": h2d_step,
                     "d2h_bytes_per_step": d2h_step, "ms_per_move_median": e_med, "ms_per_move_mean": e_mean},
-            "gpu_launches": int(d["launches"]),
+            "gpu_launches": int(d["launches"]),                           # kernels of this library in the timed span (all its moves)
             "clocks": clocks,
         }
         if other:

@@ -272,6 +272,13 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                         } else wait_block = true;                    // being computed by another warp of the block
                     } else {
                         if (kx < 0.0f) {
+                            // a node met for the first time by this simulation: besides its visit counts it will need
+                            // the return sums, the action set and maybe the plan record -- in a big tree those are
+                            // DRAM misses; ask for them now instead of one after the other
+                            asm volatile("prefetch.global.L2 [%0];" :: "l"(p.t.qfix + (size_t)X * AS));
+                            asm volatile("prefetch.global.L2 [%0];" :: "l"(p.t.qfix + (size_t)X * AS + 16));
+                            asm volatile("prefetch.global.L2 [%0];" :: "l"(p.t.legal + X));
+                            asm volatile("prefetch.global.L2 [%0];" :: "l"(p.t.plan + (size_t)X * 2));
                             const int N = row_sum(p.t.n + (size_t)X * AS);
                             if (N == 0) {
                                 virgin = true;

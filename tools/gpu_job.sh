@@ -1,5 +1,3 @@
 cd /root/repo
-timeout 300 python tools/episode_steplog.py 14 > gpurun_out/r2_episode.log 2>&1; echo "episode rc $?"
-tail -19 gpurun_out/r2_episode.log
-timeout 900 python -m pytest tests/test_gpu_parity.py tests/test_gpu_parity_full.py -q -x > gpurun_out/r2_gputests.log 2>&1; echo "gpu tests rc $?"
-tail -4 gpurun_out/r2_gputests.log
+timeout 1800 python tools/gpu_quality.py map-15-15 1000000 192 31250,4,1000000 62500,8,1000000 62500,4,1000000 125000,8,1000000 31250,4,500000 > gpurun_out/r2_quality_onegen192.txt 2>&1
+cat gpurun_out/r2_quality_onegen192.txt

@@ -42,7 +42,9 @@ def summary(vals, gen_steps):
         "dram_bytes_per_launch": val("dram__bytes_read.sum") + val("dram__bytes_write.sum"),
         "dram_pct_of_peak": val("gpu__dram_throughput.avg.pct_of_peak_sustained_elapsed"),
         "l2_hit_pct": val("lts__t_sector_hit_rate.pct"),
-        "l2_atom_sectors": val("lts__t_sectors_op_atom.sum"), "l2_red_sectors": val("lts__t_sectors_op_red.sum"),
+        "l2_atom_sectors": val("lts__t_sectors_op_atom.sum") or val("l1tex__m_l1tex2xbar_write_sectors_mem_global_op_atom.sum"),
+        "l2_red_sectors": val("lts__t_sectors_op_red.sum") or val("l1tex__m_l1tex2xbar_write_sectors_mem_global_op_red.sum"),
+        "shared_atom_wavefronts": val("l1tex__data_pipe_lsu_wavefronts_mem_shared_op_atom.sum"),
         "l1_global_load_sectors": val("l1tex__t_sectors_pipe_lsu_mem_global_op_ld.sum"),
         "l1_local_load_sectors": val("l1tex__t_sectors_pipe_lsu_mem_local_op_ld.sum"),
         "l1_local_store_sectors": val("l1tex__t_sectors_pipe_lsu_mem_local_op_st.sum"),
