@@ -96,12 +96,14 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
     const uint32_t *bag = p.bag[S->bag_sel];
     const int n_bag = S->n_bag;
     unsigned long long gstep = S->gstep;
-    const unsigned long long t_start = globaltimer_ns();
-    long long c_levels = 0, c_rollout = 0, c_created = 0, c_alloc = 0;
-    long long done = 0, gens = 0;
-    unsigned long long tp[4] = {0, 0, 0, 0}, tmark = t_start;       // phase clocks (gtid 0 only)
-#define PHASE_MARK(k) do { if (gtid == 0) { const unsigned long long now_ = globaltimer_ns(); tp[k] += now_ - tmark; \
-                                             if (gens <= 120) S->steplog[gens - 1][k] = (long long)(now_ - tmark); tmark = now_; } } while (0)
+    // bookkeeping that lives for the whole kernel is kept out of the registers of the hot loops: the phase clocks of
+    // thread 0 in shared memory, the per-thread work counters 32-bit (a thread runs far fewer than 2^31 steps a search)
+    __shared__ unsigned long long tclk[6];                           // [0..3] phase totals, [4] last mark, [5] kernel start
+    if (threadIdx.x == 0) { tclk[0] = tclk[1] = tclk[2] = tclk[3] = 0ull; tclk[4] = tclk[5] = globaltimer_ns(); }
+    int c_levels = 0, c_rollout = 0, c_created = 0, c_alloc = 0;
+    long long done = 0; int gens = 0;
+#define PHASE_MARK(k) do { if (gtid == 0) { const unsigned long long now_ = globaltimer_ns(), d_ = now_ - tclk[4]; tclk[k] += d_; \
+                                             if (gens <= 120) S->steplog[gens - 1][k] = (long long)d_; tclk[4] = now_; } } while (0)
     TSEC_DECL;
     // expected arrivals that earn a node a slot in the block caches (batch-UCB allocations only: >= 16.5)
     const float pc_min_k = fmaxf(4.0f * (float)gridDim.x, 16.5f);
@@ -507,8 +509,15 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                                                       MD::path_obs(last_ar), sim, p.move, p.key0, p.key1, d, disc, st, 0,
                                                       p.max_depth, 0.0);
                         t = po.t; sum = po.sum;
-                    } else MD::rollout(mc, S, sim, p.move, p.ks, d, disc, st, t, p.max_depth, sum);
-                } else MD::rollout(mc, S, sim, p.move, p.ks, d, disc, st, t, p.max_depth, sum);
+                    } else {
+                        const typename Mdl<0>::RollOut ro = Mdl<0>::rollout(mc.M.hdr, mc.M.thr32, mc.actual, mc.sampled, sim, p.move,
+                                                                            p.ks, d, disc, st, p.max_depth);
+                        t = ro.t; sum = ro.sum;
+                    }
+                } else {
+                    const typename Mdl<1>::RollOut ro = Mdl<1>::rollout(mc, sim, p.move, p.ks, d, disc, st, p.max_depth);
+                    t = ro.t; sum = ro.sum;
+                }
                 c_rollout += t;
             }
             if (status != 4) {
@@ -661,7 +670,7 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
         }
         for (int t = threadIdx.x; t < PC_SLOTS; t += blockDim.x) { pc[t * PC_WORDS] = 0u; pc[t * PC_WORDS + 1] = 0u; }   // next generation: new plans
         done += w;
-        if (p.timeout_ns && gtid == 0 && globaltimer_ns() - t_start > p.timeout_ns) S->stop = 1;
+        if (p.timeout_ns && gtid == 0 && globaltimer_ns() - tclk[5] > p.timeout_ns) S->stop = 1;
         GRID_SYNC();
         PHASE_MARK(3);
         if (p.timeout_ns && *((volatile int32_t *)&S->stop)) break;   // action_selection_timeout
@@ -733,11 +742,11 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
         S->sims_done = done;
         S->stop = 0;
         S->counters[5] += gens;
-        S->counters[7] = (long long)(globaltimer_ns() - t_start);
+        S->counters[7] = (long long)(globaltimer_ns() - tclk[5]);
         S->counters[8] = done;
-        for (int k = 0; k < 4; ++k) S->phase_ns[k] = (long long)tp[k];
+        for (int k = 0; k < 4; ++k) S->phase_ns[k] = (long long)tclk[k];
         if (p.world <= 1) S->phase_ns[4] = 0;
-        for (int k = 0; k < 4; ++k) S->steplog[126][k] = (long long)tp[k];   // profiling aid: phase totals of this search
+        for (int k = 0; k < 4; ++k) S->steplog[126][k] = (long long)tclk[k];   // profiling aid: phase totals of this search
     }
 }
 

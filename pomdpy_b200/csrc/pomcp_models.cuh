@@ -55,19 +55,25 @@ template <> struct Mdl<0> {
     // Rollout steps t .. t_end-1 from packed state st (uniform legal actions); true when the episode ended.
     // One Philox block per two steps: (x, y) then (z, w); word 0 picks the action, word 1 is the top 32 bits of the
     // 53-bit sensor uniform.
-    static __device__ __forceinline__ bool rollout(const Ctx &c, DevState *S, uint32_t sim, uint32_t move,
-                                                   const uint32_t *ks, int depth, const double *disc, uint32_t &st, int &t,
-                                                   int t_end, double &sum)
+    // Everything by value.  (-DROLL_NOINLINE gives the 100-step loop a register allocation of its own; measured: the
+    // caller then saves its live registers around the call and the local-memory traffic doubles -- not the default.)
+    struct RollOut { double sum; int t; };
+#ifdef ROLL_NOINLINE
+#define ROLL_INLINE __noinline__
+#else
+#define ROLL_INLINE __forceinline__
+#endif
+    static __device__ ROLL_INLINE RollOut rollout(const ModelHeader *H, const uint32_t *thr32, uint32_t actual, uint32_t sampled,
+                                                   uint32_t sim, uint32_t move, const uint32_t *ks, int depth,
+                                                   const double *disc, uint32_t st, int t_end)
     {
-        const ModelHeader *H = c.M.hdr;
+        int t = 0; double sum = 0.0;
         uint32_t cell = st & 0xFFu, rocks = st >> 8;
-        const uint32_t actual = c.actual, sampled = c.sampled;
         bool finished = false;
         // one step with the draws (w0, w1); true when the episode ended
         auto step = [&](uint32_t w0, uint32_t w1) -> bool {
             const uint32_t mask = H->legal[cell];
             const int a = nth_legal(H, mask, randbelow32(w0, (uint32_t)__popc(mask)));
-            DCHECK(S, a >= 0 && a < H->n_actions && cell < (uint32_t)H->n_cells, 41);
             if (a < 4) {
                 cell = (uint32_t)((int)cell + H->delta[a]);
                 if (H->cell[cell] == POMCP_CELL_GOAL) { sum += H->rew[REW_EXIT] * disc[t]; return true; }
@@ -80,7 +86,7 @@ template <> struct Mdl<0> {
                 const int k = a - 5;
                 if (!((sampled >> k) & 1u)) {
                     const uint32_t truth = (actual >> k) & 1u;
-                    const uint32_t correct = w1 <= c.M.thr32[cell * H->n_rocks + k];
+                    const uint32_t correct = w1 <= thr32[cell * H->n_rocks + k];
                     const uint32_t good = correct ? truth : (truth ^ 1u);
                     rocks = (rocks & ~(1u << k)) | (good << k);
                 }
@@ -95,8 +101,8 @@ template <> struct Mdl<0> {
             if (step(r.z, r.w)) { ++t; finished = true; break; }
             ++t;
         }
-        st = cell | (rocks << 8);
-        return finished;
+        (void)finished;
+        return RollOut{sum, t};
     }
     // Preferred-action rollout: the rollout carries the rock statistics of its own history -- the
     // leaf's, updated with every (action, observation) it generates (rock_position_history.py:96-137) -- and draws
@@ -166,11 +172,12 @@ template <> struct Mdl<1> {
     static __device__ __forceinline__ int path_obs(uint32_t ar) { return (int)(ar >> 5); }
     static __device__ __forceinline__ double path_reward(const Ctx &, uint32_t, const double *rew) { return *rew; }
     // word 0 picks the action (all actions are legal), word 1 the next state; observations are not drawn
-    static __device__ __forceinline__ bool rollout(const Ctx &c, DevState *, uint32_t sim, uint32_t move,
-                                                   const uint32_t *ks, int depth, const double *disc, uint32_t &st, int &t,
-                                                   int t_end, double &sum)
+    struct RollOut { double sum; int t; };
+    static __device__ ROLL_INLINE RollOut rollout(Ctx c, uint32_t sim, uint32_t move, const uint32_t *ks, int depth,
+                                                   const double *disc, uint32_t st, int t_end)
     {
         Philox4 r{0u, 0u, 0u, 0u};
+        int t = 0; double sum = 0.0;
         for (; t < t_end; ++t) {
             uint32_t w0, w1;
             if ((t & 1) == 0) {
@@ -182,8 +189,8 @@ template <> struct Mdl<1> {
             const double rew = __ldg(c.t.R + row);
             st = (uint32_t)next_state(c, row, w1);
             if (rew != 0.0) sum += rew * disc[t];
-            if (((c.h.term_action_mask >> a) & 1u) | __ldg(c.t.term_state + st)) { ++t; return true; }
+            if (((c.h.term_action_mask >> a) & 1u) | __ldg(c.t.term_state + st)) { ++t; break; }
         }
-        return false;
+        return RollOut{sum, t};
     }
 };
