@@ -212,7 +212,9 @@ def run_moves(run, n_moves, mode, torch, flush=None, stride=1):
             run.new_episode()
             t_new = time.perf_counter() - t0
         if mode == "device":
-            flush.zero_()
+            if not os.environ.get("BENCH_NO_FLUSH"):
+                flush.zero_()
+            dbg0 = run.pl.counters() if os.environ.get("BENCH_DEBUG") else None
             e = [torch.cuda.Event(enable_timing=True) for _ in range(4)]
             e[0].record()
             run.search()
@@ -228,6 +230,12 @@ def run_moves(run, n_moves, mode, torch, flush=None, stride=1):
             e[3].record()
             ev.append(e)
             fresh.append(is_fresh)
+            if dbg0 is not None:
+                torch.cuda.synchronize()
+                c = run.pl.counters()
+                print("move %d of epoch %d: search %.3f ms, generations %d, levels/sim %.2f, nodes %d, action %s" % (
+                    run.step, run.epoch, e[0].elapsed_time(e[1]), c["generations"] - dbg0["generations"],
+                    (c["levels"] - dbg0["levels"]) / run.n, c["nodes"], run._pending[0] if run._pending else None), file=sys.stderr)
         elif mode == "e2e":
             torch.cuda.synchronize()
             t0 = time.perf_counter()
