@@ -37,6 +37,7 @@ def lib():
         vp, i32, u32, i64, u64, dbl = C.c_void_p, C.c_int32, C.c_uint32, C.c_int64, C.c_uint64, C.c_double
         P = C.POINTER
         L.orc_philox4x32_10.argtypes = [P(u32), P(u32), P(u32)]
+        L.orc_philox4x32.argtypes = [P(u32), P(u32), P(u32), C.c_int]
         L.orc_model_create.restype = vp
         L.orc_model_create.argtypes = [i32, i32, P(C.c_int8), i32, P(u64), P(dbl)]
         L.orc_model_destroy.argtypes = [vp]
@@ -95,11 +96,11 @@ def _p(a, t):
     return a.ctypes.data_as(C.POINTER(t))
 
 
-def philox(ctr, key):
+def philox(ctr, key, rounds=10):
     c = np.asarray(ctr, dtype=np.uint32)
     k = np.asarray(key, dtype=np.uint32)
     out = np.zeros(4, dtype=np.uint32)
-    lib().orc_philox4x32_10(_p(c, C.c_uint32), _p(k, C.c_uint32), _p(out, C.c_uint32))
+    lib().orc_philox4x32(_p(c, C.c_uint32), _p(k, C.c_uint32), _p(out, C.c_uint32), int(rounds))
     return out
 
 

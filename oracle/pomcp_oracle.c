@@ -21,11 +21,28 @@
  *  (2) "gs"  -- the generation-synchronous tree-parallel POMCP that the CUDA
  *      product implements: identical model function,
  *      UCB1 rule, expansion rule, rollout policy and backup arithmetic, but
- *      simulations advance in lock-step generations so that the result is a
- *      deterministic function of (seed, inputs) for any degree of
- *      parallelism.  With generation width 1 it is the textbook sequential
- *      POMCP ("canonical" in SURVEY.md Appendix D).  The CUDA kernels must
- *      reproduce its root statistics exactly.
+ *      the simulations of a GENERATION -- clamp(growth x visits(root), w0,
+ *      wmax) of them -- all descend against the statistics as they were at
+ *      the generation's start and are backed up together.  Inside a
+ *      generation every node hands out its actions by a PLAN that is a pure
+ *      function of its statistics and of the number of arrivals it expects
+ *      (k(root) = width; k(child) = k * P_plan(a) * N(child) / n(a), fp32,
+ *      fixed operation order): batch-UCB water-filling thresholds for
+ *      k >= 16.5, a virtual-pull sequence for 2..16 arrivals, a uniform draw
+ *      over the untried actions otherwise.  No simulation depends on what
+ *      another one of its generation did, so the result is a deterministic
+ *      function of (seed, inputs) for any degree of parallelism.  With
+ *      generation width 1 it is the textbook sequential POMCP ("canonical"
+ *      in SURVEY.md Appendix D).  The CUDA kernels must reproduce its root
+ *      statistics, counters and belief updates exactly.
+ *      (orc_gs_set_kmode(1) switches k to the history-only estimate
+ *      w * N(X) / N(root): an experiment reported in
+ *      profiles/r02_quality.md section 4, never what the kernels compute.)
+ *      RNG: Philox4x32-10 counter blocks (seed, block, simulation, move,
+ *      domain); the blocks that drive a rollout's random steps run 7 rounds
+ *      (ORC_ROLLOUT_ROUNDS).  "gs" has no reference to be pinned to beyond
+ *      its model function and its width-1 behaviour; tests/golden/gs_pins.json
+ *      guards the specification itself.
  *
  * Build: make -C oracle   (gcc -O2 -ffp-contract=off: no FMA contraction, the
  * floating-point sequences below are part of the specification).
@@ -49,11 +66,11 @@
 /* ------------------------------------------------------------------------ */
 /* Philox4x32-10 (Salmon et al., SC'11) -- counter-based RNG shared by spec.  */
 /* ------------------------------------------------------------------------ */
-void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4])
+void orc_philox4x32(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4], int rounds)
 {
     uint32_t c0 = ctr[0], c1 = ctr[1], c2 = ctr[2], c3 = ctr[3];
     uint32_t k0 = key[0], k1 = key[1];
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < rounds; ++r) {
         uint64_t p0 = (uint64_t)0xD2511F53u * c0;
         uint64_t p1 = (uint64_t)0xCD9E8D57u * c2;
         uint32_t n0 = (uint32_t)(p1 >> 32) ^ c1 ^ k0;
@@ -65,6 +82,12 @@ void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t ou
     }
     out[0] = c0; out[1] = c1; out[2] = c2; out[3] = c3;
 }
+void orc_philox4x32_10(const uint32_t ctr[4], const uint32_t key[2], uint32_t out[4]) { orc_philox4x32(ctr, key, out, 10); }
+/* The ROLLOUT stream of the "gs" planner (the blocks that drive the <= max_depth random steps below a leaf) uses the
+ * 7-round variant -- the fewest rounds Salmon et al. found Crush-resistant; Random123 ships known answers for it
+ * (tests/test_cpu_oracle.py).  The rollouts are 85 % of a search's instructions and Philox a third of a rollout step;
+ * every draw that decides something in the tree (root particle, descent, belief update) keeps the 10 rounds. */
+#define ORC_ROLLOUT_ROUNDS 7
 
 /* integer in [0, n): multiply-shift of one 32-bit word */
 static inline uint32_t randbelow32(uint32_t x, uint32_t n) { return (uint32_t)(((uint64_t)x * n) >> 32); }
@@ -741,6 +764,11 @@ static void gs_block(const orc_gs *h, uint32_t k, uint32_t sim, uint32_t move, u
     uint32_t ctr[4] = {k, sim, move, dom};
     orc_philox4x32_10(ctr, h->key, x);
 }
+static void gs_rollout_block(const orc_gs *h, uint32_t k, uint32_t sim, uint32_t move, uint32_t x[4])
+{
+    uint32_t ctr[4] = {k, sim, move, DOM_SIM};
+    orc_philox4x32(ctr, h->key, x, ORC_ROLLOUT_ROUNDS);
+}
 
 /* Mean of an edge from its integer statistics (0 for an unvisited edge: entry.mean_q_value starts at 0). */
 static float gs_mean(const gs_node *nd, int a)
@@ -940,7 +968,7 @@ static double gs_rollout(orc_gs *h, gs_sim *s, uint32_t move)
     while (t < h->max_depth && !terminal) {
         /* one Philox block per two rollout steps: words (0,1) then (2,3); the first word picks the action, the
          * second drives the model (RockSample: top 32 bits of the 53-bit sensor uniform; tabular: next state) */
-        if ((t & 1) == 0) gs_block(h, (uint32_t)(s->depth + 1 + (t >> 1)), s->sim, move, DOM_SIM, x);
+        if ((t & 1) == 0) gs_rollout_block(h, (uint32_t)(s->depth + 1 + (t >> 1)), s->sim, move, x);
         uint32_t w0 = x[(t & 1) * 2], w1 = x[(t & 1) * 2 + 1];
         uint32_t mask = pref ? orc_smart_mask(h->m, &rst, (int)(st & 0xFFu)) : gs_tag_legal(h, gs_state_tag(h, st));
         int idx = (int)randbelow32(w0, (uint32_t)__builtin_popcount(mask)), a = -1;

@@ -14,14 +14,20 @@ enum { REW_NONE = 0, REW_ILLEGAL = 1, REW_EXIT = 2, REW_GOOD = 3, REW_BAD = 4 };
 
 // ---------------------------------------------------------------------------------------------------------
 // Philox4x32-10 counter-based generator: key = seed, counter = (block k, simulation id, move, domain).
+// The rollout stream (the blocks that drive the random steps below a leaf) runs POMCP_ROLL_ROUNDS = 7 rounds, the
+// fewest Salmon et al. found Crush-resistant (oracle: ORC_ROLLOUT_ROUNDS; Random123 known answers in
+// tests/test_cpu_oracle.py): the rollouts are 85 % of a search's instructions, Philox 26 of the 88 warp instructions of
+// a rollout step (2 IMAD.WIDE + 2 LOP3 per round).  Measured: a fresh-tree search of 10^6 simulations 0.483 -> 0.451 ms.
 // ---------------------------------------------------------------------------------------------------------
 struct Philox4 { uint32_t x, y, z, w; };
+#define POMCP_ROLL_ROUNDS 7
 
+template <int ROUNDS = 10>
 __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                  uint32_t k0, uint32_t k1)
 {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < ROUNDS; ++r) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
         const uint32_t n0 = hi1 ^ c1 ^ k0, n2 = hi0 ^ c3 ^ k1;
@@ -32,11 +38,12 @@ __device__ __forceinline__ Philox4 philox4x32_10(uint32_t c0, uint32_t c1, uint3
 }
 // The same generator with the key schedule precomputed (ks[2r], ks[2r+1] = key of round r): in the rollout loop the
 // schedule comes from the kernel's constant bank instead of 20 uniform adds per block.
+template <int ROUNDS = 10>
 __device__ __forceinline__ Philox4 philox4x32_10_ks(uint32_t c0, uint32_t c1, uint32_t c2, uint32_t c3,
                                                     const uint32_t *ks)
 {
 #pragma unroll
-    for (int r = 0; r < 10; ++r) {
+    for (int r = 0; r < ROUNDS; ++r) {
         const uint32_t hi0 = __umulhi(0xD2511F53u, c0), lo0 = 0xD2511F53u * c0;
         const uint32_t hi1 = __umulhi(0xCD9E8D57u, c2), lo1 = 0xCD9E8D57u * c2;
         const uint32_t n0 = hi1 ^ c1 ^ ks[2 * r], n2 = hi0 ^ c3 ^ ks[2 * r + 1];

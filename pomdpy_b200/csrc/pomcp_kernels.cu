@@ -109,7 +109,9 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
     const float pc_min_k = fmaxf(4.0f * (float)gridDim.x, 16.5f);
 
     if (gtid == 0) S->phase_ns[4] = 0;
-    GRID_SYNC();                                                    // everyone has read S before anyone writes it
+    // (no grid barrier here: what a block reads from S above -- root, world, belief, gstep -- is written again only in
+    // the kernel's tail, behind the barriers of the generations; a block that starts late misses nothing, the
+    // statistics stay read-only until the first generation's barrier, which waits for it)
 
     while (done < p.n_sims) {
         // Width of the generation: `growth` times the visits the root has seen, within [w0, wmax] -- from a fresh tree

@@ -95,7 +95,7 @@ template <> struct Mdl<0> {
         };
         // t is even on entry (slices are even, a finished rollout is never resumed): two steps per Philox block
         while (t < t_end) {
-            const Philox4 r = philox4x32_10_ks((uint32_t)(depth + 1 + (t >> 1)), sim, move, DOM_SIM, ks);
+            const Philox4 r = philox4x32_10_ks<POMCP_ROLL_ROUNDS>((uint32_t)(depth + 1 + (t >> 1)), sim, move, DOM_SIM, ks);
             if (step(r.x, r.y)) { ++t; finished = true; break; }
             if (++t >= t_end) break;                                 // odd horizon
             if (step(r.z, r.w)) { ++t; finished = true; break; }
@@ -127,7 +127,7 @@ template <> struct Mdl<0> {
         for (; t < t_end; ++t) {
             uint32_t w0, w1;
             if ((t & 1) == 0) {
-                r = philox4x32_10((uint32_t)(depth + 1 + (t >> 1)), sim, move, DOM_SIM, key0, key1);
+                r = philox4x32_10<POMCP_ROLL_ROUNDS>((uint32_t)(depth + 1 + (t >> 1)), sim, move, DOM_SIM, key0, key1);
                 w0 = r.x; w1 = r.y;
             } else { w0 = r.z; w1 = r.w; }
             const int a = nth_bit(mask, randbelow32(w0, (uint32_t)__popc(mask)));
@@ -181,7 +181,7 @@ template <> struct Mdl<1> {
         for (; t < t_end; ++t) {
             uint32_t w0, w1;
             if ((t & 1) == 0) {
-                r = philox4x32_10_ks((uint32_t)(depth + 1 + (t >> 1)), sim, move, DOM_SIM, ks);
+                r = philox4x32_10_ks<POMCP_ROLL_ROUNDS>((uint32_t)(depth + 1 + (t >> 1)), sim, move, DOM_SIM, ks);
                 w0 = r.x; w1 = r.y;
             } else { w0 = r.z; w1 = r.w; }
             const int a = (int)randbelow32(w0, (uint32_t)c.h.A);

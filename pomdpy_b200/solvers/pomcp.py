@@ -64,18 +64,19 @@ def auto_schedule(n_sims):
                    return, 128 starts to cost
       n <  50000   w0 = n/256, x2, <= n/8 (about a dozen generations): at 1e4 simulations this agrees with the
                    sequential planner's decisive choices in 97 % of the searches; four wide generations only in 82 %
-      n >= 50000   the throughput schedule, w0 = n/8, x8, <= n: two generations from a fresh tree (n/8, then the rest),
-                   ONE inside an episode (the re-rooted tree arrives with more than n/8 visits).  At 1e6 simulations per
-                   move on RockSample(15,15), 192 paired episodes each: 14.64 +- 0.42 at 0.96 ms per move, against
-                   13.15 +- 0.35 at 1.32 ms for n/32, x4, <= n/2 (round 1's rule; 2 ... 62 generations per move all
-                   return 12.8 ... 13.4); 100 % agreement with the sequential planner's decisive choices at 1e5"""
+      n >= 50000   the throughput schedule, w0 = n/8, x32, <= n: two generations from a fresh tree (n/8, then the rest),
+                   ONE inside an episode whenever the re-rooted tree arrives with at least n/32 visits.  At 1e6
+                   simulations per move on RockSample(15,15), 192 paired episodes each: 14.66 +- 0.42 at 0.77 ms per move
+                   (growth 8: 14.64 at 0.96 ms; growth 128 ... 1e5: 14.54 ... 14.49, RockSample(11,11) loses 0.3 ... 0.8),
+                   against 13.15 +- 0.35 at 1.32 ms for n/32, x4, <= n/2 (round 1's rule; 2 ... 62 generations per move
+                   all return 12.8 ... 13.4); 100 % agreement with the sequential planner's decisive choices at 1e5"""
     n = int(n_sims)
     if n <= 4096:
         return max(1, min(1024, (n // 4 or 1) // 16)), 2, max(32, n // 4 or 1)
     if n < 50000:
         return max(1, n // 256), 2, max(64, n // 8)
     wm = min(1 << 20, n)
-    return max(1, wm // 8), 8, wm
+    return max(1, wm // 8), 32, wm
 
 
 class POMCP(Solver):

@@ -22,6 +22,13 @@ def test_philox_known_answers():
     for ctr, key, want in kats:
         assert tuple(int(v) for v in oracle.philox(ctr, key)) == want
         assert philox.philox4x32_10(ctr, key) == want
+    # ... and for the 7-round variant the rollout stream of the "gs" planner uses (oracle/pomcp_oracle.c ORC_ROLLOUT_ROUNDS)
+    kats7 = [((0, 0, 0, 0), (0, 0), (0x5f6fb709, 0x0d893f64, 0x4f121f81, 0x4f730a48)),
+             ((0xffffffff,) * 4, (0xffffffff,) * 2, (0x5207ddc2, 0x45165e59, 0x4d8ee751, 0x8c52f662)),
+             ((0x243f6a88, 0x85a308d3, 0x13198a2e, 0x03707344), (0xa4093822, 0x299f31d0),
+              (0x4dfccaba, 0x190a87f0, 0xc47362ba, 0xb6b5242a))]
+    for ctr, key, want in kats7:
+        assert tuple(int(v) for v in oracle.philox(ctr, key, rounds=7)) == want
 
 
 @pytest.mark.parametrize("tag", MAPS)

@@ -67,10 +67,10 @@ def run_episode_parity(tag, n_sims, sched, moves, seed, node_capacity):
 
 def test_config4_rs15_1m_sims_bench_schedule_fresh_and_in_episode():
     """RockSample(15,15), 1 000 000 simulations per move on bench.py's schedule (the solver's rule for this budget:
-    125 000 x8 <= 1 000 000 -- two generations from the fresh tree, one per move afterwards): a fresh tree and three
+    125 000 x32 <= 1 000 000 -- two generations from the fresh tree, one per move afterwards): a fresh tree and three
     more moves with the belief update in between."""
     from pomdpy_b200.solvers.pomcp import auto_schedule
-    assert auto_schedule(1_000_000) == (125000, 8, 1000000)
+    assert auto_schedule(1_000_000) == (125000, 32, 1000000)
     run_episode_parity("map-15-15", 1_000_000, auto_schedule(1_000_000), 4, seed=123, node_capacity=(1 << 22) + 4096)
 
 
@@ -81,7 +81,7 @@ def test_config4_rs15_1m_sims_four_generation_schedule():
 
 def test_config3_rs11_100k_sims():
     """RockSample(11,11), 100 000 simulations per move (BASELINE config 3), five moves, on the solver's schedule for this
-    budget (12 500 x8 <= 100 000) and on round 1's (3125, 4, 50000)."""
+    budget (12 500 x32 <= 100 000) and on round 1's (3125, 4, 50000)."""
     from pomdpy_b200.solvers.pomcp import auto_schedule
     run_episode_parity("map-11-11", 100_000, auto_schedule(100_000), 5, seed=321, node_capacity=1 << 20)
     run_episode_parity("map-11-11", 100_000, (3125, 4, 50000), 5, seed=322, node_capacity=1 << 20)

@@ -20,19 +20,23 @@ for mv in range(moves):
     pl.search(n_sims, move=mv); st = pl.root_stats()
     c1 = pl.counters()
     times.append(c1["last_search_ns"] * 1e-6)
+    if mv > 0 and times[-1] >= max(times[1:]):
+        slow = (mv, pl.steplog().copy(), c1["generations"] - c0["generations"])
     print("move %d: %.3f ms, generations %d, tree levels/sim %.2f, plans %d, nodes %d" % (
         mv, times[-1], c1["generations"] - c0["generations"], (c1["levels"] - c0["levels"]) / n_sims,
-        c1["alloc_nodes"] - c0["alloc_nodes"], c1["nodes"]))
+        c1["alloc_nodes"] - c0["alloc_nodes"], c1["nodes"]), end="")
     mean = np.where(st["n"] > 0, st["qfix"] / 2.0 ** 24 / np.maximum(st["n"], 1), -1e30)
     a = int(np.argmax(mean))
+    print(", root visits before %d, action %d (n %d)" % (int(st["n"].sum()) - n_sims, a, int(st["n"][a])))
     o = om.step(cell, rocks, a, int(rng.integers(0, 1 << 53)), actual, sampled)
     cell, rocks = o.next_cell, o.next_rocks
     if o.terminal or not o.legal: break
     if a == 4: sampled |= 1 << int(t["cell"][cell])
     if pl.advance(a, o.obs_good, sampled, move=mv)["status"] == 2: break
 print("schedule", sched, "n_sims", n_sims, "median ms/move (after move 0): %.3f" % float(np.median(times[1:] or times)))
-L = pl.steplog()
-for g in range(min(120, c1["generations"] - c0["generations"])):
+print("phase log of the slowest move after move 0: move %d" % slow[0])
+L = slow[1]
+for g in range(min(120, slow[2])):
     print("gen %d: start %.1f  descend+rollout %.1f  backup %.1f  flush+barrier %.1f us" % ((g,) + tuple(L[g, k] / 1e3 for k in range(4))))
 print("phase totals us [start, descend+rollout, backup, flush+barrier]:", [round(float(x) / 1e3, 1) for x in L[126, :4]])
 if L[127].any():

@@ -8,7 +8,7 @@ scheds = [tuple(int(x) for x in s.split(',')) for s in sys.argv[4:]]
 t = golden_tables(tag); om = oracle_model(t); K = om.n_rocks
 for (w0, g, wmax) in scheds:
     pl = make_planner(t, seed=7, gen_w0=w0, gen_growth=g, gen_wmax=wmax, node_capacity=min(1 << 24, max(1 << 16, n_sims * 40)))
-    rets, steps, t0, tsearch, nsearch = [], [], time.time(), 0.0, 0
+    rets, steps, t0, tsearch, nsearch, nchecks = [], [], time.time(), 0.0, 0, 0
     for ep in range(neps):
         rng = np.random.default_rng(1000 + ep)
         actual = int(rng.integers(0, 1 << K))
@@ -22,6 +22,7 @@ for (w0, g, wmax) in scheds:
             mean[~legal] = -1e30
             best = np.flatnonzero(mean == mean.max()); a = int(best[rng.integers(0, len(best))])
             o = om.step(cell, rocks, a, int(rng.integers(0, 1 << 53)), actual, sampled)
+            nchecks += a > 4
             ret += disc * o.reward; disc *= 0.95; cell, rocks = o.next_cell, o.next_rocks
             if o.terminal or not o.legal: break
             if a == 4: sampled |= 1 << int(t["cell"][cell])
@@ -29,5 +30,5 @@ for (w0, g, wmax) in scheds:
         rets.append(ret); steps.append(mv + 1)
     r = np.array(rets)
     print(json.dumps(dict(map=tag, n_sims=n_sims, sched=(w0, g, wmax), episodes=neps, ret=round(float(r.mean()), 3), stderr=round(float(r.std() / np.sqrt(neps)), 3),
-                          steps=float(np.mean(steps)), search_ms=round(1e3 * tsearch / nsearch, 3), wall_s=round(time.time() - t0, 1))), flush=True)
+                          steps=float(np.mean(steps)), capped=float(np.mean(np.array(steps) >= 200)), check_moves=round(nchecks / nsearch, 3), search_ms=round(1e3 * tsearch / nsearch, 3), wall_s=round(time.time() - t0, 1))), flush=True)
     pl.close()
