@@ -764,10 +764,12 @@ static void gs_block(const orc_gs *h, uint32_t k, uint32_t sim, uint32_t move, u
     uint32_t ctr[4] = {k, sim, move, dom};
     orc_philox4x32_10(ctr, h->key, x);
 }
+static int g_gs_rollout_rounds = ORC_ROLLOUT_ROUNDS;   /* experiment switch (tests of the statistics only) */
+void orc_gs_set_rollout_rounds(int r) { g_gs_rollout_rounds = r; }
 static void gs_rollout_block(const orc_gs *h, uint32_t k, uint32_t sim, uint32_t move, uint32_t x[4])
 {
     uint32_t ctr[4] = {k, sim, move, DOM_SIM};
-    orc_philox4x32(ctr, h->key, x, ORC_ROLLOUT_ROUNDS);
+    orc_philox4x32(ctr, h->key, x, g_gs_rollout_rounds);
 }
 
 /* Mean of an edge from its integer statistics (0 for an unvisited edge: entry.mean_q_value starts at 0). */
