@@ -31,6 +31,22 @@ int vi_project_textbook_dev(int device, int S, int A, int Z, int G, const double
                             const double *gamma_dev, double *scratch_dev, double *proj_dev, void *stream,
                             char *err, int errlen);
 
+/* The same projection on the tcgen05 tensor cores, FAST mode: fp64 operands split into TF32 pairs (hi, lo), three
+ * kind::tf32 MMAs per k-step (hi.hi + hi.lo + lo.hi) into fp32 accumulators in tensor memory, TMA operand loads, fp64
+ * output -- fp32-grade accuracy (the fp64 DMMA path above stays the default and the parity path).
+ *   vi_split_tf32_dev:  hi[i] = tf32(x[i]), lo[i] = tf32(x[i] - hi[i])  (T is split once per model, not per backup)
+ *   vi_gemm_tf32x3_dev: C[M x N] (fp64, row-major) = A[M x K] . Bt[N x K]^T from the split operands (fp32 arrays,
+ *                       row-major = K-major); tile_n 128 or 256; M % 128 == 0, N % tile_n == 0, K % 32 == 0
+ *   vi_project_textbook_tf32x3_dev: proj as above from Thi / Tlo [A][S][S]; scratch_dev holds 2*S*Z*G floats. */
+int vi_split_tf32_dev(int device, long long n, const double *x_dev, float *hi_dev, float *lo_dev, void *stream,
+                      char *err, int errlen);
+int vi_gemm_tf32x3_dev(int device, int M, int N, int K, const float *Ahi_dev, const float *Alo_dev,
+                       const float *Bthi_dev, const float *Btlo_dev, double *C_dev, int tile_n, void *stream,
+                       char *err, int errlen);
+int vi_project_textbook_tf32x3_dev(int device, int S, int A, int Z, int G, const float *Thi_dev, const float *Tlo_dev,
+                                   const double *O_dev, const double *gamma_dev, float *scratch_dev, double *proj_dev,
+                                   int tile_n, void *stream, char *err, int errlen);
+
 /* Point-based backup for large |S| (the cross-sum of the exact backup taken at P belief points), all pointers on the
  * device, row-major fp64, asynchronous on `stream`:
  *   g*(a,p,o) = argmax_g b_p . proj[a][:, o, g]      (proj as above; scores by DMMA GEMMs [P x S] . [S x Z*G])
@@ -45,6 +61,14 @@ int vi_point_based_backup_dev(int device, int S, int A, int Z, int G, int P, con
                               double *value_dev, double *alpha_dev, int32_t *action_dev, int prune, double *pruned_dev,
                               int32_t *pruned_action_dev, int32_t *keep_dev, int32_t *n_out_dev, void *stream,
                               char *err, int errlen);
+
+/* The part of the point-based backup after the projection, for a proj_dev computed by either projection above
+ * (vi_point_based_backup_dev = vi_project_textbook_dev + this). */
+int vi_point_based_select_dev(int device, int S, int A, int Z, int G, int P, const double *R_dev,
+                              const double *beliefs_dev, double discount, const double *proj_dev, double *score_dev,
+                              int32_t *best_dev, double *value_dev, double *alpha_dev, int32_t *action_dev, int prune,
+                              double *pruned_dev, int32_t *pruned_action_dev, int32_t *keep_dev, int32_t *n_out_dev,
+                              void *stream, char *err, int errlen);
 
 /* Policy execution -- Agent.run_value_iteration (pomdpy/agent.py:215-264): per step the arg-max alpha vector gives the
  * action (value_iteration.py:161-181), the environment steps, the belief is updated (tiger_model.py:109-131 generalised

@@ -5,7 +5,7 @@ import subprocess
 HERE = os.path.dirname(os.path.abspath(__file__))
 CSRC = os.path.join(HERE, "csrc")
 LIB = os.path.join(HERE, "libpomcp_b200.so")
-SOURCES = ["pomcp_kernels.cu", "pomcp_refexact.cu", "vi_kernels.cu"]
+SOURCES = ["pomcp_kernels.cu", "pomcp_refexact.cu", "vi_kernels.cu", "vi_tcgen05.cu"]
 HEADERS = ["pomcp_device.cuh", "pomcp_state.cuh", "pomcp_models.cuh", "pomcp_plan.cuh",
            os.path.join("..", "..", "include", "pomcp_b200.h"),
            os.path.join("..", "..", "include", "vi_b200.h")]

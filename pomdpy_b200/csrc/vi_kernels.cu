@@ -337,20 +337,19 @@ __global__ void __launch_bounds__(256) vi_pb_alpha_kernel(int S, int Z, int G, i
     alpha[(size_t)p * S + s] = R[(size_t)a * S + s] + discount * fut;
 }
 
-extern "C" int vi_point_based_backup_dev(int device, int S, int A, int Z, int G, int P, const double *T_dev,
-                                         const double *O_dev, const double *R_dev, const double *gamma_dev,
-                                         const double *beliefs_dev, double discount, double *scratch_dev,
-                                         double *proj_dev, double *score_dev, int32_t *best_dev, double *value_dev,
-                                         double *alpha_dev, int32_t *action_dev, int prune, double *pruned_dev,
-                                         int32_t *pruned_action_dev, int32_t *keep_dev, int32_t *n_out_dev, void *stream,
-                                         char *err, int errlen)
+// the part of the point-based backup that follows the projection (proj_dev given, by either projection kernel)
+extern "C" int vi_point_based_select_dev(int device, int S, int A, int Z, int G, int P, const double *R_dev,
+                                         const double *beliefs_dev, double discount, const double *proj_dev,
+                                         double *score_dev, int32_t *best_dev, double *value_dev, double *alpha_dev,
+                                         int32_t *action_dev, int prune, double *pruned_dev, int32_t *pruned_action_dev,
+                                         int32_t *keep_dev, int32_t *n_out_dev, void *stream, char *err, int errlen)
 {
     const int N = Z * G;
     VCK(cudaSetDevice(device));
     if (P % GBM) { snprintf(err, errlen, "the number of belief points must be a multiple of 128"); return -1; }
+    if (S % GBK || N % GBN) { snprintf(err, errlen, "S must be a multiple of 16 and Z*G of 64"); return -1; }
     if (Z > 2048) { snprintf(err, errlen, "|Z| > 2048"); return -1; }
-    int rc = vi_project_textbook_dev(device, S, A, Z, G, T_dev, O_dev, gamma_dev, scratch_dev, proj_dev, stream, err, errlen);
-    if (rc) return rc;
+    VCK(cudaFuncSetAttribute(vi_dgemm_dmma_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)DGEMM_SMEM));
     cudaStream_t st = (cudaStream_t)stream;
     for (int a = 0; a < A; ++a) {                              // score[a] = B . proj[a]
         dim3 grid(N / GBN, P / GBM);
@@ -368,6 +367,24 @@ extern "C" int vi_point_based_backup_dev(int device, int S, int A, int Z, int G,
     }
     VCK(cudaGetLastError());
     return 0;
+}
+
+extern "C" int vi_point_based_backup_dev(int device, int S, int A, int Z, int G, int P, const double *T_dev,
+                                         const double *O_dev, const double *R_dev, const double *gamma_dev,
+                                         const double *beliefs_dev, double discount, double *scratch_dev,
+                                         double *proj_dev, double *score_dev, int32_t *best_dev, double *value_dev,
+                                         double *alpha_dev, int32_t *action_dev, int prune, double *pruned_dev,
+                                         int32_t *pruned_action_dev, int32_t *keep_dev, int32_t *n_out_dev, void *stream,
+                                         char *err, int errlen)
+{
+    VCK(cudaSetDevice(device));
+    if (P % GBM) { snprintf(err, errlen, "the number of belief points must be a multiple of 128"); return -1; }
+    if (Z > 2048) { snprintf(err, errlen, "|Z| > 2048"); return -1; }
+    int rc = vi_project_textbook_dev(device, S, A, Z, G, T_dev, O_dev, gamma_dev, scratch_dev, proj_dev, stream, err, errlen);
+    if (rc) return rc;
+    return vi_point_based_select_dev(device, S, A, Z, G, P, R_dev, beliefs_dev, discount, proj_dev, score_dev, best_dev,
+                                     value_dev, alpha_dev, action_dev, prune, pruned_dev, pruned_action_dev, keep_dev,
+                                     n_out_dev, stream, err, errlen);
 }
 
 // ---------------------------------------------------------------------------------------------------------

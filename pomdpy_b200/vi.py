@@ -99,6 +99,10 @@ def _lib():
         L.vi_point_based_backup_dev.argtypes = [C.c_int] * 6 + [vp] * 5 + [dbl] + [vp] * 7 + [C.c_int] + [vp] * 5 + \
                                                [C.c_char_p, C.c_int]
         u32, u64 = C.c_uint32, C.c_uint64
+        L.vi_split_tf32_dev.argtypes = [C.c_int, C.c_longlong, vp, vp, vp, vp, C.c_char_p, C.c_int]
+        L.vi_gemm_tf32x3_dev.argtypes = [C.c_int] * 4 + [vp] * 5 + [C.c_int, vp, C.c_char_p, C.c_int]
+        L.vi_project_textbook_tf32x3_dev.argtypes = [C.c_int] * 5 + [vp] * 6 + [C.c_int, vp, C.c_char_p, C.c_int]
+        L.vi_point_based_select_dev.argtypes = [C.c_int] * 6 + [vp] * 2 + [dbl] + [vp] * 6 + [C.c_int] + [vp] * 5 + [C.c_char_p, C.c_int]
         L.vi_policy_rollout_dev.argtypes = [C.c_int] * 5 + [vp] * 6 + [u32, dbl, C.c_int, C.c_int, u64, vp, vp, C.c_char_p, C.c_int]
         L.vi_expand_beliefs_dev.argtypes = [C.c_int] * 5 + [vp] * 3 + [u32, u64, vp, C.c_char_p, C.c_int]
         L._vi_ready = True
@@ -125,30 +129,75 @@ def solve_reference(T, O, R, discount, horizon, capacity=4096, device=0):
     return alpha[:n.value].copy(), act[:n.value].copy()
 
 
-def project_textbook(T, O, gamma, device=0):
-    """proj[a][s][o*G+g] = sum_s' T[a,s,s'] O[a,s',o] gamma[g,s'] on the fp64 tensor cores (torch CUDA tensors in,
-    torch CUDA tensor out; |S| and |O|*|G| multiples of 64)."""
+def split_tf32(x, device=0):
+    """fp64 CUDA tensor -> (hi, lo) float32 tensors with hi = tf32(x), lo = tf32(x - hi): the operands of the tcgen05
+    TF32 x 3 GEMM (include/vi_b200.h vi_split_tf32_dev)."""
+    import torch
+    assert x.is_cuda and x.dtype == torch.float64 and x.is_contiguous()
+    hi = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    lo = torch.empty(x.shape, dtype=torch.float32, device=x.device)
+    err = C.create_string_buffer(256)
+    rc = _lib().vi_split_tf32_dev(int(device), x.numel(), x.data_ptr(), hi.data_ptr(), lo.data_ptr(),
+                                  C.c_void_p(torch.cuda.current_stream().cuda_stream), err, 256)
+    if rc != 0:
+        raise native.PomcpError(err.value.decode() or "vi_split_tf32_dev failed")
+    return hi, lo
+
+
+def gemm_tf32x3(a_split, bt_split, tile_n=128, device=0):
+    """C [M x N] (fp64) = A [M x K] . Bt [N x K]^T on the tcgen05 tensor cores from split operands (split_tf32)."""
+    import torch
+    (ahi, alo), (bhi, blo) = a_split, bt_split
+    M, K = ahi.shape
+    N = bhi.shape[0]
+    out = torch.empty((M, N), dtype=torch.float64, device=ahi.device)
+    err = C.create_string_buffer(256)
+    rc = _lib().vi_gemm_tf32x3_dev(int(device), M, N, K, ahi.data_ptr(), alo.data_ptr(), bhi.data_ptr(), blo.data_ptr(),
+                                   out.data_ptr(), int(tile_n), C.c_void_p(torch.cuda.current_stream().cuda_stream), err, 256)
+    if rc != 0:
+        raise native.PomcpError(err.value.decode() or "vi_gemm_tf32x3_dev failed")
+    return out
+
+
+def project_textbook(T, O, gamma, device=0, precision="fp64", t_split=None, tile_n=128):
+    """proj[a][s][o*G+g] = sum_s' T[a,s,s'] O[a,s',o] gamma[g,s'] (torch CUDA tensors in, torch CUDA tensor out).
+    precision "fp64": the fp64 tensor cores (DMMA), exact (|S| and |O|*|G| multiples of 64);
+    precision "tf32x3": the tcgen05 tensor cores, operands split into TF32 pairs, fp32-grade (|S| a multiple of 128,
+    |O|*|G| of tile_n); t_split = split_tf32(T) can be passed to reuse the split of T across backups."""
     import torch
     A, S, _ = T.shape
     Z, G = O.shape[2], gamma.shape[0]
     for t in (T, O, gamma):
         assert t.is_cuda and t.dtype == torch.float64 and t.is_contiguous()
-    scratch = torch.empty(S * Z * G, dtype=torch.float64, device=T.device)
     proj = torch.empty((A, S, Z * G), dtype=torch.float64, device=T.device)
     err = C.create_string_buffer(256)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if precision == "tf32x3":
+        thi, tlo = t_split if t_split is not None else split_tf32(T, device)
+        scratch = torch.empty(2 * S * Z * G, dtype=torch.float32, device=T.device)
+        rc = _lib().vi_project_textbook_tf32x3_dev(int(device), S, A, Z, G, thi.data_ptr(), tlo.data_ptr(), O.data_ptr(),
+                                                   gamma.data_ptr(), scratch.data_ptr(), proj.data_ptr(), int(tile_n),
+                                                   stream, err, 256)
+        if rc != 0:
+            raise native.PomcpError(err.value.decode() or "vi_project_textbook_tf32x3_dev failed")
+        return proj
+    assert precision == "fp64"
+    scratch = torch.empty(S * Z * G, dtype=torch.float64, device=T.device)
     rc = _lib().vi_project_textbook_dev(int(device), S, A, Z, G, T.data_ptr(), O.data_ptr(), gamma.data_ptr(),
-                                        scratch.data_ptr(), proj.data_ptr(),
-                                        C.c_void_p(torch.cuda.current_stream().cuda_stream), err, 256)
+                                        scratch.data_ptr(), proj.data_ptr(), stream, err, 256)
     if rc != 0:
         raise native.PomcpError(err.value.decode() or "vi_project_textbook_dev failed")
     return proj
 
 
-def point_based_backup(T, O, R, gamma, beliefs, discount, prune=True, device=0, keep_work=False):
+def point_based_backup(T, O, R, gamma, beliefs, discount, prune=True, device=0, keep_work=False, precision="fp64",
+                       t_split=None, tile_n=128):
     """One point-based backup of `gamma` at the belief points (torch CUDA float64 tensors; |S| and the number of points
     multiples of 128, |O|*|Gamma| a multiple of 64): the textbook projection and the belief scores on the fp64 tensor
     cores, one new alpha vector per belief point, pointwise-dominance prune.  Returns (alpha [n][S], action [n]) and,
-    with keep_work, the dict of intermediate tensors (unpruned vectors, choices, values)."""
+    with keep_work, the dict of intermediate tensors (unpruned vectors, choices, values).
+    precision="tf32x3" takes the projection (95 % of the flops) on the tcgen05 tensor cores instead (fp32-grade,
+    |O|*|Gamma| a multiple of tile_n; t_split = split_tf32(T) reuses the split of T); scores and the rest stay fp64."""
     import torch
     A, S, _ = T.shape
     Z, G, P = O.shape[2], gamma.shape[0], beliefs.shape[0]
@@ -160,12 +209,21 @@ def point_based_backup(T, O, R, gamma, beliefs, discount, prune=True, device=0, 
     w = dict(scratch=f64(S * N), proj=f64(A, S, N), score=f64(A, P, N), best=i32(A, P, Z), value=f64(A, P),
              alpha=f64(P, S), action=i32(P), pruned=f64(P, S), pruned_action=i32(P), keep=i32(P), n_out=i32(1))
     err = C.create_string_buffer(256)
-    rc = _lib().vi_point_based_backup_dev(
-        int(device), S, A, Z, G, P, T.data_ptr(), O.data_ptr(), R.data_ptr(), gamma.data_ptr(), beliefs.data_ptr(),
-        float(discount), w["scratch"].data_ptr(), w["proj"].data_ptr(), w["score"].data_ptr(), w["best"].data_ptr(),
-        w["value"].data_ptr(), w["alpha"].data_ptr(), w["action"].data_ptr(), int(bool(prune)), w["pruned"].data_ptr(),
-        w["pruned_action"].data_ptr(), w["keep"].data_ptr(), w["n_out"].data_ptr(),
-        C.c_void_p(torch.cuda.current_stream().cuda_stream), err, 256)
+    stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
+    if precision == "tf32x3":
+        w["proj"] = project_textbook(T, O, gamma, device, precision="tf32x3", t_split=t_split, tile_n=tile_n)
+        rc = _lib().vi_point_based_select_dev(
+            int(device), S, A, Z, G, P, R.data_ptr(), beliefs.data_ptr(), float(discount), w["proj"].data_ptr(),
+            w["score"].data_ptr(), w["best"].data_ptr(), w["value"].data_ptr(), w["alpha"].data_ptr(),
+            w["action"].data_ptr(), int(bool(prune)), w["pruned"].data_ptr(), w["pruned_action"].data_ptr(),
+            w["keep"].data_ptr(), w["n_out"].data_ptr(), stream, err, 256)
+    else:
+        assert precision == "fp64"
+        rc = _lib().vi_point_based_backup_dev(
+            int(device), S, A, Z, G, P, T.data_ptr(), O.data_ptr(), R.data_ptr(), gamma.data_ptr(), beliefs.data_ptr(),
+            float(discount), w["scratch"].data_ptr(), w["proj"].data_ptr(), w["score"].data_ptr(), w["best"].data_ptr(),
+            w["value"].data_ptr(), w["alpha"].data_ptr(), w["action"].data_ptr(), int(bool(prune)), w["pruned"].data_ptr(),
+            w["pruned_action"].data_ptr(), w["keep"].data_ptr(), w["n_out"].data_ptr(), stream, err, 256)
     if rc != 0:
         raise native.PomcpError(err.value.decode() or "vi_point_based_backup_dev failed")
     if prune:

@@ -258,3 +258,50 @@ def test_gpu_textbook_projection_at_config5_state_count():
     want = np.einsum("art,ato,gt->arog", T[:, rows, :], O, gamma).reshape(A, len(rows), Z * G)
     assert np.abs(got - want).max() <= 1e-6 * np.abs(want).max()
     assert np.abs(got - want).max() <= 1e-12 * np.abs(want).max()      # fp64 tensor cores: far inside the bar
+
+
+@pytest.mark.gpu
+def test_gpu_tf32x3_gemm_on_tcgen05():
+    """The tcgen05 GEMM of the fast projection mode (vi_tcgen05.cu: TMA loads, kind::tf32 MMAs into TMEM, operands split
+    into TF32 pairs, three products per fp64 product) against float64 matmul.  Tolerance: 1e-5 x (|A| |B|^T) per entry --
+    fp32-grade; measured 3e-7 at K = 256, 2.7e-6 (tile 128, four partial accumulators) / 5.4e-6 (tile 256, two) at
+    K = 4096 on same-sign data, where the tensor core's fp32 accumulation is at its worst."""
+    import torch
+    from pomdpy_b200 import vi
+    torch.manual_seed(5)
+    for (M, N, K, tn) in ((256, 384, 512, 128), (128, 512, 1024, 256), (384, 256, 96, 128)):
+        a = torch.rand(M, K, dtype=torch.float64, device="cuda") - 0.3
+        bt = torch.rand(N, K, dtype=torch.float64, device="cuda") - 0.6
+        sa, sb = vi.split_tf32(a), vi.split_tf32(bt)
+        assert float(((a - sa[0].double() - sa[1].double()).abs() / a.abs().clamp_min(1e-300)).max()) < 2.0 ** -21
+        c = vi.gemm_tf32x3(sa, sb, tile_n=tn)
+        ref = a @ bt.T
+        assert float(((c - ref).abs() / (a.abs() @ bt.abs().T)).max()) < 1e-5, (M, N, K, tn)
+    with pytest.raises(Exception):
+        vi.gemm_tf32x3(vi.split_tf32(a[:100].contiguous()), sb)          # M not a multiple of 128
+
+
+@pytest.mark.gpu
+def test_gpu_tf32x3_projection_and_backup_follow_the_fp64_path():
+    """precision="tf32x3": the projection within 5e-6 of the largest entry of the exact (fp64 DMMA) one -- measured 6e-7 at
+    |S| = 256, 7e-6 at |S| = 4096, i.e. OUTSIDE the 1e-6 bar of the default path, which is why it is an option -- and a
+    point-based backup built on it gives the same value at every belief point to 1e-5."""
+    import torch
+    from pomdpy_b200 import vi
+    rng = np.random.default_rng(123)
+    S, A, Z, G, P = 256, 3, 8, 16, 128
+    T = rng.dirichlet(np.ones(S), size=(A, S))
+    O = rng.dirichlet(np.ones(Z), size=(A, S))
+    R = rng.uniform(-1, 1, size=(A, S))
+    gamma = rng.uniform(-1, 1, size=(G, S))
+    B = rng.dirichlet(np.ones(S) * 0.05, size=P)
+    Td, Od, Rd, Gd, Bd = (torch.from_numpy(np.ascontiguousarray(x)).cuda() for x in (T, O, R, gamma, B))
+    exact = vi.project_textbook(Td, Od, Gd)
+    t_split = vi.split_tf32(Td)
+    fast = vi.project_textbook(Td, Od, Gd, precision="tf32x3", t_split=t_split)
+    assert float((fast - exact).abs().max() / exact.abs().max()) < 5e-6
+    a0, _ = vi.point_based_backup(Td, Od, Rd, Gd, Bd, 0.95, prune=False)
+    a1, _ = vi.point_based_backup(Td, Od, Rd, Gd, Bd, 0.95, prune=False, precision="tf32x3", t_split=t_split)
+    v0, v1 = (Bd * a0).sum(dim=1), (Bd * a1).sum(dim=1)
+    assert float((v0 - v1).abs().max()) < 1e-5 * float(v0.abs().max())
+
