@@ -85,11 +85,12 @@ def synthetic(S=4096, A=16, Z=64, G=64):
     ev[1].record()
     torch.cuda.synchronize()
     ms_fast = ev[0].elapsed_time(ev[1]) / 3
-    fast256 = vi.project_textbook(Td, Od, Gd, precision="tf32x3", t_split=t_split, tile_n=256)
+    VARIANT2 = "persistent"
+    fast256 = vi.project_textbook(Td, Od, Gd, precision="tf32x3", t_split=t_split, variant=VARIANT2)
     torch.cuda.synchronize()
     ev[0].record()
     for _ in range(3):
-        fast256 = vi.project_textbook(Td, Od, Gd, precision="tf32x3", t_split=t_split, tile_n=256)
+        fast256 = vi.project_textbook(Td, Od, Gd, precision="tf32x3", t_split=t_split, variant=VARIANT2)
     ev[1].record()
     torch.cuda.synchronize()
     ms_fast256 = ev[0].elapsed_time(ev[1]) / 3
@@ -109,7 +110,7 @@ def synthetic(S=4096, A=16, Z=64, G=64):
                 "ms": ms_fast, "higher_is_better": True, "speedup_vs_fp64_dmma": ms / ms_fast,
                 "max_rel_err_vs_float64_numpy": err_fast, "max_rel_err_vs_fp64_kernel_all_entries": err_fast_vs_fp64_kernel,
                 "tile": "128 x 128, 4 partial accumulators (the default of precision='tf32x3')",
-                "tile_128x256_2_accumulators": {"ms": ms_fast256, "tflops_fp64_equivalent": flop / (ms_fast256 * 1e-3) / 1e12,
+                "persistent_2_accumulator_sets": {"ms": ms_fast256, "tflops_fp64_equivalent": flop / (ms_fast256 * 1e-3) / 1e12,
                                                 "max_rel_err_vs_fp64_kernel_all_entries": err_fast256,
                                                 "tf32_roofline_frac": 3.0 * flop / (ms_fast256 * 1e-3) / 1e12 / tf32_peak},
                 "roofline": {"bound": "tensor", "achieved": 3.0 * flop / (ms_fast * 1e-3) / 1e12, "peak": tf32_peak, "unit": "TFLOP/s",

@@ -36,16 +36,21 @@ int vi_project_textbook_dev(int device, int S, int A, int Z, int G, const double
  * output -- fp32-grade accuracy (the fp64 DMMA path above stays the default and the parity path).
  *   vi_split_tf32_dev:  hi[i] = tf32(x[i]), lo[i] = tf32(x[i] - hi[i])  (T is split once per model, not per backup)
  *   vi_gemm_tf32x3_dev: C[M x N] (fp64, row-major) = A[M x K] . Bt[N x K]^T from the split operands (fp32 arrays,
- *                       row-major = K-major); tile_n 128 or 256; M % 128 == 0, N % tile_n == 0, K % 32 == 0
+ *                       row-major = K-major); M % 128 == 0, N % 128 == 0, K % 32 == 0.
+ *                       variant: VI_TC_TILE128    one CTA per 128 x 128 tile, K in 4 partial accumulators (most accurate)
+ *                                VI_TC_PERSISTENT one CTA per SM walking the tiles, 2 partial accumulators, two accumulator
+ *                                                 sets in tensor memory: a tile's epilogue runs under the next tile's MMAs
  *   vi_project_textbook_tf32x3_dev: proj as above from Thi / Tlo [A][S][S]; scratch_dev holds 2*S*Z*G floats. */
+#define VI_TC_TILE128 0
+#define VI_TC_PERSISTENT 1
 int vi_split_tf32_dev(int device, long long n, const double *x_dev, float *hi_dev, float *lo_dev, void *stream,
                       char *err, int errlen);
 int vi_gemm_tf32x3_dev(int device, int M, int N, int K, const float *Ahi_dev, const float *Alo_dev,
-                       const float *Bthi_dev, const float *Btlo_dev, double *C_dev, int tile_n, void *stream,
+                       const float *Bthi_dev, const float *Btlo_dev, double *C_dev, int variant, void *stream,
                        char *err, int errlen);
 int vi_project_textbook_tf32x3_dev(int device, int S, int A, int Z, int G, const float *Thi_dev, const float *Tlo_dev,
                                    const double *O_dev, const double *gamma_dev, float *scratch_dev, double *proj_dev,
-                                   int tile_n, void *stream, char *err, int errlen);
+                                   int variant, void *stream, char *err, int errlen);
 
 /* Point-based backup for large |S| (the cross-sum of the exact backup taken at P belief points), all pointers on the
  * device, row-major fp64, asynchronous on `stream`:

@@ -144,8 +144,13 @@ def split_tf32(x, device=0):
     return hi, lo
 
 
-def gemm_tf32x3(a_split, bt_split, tile_n=128, device=0):
-    """C [M x N] (fp64) = A [M x K] . Bt [N x K]^T on the tcgen05 tensor cores from split operands (split_tf32)."""
+TC_VARIANTS = {"tile128": 0, "persistent": 1}      # include/vi_b200.h VI_TC_*
+
+
+def gemm_tf32x3(a_split, bt_split, variant="tile128", device=0):
+    """C [M x N] (fp64) = A [M x K] . Bt [N x K]^T on the tcgen05 tensor cores from split operands (split_tf32).
+    variant: "tile128" (one CTA per 128 x 128 tile, 4 partial accumulators: most accurate) or "persistent" (one CTA per
+    SM, 2 partial accumulators, a tile's epilogue under the next tile's MMAs: 3 % faster)."""
     import torch
     (ahi, alo), (bhi, blo) = a_split, bt_split
     M, K = ahi.shape
@@ -153,17 +158,18 @@ def gemm_tf32x3(a_split, bt_split, tile_n=128, device=0):
     out = torch.empty((M, N), dtype=torch.float64, device=ahi.device)
     err = C.create_string_buffer(256)
     rc = _lib().vi_gemm_tf32x3_dev(int(device), M, N, K, ahi.data_ptr(), alo.data_ptr(), bhi.data_ptr(), blo.data_ptr(),
-                                   out.data_ptr(), int(tile_n), C.c_void_p(torch.cuda.current_stream().cuda_stream), err, 256)
+                                   out.data_ptr(), TC_VARIANTS[variant], C.c_void_p(torch.cuda.current_stream().cuda_stream), err, 256)
     if rc != 0:
         raise native.PomcpError(err.value.decode() or "vi_gemm_tf32x3_dev failed")
     return out
 
 
-def project_textbook(T, O, gamma, device=0, precision="fp64", t_split=None, tile_n=128):
+def project_textbook(T, O, gamma, device=0, precision="fp64", t_split=None, variant="tile128"):
     """proj[a][s][o*G+g] = sum_s' T[a,s,s'] O[a,s',o] gamma[g,s'] (torch CUDA tensors in, torch CUDA tensor out).
     precision "fp64": the fp64 tensor cores (DMMA), exact (|S| and |O|*|G| multiples of 64);
     precision "tf32x3": the tcgen05 tensor cores, operands split into TF32 pairs, fp32-grade (|S| a multiple of 128,
-    |O|*|G| of tile_n); t_split = split_tf32(T) can be passed to reuse the split of T across backups."""
+    |O|*|G| of 128; variant as in gemm_tf32x3); t_split = split_tf32(T) can be passed to reuse the
+    split of T across backups."""
     import torch
     A, S, _ = T.shape
     Z, G = O.shape[2], gamma.shape[0]
@@ -176,7 +182,7 @@ def project_textbook(T, O, gamma, device=0, precision="fp64", t_split=None, tile
         thi, tlo = t_split if t_split is not None else split_tf32(T, device)
         scratch = torch.empty(2 * S * Z * G, dtype=torch.float32, device=T.device)
         rc = _lib().vi_project_textbook_tf32x3_dev(int(device), S, A, Z, G, thi.data_ptr(), tlo.data_ptr(), O.data_ptr(),
-                                                   gamma.data_ptr(), scratch.data_ptr(), proj.data_ptr(), int(tile_n),
+                                                   gamma.data_ptr(), scratch.data_ptr(), proj.data_ptr(), TC_VARIANTS[variant],
                                                    stream, err, 256)
         if rc != 0:
             raise native.PomcpError(err.value.decode() or "vi_project_textbook_tf32x3_dev failed")
@@ -191,13 +197,13 @@ def project_textbook(T, O, gamma, device=0, precision="fp64", t_split=None, tile
 
 
 def point_based_backup(T, O, R, gamma, beliefs, discount, prune=True, device=0, keep_work=False, precision="fp64",
-                       t_split=None, tile_n=128):
+                       t_split=None, variant="tile128"):
     """One point-based backup of `gamma` at the belief points (torch CUDA float64 tensors; |S| and the number of points
     multiples of 128, |O|*|Gamma| a multiple of 64): the textbook projection and the belief scores on the fp64 tensor
     cores, one new alpha vector per belief point, pointwise-dominance prune.  Returns (alpha [n][S], action [n]) and,
     with keep_work, the dict of intermediate tensors (unpruned vectors, choices, values).
     precision="tf32x3" takes the projection (95 % of the flops) on the tcgen05 tensor cores instead (fp32-grade,
-    |O|*|Gamma| a multiple of tile_n; t_split = split_tf32(T) reuses the split of T); scores and the rest stay fp64."""
+    variant as in gemm_tf32x3; t_split = split_tf32(T) reuses the split of T); scores and the rest stay fp64."""
     import torch
     A, S, _ = T.shape
     Z, G, P = O.shape[2], gamma.shape[0], beliefs.shape[0]
@@ -211,7 +217,7 @@ def point_based_backup(T, O, R, gamma, beliefs, discount, prune=True, device=0, 
     err = C.create_string_buffer(256)
     stream = C.c_void_p(torch.cuda.current_stream().cuda_stream)
     if precision == "tf32x3":
-        w["proj"] = project_textbook(T, O, gamma, device, precision="tf32x3", t_split=t_split, tile_n=tile_n)
+        w["proj"] = project_textbook(T, O, gamma, device, precision="tf32x3", t_split=t_split, variant=variant)
         rc = _lib().vi_point_based_select_dev(
             int(device), S, A, Z, G, P, R.data_ptr(), beliefs.data_ptr(), float(discount), w["proj"].data_ptr(),
             w["score"].data_ptr(), w["best"].data_ptr(), w["value"].data_ptr(), w["alpha"].data_ptr(),

@@ -264,17 +264,18 @@ def test_gpu_textbook_projection_at_config5_state_count():
 def test_gpu_tf32x3_gemm_on_tcgen05():
     """The tcgen05 GEMM of the fast projection mode (vi_tcgen05.cu: TMA loads, kind::tf32 MMAs into TMEM, operands split
     into TF32 pairs, three products per fp64 product) against float64 matmul.  Tolerance: 1e-5 x (|A| |B|^T) per entry --
-    fp32-grade; measured 3e-7 at K = 256, 2.7e-6 (tile 128, four partial accumulators) / 5.4e-6 (tile 256, two) at
+    fp32-grade; measured 3e-7 at K = 256, 2.7e-6 (tile 128, four partial accumulators) / 5.4e-6 (the persistent variant, two; 2048 x 2560 gives it more tiles than SMs, so both accumulator sets cycle) at
     K = 4096 on same-sign data, where the tensor core's fp32 accumulation is at its worst."""
     import torch
     from pomdpy_b200 import vi
     torch.manual_seed(5)
-    for (M, N, K, tn) in ((256, 384, 512, 128), (128, 512, 1024, 256), (384, 256, 96, 128)):
+    for (M, N, K, tn) in ((256, 384, 512, "tile128"), (128, 512, 1024, "persistent"), (384, 256, 96, "tile128"),
+                         (2048, 2560, 160, "persistent"), (128, 128, 32, "tile128")):
         a = torch.rand(M, K, dtype=torch.float64, device="cuda") - 0.3
         bt = torch.rand(N, K, dtype=torch.float64, device="cuda") - 0.6
         sa, sb = vi.split_tf32(a), vi.split_tf32(bt)
         assert float(((a - sa[0].double() - sa[1].double()).abs() / a.abs().clamp_min(1e-300)).max()) < 2.0 ** -21
-        c = vi.gemm_tf32x3(sa, sb, tile_n=tn)
+        c = vi.gemm_tf32x3(sa, sb, variant=tn)
         ref = a @ bt.T
         assert float(((c - ref).abs() / (a.abs() @ bt.abs().T)).max()) < 1e-5, (M, N, K, tn)
     with pytest.raises(Exception):
