@@ -272,7 +272,7 @@ vi_tf32x3_gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapAhi, con
             // ---- TMA producer: the ring runs on across tiles ----
             int s = 0; uint32_t ph = 0u;
             for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x) {
-                const int m0 = (tile % tiles_m) * TC_M, n0 = (tile / tiles_m) * TN;
+                const int m0 = (tile / tiles_n) * TC_M, n0 = (tile % tiles_n) * TN;   // as the per-tile kernel's grid: n fastest
                 for (int kb = 0; kb < nkb; ++kb) {
                     mbar_wait(smem_u32(&empty_bar[s]), ph ^ 1u);
                     const uint32_t st = ring + (uint32_t)s * L::STAGE_BYTES, fb = smem_u32(&full_bar[s]);
@@ -327,7 +327,7 @@ vi_tf32x3_gemm_persistent_kernel(const __grid_constant__ CUtensorMap mapAhi, con
         int it = 0;
         for (int tile = blockIdx.x; tile < n_tiles; tile += gridDim.x, ++it) {
             const int buf = it & 1; const uint32_t bph = (uint32_t)(it >> 1) & 1u;
-            const int m0 = (tile % tiles_m) * TC_M, n0 = (tile / tiles_m) * TN;
+            const int m0 = (tile / tiles_n) * TC_M, n0 = (tile % tiles_n) * TN;   // as the per-tile kernel's grid: n fastest
             mbar_wait(smem_u32(&acc_full[buf]), bph);
             asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
             double *crow = C + (size_t)(m0 + quarter * 32 + lane) * ldc + n0;
