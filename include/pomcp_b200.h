@@ -21,7 +21,8 @@ extern "C" {
 #define POMCP_MAX_CELLS 256
 #define POMCP_MAX_ROCKS 24
 #define POMCP_MAX_PEERS 8      /* root-parallel merge inside the search kernel: the GPUs of one NVSwitch box */
-#define POMCP_MAX_OBS 32       /* tabular models: |Z| <= 32 observations */
+#define POMCP_MAX_OBS 2048     /* tabular models: |Z| <= 2048 observations (11 bits of a path entry) */
+#define POMCP_MAX_OBS_DIRECT 32 /* ... up to here the child table is direct-indexed [node][action][Z]; above, hashed */
 #define POMCP_QFIX_SCALE 16777216.0 /* root statistics carry sum(q) as a 2^-24 fixed-point integer */
 
 typedef struct pomcp_handle pomcp_handle;
@@ -40,7 +41,9 @@ typedef struct {
     int32_t gen_w0;             /* generation schedule: w0, w0*growth, ... <= wmax simulations in flight */
     int32_t gen_growth;
     int32_t gen_wmax;
-    int32_t reserved1;
+    int32_t child_table;        /* tabular models: 0 = direct-indexed child table up to POMCP_MAX_OBS_DIRECT observations and
+                                 * hashed above; 1 = hashed always (same results; the reference's observation map is a dict
+                                 * per action node, discrete_pomdp/discrete_observation_mapping.py:12-47) */
 } pomcp_config;
 
 /* POMCP.__init__ / POMCP.reset(agent)  (pomdpy/solvers/pomcp.py:23-50, belief_tree_solver.py:20-40) */
@@ -60,7 +63,10 @@ int pomcp_set_model_rocksample(pomcp_handle *h, int rows, int cols, const int8_t
  * Oc[a][s'][z] likewise (every row must end at 0xFFFFFFFF); R[a][s]; term_action_mask marks the actions that end an
  * episode (Tiger: opening a door), term_state[s'] the absorbing states (may be NULL).  A packed state is the state
  * index; observations are indices 0..n_obs-1 (the obs_good argument of pomcp_advance / pomcp_node_stats).  Rows of
- * 64 or more states get a guide table on the device (same draws, fewer loads). */
+ * 64 or more states get a guide table on the device (same draws, fewer loads).  The reference keeps the children of an
+ * action node in a dict keyed by observation (discrete_pomdp/discrete_observation_mapping.py:12-47): up to
+ * POMCP_MAX_OBS_DIRECT observations the device table is direct-indexed, above it is an open-addressing hash table over
+ * (node, action, observation) -- same tree, same statistics (pomcp_config.child_table forces the hashed table). */
 int pomcp_set_model_tabular(pomcp_handle *h, int n_states, int n_actions, int n_obs, const uint32_t *Tc,
                             const uint32_t *Oc, const double *R, uint32_t term_action_mask,
                             const uint8_t *term_state);

@@ -604,9 +604,9 @@ float orc_det_logf_u32(uint32_t x)
  * A draw w picks the first index k with cdf[k] > min(w, 2^32 - 2): zero-probability entries are never picked.
  * An episode ends after an action of term_action_mask (Tiger: opening a door) or on entering a term_state.
  * ---------------------------------------------------------------------------------------------------------- */
-#define ORC_ZS_MAX 32
+#define ORC_Z_MAX 2048                   /* an observation index travels in 11 bits of a path entry on the device */
 typedef struct {
-    int32_t S, A, Z, ZS;                 /* ZS: observation stride of the child table (power of two >= Z) */
+    int32_t S, A, Z, ZS;                 /* ZS: power of two >= Z (the device's observation stride; unused here) */
     uint32_t term_action_mask;
     uint32_t *Tc, *Oc; double *R; uint8_t *term_state;
 } orc_tab;
@@ -614,7 +614,7 @@ typedef struct {
 orc_tab *orc_tab_create(int S, int A, int Z, const uint32_t *Tc, const uint32_t *Oc, const double *R,
                         uint32_t term_action_mask, const uint8_t *term_state)
 {
-    if (S < 1 || A < 1 || A > ORC_MAX_ACTIONS || Z < 1 || Z > ORC_ZS_MAX) return NULL;
+    if (S < 1 || A < 1 || A > ORC_MAX_ACTIONS || Z < 1 || Z > ORC_Z_MAX) return NULL;
     orc_tab *m = (orc_tab *)calloc(1, sizeof(orc_tab));
     m->S = S; m->A = A; m->Z = Z; m->ZS = 2; while (m->ZS < Z) m->ZS *= 2;
     m->term_action_mask = term_action_mask;
@@ -657,9 +657,13 @@ typedef struct {
 typedef struct {
     const orc_model *m; orc_world w;           /* RockSample ... */
     const orc_tab *tm;                         /* ... or a tabular model (m == NULL) */
-    int32_t A, ZS;                             /* action count, observation stride of the child table */
+    int32_t A, ZS;                             /* action count, observation count rounded up to a power of two */
     gs_node *nodes; int32_t n_nodes, cap_nodes; int32_t root;
-    int32_t *child;                            /* [cap_nodes][32][ZS] child ids keyed (action, observation), -1 = none */
+    /* Observation map of every action node, as the reference keeps it: a mapping observation -> child belief node
+     * that grows with the observations actually seen (discrete_observation_mapping.py:12-47, a dict per action
+     * node), so |Z| is unbounded.  Here: a chain of entries per (node, action). */
+    int32_t *omap_head;                        /* [cap_nodes][32] first entry of the chain, -1 = empty */
+    struct gs_oentry { int32_t obs, child, next; } *omap; int32_t n_omap, cap_omap;
     uint32_t *bag; int32_t n_bag;              /* packed states: cell | rocks << 8 */
     int32_t max_depth, dcap; double ucb_c, discount;
     uint32_t key[2];
@@ -691,21 +695,37 @@ static void gs_step(const orc_gs *h, uint32_t st, int a, uint32_t w1, uint32_t w
     }
 }
 
-static int32_t *gs_child(const orc_gs *h, int32_t X, int a, int o)
-{ return &h->child[((size_t)X * ORC_MAX_ACTIONS + (size_t)a) * (size_t)h->ZS + (size_t)o]; }
+/* get_belief / get_entry (discrete_observation_mapping.py:18-23, 43-47: a scan over the entries): the child of
+ * action node (X, a) under observation o, or -1 */
+static int32_t gs_child(const orc_gs *h, int32_t X, int a, int o)
+{
+    for (int32_t e = h->omap_head[(size_t)X * ORC_MAX_ACTIONS + (size_t)a]; e >= 0; e = h->omap[e].next)
+        if (h->omap[e].obs == o) return h->omap[e].child;
+    return -1;
+}
+/* create_belief (discrete_observation_mapping.py:25-31): a new entry; the caller has checked that there is none */
+static void gs_set_child(orc_gs *h, int32_t X, int a, int o, int32_t child)
+{
+    if (h->n_omap == h->cap_omap) {
+        h->cap_omap = h->cap_omap ? h->cap_omap * 2 : 1024;
+        h->omap = (struct gs_oentry *)realloc(h->omap, sizeof(struct gs_oentry) * (size_t)h->cap_omap);
+    }
+    int32_t *head = &h->omap_head[(size_t)X * ORC_MAX_ACTIONS + (size_t)a];
+    h->omap[h->n_omap].obs = o; h->omap[h->n_omap].child = child; h->omap[h->n_omap].next = *head;
+    *head = h->n_omap++;
+}
 
 static int32_t gs_new_node(orc_gs *h, int32_t cell)
 {
     if (h->n_nodes == h->cap_nodes) {
         h->cap_nodes = h->cap_nodes ? h->cap_nodes * 2 : 1024;
         h->nodes = (gs_node *)realloc(h->nodes, sizeof(gs_node) * (size_t)h->cap_nodes);
-        h->child = (int32_t *)realloc(h->child, sizeof(int32_t) * (size_t)h->cap_nodes * ORC_MAX_ACTIONS * (size_t)h->ZS);
+        h->omap_head = (int32_t *)realloc(h->omap_head, sizeof(int32_t) * (size_t)h->cap_nodes * ORC_MAX_ACTIONS);
     }
     gs_node *nd = &h->nodes[h->n_nodes];
     memset(nd, 0, sizeof(*nd));
     nd->cell = cell; nd->legal = gs_tag_legal(h, cell);
-    int32_t *c = gs_child(h, h->n_nodes, 0, 0);
-    for (int i = 0; i < ORC_MAX_ACTIONS * h->ZS; ++i) c[i] = -1;
+    for (int a = 0; a < ORC_MAX_ACTIONS; ++a) h->omap_head[(size_t)h->n_nodes * ORC_MAX_ACTIONS + a] = -1;
     return h->n_nodes++;
 }
 
@@ -736,7 +756,7 @@ orc_gs *orc_gs_create_tab(const orc_tab *tm, const uint32_t *bag_packed, int n_b
     h->root = gs_new_node(h, 0);
     return h;
 }
-void orc_gs_destroy(orc_gs *h) { if (!h) return; free(h->nodes); free(h->child); free(h->bag); free(h); }
+void orc_gs_destroy(orc_gs *h) { if (!h) return; free(h->nodes); free(h->omap_head); free(h->omap); free(h->bag); free(h); }
 void orc_gs_set_world(orc_gs *h, uint32_t actual, uint32_t sampled) { h->w.actual_mask = actual; h->w.sampled_mask = sampled; }
 
 /* --preferred_actions (rock_position_history.py:52-55): call right after orc_gs_create; the root gets fresh
@@ -1066,12 +1086,12 @@ int orc_gs_search(orc_gs *h, int64_t n_sims, uint32_t sim_offset, uint32_t move,
                 if (s->depth > h->max_tree_depth) h->max_tree_depth = s->depth;
                 s->st = o.next;
                 if (o.terminal) { s->status = 2; break; }
-                int32_t child = *gs_child(h, X, a, o.obs);                     /* :106 */
+                int32_t child = gs_child(h, X, a, o.obs);                      /* :106 */
                 if (child < 0) {
                     if (d + 1 >= dcap) { s->status = 1; break; }              /* depth cap of the tree: leaf (:119) */
                     child = gs_new_node(h, o.tag);                             /* :107-108 (N(X) > 0 here) */
                     gs_init_child(h, child, X, a, o.obs);
-                    *gs_child(h, X, a, o.obs) = child; h->n_created++;
+                    gs_set_child(h, X, a, o.obs, child); h->n_created++;
                 }
                 const int64_t Nc = child < nn0 ? gs_visits(&h->nodes[child]) : 0;
                 if (Nc == 0) { gs_virgin_step(h, s, child, move); break; }
@@ -1118,7 +1138,7 @@ void orc_gs_counters(const orc_gs *h, int64_t out[8])
 int orc_gs_node_stats(const orc_gs *h, const int32_t *path_ao, int len, int64_t *n, int64_t *qfix, uint32_t *legal, int32_t *cell)
 {
     int32_t X = h->root;
-    for (int i = 0; i < len; ++i) { X = *gs_child(h, X, path_ao[2 * i], path_ao[2 * i + 1]); if (X < 0) return 1; }
+    for (int i = 0; i < len; ++i) { X = gs_child(h, X, path_ao[2 * i], path_ao[2 * i + 1]); if (X < 0) return 1; }
     const gs_node *nd = &h->nodes[X];
     for (int a = 0; a < h->A; ++a) { n[a] = nd->n[a]; qfix[a] = nd->qfix[a]; }
     *legal = nd->legal; *cell = nd->cell;
@@ -1160,7 +1180,7 @@ int64_t orc_gs_update(orc_gs *h, int action, int obs_good, uint32_t sampled_mask
     *tries_used = t;
     if (got == 0) { free(nb); *status = 2; return 0; }
     /* child position: make_next_position on the node's cell (rock_position_history.py:96-99) */
-    int32_t child = *gs_child(h, h->root, action, obs);
+    int32_t child = gs_child(h, h->root, action, obs);
     *status = 0;
     if (child < 0) {
         int32_t tag = 0;

@@ -27,6 +27,9 @@ CASES = [
     dict(kind="tab", model="tiger", seed=7, n_sims=20000, sched=(32, 2, 2048), ucb=30.0),
     dict(kind="tab", model="rand-40-6-8", seed=8, n_sims=10000, sched=(16, 4, 1024), ucb=10.0),
     dict(kind="tab", model="rand-300-32-3", seed=9, n_sims=10000, sched=(64, 4, 4096), ucb=8.0),
+    # more than 32 observations: the observation map is unbounded (hashed child table on the device)
+    dict(kind="tab", model="rand-48-4-64", seed=10, n_sims=12000, sched=(32, 4, 4096), ucb=10.0),
+    dict(kind="tab", model="rand-24-3-300", seed=11, n_sims=8000, sched=(16, 4, 2048), ucb=6.0),
 ]
 
 

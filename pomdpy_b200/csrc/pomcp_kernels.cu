@@ -182,19 +182,10 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
             const float pa = (float)(r.th - (lane == 0 ? 0u : th_prev)) * (1.0f / 4294967296.0f);
             const float kpre = kx * pa;
             const int na = lane < A ? p.t.n[(size_t)X * AS + lane] : 0;
-            for (int o = 0; o < ZS; ++o) {
-                int child = -1; float kc = 0.0f;
-                if (lane < A && na > 0 && kpre >= pc_min_k) {
-                    const uint32_t c = p.t.child[((size_t)X * AS + lane) * ZS + o];
-                    if (c != 0u && c != CHILD_LOCKED) {
-                        const int id = CHILD_ID(c);
-                        const int N = row_sum(p.t.n + (size_t)id * AS);
-                        kc = kpre * ((float)N / (float)na);
-                        if (N > 0 && kc >= pc_min_k) child = id;
-                    }
-                }
+            // queue the hot children a round of lanes found: reserve, write, publish in reservation order
+            const auto enqueue = [&](int child, float kc) {
                 const unsigned hot = __ballot_sync(FULL, child >= 0);
-                if (hot) {                                           // queue them: reserve, write, publish in reservation order
+                if (hot) {
                     const int m = __popc(hot);
                     int base_slot = 0;
                     if (lane == 0) { atomicAdd(&sq[2], m); base_slot = atomicAdd(&sq[3], m); }
@@ -210,6 +201,47 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                             while (*((volatile int *)&sq[1]) != base_slot) { }     // earlier reservations publish first
                             *((volatile int *)&sq[1]) = base_slot + n_ok;
                         }
+                    }
+                }
+            };
+            bool hashed = false;
+            if constexpr (KIND == 1) hashed = p.t.ckey != nullptr;
+            if (!hashed) {
+                for (int o = 0; o < ZS; ++o) {
+                    int child = -1; float kc = 0.0f;
+                    if (lane < A && na > 0 && kpre >= pc_min_k) {
+                        const uint32_t c = p.t.child[((size_t)X * AS + lane) * ZS + o];
+                        if (c != 0u && c != CHILD_LOCKED) {
+                            const int id = CHILD_ID(c);
+                            const int N = row_sum(p.t.n + (size_t)id * AS);
+                            kc = kpre * ((float)N / (float)na);
+                            if (N > 0 && kc >= pc_min_k) child = id;
+                        }
+                    }
+                    enqueue(child, kc);
+                }
+            } else {
+                // hashed child table: only a few actions carry enough simulations; for each of them the lanes probe
+                // 32 observations at a time (which children end up in the cache changes no result, see above)
+                unsigned hot_a = __ballot_sync(FULL, lane < A && na > 0 && kpre >= pc_min_k);
+                while (hot_a) {
+                    const int a = __ffs((int)hot_a) - 1;
+                    hot_a &= hot_a - 1;
+                    const float kpre_a = __shfl_sync(FULL, kpre, a);
+                    const int na_a = __shfl_sync(FULL, na, a);
+                    for (int o0 = 0; o0 < MD::n_obs(mc); o0 += 32) {
+                        int child = -1; float kc = 0.0f;
+                        const long long cs = o0 + lane < MD::n_obs(mc) ? child_slot_hashed<false>(p.t, X, a, o0 + lane) : -1;
+                        if (cs >= 0) {
+                            const uint32_t c = __ldcg(&p.t.child[cs]);
+                            if (c != 0u && c != CHILD_LOCKED) {
+                                const int id = CHILD_ID(c);
+                                const int N = row_sum(p.t.n + (size_t)id * AS);
+                                kc = kpre_a * ((float)N / (float)na_a);
+                                if (N > 0 && kc >= pc_min_k) child = id;
+                            }
+                        }
+                        enqueue(child, kc);
                     }
                 }
             }
@@ -423,10 +455,16 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                     if (so.terminal) status = 2;
                     else if (virgin) status = 1;                     // leaf
                     else {
-                        const size_t cslot = ((size_t)X * AS + a) * ZS + so.obs;
+                        size_t cslot = ((size_t)X * AS + a) * ZS + so.obs;
+                        bool have_slot = true;
+                        if constexpr (KIND == 1) if (p.t.ckey) {                            // hashed table: the edge's slot
+                            const long long cs = d < p.dcap ? child_slot_hashed<true>(p.t, X, a, so.obs)
+                                                            : child_slot_hashed<false>(p.t, X, a, so.obs);
+                            have_slot = cs >= 0; cslot = have_slot ? (size_t)cs : 0;
+                        }
                         uint32_t cmask = MD::tag_legal(mc, so.tag); bool have_mask = false;   // the child's action set
-                        uint32_t c = p.t.child[cslot];                                      // :106
-                        if (c == 0 && d < p.dcap) {                                         // :107-108 (N(X) > 0 here)
+                        uint32_t c = have_slot ? p.t.child[cslot] : 0u;                     // :106
+                        if (c == 0 && d < p.dcap && have_slot) {                            // :107-108 (N(X) > 0 here)
                             // one CAS per distinct child slot among the lanes that got here together
                             const unsigned cm = __activemask();
                             const unsigned same = __match_any_sync(cm, (unsigned long long)cslot);
@@ -850,7 +888,13 @@ __device__ __forceinline__ void advance_body(const AdvanceParams &p, unsigned ch
         S->sampled = sampled;                                        // belief_tree_solver.py:165 happens first
         if (accepted == 0) { S->adv_status = 2; S->adv_root_cell = p.t.cell[root]; }
         else {
-            uint32_t c = p.obs_good < 0 ? 0u : p.t.child[((size_t)root * AS + p.action) * ZS + p.obs_good];  // belief_tree_solver.py:167
+            uint32_t c = 0u;                                                          // belief_tree_solver.py:167
+            bool hashed = false;
+            if constexpr (KIND == 1) hashed = p.t.ckey != nullptr;
+            if (p.obs_good >= 0 && hashed) {
+                const long long cs = child_slot_hashed<false>(p.t, root, p.action, p.obs_good);
+                if (cs >= 0) c = __ldcg(&p.t.child[cs]);
+            } else if (p.obs_good >= 0) c = p.t.child[((size_t)root * AS + p.action) * ZS + p.obs_good];
             int status = 0, id;
             if (c == 0) {                                            // never expanded: fresh node at the next position
                 id = S->node_count++;
@@ -949,15 +993,32 @@ __global__ void pomcp_clear_arena_kernel(const DevState *S, Tree t, int zs, long
 {
     long long n = S->node_count;
     if (n > upper) n = upper;
-    const long long n4 = n * (AS * 4 / 16), q4 = n * (AS * 8 / 16), c4 = n * ((long long)AS * zs * 4 / 16);
+    const long long n4 = n * (AS * 4 / 16), q4 = n * (AS * 8 / 16);
+    // direct table: the rows of the used nodes; hashed table: every slot, keys and values (entries sit anywhere)
+    const long long c4 = t.ckey ? ((long long)t.cmask + 1) * 4 / 16 : n * ((long long)AS * zs * 4 / 16);
+    const long long k4 = t.ckey ? ((long long)t.cmask + 1) * 8 / 16 : 0;
     const uint4 z = make_uint4(0u, 0u, 0u, 0u);
     uint4 *pn = reinterpret_cast<uint4 *>(t.n), *pq = reinterpret_cast<uint4 *>(t.qfix), *pc = reinterpret_cast<uint4 *>(t.child);
+    uint4 *pk = reinterpret_cast<uint4 *>(t.ckey);
     const long long stride = (long long)gridDim.x * blockDim.x;
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < q4; i += stride) {
         pq[i] = z;
         if (i < n4) pn[i] = z;
     }
     for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < c4; i += stride) pc[i] = z;
+    for (long long i = blockIdx.x * (long long)blockDim.x + threadIdx.x; i < k4; i += stride) pk[i] = z;
+}
+
+// The child entry of edge (X, a, o) -- id + 1, 0 = none, ~0 = being created -- into *out (pomcp_node_stats walks a
+// path with it; direct or hashed table alike).
+__global__ void pomcp_find_child_kernel(Tree t, int zs, int X, int a, int o, uint32_t *out)
+{
+    uint32_t c = 0u;
+    if (t.ckey) {
+        const long long cs = child_slot_hashed<false>(t, X, a, o);
+        if (cs >= 0) c = t.child[cs];
+    } else c = t.child[((size_t)X * AS + a) * (size_t)zs + o];
+    *out = c;
 }
 
 // Root edge statistics as 2*AS 64-bit integers (n[0..AS), qfix[0..AS)) in a caller-provided device buffer: the
@@ -986,6 +1047,7 @@ struct pomcp_handle {
     int n_thr = 0;
     int kind = 0;                   // 0 RockSample, 1 tabular
     int zs = 2;                     // observation stride of the child table
+    bool hashed = false;            // ... or a hashed child table (tabular models with more than 32 observations)
     int n_actions = 0;
     TabHeader tab{};
     TabTables tt{};
@@ -1054,6 +1116,7 @@ extern "C" int pomcp_create(const pomcp_config *cfg, int device, pomcp_handle **
     *out = h;                          // returned even on failure so that pomcp_last_error() can be read
     h->cfg = *cfg; h->device = device;
     if (cfg->max_depth < 1 || cfg->max_depth > 4096) return fail(h, "max_depth out of range [1, 4096]");
+    if (cfg->child_table < 0 || cfg->child_table > 1) return fail(h, "child_table must be 0 (auto) or 1 (hashed)");
     if (cfg->tree_depth_cap < 2 || cfg->tree_depth_cap > 64) return fail(h, "tree_depth_cap out of range [2, 64]");
     if (cfg->gen_w0 < 1 || cfg->gen_growth < 1 || cfg->gen_wmax < cfg->gen_w0) return fail(h, "bad generation schedule");
     if (cfg->node_capacity < 2 || cfg->node_capacity > (1ll << 25)) return fail(h, "node_capacity out of range [2, 2^25]");
@@ -1102,15 +1165,34 @@ static int release_tabular(pomcp_handle *h)
     return 0;
 }
 
-// (Re)allocate the child table for an observation stride of `zs` slots per (node, action).
-static int set_child_stride(pomcp_handle *h, int zs)
+// (Re)allocate the child table: direct-indexed with an observation stride of `zs` slots per (node, action), or
+// hashed over (node, action, observation) with a power-of-two slot count >= 2 * node_capacity (pomcp_state.cuh).
+static int set_child_stride(pomcp_handle *h, int zs, bool hashed)
 {
+    if (hashed) {
+        size_t slots = 1024;
+        while (slots < 2 * (size_t)h->cap) slots *= 2;            // cap <= 2^25: at most 2^26 slots (pending refs fit 31 bits)
+        if (!h->hashed || h->t.cmask != (uint32_t)(slots - 1)) {
+            CK(cudaDeviceSynchronize());
+            cudaFree(h->t.child); h->t.child = nullptr;
+            cudaFree(h->t.ckey); h->t.ckey = nullptr;
+            CK(cudaMalloc(&h->t.child, slots * sizeof(uint32_t)));
+            CK(cudaMalloc(&h->t.ckey, slots * sizeof(unsigned long long)));
+            CK(cudaMemset(h->t.child, 0, slots * sizeof(uint32_t)));
+            CK(cudaMemset(h->t.ckey, 0, slots * sizeof(unsigned long long)));
+            h->t.cmask = (uint32_t)(slots - 1);
+            h->hashed = true; h->zs = zs;
+        }
+        h->zs = zs;
+        return 0;
+    }
     // a child slot that is still being created is referred to as -1 - slot index in a 32-bit path entry
     if ((unsigned long long)h->cap * AS * (unsigned long long)zs > (1ull << 31))
         return fail(h, "node_capacity * 32 * observation stride exceeds 2^31 child slots: lower node_capacity");
-    if (zs != h->zs) {
+    if (zs != h->zs || h->hashed) {
         CK(cudaDeviceSynchronize());
         cudaFree(h->t.child); h->t.child = nullptr;
+        cudaFree(h->t.ckey); h->t.ckey = nullptr; h->t.cmask = 0u; h->hashed = false;
         CK(cudaMalloc(&h->t.child, (size_t)h->cap * AS * (size_t)zs * sizeof(uint32_t)));
         CK(cudaMemset(h->t.child, 0, (size_t)h->cap * AS * (size_t)zs * sizeof(uint32_t)));
         h->zs = zs;
@@ -1159,7 +1241,7 @@ extern "C" int pomcp_set_model_rocksample(pomcp_handle *h, int rows, int cols, c
     CK(cudaMemcpy(h->dmodel, &m, sizeof(m), cudaMemcpyHostToDevice));
     if (release_tabular(h)) return -1;
     h->kind = 0; h->n_actions = m.n_actions;
-    if (set_child_stride(h, 2)) return -1;
+    if (set_child_stride(h, 2, false)) return -1;
     // launch geometry of the cooperative search kernel
     const int A = m.n_actions;
     size_t smem = ((sizeof(ModelHeader) + 15) & ~size_t(15)) + (((size_t)h->n_thr * 4 + 15) & ~size_t(15)) +
@@ -1186,7 +1268,7 @@ extern "C" int pomcp_set_model_tabular(pomcp_handle *h, int n_states, int n_acti
     CK(cudaSetDevice(h->device));
     if (n_states < 1 || n_states > (1 << 16)) return fail(h, "n_states out of range [1, 65536]");
     if (n_actions < 1 || n_actions > POMCP_MAX_ACTIONS) return fail(h, "n_actions out of range [1, 32]");
-    if (n_obs < 1 || n_obs > POMCP_MAX_OBS) return fail(h, "n_obs out of range [1, 32]");
+    if (n_obs < 1 || n_obs > POMCP_MAX_OBS) return fail(h, "n_obs out of range [1, 2048]");
     if (!Tc || !Oc || !R) return fail(h, "null model table");
     const size_t S = (size_t)n_states, A = (size_t)n_actions, Z = (size_t)n_obs;
     for (size_t r = 0; r < A * S; ++r) {                    // every cumulative row must end saturated
@@ -1209,7 +1291,9 @@ extern "C" int pomcp_set_model_tabular(pomcp_handle *h, int n_states, int n_acti
     TabHeader &t = h->tab;
     memset(&t, 0, sizeof(t));
     t.S = n_states; t.A = n_actions; t.Z = n_obs; t.ZS = zs; t.term_action_mask = term_action_mask;
-    t.stage_d1 = ((size_t)(1 + zs * n_actions) * n_actions * 12 <= (size_t)(24 << 10)) ? 1 : 0;
+    // child table: direct-indexed [node][action][zs] up to POMCP_MAX_OBS_DIRECT observations, hashed above (or on request)
+    const bool hashed = n_obs > POMCP_MAX_OBS_DIRECT || h->cfg.child_table == 1;
+    t.stage_d1 = (!hashed && (size_t)(1 + zs * n_actions) * n_actions * 12 <= (size_t)(24 << 10)) ? 1 : 0;
     // Guide table of the transition rows (|S| >= 64): 2^bits buckets per row, about four thresholds per bucket, at
     // most 256 MB in total.  guide[j] = first index whose threshold exceeds j << (32 - bits); guide[2^bits] = S - 1.
     int gbits = 0;
@@ -1241,7 +1325,7 @@ extern "C" int pomcp_set_model_tabular(pomcp_handle *h, int n_states, int n_acti
     h->hmodel.n_actions = n_actions; h->hmodel.n_cells = 1;
     h->hmodel.legal[0] = n_actions >= 32 ? 0xFFFFFFFFu : ((1u << n_actions) - 1u);
     CK(cudaMemcpy(h->dmodel, &h->hmodel, sizeof(h->hmodel), cudaMemcpyHostToDevice));
-    if (set_child_stride(h, zs)) return -1;
+    if (set_child_stride(h, zs, hashed)) return -1;
     if (!h->b.path_rew)
         CK(cudaMalloc(&h->b.path_rew, (size_t)h->cfg.gen_wmax * (size_t)h->cfg.tree_depth_cap * sizeof(double)));
     const size_t n_acc = t.stage_d1 ? (size_t)(1 + zs * n_actions) * n_actions : (size_t)n_actions;
@@ -1312,7 +1396,7 @@ static int clear_arena(pomcp_handle *h, cudaStream_t s)
     const long long n = h->zeroed_upto < h->cap ? h->zeroed_upto : h->cap;
     if (n > 0) {                                             // `arrive` keeps its stamps: they are never reused
         long long blocks = (n * (AS * 8 / 16) + 255) / 256;
-        if (blocks > 148 * 8) blocks = 148 * 8;
+        if (blocks > 148 * 8 || h->hashed) blocks = 148 * 8;    // (a hashed child table is cleared as a whole)
         pomcp_clear_arena_kernel<<<(int)blocks, 256, 0, s>>>(h->dS, h->t, h->zs, n);
         CK(cudaGetLastError());
         ++h->launches;
@@ -1487,7 +1571,11 @@ extern "C" int pomcp_node_stats(pomcp_handle *h, const int32_t *path_ao, int len
         const int a = path_ao[2 * i], o = path_ao[2 * i + 1];
         if (a < 0 || a >= h->n_actions || o < 0 || o >= h->zs) return fail(h, "bad path entry");
         uint32_t c;
-        CK(cudaMemcpy(&c, h->t.child + ((size_t)X * AS + a) * (size_t)h->zs + o, sizeof(c), cudaMemcpyDeviceToHost));
+        uint32_t *cell_c = reinterpret_cast<uint32_t *>(&h->dS->pad_c[0]);
+        pomcp_find_child_kernel<<<1, 1, 0, h->last_stream>>>(h->t, h->zs, X, a, o, cell_c);
+        CK(cudaGetLastError());
+        CK(cudaStreamSynchronize(h->last_stream));
+        CK(cudaMemcpy(&c, cell_c, sizeof(c), cudaMemcpyDeviceToHost));
         if (c == 0 || c == CHILD_LOCKED) return 1;
         X = CHILD_ID(c);
     }

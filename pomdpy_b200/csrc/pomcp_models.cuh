@@ -39,6 +39,7 @@ template <> struct Mdl<0> {
     }
     static __device__ __forceinline__ int n_actions(const Ctx &c, const ModelHeader *gm) { return gm->n_actions; }
     static __device__ __forceinline__ int zs(const Ctx &) { return 2; }
+    static __device__ __forceinline__ int n_obs(const Ctx &) { return 2; }
     static __device__ __forceinline__ bool stage_d1(const Ctx &) { return true; }
     static __device__ __forceinline__ uint32_t state_tag(uint32_t st) { return st & 0xFFu; }
     static __device__ __forceinline__ uint32_t tag_legal(const Ctx &c, uint32_t tag) { return c.M.hdr->legal[tag]; }
@@ -149,6 +150,7 @@ template <> struct Mdl<1> {
     { c.h = h; c.t = t; return 0; }
     static __device__ __forceinline__ int n_actions(const Ctx &c, const ModelHeader *) { return c.h.A; }
     static __device__ __forceinline__ int zs(const Ctx &c) { return c.h.ZS; }
+    static __device__ __forceinline__ int n_obs(const Ctx &c) { return c.h.Z; }
     static __device__ __forceinline__ bool stage_d1(const Ctx &c) { return c.h.stage_d1 != 0; }
     static __device__ __forceinline__ uint32_t state_tag(uint32_t) { return 0u; }
     static __device__ __forceinline__ uint32_t tag_legal(const Ctx &c, uint32_t)

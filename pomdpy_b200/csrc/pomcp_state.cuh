@@ -97,6 +97,10 @@ struct Tree {                          // structure-of-arrays belief-tree arena
     long long *qfix;                   // [cap][AS]   sum of q in 2^-24 fixed point
     uint32_t *child;                   // [cap][AS][ZS] child id + 1 keyed (action, observation); 0 = none, ~0 = being
                                        //              created.  ZS = 2 for RockSample (obs_good)
+                                       // hashed table (ckey != null): [cmask + 1] values, slot found through ckey
+    unsigned long long *ckey;          // hashed child table (tabular models with |Z| > 32): [cmask + 1] keys
+                                       //              1 + ((node * AS + action) << 11 | observation); 0 = free slot
+    uint32_t cmask, cpad;              //              slots - 1 (a power of two >= 2 * cap: load factor <= 1/2)
     uint32_t *legal;                   // [cap]       legal-action mask (fixed at creation)
     int32_t *cell;                     // [cap]       tag of the node: robot cell (RockSample), 0 (tabular)
     uint4 *plan;                       // [cap][2]    action plan of the node for the generation `stamp`:
@@ -107,6 +111,33 @@ struct Tree {                          // structure-of-arrays belief-tree arena
     int16_t *good;                     // [cap][24]   --preferred_actions: goodness number per rock
     const double *prob;                // [cells][n_rocks] sensor correctness probability
 };
+
+// Hashed child table.  The reference's observation map is a dict per action node that grows with the observations
+// seen (discrete_pomdp/discrete_observation_mapping.py:12-47), so |Z| is unbounded; a direct-indexed [node][action][Z]
+// table is 128 * Z bytes per node, while a node has exactly one parent edge.  For |Z| > 32 the table is open
+// addressing over (node, action, observation) with linear probing: the KEY array fixes which slot an edge owns
+// (insert-only, CAS 0 -> key: every thread that asks for the same edge gets the same slot, whoever came first), the
+// VALUE array keeps the protocol of the direct table (0 -> CHILD_LOCKED -> id + 1).  Slot numbers depend on insertion
+// order and never leave the table code; ids, statistics and results do not.
+__device__ __forceinline__ unsigned long long child_key(int X, int a, int obs)
+{ return (((((unsigned long long)(unsigned)X * AS) + (unsigned)a) << 11) | (unsigned)obs) + 1ull; }
+
+template <bool CREATE>
+__device__ __forceinline__ long long child_slot_hashed(const Tree &t, int X, int a, int obs)
+{
+    const unsigned long long key = child_key(X, a, obs);
+    uint32_t s = (uint32_t)((key * 0x9E3779B97F4A7C15ull) >> 32) & t.cmask;
+    for (uint32_t probe = 0; probe <= t.cmask; ++probe, s = (s + 1u) & t.cmask) {
+        unsigned long long k = __ldcg(&t.ckey[s]);                  // (keys land in this very phase: never from L1)
+        if (k == key) return (long long)s;
+        if (k == 0ull) {
+            if (!CREATE) return -1;
+            k = atomicCAS(&t.ckey[s], 0ull, key);
+            if (k == 0ull || k == key) return (long long)s;
+        }
+    }
+    return -1;                                                       // table full (cannot happen below node_capacity)
+}
 
 struct SimBuf {                        // what a simulation hands from the descent to the backup, SoA over the generation
     uint8_t *flag;                     // 2 ended in the tree (terminal / horizon), 3 ended with a rollout

@@ -23,7 +23,7 @@ class Config(C.Structure):
     _fields_ = [("max_depth", C.c_int32), ("tree_depth_cap", C.c_int32), ("max_particle_count", C.c_int32),
                 ("reserved0", C.c_int32), ("ucb_coefficient", C.c_double), ("discount", C.c_double),
                 ("seed", C.c_uint64), ("node_capacity", C.c_int64), ("gen_w0", C.c_int32),
-                ("gen_growth", C.c_int32), ("gen_wmax", C.c_int32), ("reserved1", C.c_int32)]
+                ("gen_growth", C.c_int32), ("gen_wmax", C.c_int32), ("child_table", C.c_int32)]
 
 
 EXPORTS = ["pomcp_create", "pomcp_destroy", "pomcp_last_error", "pomcp_set_model_rocksample", "pomcp_set_world",
@@ -105,11 +105,11 @@ class Planner:
     """One device-resident POMCP planner (tree arena + belief) behind the C ABI."""
 
     def __init__(self, max_depth=100, tree_depth_cap=64, max_particle_count=2000, ucb_coefficient=3.0,
-                 discount=0.95, seed=0, node_capacity=1 << 20, gen_w0=32, gen_growth=2, gen_wmax=1 << 17, device=0):
+                 discount=0.95, seed=0, node_capacity=1 << 20, gen_w0=32, gen_growth=2, gen_wmax=1 << 17, device=0, hashed_children=False):
         self.lib = load()
         self.cfg = Config(int(max_depth), int(tree_depth_cap), int(max_particle_count), 0, float(ucb_coefficient),
                           float(discount), int(seed) & 0xFFFFFFFFFFFFFFFF, int(node_capacity), int(gen_w0),
-                          int(gen_growth), int(gen_wmax), 0)
+                          int(gen_growth), int(gen_wmax), 1 if hashed_children else 0)
         self.h = C.c_void_p()
         self.n_actions = 0
         self.tabular = False

@@ -202,7 +202,7 @@ def test_preferred_action_heuristic_golden():
 
 def test_gs_oracle_regression_pins():
     """The generation-synchronous oracle is the specification of the CUDA kernels; tests/golden/gs_pins.json pins its
-    output on nine fixed searches (RockSample with and without preferred actions / rollouts, tabular models) so that
+    output on eleven fixed searches (RockSample with and without preferred actions / rollouts, tabular models) so that
     a change of the specification cannot slip in unnoticed (oracle/refharness/make_gs_pins.py regenerates them)."""
     import importlib.util
     spec = importlib.util.spec_from_file_location("make_gs_pins", os.path.join(ROOT, "oracle", "refharness", "make_gs_pins.py"))

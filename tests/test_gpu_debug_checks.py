@@ -1,5 +1,6 @@
 """The -DPOMCP_CHECKS build (device-side bounds and invariant checks; compute-sanitizer is closed on the GPU pool):
-a multi-move episode with and without preferred actions must trip no check and still equal the oracle."""
+a multi-move episode with and without preferred actions, and a tabular model on the hashed child table, must trip no
+check and still equal the oracle."""
 import os
 import subprocess
 import sys
@@ -38,6 +39,27 @@ for tag, n_sims, sched, pref in (("map-15-15", 60000, (256, 4, 32768), False), (
     c = pl.counters()
     assert c["check_failed"] == 0, c["check_failed"]
     pl.close()
+# a tabular model with more than 32 observations: the hashed child table under the same checks
+from pomdpy_b200 import native
+from pomdpy_b200.tabular import random_pomdp
+m = random_pomdp(48, 4, 64, seed=10)
+om = oracle.TabularModel(m.Tc, m.Oc, m.R, m.term_action_mask, m.term_state)
+bag = m.sample_init_states_packed(2000, np.random.RandomState(1))
+g = oracle.GsPOMCP(om, 0, 0, bag, max_depth=30, ucb_c=10.0, seed=3)
+pl = native.Planner(max_depth=30, ucb_coefficient=10.0, seed=3, gen_w0=32, gen_growth=4, gen_wmax=8192,
+                    node_capacity=1 << 17, max_particle_count=1000)
+pl.set_model_tabular(m.Tc, m.Oc, m.R, m.term_action_mask, m.term_state); pl.set_root_particles(bag)
+for mv in range(3):
+    g.search(20000, move=mv, w0=32, growth=4, wmax=8192); pl.search(20000, move=mv)
+    a, b = g.root_stats(), pl.root_stats()
+    assert np.array_equal(a["n"], b["n"]) and np.array_equal(a["qfix"], b["qfix"])
+    act = g.greedy(move=mv, stats=b)
+    u, v = g.update(act, 7 * mv + 1, 0, move=mv, need=1000), pl.advance(act, 7 * mv + 1, 0, move=mv)
+    assert (u["status"], u["tries"], u["accepted"]) == (v["status"], v["tries"], v["accepted"])
+    if u["status"] == 2: break
+c = pl.counters()
+assert c["check_failed"] == 0, c["check_failed"]
+pl.close()
 print("CHECKS-OK")
 '''
 

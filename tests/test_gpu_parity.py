@@ -257,7 +257,7 @@ def test_preferred_actions_episode_bit_exact(tag, seed, n_sims, sched, rollouts)
 
 def test_cuda_planner_reproduces_committed_gs_pins():
     """The CUDA planner against the COMMITTED fixtures of the specification (tests/golden/gs_pins.json): no oracle in
-    the loop -- root statistics, greedy actions, counters, belief updates of nine fixed searches."""
+    the loop -- root statistics, greedy actions, counters, belief updates of eleven fixed searches."""
     import json
     import os
     from helpers import GOLDEN

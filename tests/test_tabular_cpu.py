@@ -83,6 +83,38 @@ def test_gs_tabular_invariants_and_width_one():
     assert u["status"] in (0, 1) and u["accepted"] == 200 and g.bag().max() < 12
 
 
+def test_gs_observation_map_is_unbounded():
+    """More than 32 observations: the oracle's observation map is a chain per action node, as the reference's is a dict
+    (discrete_observation_mapping.py:12-47); children are found again under the observation they were created for,
+    re-rooting lands on them, and the index range ends at 2048 (11 bits of a device path entry)."""
+    m = random_pomdp(24, 3, 300, seed=11)
+    om = oracle_tab(m)
+    bag = m.sample_init_states_packed(500, np.random.RandomState(0))
+    g = oracle.GsPOMCP(om, 0, 0, bag, seed=4, max_depth=25, ucb_c=6.0)
+    g.search(8000, w0=16, growth=4, wmax=2048)
+    st = g.root_stats()
+    assert int(st["n"].sum()) == 8000
+    kids = {(a, z): g.node_stats([(a, z)]) for a in range(3) for z in range(300)}
+    seen = {k: v for k, v in kids.items() if v is not None}
+    assert len(seen) > 32 and max(z for _, z in seen) > 32
+    for a in range(3):                                   # every visit of edge a ended in one of its children (or was
+        below = sum(int(v["n"].sum()) for (aa, _), v in seen.items() if aa == a)   # the visit that created one)
+        made = sum(1 for (aa, _) in seen if aa == a)
+        assert below <= int(st["n"][a]) and below + made >= int(st["n"][a]) - 300
+    a0 = int(np.argmax(st["n"]))
+    z0 = max((k for k in seen if k[0] == a0), key=lambda k: int(seen[k]["n"].sum()))[1]
+    want = seen[(a0, z0)]
+    u = g.update(a0, z0, 0, need=50)
+    assert u["status"] == 0 and np.array_equal(g.root_stats()["n"], want["n"])
+    # limits
+    two = random_pomdp(2, 1, 2048, seed=0)
+    assert oracle_tab(two) is not None
+    import pytest
+    bad = random_pomdp(2, 1, 2049, seed=0)
+    with pytest.raises(Exception):
+        oracle_tab(bad)
+
+
 def test_tiger_planner_prefers_listening_then_the_right_door():
     m = tiger()
     om = oracle_tab(m)
