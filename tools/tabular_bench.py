@@ -10,8 +10,12 @@ from pomdpy_b200 import native
 from pomdpy_b200.tabular import random_pomdp, tiger
 
 n_sims = int(sys.argv[1]) if len(sys.argv) > 1 else 1000000
+m256 = random_pomdp(256, 16, 16, seed=1)
 for name, m, kw in (("tiger", tiger(), dict(ucb_coefficient=30.0)),
-                    ("rand-256-16-16", random_pomdp(256, 16, 16, seed=1), dict(ucb_coefficient=10.0)),
+                    ("rand-256-16-16", m256, dict(ucb_coefficient=10.0)),
+                    ("rand-256-16-16 hashed child table", m256, dict(ucb_coefficient=10.0, hashed_children=True)),
+                    ("rand-256-8-64 (hashed)", random_pomdp(256, 8, 64, seed=3), dict(ucb_coefficient=10.0)),
+                    ("rand-64-4-1024 (hashed)", random_pomdp(64, 4, 1024, seed=4), dict(ucb_coefficient=10.0)),
                     ("rand-4096-8-8", random_pomdp(4096, 8, 8, seed=2, sparsity=0.98), dict(ucb_coefficient=10.0))):
     pl = native.Planner(seed=1, gen_w0=4096, gen_growth=4, gen_wmax=1 << 19, node_capacity=1 << 22, **kw)
     pl.set_model_tabular(m.Tc, m.Oc, m.R, m.term_action_mask, m.term_state)
