@@ -106,7 +106,7 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                                              if (gens <= 120) S->steplog[gens - 1][k] = (long long)d_; tclk[4] = now_; } } while (0)
     TSEC_DECL;
     // expected arrivals that earn a node a slot in the block caches (batch-UCB allocations only: >= 16.5)
-    const float pc_min_k = fmaxf(4.0f * (float)gridDim.x, 16.5f);
+    const float pc_min_k = fmaxf((float)p.pc_mult * (float)gridDim.x, 16.5f);
 
     if (gtid == 0) S->phase_ns[4] = 0;
     // (no grid barrier here: what a block reads from S above -- root, world, belief, gstep -- is written again only in
@@ -677,9 +677,23 @@ __device__ __forceinline__ void search_body(const SearchParams &p, unsigned char
                         atomicAdd(&acc_n[key - 1u], 1);
                         smem_add64(&acc_q[key - 1u], qi);
                     } else {
-                        const size_t e = key & 0x7FFFFFFFu;
-                        atomicAdd(&p.t.n[e], 1);
-                        atomicAdd(reinterpret_cast<unsigned long long *>(&p.t.qfix[e]), (unsigned long long)qi);
+                        // an edge a few levels below the root is shared by many simulations of the BLOCK even when no
+                        // other lane of this warp holds it: those go through the block table too (one global update
+                        // per block and edge instead of one per simulation); deeper down edges rarely repeat within a
+                        // block, a table slot would only add the flush to the update
+                        bool staged = false;
+                        if (d <= BACKUP_TABLE_DEPTH) {
+                            uint32_t hq = ((key * 2654435761u) >> 16) & (ARR_HT - 1);
+                            for (int probe = 0; probe < BACKUP_TABLE_PROBES && !staged; ++probe, hq = (hq + 1u) & (ARR_HT - 1)) {
+                                const uint32_t prev = atomicCAS(&ht_key[hq], 0u, key);
+                                if (prev == 0u || prev == key) { atomicAdd(&ht_cnt[hq], 1); smem_add64(&ht_q[hq], qi); staged = true; }
+                            }
+                        }
+                        if (!staged) {
+                            const size_t e = key & 0x7FFFFFFFu;
+                            atomicAdd(&p.t.n[e], 1);
+                            atomicAdd(reinterpret_cast<unsigned long long *>(&p.t.qfix[e]), (unsigned long long)qi);
+                        }
                     }
                 }
                 // rotate the read-ahead registers only now: the loads issued at the top of the iteration had the whole
@@ -1048,6 +1062,8 @@ struct pomcp_handle {
     int kind = 0;                   // 0 RockSample, 1 tabular
     int zs = 2;                     // observation stride of the child table
     bool hashed = false;            // ... or a hashed child table (tabular models with more than 32 observations)
+    int pc_mult = 16;               // a node is hot (plan cached per block, computed in the prologue) from pc_mult expected
+                                    // arrivals per block (POMCP_PC_MULT; results do not depend on it)
     int n_actions = 0;
     TabHeader tab{};
     TabTables tt{};
@@ -1128,6 +1144,7 @@ extern "C" int pomcp_create(const pomcp_config *cfg, int device, pomcp_handle **
     CK(cudaDeviceGetAttribute(&coop, cudaDevAttrCooperativeLaunch, device));
     if (!coop) return fail(h, "device lacks cooperative launch");
     h->cap = cfg->node_capacity;
+    if (const char *e = getenv("POMCP_PC_MULT")) { const int v = atoi(e); if (v >= 1 && v <= 4096) h->pc_mult = v; }
     if (const char *mt = getenv("POMCP_MERGE_TIMEOUT_S")) {
         const double v = atof(mt);
         if (v > 0) h->merge_timeout_ns = (unsigned long long)(v * 1e9);
@@ -1490,6 +1507,7 @@ extern "C" int pomcp_search(pomcp_handle *h, int64_t n_sims, uint32_t sim_offset
     p.timeout_ns = timeout_s > 0 ? (unsigned long long)(timeout_s * 1e9) : 0ull;   // checked between generations
     p.merge_timeout_ns = h->merge_timeout_ns;
     p.pref_rollout = h->pref_rollout;
+    p.pc_mult = h->pc_mult;
     p.world = h->world; p.rank = h->rank;
     if (h->world > 1) {
         for (int r = 0; r < h->world; ++r) p.peer_buf[r] = h->peer_buf[r];

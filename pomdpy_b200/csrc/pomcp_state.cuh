@@ -39,6 +39,8 @@
 #define ARR_HT 1024            // per-block backup table (shared memory): slots of {edge, visits, return sum} of shared edges
 #endif
 #define ARR_PROBES 8
+#define BACKUP_TABLE_DEPTH 3   // backup: unshared-in-the-warp edges down to this path depth still go through the block table
+#define BACKUP_TABLE_PROBES 2
 #define PLAN_MASK 0            // kinds of a node's action plan (warp_plan)
 #define PLAN_PULLS 1
 #define PLAN_THRESHOLDS 2
@@ -171,6 +173,7 @@ struct SearchParams {
     unsigned long long merge_seq;
     unsigned long long merge_timeout_ns;
     int32_t pref_rollout, pad_pr;      // --preferred_actions with preferred rollouts (RockSample)
+    int32_t pc_mult, pad_pm;           // tuning (no effect on results): a node is hot from k >= pc_mult * blocks
 };
 
 // Exchange buffer of one rank (int64 words): slots[2][POMCP_MAX_PEERS][64] then flags[2][POMCP_MAX_PEERS].  Set
