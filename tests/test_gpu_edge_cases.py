@@ -143,3 +143,36 @@ def test_timeout_guard_stops_between_generations():
     st = pl.root_stats()
     assert 0 < st["sims_done"] < 200000 and int(st["n"].sum()) == st["sims_done"]
     pl.close()
+
+
+@pytest.mark.parametrize("max_depth", [300, 700])
+def test_long_horizons_beyond_256_steps(golden_dir, max_depth):
+    """--max_depth above 255: rollout step counters, the discount table in shared memory and the Philox block index
+    all run past 8 bits (the ABI accepts max_depth up to 4096).  A tabular model without terminal states rolls out
+    the full horizon every time; RockSample(11,11) at the same horizon as the second case.  Bit-exact vs the oracle."""
+    from helpers import golden_tables
+    from pomdpy_b200 import native
+    from pomdpy_b200.tabular import random_pomdp
+    m = random_pomdp(32, 6, 8, seed=1)
+    om = oracle.TabularModel(m.Tc, m.Oc, m.R, m.term_action_mask, m.term_state)
+    bag = m.sample_init_states_packed(1000, np.random.RandomState(2))
+    g = oracle.GsPOMCP(om, 0, 0, bag, max_depth=max_depth, ucb_c=10.0, discount=0.995, seed=5)
+    pl = native.Planner(max_depth=max_depth, ucb_coefficient=10.0, discount=0.995, seed=5, gen_w0=16, gen_growth=4,
+                        gen_wmax=2048, node_capacity=1 << 16)
+    pl.set_model_tabular(m.Tc, m.Oc, m.R, m.term_action_mask, m.term_state)
+    pl.set_root_particles(bag)
+    g.search(6000, w0=16, growth=4, wmax=2048)
+    pl.search(6000)
+    _same(g, pl)
+    gc, pc = g.counters(), pl.counters()
+    assert gc["rollout_steps"] == pc["rollout_steps"] and gc["levels"] == pc["levels"]
+    assert pc["rollout_steps"] > 6000 * (max_depth - 10)            # no terminal states: (almost) full-length rollouts
+    pl.close()
+    t = golden_tables("map-11-11")
+    kw = dict(seed=9, gen_w0=16, gen_growth=4, gen_wmax=2048, node_capacity=1 << 16, max_depth=max_depth)
+    om, g, pl, actual, bag, rng = _pair(t, 9, **kw)
+    g.search(5000, w0=16, growth=4, wmax=2048)
+    pl.search(5000)
+    _same(g, pl)
+    assert g.counters()["rollout_steps"] == pl.counters()["rollout_steps"]
+    pl.close()
