@@ -213,3 +213,27 @@ def test_observation_count_limits():
         pl.set_model_tabular(Tc, Oc, R, 0, None)
     pl.set_model_tabular(Tc, np.ascontiguousarray(Oc[:, :, 1:]), R, 0, None)        # 2048 observations: accepted
     pl.close()
+
+
+def test_switching_models_on_one_handle():
+    """One planner handle, three models in turn: hashed table (|Z| = 64) -> direct table (Tiger) -> hashed again; the
+    child table is re-allocated on every switch and each search equals the oracle's."""
+    pl = native.Planner(gen_w0=32, gen_growth=4, gen_wmax=4096, node_capacity=1 << 16, max_depth=30, ucb_coefficient=10.0)
+    for name in ("rand-48-4-64", "tiger", "rand-24-3-300", "rand-64-16-32"):
+        m = MODELS[name]()
+        om = oracle.TabularModel(m.Tc, m.Oc, m.R, m.term_action_mask, m.term_state)
+        bag = m.sample_init_states_packed(1000, np.random.RandomState(3))
+        g = oracle.GsPOMCP(om, 0, 0, bag, max_depth=30, ucb_c=10.0, seed=0)
+        pl.set_model_tabular(m.Tc, m.Oc, m.R, m.term_action_mask, m.term_state)
+        pl.set_root_particles(bag)
+        g.search(15000, w0=32, growth=4, wmax=4096)
+        pl.search(15000)
+        _same(g.root_stats(), pl.root_stats())
+        assert g.counters()["nodes"] == pl.counters()["nodes"]
+        z = int(m.num_observations) - 1
+        for act in range(min(m.num_actions, 3)):
+            x, y = g.node_stats([(act, z)]), pl.node_stats([(act, z)])
+            assert (x is None) == (y is None)
+            if x is not None:
+                _same(x, y)
+    pl.close()
