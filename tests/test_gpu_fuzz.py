@@ -69,9 +69,19 @@ def test_fuzz_rocksample(case):
 
 @pytest.mark.parametrize("case", range(16))
 def test_fuzz_tabular(case):
+    _fuzz_tabular(case, [1, 2, 3, 8, 32])
+
+
+@pytest.mark.parametrize("case", range(16, 26))
+def test_fuzz_tabular_many_observations(case):
+    """The same over observation counts beyond the direct-indexed child table (hashed table)."""
+    _fuzz_tabular(case, [33, 64, 100, 513, 2048])
+
+
+def _fuzz_tabular(case, z_choices):
     rng = np.random.default_rng(7000 + case)
     c = _config(rng)
-    S, A, Z = int(rng.choice([1, 2, 5, 33, 80, 200])), int(rng.choice([1, 2, 3, 9, 32])), int(rng.choice([1, 2, 3, 8, 32]))
+    S, A, Z = int(rng.choice([1, 2, 5, 33, 80, 200])), int(rng.choice([1, 2, 3, 9, 32])), int(rng.choice(z_choices))
     m = random_pomdp(S, A, Z, seed=case, sparsity=float(rng.choice([0.0, 0.5, 0.9])))
     if case % 4 == 1:                                     # some episode-ending actions / absorbing states
         m.term_action_mask = 1 << (A - 1)
